@@ -1,0 +1,314 @@
+"""ctypes binding of the CPU ORACLE (oracle/liborb_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+The product package (orb_slam_b200) must never import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborb_oracle.so")
+
+MAX_LEVELS = 32
+EDGE = 16
+TIES_CANONICAL, TIES_NTH_ELEMENT = 0, 1
+TRIG_RN, TRIG_LIBMF = 0, 1
+GRID_COLS, GRID_ROWS = 64, 48
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("nlevels", C.c_int), ("score_type", C.c_int), ("fast_th", C.c_int),
+                ("scale_factor", C.c_double),
+                ("scale", C.c_float * MAX_LEVELS), ("inv_scale", C.c_float * MAX_LEVELS),
+                ("quota", C.c_int * MAX_LEVELS), ("umax", C.c_int * 16),
+                ("ties_mode", C.c_int), ("trig_mode", C.c_int)]
+
+
+class CellGrid(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("cols", "rows", "cell_w", "cell_h", "n_cells", "nf_cell", "Wd", "Hd")]
+
+
+class Dump(C.Structure):
+    _fields_ = [("nlevels", C.c_int), ("w", C.c_int * MAX_LEVELS), ("h", C.c_int * MAX_LEVELS),
+                ("stride", C.c_size_t * MAX_LEVELS),
+                ("level", C.POINTER(C.c_uint8) * MAX_LEVELS), ("blurred", C.POINTER(C.c_uint8) * MAX_LEVELS),
+                ("n_level_kp", C.c_int * MAX_LEVELS), ("n_ties_at_cut", C.c_long), ("n_fallback_cells", C.c_long)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("n", C.c_int), ("keys_un", C.c_void_p), ("desc", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float),
+                ("nlevels", C.c_int), ("scale_factors", C.c_void_p),
+                ("cell_start", C.c_int * (GRID_COLS * GRID_ROWS + 1)), ("cell_items", C.c_void_p)]
+
+
+def build(force=False):
+    """Compile the oracle with oracle/Makefile (gcc/g++). Building the checker is not using it."""
+    srcs = ["orb_oracle.c", "orb_oracle_match.c", "orb_oracle_nth.cpp", "orb_oracle.h",
+            os.path.join("..", "include", "orbfe_brief_pattern.inc")]
+    stale = force or not os.path.exists(_SO) or any(
+        os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_SO) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc", "CXX": "g++"})
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        u8p, i32p, f32p = C.c_void_p, C.c_void_p, C.c_void_p
+        L.orb_oracle_params_init.argtypes = [C.POINTER(Params), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orb_oracle_level_size.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orb_oracle_cell_grid.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(CellGrid)]
+        L.orb_oracle_resize_linear_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_int, C.c_int, C.c_size_t]
+        L.orb_oracle_resize_linear_u8.restype = None
+        L.orb_oracle_reflect101_frame.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int]
+        L.orb_oracle_reflect101_frame.restype = None
+        L.orb_oracle_fast_m.argtypes = [u8p, C.c_size_t]
+        L.orb_oracle_fast_detect.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, i32p, i32p, i32p, C.c_int]
+        L.orb_oracle_blur7_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, u8p, C.c_size_t]
+        L.orb_oracle_blur7_u8.restype = None
+        L.orb_oracle_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orb_oracle_fast_atan2.restype = C.c_float
+        L.orb_oracle_ic_angle.argtypes = [u8p, C.c_size_t, i32p]
+        L.orb_oracle_ic_angle.restype = C.c_float
+        L.orb_oracle_ic_moments.argtypes = [u8p, C.c_size_t, i32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orb_oracle_ic_moments.restype = None
+        L.orb_oracle_brief.argtypes = [u8p, C.c_size_t, C.c_float, C.c_int, u8p]
+        L.orb_oracle_brief.restype = None
+        L.orb_oracle_extract.argtypes = [C.POINTER(Params), u8p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, u8p,
+                                         C.c_int, C.POINTER(C.c_int), C.POINTER(Dump)]
+        L.orb_oracle_dump_free.argtypes = [C.POINTER(Dump)]
+        L.orb_oracle_dump_free.restype = None
+        L.orb_oracle_hamming.argtypes = [u8p, u8p]
+        L.orb_oracle_frame_grid.argtypes = [C.POINTER(Frame)]
+        L.orb_oracle_frame_grid.restype = None
+        L.orb_oracle_features_in_area.argtypes = [C.POINTER(Frame), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, i32p, C.c_int]
+        L.orb_oracle_frame_scale_factors.argtypes = [C.c_float, C.c_int, f32p]
+        L.orb_oracle_frame_scale_factors.restype = None
+        L.orb_oracle_three_maxima.argtypes = [i32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orb_oracle_three_maxima.restype = None
+        L.orb_oracle_search_by_projection_ff.argtypes = [C.POINTER(Frame), C.POINTER(Frame), u8p, u8p, f32p, f32p,
+                                                         C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, i32p]
+        L.orb_oracle_window_search.argtypes = [C.POINTER(Frame), C.POINTER(Frame), u8p, C.c_int, C.c_int, C.c_int,
+                                               C.c_float, C.c_int, i32p]
+        L.orb_oracle_search_for_initialization.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f32p, C.c_int, C.c_float, C.c_int, i32p]
+        L.orb_oracle_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p, i32p]
+        L.orb_oracle_knn2.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_params(nfeatures=1000, scale_factor=1.2, nlevels=8, score_type=1, fast_th=20,
+                ties_mode=TIES_CANONICAL, trig_mode=TRIG_RN):
+    p = Params()
+    rc = lib().orb_oracle_params_init(C.byref(p), nfeatures, scale_factor, nlevels, score_type, fast_th)
+    if rc:
+        raise ValueError("orb_oracle_params_init failed: %d" % rc)
+    p.ties_mode, p.trig_mode = ties_mode, trig_mode
+    return p
+
+
+def level_size(p, level, W, H):
+    w, h = C.c_int(), C.c_int()
+    lib().orb_oracle_level_size(C.byref(p), level, W, H, C.byref(w), C.byref(h))
+    return w.value, h.value
+
+
+def cell_grid(p, level, W0, H0, w, h):
+    g = CellGrid()
+    rc = lib().orb_oracle_cell_grid(C.byref(p), level, W0, H0, w, h, C.byref(g))
+    return rc, g
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orb_oracle_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dst.strides[0])
+    return dst
+
+
+def reflect101_pad(img, b=EDGE):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    buf = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    buf[b:b + h, b:b + w] = img
+    lib().orb_oracle_reflect101_frame(_p(buf), w, h, buf.strides[0], b)
+    return buf
+
+
+def fast_m_map(img):
+    """m value of every pixel with a full ring (3-px margin); zero elsewhere. Slow: small images only."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    out = np.zeros((h, w), np.int32)
+    L = lib()
+    base = img.ctypes.data
+    for y in range(3, h - 3):
+        for x in range(3, w - 3):
+            out[y, x] = L.orb_oracle_fast_m(C.c_void_p(base + y * img.strides[0] + x), img.strides[0])
+    return out
+
+
+def fast_detect(img, th):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    cap = max(16, (w * h) // 4 + 16)
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orb_oracle_fast_detect(_p(img), w, h, img.strides[0], th, _p(xs), _p(ys), _p(sc), cap)
+    assert n <= cap
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def blur7(img):
+    """GaussianBlur 7x7 sigma 2 with BORDER_REFLECT_101 (integer 2.4 engine) of a whole image."""
+    buf = reflect101_pad(img, 3)
+    h, w = img.shape
+    dst = np.empty((h, w), np.uint8)
+    lib().orb_oracle_blur7_u8(C.c_void_p(buf.ctypes.data + 3 * buf.strides[0] + 3), w, h, buf.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().orb_oracle_fast_atan2(float(y), float(x))
+
+
+UMAX = np.array([15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3], np.int32)
+
+
+def ic_angle(padded, stride_elems_unused, x, y, pad=EDGE):
+    """padded: reflect-101 padded level (pad px); (x, y) in interior coordinates."""
+    return lib().orb_oracle_ic_angle(C.c_void_p(padded.ctypes.data + (y + pad) * padded.strides[0] + (x + pad)),
+                                     padded.strides[0], _p(UMAX))
+
+
+def ic_moments(padded, x, y, pad=EDGE):
+    m01, m10 = C.c_int(), C.c_int()
+    lib().orb_oracle_ic_moments(C.c_void_p(padded.ctypes.data + (y + pad) * padded.strides[0] + (x + pad)),
+                                padded.strides[0], _p(UMAX), C.byref(m01), C.byref(m10))
+    return m01.value, m10.value
+
+
+def brief(padded, x, y, angle_deg, trig_mode=TRIG_RN, pad=EDGE):
+    d = np.empty(32, np.uint8)
+    lib().orb_oracle_brief(C.c_void_p(padded.ctypes.data + (y + pad) * padded.strides[0] + (x + pad)),
+                           padded.strides[0], float(angle_deg), trig_mode, _p(d))
+    return d
+
+
+def extract(p, img, cap=None, want_dump=False):
+    """ORBextractor::operator(): returns (rc, keypoints[KP_DTYPE], descriptors[N,32], dump or None).
+
+    dump = dict(levels=[unblurred interior arrays], blurred=[...], n_level_kp=[...], ties=int, fallback=int)
+    """
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    cap = cap or max(p.nfeatures, 1)
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = C.c_int(0)
+    d = Dump() if want_dump else None
+    rc = lib().orb_oracle_extract(C.byref(p), _p(img), W, H, img.strides[0], _p(kps), _p(desc), cap, C.byref(n),
+                                  C.byref(d) if want_dump else None)
+    out = None
+    if want_dump and rc in (0, -3):
+        out = {"levels": [], "blurred": [], "n_level_kp": [], "ties": d.n_ties_at_cut, "fallback": d.n_fallback_cells}
+        for l in range(d.nlevels):
+            w, h, s = d.w[l], d.h[l], d.stride[l]
+            for key, ptr in (("levels", d.level[l]), ("blurred", d.blurred[l])):
+                full = np.ctypeslib.as_array(ptr, shape=(h + 2 * EDGE, s)).copy()
+                out[key].append(full[:, :w + 2 * EDGE])
+            out["n_level_kp"].append(d.n_level_kp[l])
+    if want_dump:
+        lib().orb_oracle_dump_free(C.byref(d))
+    m = min(n.value, cap)
+    return rc, kps[:m].copy(), desc[:m].copy(), out
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orb_oracle_hamming(_p(a), _p(b))
+
+
+def knn2(q, db):
+    q = np.ascontiguousarray(q, np.uint8)
+    db = np.ascontiguousarray(db, np.uint8)
+    nq, ndb = q.shape[0], db.shape[0]
+    bd, bi, sd = (np.empty(nq, np.int32) for _ in range(3))
+    lib().orb_oracle_knn2(_p(q), nq, _p(db), ndb, _p(bd), _p(bi), _p(sd))
+    return bd, bi, sd
+
+
+class OracleFrame:
+    """The slice of ORB_SLAM::Frame the matchers read (Frame.cc:56-125), zero distortion."""
+
+    def __init__(self, kps, desc, width, height, scale_factor=1.2, nlevels=8):
+        self.kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, dtype=np.uint8)
+        self.n = int(self.kps.shape[0])
+        self.sf = np.empty(nlevels, np.float32)
+        lib().orb_oracle_frame_scale_factors(scale_factor, nlevels, _p(self.sf))
+        self.items = np.zeros(max(self.n, 1), np.int32)
+        f = Frame()
+        f.n = self.n
+        f.keys_un = self.kps.ctypes.data
+        f.desc = self.desc.ctypes.data
+        f.min_x, f.min_y, f.max_x, f.max_y = 0.0, 0.0, float(width), float(height)  # Frame.cc:342-348
+        f.grid_inv_w = np.float32(GRID_COLS) / np.float32(width)   # Frame.cc:77
+        f.grid_inv_h = np.float32(GRID_ROWS) / np.float32(height)  # Frame.cc:78
+        f.nlevels = nlevels
+        f.scale_factors = self.sf.ctypes.data
+        f.cell_items = self.items.ctypes.data
+        self.c = f
+        lib().orb_oracle_frame_grid(C.byref(f))
+
+    def features_in_area(self, x, y, r, min_level, max_level):
+        out = np.empty(max(self.n, 1), np.int32)
+        n = lib().orb_oracle_features_in_area(C.byref(self.c), x, y, r, min_level, max_level, _p(out), self.n)
+        return out[:n].copy()
+
+
+def search_by_projection_ff(cur, last, last_has_mp, last_outlier, last_world, Tcw, fx, fy, cx, cy, th,
+                            check_orientation=True, cur_mp=None):
+    cur_mp = np.full(cur.n, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp, np.int32).copy()
+    has = np.ascontiguousarray(last_has_mp, np.uint8)
+    outl = np.ascontiguousarray(last_outlier, np.uint8)
+    world = np.ascontiguousarray(last_world, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32)
+    n = lib().orb_oracle_search_by_projection_ff(C.byref(cur.c), C.byref(last.c), _p(has), _p(outl), _p(world), _p(T),
+                                                 fx, fy, cx, cy, th, int(check_orientation), _p(cur_mp))
+    return n, cur_mp
+
+
+def window_search(f1, f2, f1_has_mp, window, min_level=-1, max_level=2 ** 31 - 1, nnratio=0.6, check_orientation=True):
+    has = np.ascontiguousarray(f1_has_mp, np.uint8)
+    m21 = np.empty(max(f2.n, 1), np.int32)
+    n = lib().orb_oracle_window_search(C.byref(f1.c), C.byref(f2.c), _p(has), window, min_level, max_level, nnratio,
+                                       int(check_orientation), _p(m21))
+    return n, m21[:f2.n]
+
+
+def search_for_initialization(f1, f2, prev_matched, window, nnratio=0.9, check_orientation=True):
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.empty(max(f1.n, 1), np.int32)
+    n = lib().orb_oracle_search_for_initialization(C.byref(f1.c), C.byref(f2.c), _p(prev), window, nnratio,
+                                                   int(check_orientation), _p(m12))
+    return n, m12[:f1.n], prev

@@ -1,0 +1,330 @@
+/*
+ * orb_oracle_match.c -- CPU ORACLE (matcher half).  TEST INFRASTRUCTURE ONLY -- see orb_oracle.h.
+ *
+ * Restates reference src/ORBmatcher.cc (DescriptorDistance, SearchByProjection(Frame,Frame),
+ * WindowSearch, SearchForInitialization, ComputeThreeMaxima) and the candidate generator
+ * src/Frame.cc (grid fill, PosInGrid, GetFeaturesInArea) on plain arrays.
+ */
+#include "orb_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define TH_HIGH 100      /* ORBmatcher.cc:40 */
+#define TH_LOW 50        /* ORBmatcher.cc:41 */
+#define HISTO_LENGTH 30  /* ORBmatcher.cc:42 */
+
+/* ORBmatcher::DescriptorDistance, ORBmatcher.cc:1794-1810 (SWAR popcount over 8 x 32-bit words) */
+int orb_oracle_hamming(const uint8_t *a, const uint8_t *b) {
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t wa, wb;
+        memcpy(&wa, a + 4 * i, 4);
+        memcpy(&wb, b + 4 * i, 4);
+        uint32_t v = wa ^ wb;
+        v = v - ((v >> 1) & 0x55555555u);
+        v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+        dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+    }
+    return dist;
+}
+
+/* Frame.cc:95-103: mvScaleFactors[i] = mvScaleFactors[i-1]*mfScaleFactor (float*float) where
+ * mfScaleFactor = GetScaleFactor() = (float)(double member) == the ctor's float argument. */
+void orb_oracle_frame_scale_factors(float sf, int nlevels, float *out) {
+    out[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) out[i] = out[i - 1] * sf;
+}
+
+/* Frame::PosInGrid, Frame.cc:267-277: round() (half away from zero) of a float expression */
+static int pos_in_grid(const OrbOracleFrame *f, const OrbOracleKeyPoint *kp, int *px, int *py) {
+    *px = (int)round((double)((kp->x - f->min_x) * f->grid_inv_w));
+    *py = (int)round((double)((kp->y - f->min_y) * f->grid_inv_h));
+    if (*px < 0 || *px >= ORB_ORACLE_GRID_COLS || *py < 0 || *py >= ORB_ORACLE_GRID_ROWS) return 0;
+    return 1;
+}
+
+/* Frame.cc:116-123: features pushed to their cell in ascending index order */
+void orb_oracle_frame_grid(OrbOracleFrame *f) {
+    const int NC = ORB_ORACLE_GRID_COLS * ORB_ORACLE_GRID_ROWS;
+    int *cnt = (int *)calloc((size_t)NC + 1, sizeof(int));
+    int *cell = (int *)malloc(sizeof(int) * (size_t)(f->n > 0 ? f->n : 1));
+    for (int i = 0; i < f->n; i++) {
+        int px, py;
+        cell[i] = pos_in_grid(f, &f->keys_un[i], &px, &py) ? px * ORB_ORACLE_GRID_ROWS + py : -1;
+        if (cell[i] >= 0) cnt[cell[i]]++;
+    }
+    f->cell_start[0] = 0;
+    for (int c = 0; c < NC; c++) f->cell_start[c + 1] = f->cell_start[c] + cnt[c];
+    memset(cnt, 0, sizeof(int) * (size_t)NC);
+    for (int i = 0; i < f->n; i++)
+        if (cell[i] >= 0) f->cell_items[f->cell_start[cell[i]] + cnt[cell[i]]++] = i;
+    free(cnt);
+    free(cell);
+}
+
+/* Frame::GetFeaturesInArea, Frame.cc:200-265 */
+int orb_oracle_features_in_area(const OrbOracleFrame *f, float x, float y, float r, int minLevel,
+                                int maxLevel, int *out, int cap) {
+    int n = 0;
+    int nMinCellX = (int)floor((double)((x - f->min_x - r) * f->grid_inv_w)); /* :205 */
+    if (nMinCellX < 0) nMinCellX = 0;
+    if (nMinCellX >= ORB_ORACLE_GRID_COLS) return 0;
+    int nMaxCellX = (int)ceil((double)((x - f->min_x + r) * f->grid_inv_w)); /* :210 */
+    if (nMaxCellX > ORB_ORACLE_GRID_COLS - 1) nMaxCellX = ORB_ORACLE_GRID_COLS - 1;
+    if (nMaxCellX < 0) return 0;
+    int nMinCellY = (int)floor((double)((y - f->min_y - r) * f->grid_inv_h)); /* :215 */
+    if (nMinCellY < 0) nMinCellY = 0;
+    if (nMinCellY >= ORB_ORACLE_GRID_ROWS) return 0;
+    int nMaxCellY = (int)ceil((double)((y - f->min_y + r) * f->grid_inv_h)); /* :220 */
+    if (nMaxCellY > ORB_ORACLE_GRID_ROWS - 1) nMaxCellY = ORB_ORACLE_GRID_ROWS - 1;
+    if (nMaxCellY < 0) return 0;
+
+    int bCheckLevels = 1, bSameLevel = 0; /* :225-231 */
+    if (minLevel == -1 && maxLevel == -1) bCheckLevels = 0;
+    else if (minLevel == maxLevel) bSameLevel = 1;
+
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const int c = ix * ORB_ORACLE_GRID_ROWS + iy;
+            for (int j = f->cell_start[c]; j < f->cell_start[c + 1]; j++) {
+                const int idx = f->cell_items[j];
+                const OrbOracleKeyPoint *kp = &f->keys_un[idx];
+                if (bCheckLevels && !bSameLevel) {
+                    if (kp->octave < minLevel || kp->octave > maxLevel) continue;
+                } else if (bSameLevel) {
+                    if (kp->octave != minLevel) continue;
+                }
+                if (fabsf(kp->x - x) > r || fabsf(kp->y - y) > r) continue; /* :254 */
+                if (n < cap) out[n] = idx;
+                n++;
+            }
+        }
+    return n;
+}
+
+/* ComputeThreeMaxima, ORBmatcher.cc:1748-1789 */
+void orb_oracle_three_maxima(const int *counts, int L, int *ind1, int *ind2, int *ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    *ind1 = *ind2 = *ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = counts[i];
+        if (s > max1) {
+            max3 = max2; max2 = max1; max1 = s;
+            *ind3 = *ind2; *ind2 = *ind1; *ind1 = i;
+        } else if (s > max2) {
+            max3 = max2; max2 = s;
+            *ind3 = *ind2; *ind2 = i;
+        } else if (s > max3) {
+            max3 = s; *ind3 = i;
+        }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+
+/* rotation-histogram bin, e.g. ORBmatcher.cc:1583-1590 */
+static int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)roundf(rot * factor); /* round(float) -> half away from zero */
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+typedef struct { int *v; int n, cap; } IVec;
+static void ivec_push(IVec *a, int x) {
+    if (a->n == a->cap) { a->cap = a->cap ? a->cap * 2 : 64; a->v = (int *)realloc(a->v, sizeof(int) * (size_t)a->cap); }
+    a->v[a->n++] = x;
+}
+
+/* SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, float th), ORBmatcher.cc:1507-1620 */
+int orb_oracle_search_by_projection_ff(const OrbOracleFrame *cur, const OrbOracleFrame *last,
+                                       const uint8_t *last_has_mp, const uint8_t *last_outlier,
+                                       const float *last_world, const float *Tcw,
+                                       float fx, float fy, float cx, float cy, float th,
+                                       int check_orientation, int *cur_mp) {
+    int nmatches = 0;
+    IVec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(cur->n > 0 ? cur->n : 1));
+    for (int i = 0; i < last->n; i++) {
+        if (!last_has_mp[i] || last_outlier[i]) continue;
+        /* :1527-1528: x3Dc = Rcw*x3Dw+tcw -- cv::gemm on CV_32F accumulates in double, adds tcw in double */
+        const float *X = last_world + 3 * i;
+        float xc3[3];
+        for (int k = 0; k < 3; k++) {
+            double s = (double)Tcw[4 * k + 0] * (double)X[0] + (double)Tcw[4 * k + 1] * (double)X[1] +
+                       (double)Tcw[4 * k + 2] * (double)X[2];
+            xc3[k] = (float)(s + (double)Tcw[4 * k + 3]);
+        }
+        const float xc = xc3[0], yc = xc3[1];
+        const float invzc = (float)(1.0 / (double)xc3[2]); /* :1532 */
+        const float u = fx * xc * invzc + cx;              /* :1534-1535 */
+        const float v = fy * yc * invzc + cy;
+        if (u < cur->min_x || u > cur->max_x) continue;
+        if (v < cur->min_y || v > cur->max_y) continue;
+        const int oct = last->keys_un[i].octave; /* LastFrame.mvKeys[i].octave */
+        const float radius = th * cur->scale_factors[oct]; /* :1547 */
+        const int nc = orb_oracle_features_in_area(cur, u, v, radius, oct - 1, oct + 1, cand, cur->n);
+        if (nc == 0) continue;
+        const uint8_t *dMP = last->desc + (size_t)i * 32;
+        int bestDist = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (cur_mp[i2] >= 0) continue; /* :1562 */
+            const int dist = orb_oracle_hamming(dMP, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            cur_mp[bestIdx2] = i;
+            nmatches++;
+            if (check_orientation)
+                ivec_push(&hist[rot_bin(last->keys_un[i].angle, cur->keys_un[bestIdx2].angle)], bestIdx2);
+        }
+    }
+    if (check_orientation) {
+        int counts[HISTO_LENGTH], i1, i2, i3;
+        for (int b = 0; b < HISTO_LENGTH; b++) counts[b] = hist[b].n;
+        orb_oracle_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int b = 0; b < HISTO_LENGTH; b++) {
+            if (b == i1 || b == i2 || b == i3) continue;
+            for (int j = 0; j < hist[b].n; j++) { cur_mp[hist[b].v[j]] = -1; nmatches--; }
+        }
+    }
+    for (int b = 0; b < HISTO_LENGTH; b++) free(hist[b].v);
+    free(cand);
+    return nmatches;
+}
+
+/* WindowSearch, ORBmatcher.cc:409-516 */
+int orb_oracle_window_search(const OrbOracleFrame *f1, const OrbOracleFrame *f2, const uint8_t *f1_has_mp,
+                             int window, int minLevel, int maxLevel, float nnratio,
+                             int check_orientation, int *m21) {
+    int nmatches = 0;
+    for (int i = 0; i < f2->n; i++) m21[i] = -1;
+    IVec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    const int bMin = minLevel > 0, bMax = maxLevel < INT_MAX;
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(f2->n > 0 ? f2->n : 1));
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        if (!f1_has_mp[i1]) continue;
+        const OrbOracleKeyPoint *kp1 = &f1->keys_un[i1];
+        const int level1 = kp1->octave;
+        if (bMin && level1 < minLevel) continue;
+        if (bMax && level1 > maxLevel) continue;
+        const int nc = orb_oracle_features_in_area(f2, kp1->x, kp1->y, (float)window, level1, level1, cand, f2->n);
+        if (nc == 0) continue;
+        const uint8_t *d1 = f1->desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (m21[i2] >= 0) continue; /* :451 */
+            const int dist = orb_oracle_hamming(d1, f2->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        /* :469  int <= int*float  (bestDist2 may be INT_MAX -> float) */
+        if ((float)bestDist <= (float)bestDist2 * nnratio && bestDist <= TH_HIGH) {
+            m21[bestIdx2] = i1;
+            nmatches++;
+            ivec_push(&hist[rot_bin(kp1->angle, f2->keys_un[bestIdx2].angle)], bestIdx2);
+        }
+    }
+    if (check_orientation) {
+        int counts[HISTO_LENGTH], i1, i2, i3;
+        for (int b = 0; b < HISTO_LENGTH; b++) counts[b] = hist[b].n;
+        orb_oracle_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int b = 0; b < HISTO_LENGTH; b++) {
+            if (b == i1 || b == i2 || b == i3) continue;
+            for (int j = 0; j < hist[b].n; j++) { m21[hist[b].v[j]] = -1; nmatches--; }
+        }
+    }
+    for (int b = 0; b < HISTO_LENGTH; b++) free(hist[b].v);
+    free(cand);
+    return nmatches;
+}
+
+/* SearchForInitialization, ORBmatcher.cc:598-713 */
+int orb_oracle_search_for_initialization(const OrbOracleFrame *f1, const OrbOracleFrame *f2,
+                                         float *prev, int window, float nnratio,
+                                         int check_orientation, int *m12) {
+    int nmatches = 0;
+    for (int i = 0; i < f1->n; i++) m12[i] = -1;
+    IVec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    int *mdist = (int *)malloc(sizeof(int) * (size_t)(f2->n > 0 ? f2->n : 1));
+    int *m21 = (int *)malloc(sizeof(int) * (size_t)(f2->n > 0 ? f2->n : 1));
+    for (int i = 0; i < f2->n; i++) { mdist[i] = INT_MAX; m21[i] = -1; }
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(f2->n > 0 ? f2->n : 1));
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        const OrbOracleKeyPoint *kp1 = &f1->keys_un[i1];
+        const int level1 = kp1->octave;
+        if (level1 > 0) continue; /* :615-616 */
+        const int nc = orb_oracle_features_in_area(f2, prev[2 * i1], prev[2 * i1 + 1], (float)window, level1, level1, cand, f2->n);
+        if (nc == 0) continue;
+        const uint8_t *d1 = f1->desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            const int dist = orb_oracle_hamming(d1, f2->desc + (size_t)i2 * 32);
+            if (mdist[i2] <= dist) continue; /* :637 */
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if ((float)bestDist < (float)bestDist2 * nnratio) { /* :654 */
+                if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; nmatches--; }
+                m12[i1] = bestIdx2;
+                m21[bestIdx2] = i1;
+                mdist[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_orientation)
+                    ivec_push(&hist[rot_bin(kp1->angle, f2->keys_un[bestIdx2].angle)], i1);
+            }
+        }
+    }
+    if (check_orientation) {
+        int counts[HISTO_LENGTH], a, b2, c3;
+        for (int b = 0; b < HISTO_LENGTH; b++) counts[b] = hist[b].n;
+        orb_oracle_three_maxima(counts, HISTO_LENGTH, &a, &b2, &c3);
+        for (int b = 0; b < HISTO_LENGTH; b++) {
+            if (b == a || b == b2 || b == c3) continue;
+            for (int j = 0; j < hist[b].n; j++) {
+                const int idx1 = hist[b].v[j];
+                if (m12[idx1] >= 0) { m12[idx1] = -1; nmatches--; } /* :697-701 */
+            }
+        }
+    }
+    for (int i1 = 0; i1 < f1->n; i1++) /* :708-710 */
+        if (m12[i1] >= 0) {
+            prev[2 * i1] = f2->keys_un[m12[i1]].x;
+            prev[2 * i1 + 1] = f2->keys_un[m12[i1]].y;
+        }
+    for (int b = 0; b < HISTO_LENGTH; b++) free(hist[b].v);
+    free(mdist); free(m21); free(cand);
+    return nmatches;
+}
+
+/* dense best/second-best sweep (config 5 primitive): strict-< update in ascending db order */
+void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,
+                     int *best_dist, int *best_idx, int *second_dist) {
+    for (int i = 0; i < nq; i++) {
+        const uint64_t *a = (const uint64_t *)(const void *)(q + (size_t)i * 32);
+        uint64_t a0, a1, a2, a3;
+        memcpy(&a0, a, 8); memcpy(&a1, a + 1, 8); memcpy(&a2, a + 2, 8); memcpy(&a3, a + 3, 8);
+        int b1 = INT_MAX, b2 = INT_MAX, bi = -1;
+        for (long j = 0; j < ndb; j++) {
+            uint64_t w[4];
+            memcpy(w, db + (size_t)j * 32, 32);
+            int d = __builtin_popcountll(a0 ^ w[0]) + __builtin_popcountll(a1 ^ w[1]) +
+                    __builtin_popcountll(a2 ^ w[2]) + __builtin_popcountll(a3 ^ w[3]);
+            if (d < b1) { b2 = b1; b1 = d; bi = (int)j; }
+            else if (d < b2) b2 = d;
+        }
+        best_dist[i] = b1; best_idx[i] = bi; second_dist[i] = b2;
+    }
+}
