@@ -1,0 +1,650 @@
+// extract_kernels.cu -- hand-written sm_100a kernels of the ORB extractor hot path.
+//
+// Stage map (reference src/ORBextractor.cc; canonical algorithm = SURVEY.md Appendix A):
+//   resize_level_kernel   ComputePyramid: cv::resize INTER_LINEAR u8 (:800), integer fixed point
+//   fast_nms_kernel       cv::FAST per cell (:599-614) as ONE threshold-free score map + windowed NMS
+//   cell_quota_kernel     per-cell quota redistribution (:622-670)
+//   cell_select_kernel    per-cell retainBest (:683-685) as an exact radix select on unique keys
+//   level_select_kernel   level-wide retainBest (:697-701) + canonical ordering
+//   blur7_kernel          cv::GaussianBlur 7x7 sigma 2 (:760), OpenCV-2.4 integer engine
+//   describe_kernel       IC_Angle (:124-151) + computeOrbDescriptor (:155-194) + output packing (:768-777)
+//
+// All pixel arithmetic is integer; floats appear only in IC_Angle's atan2 polynomial, the BRIEF
+// rotation and the coordinate rescale, each written with explicit round-to-nearest intrinsics
+// (no FMA contraction).  No tensor cores: there is no dense contraction on this path.
+#include "orbfe_internal.h"
+
+namespace orbfe {
+
+__device__ __forceinline__ int find_level_by(const PlanDev *plan, int idx, int which) {
+    // which: 0 = ftile_base, 1 = btile_base, 2 = cell_base, 3 = kp_base
+    int l = 0;
+    const int n = plan->nlevels;
+    for (int k = 1; k < n; k++) {
+        const LevelDev &L = plan->lv[k];
+        const int base = which == 0 ? L.ftile_base : which == 1 ? L.btile_base : which == 2 ? L.cell_base : L.kp_base;
+        // levels with zero extent share a base with their successor: the LAST level whose base <= idx wins
+        if (idx >= base) l = k;
+    }
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid: level l from level l-1.  One thread = 4 adjacent destination pixels (one uchar4 store).
+// Horizontal/vertical tap tables were computed on the host exactly as OpenCV computes them, so the
+// device part is pure integer: r = S[x0]*a0 + S[x1]*a1 ; v = (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__restrict__ plan, int level) {
+    const LevelDev &D = plan->lv[level];
+    const LevelDev &S = plan->lv[level - 1];
+    const int f = blockIdx.z;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int dw = D.w, dh = D.h;
+    if (y >= dh || x4 >= dw) return;
+    const int2 rr = __ldg(&D.yrows[y]);
+    const short2 bb = __ldg(&D.yab[y]);
+    const uint8_t *__restrict__ s0 = S.pyr + (size_t)f * S.plane + (size_t)rr.x * S.pitch;
+    const uint8_t *__restrict__ s1 = S.pyr + (size_t)f * S.plane + (size_t)rr.y * S.pitch;
+    const int swm1 = S.w - 1;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = min(x4 + i, dw - 1);
+        const int xo = __ldg(&D.xofs[x]);
+        const short2 ab = __ldg(&D.xab[x]);
+        const int x1 = min(xo + 1, swm1);
+        const int r0 = (int)__ldg(s0 + xo) * ab.x + (int)__ldg(s0 + x1) * ab.y;
+        const int r1 = (int)__ldg(s1 + xo) * ab.x + (int)__ldg(s1 + x1) * ab.y;
+        int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        out |= (uint32_t)v << (8 * i);
+    }
+    // pitch is a multiple of 128 and x4 a multiple of 4: aligned 32-bit store (bytes beyond w land in row padding)
+    *reinterpret_cast<uint32_t *>(D.pyr + (size_t)f * D.plane + (size_t)y * D.pitch + x4) = out;
+}
+
+void launch_resize_level(const PlanDev *d_plan, const PlanDev &hp, int level, cudaStream_t s) {
+    const LevelDev &D = hp.lv[level];
+    dim3 block(64, 4);
+    dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, hp.batch);
+    resize_level_kernel<<<grid, block, 0, s>>>(d_plan, level);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST-9/16 score map + windowed 3x3 NMS + candidate emission.
+//
+// m(p) = max over the 16 contiguous 9-arcs of min(ring - v) and of min(v - ring)  (clamped at 0).
+// p is a FAST corner at threshold t  <=>  m > t ; OpenCV's score = m - 1 (threshold independent).
+// NMS: strict maximum over the 8 neighbours that lie inside the same cell's detect window
+// (cv::FAST ran on the cell image, so it never saw the neighbouring cell; :599-607).
+// Because any neighbour that is not a corner at t has m' <= t < m, the NMS outcome does not depend
+// on t: one pass emits every local maximum with m > min(fastTh,7) and the per-cell threshold
+// (fastTh, or 7 when fastTh yields <= 3 keypoints, :609-614) is applied later as a key threshold.
+// ------------------------------------------------------------------------------------------------
+#define FPW (ORBFE_FT_W + 8)  // pixel tile width  (72)
+#define FPH (ORBFE_FT_H + 8)  // pixel tile height (40)
+#define FMW (ORBFE_FT_W + 2)  // m tile width (66)
+#define FMH (ORBFE_FT_H + 2)  // m tile height (34)
+#define FPS 80                // pixel tile row stride in smem (bytes, multiple of 4)
+#define FMS 68                // m tile row stride
+
+__device__ __forceinline__ int fast_m_at(const uint8_t *c /* smem centre */, int tlo) {
+    // ring offsets, radius-3 Bresenham circle, clockwise from (0,+3)
+    const int v = c[0];
+    int d[16];
+    d[0] = c[3 * FPS + 0];
+    d[8] = c[-3 * FPS + 0];
+    // early reject: any 9-arc contains one pixel of every opposite pair
+    {
+        const int a0 = d[0] - v, a8 = d[8] - v;
+        if (abs(a0) <= tlo && abs(a8) <= tlo) return 0;
+    }
+    d[4] = c[0 * FPS + 3];
+    d[12] = c[0 * FPS - 3];
+    {
+        const int a4 = d[4] - v, a12 = d[12] - v;
+        if (abs(a4) <= tlo && abs(a12) <= tlo) return 0;
+    }
+    d[1] = c[3 * FPS + 1];
+    d[2] = c[2 * FPS + 2];
+    d[3] = c[1 * FPS + 3];
+    d[5] = c[-1 * FPS + 3];
+    d[6] = c[-2 * FPS + 2];
+    d[7] = c[-3 * FPS + 1];
+    d[9] = c[-3 * FPS - 1];
+    d[10] = c[-2 * FPS - 2];
+    d[11] = c[-1 * FPS - 3];
+    d[13] = c[1 * FPS - 3];
+    d[14] = c[2 * FPS - 2];
+    d[15] = c[3 * FPS - 1];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] -= v;
+    int tmin[16], tmax[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        tmin[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        tmax[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    }
+    int mb = 0, md = 0;  // bright: max of window-min ; dark: max of -(window-max)
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int wmin = __vimin3_s32(tmin[k], tmin[(k + 3) & 15], tmin[(k + 6) & 15]);
+        const int wmax = __vimax3_s32(tmax[k], tmax[(k + 3) & 15], tmax[(k + 6) & 15]);
+        mb = max(mb, wmin);
+        md = max(md, -wmax);
+    }
+    return max(mb, md);
+}
+
+__global__ void __launch_bounds__(256) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+    __shared__ __align__(16) uint8_t pix[FPH * FPS];
+    __shared__ __align__(16) uint8_t mm[FMH * FMS];
+
+    const int f = blockIdx.y;
+    const int l = find_level_by(plan, blockIdx.x, 0);
+    const LevelDev &L = plan->lv[l];
+    const int tile = blockIdx.x - L.ftile_base;
+    const int ty = tile / L.ftiles_x, tx = tile - ty * L.ftiles_x;
+    const int x0 = ORBFE_EDGE + tx * ORBFE_FT_W, y0 = ORBFE_EDGE + ty * ORBFE_FT_H;
+    const int w = L.w, h = L.h, pitch = L.pitch;
+    const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
+    const int tlo = plan->t_lo, thi = plan->t_hi;
+
+    // ---- stage the pixel tile: rows y0-4 .. y0+FT_H+3, cols x0-4 .. x0+FT_W+3 (x0-4 is 4-byte aligned) ----
+    {
+        const int words_per_row = FPW / 4;  // 18
+        const int max_word = pitch / 4 - 1;
+        const int wx0 = (x0 - 4) >> 2;
+        for (int i = threadIdx.x; i < FPH * words_per_row; i += blockDim.x) {
+            const int r = i / words_per_row, c = i - r * words_per_row;
+            const int gy = min(y0 - 4 + r, h - 1);
+            const int gw = min(wx0 + c, max_word);
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gy * pitch) + gw);
+            *reinterpret_cast<uint32_t *>(&pix[r * FPS + c * 4]) = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- m for the (FT_H+2) x (FT_W+2) tile (1-px apron for the NMS) ----
+    const int xmax = w - ORBFE_EDGE, ymax = h - ORBFE_EDGE;  // detect area is [16, xmax) x [16, ymax)
+    for (int i = threadIdx.x; i < FMH * FMW; i += blockDim.x) {
+        const int my = i / FMW, mx = i - my * FMW;
+        const int x = x0 - 1 + mx, y = y0 - 1 + my;
+        int m = 0;
+        if (x >= ORBFE_EDGE && x < xmax && y >= ORBFE_EDGE && y < ymax) m = fast_m_at(&pix[(my + 3) * FPS + (mx + 3)], tlo);
+        mm[my * FMS + mx] = (uint8_t)m;
+    }
+    __syncthreads();
+
+    // ---- windowed NMS + emission ----
+    const int cw = L.cw, ch = L.ch, cols = L.cols, rows = L.rows;
+    for (int i = threadIdx.x; i < ORBFE_FT_H * ORBFE_FT_W; i += blockDim.x) {
+        const int iy = i / ORBFE_FT_W, ix = i - iy * ORBFE_FT_W;
+        const int x = x0 + ix, y = y0 + iy;
+        const uint8_t *c = &mm[(iy + 1) * FMS + (ix + 1)];
+        const int m = c[0];
+        if (m <= tlo || x >= xmax || y >= ymax) continue;
+        const int cj = min((x - ORBFE_EDGE) / cw, cols - 1), ci = min((y - ORBFE_EDGE) / ch, rows - 1);
+        const int xa = ORBFE_EDGE + cj * cw, ya = ORBFE_EDGE + ci * ch;
+        const int xb = (cj == cols - 1) ? xmax - 1 : xa + cw - 1;
+        const int yb = (ci == rows - 1) ? ymax - 1 : ya + ch - 1;
+        const bool L_ = x > xa, R_ = x < xb, U_ = y > ya, D_ = y < yb;
+        bool keep = true;
+        keep &= !(L_) || m > c[-1];
+        keep &= !(R_) || m > c[+1];
+        keep &= !(U_) || m > c[-FMS];
+        keep &= !(D_) || m > c[+FMS];
+        keep &= !(L_ && U_) || m > c[-FMS - 1];
+        keep &= !(R_ && U_) || m > c[-FMS + 1];
+        keep &= !(L_ && D_) || m > c[+FMS - 1];
+        keep &= !(R_ && D_) || m > c[+FMS + 1];
+        if (!keep) continue;
+        const int gcell = L.cell_base + ci * cols + cj;
+        const size_t fc = (size_t)f * plan->ncells_total + gcell;
+        const int slot = atomicAdd(&wk.cell_cnt_lo[fc], 1);
+        if (m > thi) atomicAdd(&wk.cell_cnt_hi[fc], 1);
+        if (slot < wk.cell_cand_cap[gcell]) {
+            const uint32_t raster = (uint32_t)((y - ya) * cw + (x - xa));
+            wk.cand_keys[(size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + slot] =
+                ((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster);
+        } else {
+            atomicExch(wk.err_flag, 1);
+        }
+    }
+}
+
+void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
+    dim3 grid(hp.nftiles_total, hp.batch);
+    fast_nms_kernel<<<grid, 256, 0, s>>>(d_plan, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-level quota redistribution (ORBextractor.cc:622-670).  One warp per (level, frame).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(32) cell_quota_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+    __shared__ uint32_t no_more[128];  // bitmap, up to 4096 cells per level
+    const int l = blockIdx.x, f = blockIdx.y;
+    const LevelDev &L = plan->lv[l];
+    const int lane = threadIdx.x;
+    const int nCells = L.ncells, nfc = L.nfc;
+    const size_t fb = (size_t)f * plan->ncells_total + L.cell_base;
+    const int t1_is_lo = plan->t1_is_lo;
+    const int t1 = t1_is_lo ? plan->t_lo : plan->t_hi;  // fastTh
+    const int t2 = t1_is_lo ? plan->t_hi : plan->t_lo;  // 7
+    for (int i = lane; i < 128; i += 32) no_more[i] = 0;
+    __syncwarp();
+
+    int toDist = 0, nNoMore = 0;
+    for (int c = lane; c < nCells; c += 32) {
+        const int lo = wk.cell_cnt_lo[fb + c], hi = wk.cell_cnt_hi[fb + c];
+        const int n1 = t1_is_lo ? lo : hi, n2 = t1_is_lo ? hi : lo;
+        const bool fallback = n1 <= 3;  // :609
+        const int nTotal = fallback ? n2 : n1;
+        wk.cell_min_key[fb + c] = (uint32_t)(fallback ? t2 : t1) << 24;  // score = m-1 >= t  <=>  m > t
+        // park nTotal in cell_cnt_lo? no: keep counts intact, recompute below
+        int keep;
+        if (nTotal > nfc) keep = nfc;
+        else { keep = nTotal; toDist += nfc - nTotal; nNoMore++; atomicOr(&no_more[c >> 5], 1u << (c & 31)); }
+        wk.cell_keep[fb + c] = keep;
+    }
+    toDist = warp_sum(toDist);
+    nNoMore = warp_sum(nNoMore);
+    __syncwarp();
+
+    while (toDist > 0 && nNoMore < nCells) {
+        const int nNew = nfc + (int)ceilf(__fdiv_rn((float)toDist, (float)(nCells - nNoMore)));  // :646
+        int dist = 0, more = 0;
+        for (int c = lane; c < nCells; c += 32) {
+            if (no_more[c >> 5] & (1u << (c & 31))) continue;
+            const int lo = wk.cell_cnt_lo[fb + c], hi = wk.cell_cnt_hi[fb + c];
+            const int n1 = t1_is_lo ? lo : hi, n2 = t1_is_lo ? hi : lo;
+            const int nTotal = (n1 <= 3) ? n2 : n1;
+            if (nTotal > nNew) wk.cell_keep[fb + c] = nNew;
+            else {
+                wk.cell_keep[fb + c] = nTotal;
+                dist += nNew - nTotal;
+                more++;
+                atomicOr(&no_more[c >> 5], 1u << (c & 31));
+            }
+        }
+        toDist = warp_sum(dist);
+        nNoMore += warp_sum(more);
+        __syncwarp();
+    }
+}
+
+void launch_cell_quota(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
+    dim3 grid(hp.nlevels, hp.batch);
+    cell_quota_kernel<<<grid, 32, 0, s>>>(d_plan, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-cell retention: keep the `keep` largest keys among the eligible ones (key >= min_key).
+// Keys are unique (score<<24 | inverted raster), so "top-n, ties at the cut broken by earlier raster
+// position" (the canonical retainBest rule) is simply an exact n-th-largest-key radix select.
+// Survivors are appended (order irrelevant) to the level's kept list as 64-bit selection keys
+//   score(8) << 36 | (4095 - cell)(12) << 24 | (0xFFFFFF - raster)(24).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix, s_mask;
+    __shared__ int s_k, s_base, s_fill;
+
+    const int gcell = blockIdx.x, f = blockIdx.y;
+    const size_t fc = (size_t)f * plan->ncells_total + gcell;
+    const int keep = wk.cell_keep[fc];
+    if (keep <= 0) return;
+    const int l = find_level_by(plan, gcell, 2);
+    const LevelDev &L = plan->lv[l];
+    const int n = min(wk.cell_cnt_lo[fc], wk.cell_cand_cap[gcell]);
+    const uint32_t min_key = wk.cell_min_key[fc];
+    const uint32_t *__restrict__ keys = wk.cand_keys + (size_t)f * plan->cand_total + wk.cell_cand_base[gcell];
+    const int tid = threadIdx.x;
+
+    // number of eligible candidates
+    const int lo = wk.cell_cnt_lo[fc], hi = wk.cell_cnt_hi[fc];
+    const int n1 = plan->t1_is_lo ? lo : hi, n2 = plan->t1_is_lo ? hi : lo;
+    const int n_elig = (n1 <= 3) ? n2 : n1;
+
+    uint32_t cut = min_key;
+    if (n_elig > keep) {
+        if (tid == 0) { s_prefix = 0; s_mask = 0; s_k = keep; }
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const uint32_t prefix = s_prefix, mask = s_mask;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const uint32_t k = keys[i];
+                if (k >= min_key && (k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xFF], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int k = s_k, cum = 0, b = 255;
+                for (; b >= 0; b--) {
+                    if (cum + hist[b] >= k) break;
+                    cum += hist[b];
+                }
+                s_k = k - cum;  // rank inside bin b
+                s_prefix = prefix | ((uint32_t)b << shift);
+                s_mask = mask | (0xFFu << shift);
+            }
+            __syncthreads();
+        }
+        cut = s_prefix;  // the keep-th largest eligible key
+    }
+    const int nk = min(keep, n_elig);
+    if (tid == 0) {
+        s_base = atomicAdd(&wk.kept_cnt[(size_t)f * plan->nlevels + l], nk);
+        s_fill = 0;
+    }
+    __syncthreads();
+    const int base = s_base;
+    const unsigned long long cell_part = (unsigned long long)(4095 - (gcell - L.cell_base)) << 24;
+    unsigned long long *__restrict__ kept = wk.kept_keys + (size_t)f * plan->kept_total + L.kept_base;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const uint32_t k = keys[i];
+        if (k >= cut) {
+            const int p = base + atomicAdd(&s_fill, 1);
+            if (p < L.kept_cap)
+                kept[p] = ((unsigned long long)(k >> 24) << 36) | cell_part | (unsigned long long)(k & 0xFFFFFFu);
+            else
+                atomicExch(wk.err_flag, 2);
+        }
+    }
+}
+
+void launch_cell_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
+    dim3 grid(hp.ncells_total, hp.batch);
+    cell_select_kernel<<<grid, 128, 0, s>>>(d_plan, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Level-wide trim (:697-701) and canonical ordering.  One CTA per (level, frame); bitonic sorts in smem.
+// ------------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_desc(unsigned long long *a, int n2) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = a[i], y = a[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) level_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+    extern __shared__ unsigned long long skeys[];
+    const int l = blockIdx.x, f = blockIdx.y;
+    const LevelDev &L = plan->lv[l];
+    int n = min(wk.kept_cnt[(size_t)f * plan->nlevels + l], L.kept_cap);
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    const unsigned long long *__restrict__ kept = wk.kept_keys + (size_t)f * plan->kept_total + L.kept_base;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) skeys[i] = i < n ? kept[i] : 0ull;
+    __syncthreads();
+    int n_out = n;
+    if (n > L.quota) {
+        bitonic_sort_desc(skeys, n2);
+        n_out = L.quota;
+    }
+    // order key: (cell asc, raster asc) == inverted fields descending; carry the score in the low byte
+    const unsigned long long m36 = (1ull << 36) - 1ull;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const unsigned long long k = skeys[i];
+        skeys[i] = i < n_out ? (((k & m36) << 8) | (k >> 36)) : 0ull;
+    }
+    __syncthreads();
+    int m2 = 1;
+    while (m2 < n_out) m2 <<= 1;
+    bitonic_sort_desc(skeys, m2);
+    int2 *__restrict__ out = wk.kp_xy_score + (size_t)f * plan->nfeatures + L.kp_base;
+    for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+        const unsigned long long k = skeys[i];
+        const int score = (int)(k & 0xFF);
+        const unsigned long long inv = k >> 8;
+        const int cell = 4095 - (int)(inv >> 24);
+        const int raster = 0xFFFFFF - (int)(inv & 0xFFFFFF);
+        const int ci = cell / L.cols, cj = cell - ci * L.cols;
+        const int ly = raster / L.cw, lx = raster - ly * L.cw;
+        const int x = ORBFE_EDGE + cj * L.cw + lx, y = ORBFE_EDGE + ci * L.ch + ly;
+        out[i] = make_int2(x | (y << 16), score);
+    }
+    if (threadIdx.x == 0) wk.level_cnt[(size_t)f * plan->nlevels + l] = n_out;
+}
+
+int level_select_smem_bytes(int max_kept) {
+    int n2 = 1;
+    while (n2 < max_kept) n2 <<= 1;
+    return n2 * (int)sizeof(unsigned long long);
+}
+
+int set_level_select_smem(int bytes) {
+    return (int)cudaFuncSetAttribute(level_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+void launch_level_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, size_t smem_bytes, cudaStream_t s) {
+    dim3 grid(hp.nlevels, hp.batch);
+    level_select_kernel<<<grid, 512, smem_bytes, s>>>(d_plan, w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 7x7 Gaussian, OpenCV-2.4 integer engine: taps [18,34,49,55,49,34,18] per pass (sum 257), exact
+// int accumulation, (sum)/65536 rounded half-to-even, saturated.  BORDER_REFLECT_101 by index reflection.
+// Row sums fit u16 exactly (255*257 = 65535).
+// ------------------------------------------------------------------------------------------------
+#define BPW (ORBFE_BT_W + 8)  // staged width: x0-4 .. x0+BT_W+3 (word aligned; the taps use x0-3 .. x0+BT_W+2)
+#define BPH (ORBFE_BT_H + 6)
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ plan) {
+    __shared__ __align__(16) uint8_t pix[BPH * BPW];
+    __shared__ __align__(16) uint16_t rowsum[BPH * ORBFE_BT_W];
+
+    const int f = blockIdx.y;
+    const int l = find_level_by(plan, blockIdx.x, 1);
+    const LevelDev &L = plan->lv[l];
+    const int tile = blockIdx.x - L.btile_base;
+    const int ty = tile / L.btiles_x, tx = tile - ty * L.btiles_x;
+    const int x0 = tx * ORBFE_BT_W, y0 = ty * ORBFE_BT_H;
+    const int w = L.w, h = L.h, pitch = L.pitch;
+    const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
+
+    const bool interior = (x0 >= 4) && (x0 + ORBFE_BT_W + 4 <= w) && (y0 >= 3) && (y0 + ORBFE_BT_H + 3 <= h);
+    if (interior) {
+        const int wpr = BPW / 4;  // 34 words per staged row
+        for (int i = threadIdx.x; i < BPH * wpr; i += blockDim.x) {
+            const int r = i / wpr, c = i - r * wpr;
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)(y0 - 3 + r) * pitch + (x0 - 4)) + c);
+            *reinterpret_cast<uint32_t *>(&pix[r * BPW + c * 4]) = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < BPH * BPW; i += blockDim.x) {
+            const int r = i / BPW, c = i - r * BPW;
+            const int gy = reflect101(y0 - 3 + r, h);
+            const int gx = reflect101(x0 - 4 + c, w);
+            pix[i] = __ldg(img + (size_t)gy * pitch + gx);
+        }
+    }
+    __syncthreads();
+    // horizontal pass: rowsum[r][x] for r in [0,BPH), x in [0,BT_W): centre column = x + 4 in pix
+    for (int i = threadIdx.x; i < BPH * ORBFE_BT_W; i += blockDim.x) {
+        const int r = i / ORBFE_BT_W, x = i - r * ORBFE_BT_W;
+        const uint8_t *p = &pix[r * BPW + x + 4];
+        const int s = 55 * p[0] + 49 * (p[-1] + p[1]) + 34 * (p[-2] + p[2]) + 18 * (p[-3] + p[3]);
+        rowsum[i] = (uint16_t)s;
+    }
+    __syncthreads();
+    // vertical pass, 4 pixels per thread, one 32-bit store
+    uint8_t *__restrict__ dst = L.blur + (size_t)f * L.plane;
+    for (int i = threadIdx.x; i < ORBFE_BT_H * (ORBFE_BT_W / 4); i += blockDim.x) {
+        const int y = i / (ORBFE_BT_W / 4), xq = (i - y * (ORBFE_BT_W / 4)) * 4;
+        const int gy = y0 + y, gx = x0 + xq;
+        if (gy >= h || gx >= w) continue;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint16_t *q = &rowsum[(y + 3) * ORBFE_BT_W + xq + k];
+            const int s = 55 * (int)q[0] + 49 * ((int)q[-ORBFE_BT_W] + (int)q[ORBFE_BT_W]) +
+                          34 * ((int)q[-2 * ORBFE_BT_W] + (int)q[2 * ORBFE_BT_W]) +
+                          18 * ((int)q[-3 * ORBFE_BT_W] + (int)q[3 * ORBFE_BT_W]);
+            int v = s >> 16;
+            const int r = s & 0xFFFF;
+            v += (r > 0x8000) | ((r == 0x8000) & (v & 1));
+            v = min(v, 255);
+            out |= (uint32_t)v << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(dst + (size_t)gy * pitch + gx) = out;
+    }
+}
+
+void launch_blur(const PlanDev *d_plan, const PlanDev &hp, cudaStream_t s) {
+    dim3 grid(hp.nbtiles_total, hp.batch);
+    blur7_kernel<<<grid, 256, 0, s>>>(d_plan);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Orientation + descriptor + output packing.  One warp per keypoint slot.
+// ------------------------------------------------------------------------------------------------
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// cv::fastAtan2: 7th-order odd polynomial, every operation rounded to binary32, no FMA
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = (float)2.2204460492503131e-16;  // (float)DBL_EPSILON
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a;
+    if (ax >= ay) {
+        const float c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        const float c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        const float c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        const float c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) describe_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
+                                                       const int8_t *__restrict__ g_pattern,
+                                                       OrbfeKeyPoint *__restrict__ out_kps,
+                                                       uint8_t *__restrict__ out_desc, int *__restrict__ out_counts) {
+    __shared__ __align__(16) int8_t pat[1024];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(pat)[i] = __ldg(reinterpret_cast<const uint32_t *>(g_pattern) + i);
+    __syncthreads();
+
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nlev = plan->nlevels;
+    const int *__restrict__ lcnt = wk.level_cnt + (size_t)f * nlev;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < nlev; k++) tot += lcnt[k];
+        out_counts[f] = tot;
+    }
+    if (slot >= plan->nfeatures) return;
+    const int l = find_level_by(plan, slot, 3);
+    const LevelDev &L = plan->lv[l];
+    const int idx = slot - L.kp_base;
+    if (idx >= lcnt[l]) return;
+    int out_idx = idx;
+    for (int k = 0; k < l; k++) out_idx += lcnt[k];
+
+    const int2 kp = wk.kp_xy_score[(size_t)f * plan->nfeatures + slot];
+    const int x = kp.x & 0xFFFF, y = kp.x >> 16;
+    const int w = L.w, h = L.h, pitch = L.pitch;
+    const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
+    const uint8_t *__restrict__ blr = L.blur + (size_t)f * L.plane;
+
+    // ---- IC_Angle: lane <-> column u = lane-15, loop over rows v ----
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - 15;
+        const int au = abs(u);
+        if (lane < 31) {
+            const uint8_t *c = img + (size_t)y * pitch + x + u;
+#pragma unroll 1
+            for (int v = -15; v <= 15; v++) {
+                if (au <= c_umax[abs(v)]) {
+                    const int val = __ldg(c + (ptrdiff_t)v * pitch);
+                    m10 += u * val;
+                    m01 += v * val;
+                }
+            }
+        }
+        m10 = warp_sum(m10);
+        m01 = warp_sum(m01);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- rotated BRIEF: lane <-> descriptor byte ----
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);  // (float)(CV_PI/180.f)
+    const float th = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)th), b = (float)sin((double)th);
+    int val = 0;
+    const int8_t *pp = pat + lane * 32;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int t[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float px = (float)pp[4 * k + 2 * e], py = (float)pp[4 * k + 2 * e + 1];
+            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const int sx = x + rx, sy = y + ry;
+            if (sx >= 0 && sx < w && sy >= 0 && sy < h) t[e] = __ldg(blr + (size_t)sy * pitch + sx);
+            else t[e] = __ldg(img + (size_t)reflect101(sy, h) * pitch + reflect101(sx, w));  // unblurred frame
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    // pack 4 lanes' bytes into a word; lanes 0,4,8,.. store
+    uint32_t word = (uint32_t)val;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 1) << 8;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 2) << 16;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 3) << 24;
+    const size_t o = (size_t)f * plan->nfeatures + out_idx;
+    if ((lane & 3) == 0) reinterpret_cast<uint32_t *>(out_desc + o * 32)[lane >> 2] = word;
+    if (lane == 0) {
+        OrbfeKeyPoint r;
+        r.x = l ? __fmul_rn((float)x, L.scale) : (float)x;  // :768-775
+        r.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
+        r.size = L.patch_size;
+        r.angle = angle;
+        r.response = (float)kp.y;
+        r.octave = l;
+        r.class_id = -1;
+        out_kps[o] = r;
+    }
+}
+
+void launch_describe(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, const int8_t *d_pattern,
+                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s) {
+    dim3 grid((hp.nfeatures + 7) / 8, hp.batch);
+    if (grid.x == 0) grid.x = 1;
+    describe_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, d_kps, d_desc, d_counts);
+}
+
+}  // namespace orbfe

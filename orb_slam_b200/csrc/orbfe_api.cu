@@ -1,0 +1,696 @@
+// orbfe_api.cu -- host side of liborbfe.so: the extractor/matcher handles, the per-geometry plan and the
+// extern "C" entry points declared in include/orbfe.h.
+//
+// Host float arithmetic here reproduces the reference constructor and OpenCV's resize tables
+// (src/ORBextractor.cc:457-511, :785-786, :527-547); this translation unit is compiled with
+// -ffp-contract=off so that every float operation is individually rounded, as the canonical
+// semantics require.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "orbfe_internal.h"
+
+using namespace orbfe;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ORBFE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *orbfe_last_error(void) { return g_err; }
+extern "C" int orbfe_version(void) { return ORBFE_VERSION; }
+extern "C" int orbfe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static const int8_t kBriefPattern[1024] = {
+#include "../../include/orbfe_brief_pattern.inc"
+};
+
+// OpenCV rounding helpers: cvRound = round-half-even of the double value
+static inline int cv_round(double v) { return (int)std::lrint(v); }
+static inline int cv_floor(double v) { int i = (int)v; return i - (i > v); }
+
+// ------------------------------------------------------------------------------------------------
+// Extractor
+// ------------------------------------------------------------------------------------------------
+struct StageTimer {
+    std::vector<std::string> names;
+    std::vector<cudaEvent_t> ev;  // names.size()+1 events
+};
+
+struct OrbfeExtractor {
+    int nfeatures = 0, nlevels = 0, score_type = 1, fast_th = 20, device = 0;
+    double scale_factor = 1.2;  // double member initialised from a float (ORBextractor.h:62, .cc:459)
+    float scale[ORBFE_MAX_LEVELS], inv_scale[ORBFE_MAX_LEVELS];
+    int quota[ORBFE_MAX_LEVELS];
+
+    // plan
+    int W = 0, H = 0, Bcap = 0;
+    PlanDev hplan;
+    PlanDev *dplan = nullptr;
+    WorkDev work;
+    std::vector<void *> allocs;  // device allocations of the current plan
+    void *counters = nullptr;    // cell_cnt_lo | cell_cnt_hi | kept_cnt (zeroed per call)
+    size_t counters_bytes = 0;
+    size_t ls_smem = 0;
+    int8_t *d_pattern = nullptr;
+    // own outputs (host-API path)
+    OrbfeKeyPoint *d_kps = nullptr;
+    uint8_t *d_desc = nullptr;
+    int *d_counts = nullptr;
+    int *h_counts = nullptr;  // pinned
+    int *h_err = nullptr;     // pinned
+    size_t h_counts_cap = 0;
+
+    cudaStream_t stream = nullptr;
+    int last_launches = 0;
+    bool profiling = false;
+    StageTimer timer;
+    std::vector<float> stage_ms;
+};
+
+static void free_plan(OrbfeExtractor *ex) {
+    for (void *p : ex->allocs) cudaFree(p);
+    ex->allocs.clear();
+    ex->dplan = nullptr;
+    ex->counters = nullptr;
+    ex->d_kps = nullptr;
+    ex->d_desc = nullptr;
+    ex->d_counts = nullptr;
+    ex->W = ex->H = ex->Bcap = 0;
+}
+
+template <typename T>
+static cudaError_t dmalloc(OrbfeExtractor *ex, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 256));
+    if (e == cudaSuccess) { ex->allocs.push_back(q); *p = (T *)q; }
+    return e;
+}
+
+// cv::resize INTER_LINEAR tap tables for one axis (OpenCV imgproc resize.cpp semantics)
+static void resize_axis(int dn, int sn, bool clamp_weights, std::vector<int> &ofs, std::vector<short2> &ab) {
+    ofs.resize(dn);
+    ab.resize(dn);
+    const double scale = 1.0 / ((double)dn / (double)sn);
+    for (int d = 0; d < dn; d++) {
+        float f = (float)(((double)d + 0.5) * scale - 0.5);
+        int s = cv_floor((double)f);
+        f -= (float)s;
+        if (clamp_weights) {  // horizontal: sx<0 -> (0,f=0); sx>=sn-1 -> (sn-1,f=0)
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+        }
+        ofs[d] = s;
+        ab[d].x = (short)cv_round((double)((1.f - f) * 2048.f));
+        ab[d].y = (short)cv_round((double)(f * 2048.f));
+    }
+}
+
+static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
+    if (ex->W == W && ex->H == H && B <= ex->Bcap) return ORBFE_OK;
+    free_plan(ex);
+    PlanDev &P = ex->hplan;
+    memset(&P, 0, sizeof(P));
+    P.nlevels = ex->nlevels;
+    P.batch = B;
+    P.nfeatures = ex->nfeatures;
+    P.t_lo = std::min(ex->fast_th, 7);
+    P.t_hi = std::max(ex->fast_th, 7);
+    P.t1_is_lo = ex->fast_th <= 7;
+    P.score_type = ex->score_type;
+
+    const float ratio = (float)W / (float)H;  // :527 (level-0 dims)
+    int cell_base = 0, kp_base = 0, kept_base = 0, ft_base = 0, bt_base = 0, max_kept = 0;
+    std::vector<long long> cand_base;
+    std::vector<int> cand_cap;
+    long long cand_total = 0;
+    for (int l = 0; l < ex->nlevels; l++) {
+        LevelDev &L = P.lv[l];
+        L.w = cv_round((double)((float)W * ex->inv_scale[l]));  // :785-786
+        L.h = cv_round((double)((float)H * ex->inv_scale[l]));
+        if (L.w < 1 || L.h < 1 || L.w > 65535 || L.h > 32767)
+            return fail(ORBFE_ERR_UNSUPPORTED, "level %d size %dx%d outside the supported domain", l, L.w, L.h);
+        L.pitch = (L.w + 127) / 128 * 128;
+        L.plane = (size_t)L.pitch * L.h;
+        L.quota = ex->quota[l];
+        L.scale = ex->scale[l];
+        L.patch_size = (float)(int)(31.0f * ex->scale[l]);  // :675
+        // cell grid, :533-547
+        L.cols = (int)std::sqrt((float)L.quota / (5.0f * ratio));
+        L.rows = (int)(ratio * (float)L.cols);
+        const int Wd = L.w - 2 * ORBFE_EDGE, Hd = L.h - 2 * ORBFE_EDGE;
+        if (L.cols < 1 || L.rows < 1 || Wd < 1 || Hd < 1)
+            return fail(ORBFE_ERR_UNSUPPORTED, "level %d (%dx%d, quota %d): degenerate cell grid %dx%d", l, L.w, L.h,
+                        L.quota, L.cols, L.rows);
+        L.cw = (int)std::ceil((float)Wd / (float)L.cols);
+        L.ch = (int)std::ceil((float)Hd / (float)L.rows);
+        L.ncells = L.rows * L.cols;
+        L.nfc = (int)std::ceil((float)L.quota / (float)L.ncells);
+        if ((L.cols - 1) * L.cw > Wd || (L.rows - 1) * L.ch > Hd)
+            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cell grid does not tile the detect area (image too small)", l);
+        if (L.ncells > 4096 || (long long)L.cw * L.ch > (1 << 24))
+            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %d cells of %dx%d exceed the key layout", l, L.ncells, L.cw, L.ch);
+        L.cell_base = cell_base;
+        cell_base += L.ncells;
+        L.kp_base = kp_base;
+        kp_base += L.quota;
+        L.kept_base = kept_base;
+        L.kept_cap = L.quota + 2 * L.ncells + 64;
+        kept_base += L.kept_cap;
+        max_kept = std::max(max_kept, L.kept_cap);
+        L.ftiles_x = (Wd + ORBFE_FT_W - 1) / ORBFE_FT_W;
+        L.ftiles_y = (Hd + ORBFE_FT_H - 1) / ORBFE_FT_H;
+        L.ftile_base = ft_base;
+        ft_base += L.ftiles_x * L.ftiles_y;
+        L.btiles_x = (L.w + ORBFE_BT_W - 1) / ORBFE_BT_W;
+        L.btiles_y = (L.h + ORBFE_BT_H - 1) / ORBFE_BT_H;
+        L.btile_base = bt_base;
+        bt_base += L.btiles_x * L.btiles_y;
+        for (int i = 0; i < L.rows; i++)
+            for (int j = 0; j < L.cols; j++) {
+                const int ww = (j == L.cols - 1) ? Wd - j * L.cw : L.cw;
+                const int hh = (i == L.rows - 1) ? Hd - i * L.ch : L.ch;
+                const int cap = std::max(1, ((ww + 1) / 2) * ((hh + 1) / 2));  // strict 8-neighbour maxima bound
+                cand_base.push_back(cand_total);
+                cand_cap.push_back(cap);
+                cand_total += cap;
+            }
+    }
+    P.ncells_total = cell_base;
+    P.nftiles_total = ft_base;
+    P.nbtiles_total = bt_base;
+    P.kept_total = kept_base;
+    P.cand_total = cand_total;
+    // keypoint slots = sum of the per-level quotas; equals nfeatures whenever the last-level remainder
+    // max(nfeatures - sum, 0) is not clipped (:487)
+    P.nfeatures = kp_base;
+
+    ex->ls_smem = (size_t)level_select_smem_bytes(max_kept);
+    if (ex->ls_smem > 200 * 1024)
+        return fail(ORBFE_ERR_UNSUPPORTED, "nfeatures too large for the level-select kernel (%zu B smem)", ex->ls_smem);
+
+    CU_TRY(cudaSetDevice(ex->device));
+    if (ex->ls_smem > 48 * 1024) {
+        cudaError_t e = (cudaError_t)set_level_select_smem((int)ex->ls_smem);
+        if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    // ---- device memory ----
+    for (int l = 0; l < ex->nlevels; l++) {
+        LevelDev &L = P.lv[l];
+        CU_TRY(dmalloc(ex, &L.pyr, L.plane * B + 256));
+        CU_TRY(dmalloc(ex, &L.blur, L.plane * B + 256));
+        CU_TRY(cudaMemsetAsync(L.pyr, 0, L.plane * B + 256, ex->stream));
+        if (l > 0) {
+            const LevelDev &S = P.lv[l - 1];
+            std::vector<int> xo, yo;
+            std::vector<short2> xab, yab;
+            resize_axis(L.w, S.w, true, xo, xab);
+            resize_axis(L.h, S.h, false, yo, yab);
+            std::vector<int2> yr(L.h);
+            for (int y = 0; y < L.h; y++) {  // rows sy, sy+1 clipped to [0, sh-1]; weights not reset at the clip
+                yr[y].x = std::min(std::max(yo[y], 0), S.h - 1);
+                yr[y].y = std::min(std::max(yo[y] + 1, 0), S.h - 1);
+            }
+            int *dxo; short2 *dxab; int2 *dyr; short2 *dyab;
+            CU_TRY(dmalloc(ex, &dxo, (size_t)L.w));
+            CU_TRY(dmalloc(ex, &dxab, (size_t)L.w));
+            CU_TRY(dmalloc(ex, &dyr, (size_t)L.h));
+            CU_TRY(dmalloc(ex, &dyab, (size_t)L.h));
+            CU_TRY(cudaMemcpy(dxo, xo.data(), sizeof(int) * L.w, cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(dxab, xab.data(), sizeof(short2) * L.w, cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(dyr, yr.data(), sizeof(int2) * L.h, cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(dyab, yab.data(), sizeof(short2) * L.h, cudaMemcpyHostToDevice));
+            L.xofs = dxo; L.xab = dxab; L.yrows = dyr; L.yab = dyab;
+        }
+    }
+    WorkDev &Wk = ex->work;
+    memset(&Wk, 0, sizeof(Wk));
+    long long *d_cb; int *d_cc;
+    CU_TRY(dmalloc(ex, &d_cb, cand_base.size()));
+    CU_TRY(dmalloc(ex, &d_cc, cand_cap.size()));
+    CU_TRY(cudaMemcpy(d_cb, cand_base.data(), sizeof(long long) * cand_base.size(), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_cc, cand_cap.data(), sizeof(int) * cand_cap.size(), cudaMemcpyHostToDevice));
+    Wk.cell_cand_base = d_cb;
+    Wk.cell_cand_cap = d_cc;
+    CU_TRY(dmalloc(ex, &Wk.cand_keys, (size_t)cand_total * B));
+    const size_t nc = (size_t)P.ncells_total * B, nl = (size_t)P.nlevels * B;
+    int *cnt;
+    ex->counters_bytes = sizeof(int) * (2 * nc + nl);
+    CU_TRY(dmalloc(ex, &cnt, 2 * nc + nl));
+    ex->counters = cnt;
+    Wk.cell_cnt_lo = cnt;
+    Wk.cell_cnt_hi = cnt + nc;
+    Wk.kept_cnt = cnt + 2 * nc;
+    CU_TRY(dmalloc(ex, &Wk.cell_keep, nc));
+    CU_TRY(dmalloc(ex, &Wk.cell_min_key, nc));
+    CU_TRY(dmalloc(ex, &Wk.kept_keys, (size_t)P.kept_total * B));
+    CU_TRY(dmalloc(ex, &Wk.kp_xy_score, (size_t)std::max(P.nfeatures, 1) * B));
+    CU_TRY(dmalloc(ex, &Wk.level_cnt, nl));
+    CU_TRY(dmalloc(ex, &Wk.err_flag, 1));
+    CU_TRY(cudaMemsetAsync(Wk.err_flag, 0, sizeof(int), ex->stream));
+    CU_TRY(dmalloc(ex, &ex->d_kps, (size_t)std::max(P.nfeatures, 1) * B));
+    CU_TRY(dmalloc(ex, &ex->d_desc, (size_t)std::max(P.nfeatures, 1) * B * 32));
+    CU_TRY(dmalloc(ex, &ex->d_counts, (size_t)B));
+    CU_TRY(dmalloc(ex, &ex->dplan, 1));
+    CU_TRY(cudaMemcpyAsync(ex->dplan, &P, sizeof(P), cudaMemcpyHostToDevice, ex->stream));
+    if (ex->h_counts_cap < (size_t)B) {
+        if (ex->h_counts) cudaFreeHost(ex->h_counts);
+        CU_TRY(cudaHostAlloc((void **)&ex->h_counts, sizeof(int) * B, cudaHostAllocDefault));
+        ex->h_counts_cap = B;
+    }
+    CU_TRY(cudaStreamSynchronize(ex->stream));
+    ex->W = W; ex->H = H; ex->Bcap = B;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_extractor_create(int nfeatures, float scale_factor, int nlevels, int score_type, int fast_th,
+                                      int device, OrbfeExtractor **out) {
+    if (!out) return fail(ORBFE_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (nfeatures < 0 || nlevels < 1 || nlevels > ORBFE_MAX_LEVELS || !(scale_factor > 1.0f) || fast_th < 0 || fast_th > 254)
+        return fail(ORBFE_ERR_ARG, "bad extractor parameters (nfeatures=%d scale=%g nlevels=%d fastTh=%d)", nfeatures,
+                    (double)scale_factor, nlevels, fast_th);
+    if (score_type != 0 && score_type != 1) return fail(ORBFE_ERR_ARG, "score_type must be 0 (HARRIS) or 1 (FAST)");
+    if (score_type == 0)
+        return fail(ORBFE_ERR_UNSUPPORTED, "HARRIS_SCORE (ORBextractor.cc:616-620) is not implemented yet; use FAST_SCORE");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ORBFE_ERR_NO_DEVICE, "no CUDA device available: liborbfe has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(ORBFE_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    OrbfeExtractor *ex = new OrbfeExtractor();
+    ex->nfeatures = nfeatures;
+    ex->nlevels = nlevels;
+    ex->score_type = score_type;
+    ex->fast_th = fast_th;
+    ex->device = device;
+    ex->scale_factor = (double)scale_factor;
+    const double sf = ex->scale_factor;
+    // mvScaleFactor / mvInvScaleFactor, :461-471
+    ex->scale[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) ex->scale[i] = (float)((double)ex->scale[i - 1] * sf);
+    const float inv = (float)(1.0f / sf);
+    ex->inv_scale[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) ex->inv_scale[i] = ex->inv_scale[i - 1] * inv;
+    // mnFeaturesPerLevel, :476-487
+    const float factor = (float)(1.0 / sf);
+    float nd = (float)nfeatures * (1.0f - factor) / (1.0f - (float)std::pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        ex->quota[l] = cv_round((double)nd);
+        sum += ex->quota[l];
+        nd *= factor;
+    }
+    ex->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ex->d_pattern, 1024);
+    if (e == cudaSuccess) e = cudaMemcpy(ex->d_pattern, kBriefPattern, 1024, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&ex->h_err, sizeof(int), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        delete ex;
+        return fail(ORBFE_ERR_CUDA, "extractor setup failed: %s", cudaGetErrorString(e));
+    }
+    *out = ex;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_extractor_destroy(OrbfeExtractor *ex) {
+    if (!ex) return ORBFE_OK;
+    cudaSetDevice(ex->device);
+    if (ex->stream) cudaStreamSynchronize(ex->stream);
+    free_plan(ex);
+    if (ex->d_pattern) cudaFree(ex->d_pattern);
+    if (ex->h_counts) cudaFreeHost(ex->h_counts);
+    if (ex->h_err) cudaFreeHost(ex->h_err);
+    for (cudaEvent_t ev : ex->timer.ev) cudaEventDestroy(ev);
+    if (ex->stream) cudaStreamDestroy(ex->stream);
+    delete ex;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_extractor_levels(const OrbfeExtractor *ex) { return ex ? ex->nlevels : 0; }
+extern "C" float orbfe_extractor_scale_factor(const OrbfeExtractor *ex) { return ex ? (float)ex->scale_factor : 0.f; }
+extern "C" int orbfe_extractor_tables(const OrbfeExtractor *ex, float *scale, float *inv_scale, int *quota) {
+    if (!ex) return fail(ORBFE_ERR_ARG, "ex is NULL");
+    for (int l = 0; l < ex->nlevels; l++) {
+        if (scale) scale[l] = ex->scale[l];
+        if (inv_scale) inv_scale[l] = ex->inv_scale[l];
+        if (quota) quota[l] = ex->quota[l];
+    }
+    return ORBFE_OK;
+}
+
+static void stage_mark(OrbfeExtractor *ex, cudaStream_t s, const char *name) {
+    if (!ex->profiling) return;
+    StageTimer &T = ex->timer;
+    const size_t i = T.names.size();
+    if (T.ev.size() < i + 2) {
+        while (T.ev.size() < i + 2) { cudaEvent_t e; cudaEventCreate(&e); T.ev.push_back(e); }
+    }
+    if (i == 0 && name == nullptr) { cudaEventRecord(T.ev[0], s); return; }
+    T.names.push_back(name);
+    cudaEventRecord(T.ev[i + 1], s);
+}
+
+// Enqueue the whole device pipeline for `B` frames whose level-0 images are already in lv[0].pyr.
+static int enqueue_pipeline(OrbfeExtractor *ex, int B, OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts,
+                            cudaStream_t s) {
+    PlanDev hp = ex->hplan;
+    hp.batch = B;
+    int launches = 0;
+    CU_TRY(cudaMemsetAsync(ex->counters, 0, ex->counters_bytes, s));
+    for (int l = 1; l < hp.nlevels; l++) { launch_resize_level(ex->dplan, hp, l, s); launches++; }
+    stage_mark(ex, s, "pyramid");
+    launch_fast_nms(ex->dplan, hp, ex->work, s); launches++;
+    stage_mark(ex, s, "fast_nms");
+    launch_cell_quota(ex->dplan, hp, ex->work, s); launches++;
+    stage_mark(ex, s, "cell_quota");
+    launch_cell_select(ex->dplan, hp, ex->work, s); launches++;
+    stage_mark(ex, s, "cell_select");
+    launch_level_select(ex->dplan, hp, ex->work, ex->ls_smem, s); launches++;
+    stage_mark(ex, s, "level_select");
+    launch_blur(ex->dplan, hp, s); launches++;
+    stage_mark(ex, s, "blur7");
+    launch_describe(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, s); launches++;
+    stage_mark(ex, s, "describe");
+    CU_TRY(cudaGetLastError());
+    ex->last_launches = launches;
+    return ORBFE_OK;
+}
+
+static void profiling_begin(OrbfeExtractor *ex, cudaStream_t s) {
+    if (!ex->profiling) return;
+    ex->timer.names.clear();
+    stage_mark(ex, s, nullptr);
+}
+
+static void profiling_end(OrbfeExtractor *ex) {
+    if (!ex->profiling) return;
+    ex->stage_ms.assign(ex->timer.names.size(), 0.f);
+    for (size_t i = 0; i < ex->timer.names.size(); i++)
+        cudaEventElapsedTime(&ex->stage_ms[i], ex->timer.ev[i], ex->timer.ev[i + 1]);
+}
+
+extern "C" int orbfe_extract_batch_device(OrbfeExtractor *ex, const uint8_t *d_imgs, int width, int height,
+                                          size_t stride, size_t frame_stride, int batch, OrbfeKeyPoint *d_kps,
+                                          uint8_t *d_desc, int *d_counts, void *stream) {
+    if (!ex || !d_imgs || !d_kps || !d_desc || !d_counts) return fail(ORBFE_ERR_ARG, "NULL argument");
+    if (width <= 0 || height <= 0 || batch <= 0 || stride < (size_t)width) return fail(ORBFE_ERR_ARG, "bad geometry");
+    CU_TRY(cudaSetDevice(ex->device));
+    int rc = build_plan(ex, width, height, batch);
+    if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ex->stream;
+    const LevelDev &L0 = ex->hplan.lv[0];
+    profiling_begin(ex, s);
+    if (frame_stride == stride * (size_t)height && L0.plane == (size_t)L0.pitch * height) {
+        // frames are stacked: one 2-D copy of batch*height rows
+        CU_TRY(cudaMemcpy2DAsync(L0.pyr, L0.pitch, d_imgs, stride, width, (size_t)height * batch, cudaMemcpyDeviceToDevice, s));
+    } else {
+        for (int f = 0; f < batch; f++)
+            CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, d_imgs + f * frame_stride, stride, width, height,
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+    stage_mark(ex, s, "ingest");
+    return enqueue_pipeline(ex, batch, d_kps, d_desc, d_counts, s);
+}
+
+extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int width, int height, size_t stride,
+                                   size_t frame_stride, int batch, OrbfeKeyPoint *kps, uint8_t *desc, int cap,
+                                   int *n_out) {
+    if (!ex || !n_out) return fail(ORBFE_ERR_ARG, "NULL argument");
+    for (int f = 0; f < std::max(batch, 0); f++) n_out[f] = 0;
+    if (!imgs || width <= 0 || height <= 0) return ORBFE_OK;  // empty image: silent return (ORBextractor.cc:721-722)
+    if (batch <= 0 || stride < (size_t)width || cap < 0 || (cap > 0 && (!kps || !desc))) return fail(ORBFE_ERR_ARG, "bad arguments");
+    CU_TRY(cudaSetDevice(ex->device));
+    int rc = build_plan(ex, width, height, batch);
+    if (rc) return rc;
+    cudaStream_t s = ex->stream;
+    const PlanDev &P = ex->hplan;
+    const LevelDev &L0 = P.lv[0];
+    profiling_begin(ex, s);
+    if (frame_stride == stride * (size_t)height) {
+        CU_TRY(cudaMemcpy2DAsync(L0.pyr, L0.pitch, imgs, stride, width, (size_t)height * batch, cudaMemcpyHostToDevice, s));
+    } else {
+        for (int f = 0; f < batch; f++)
+            CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, width, height,
+                                     cudaMemcpyHostToDevice, s));
+    }
+    stage_mark(ex, s, "h2d");
+    rc = enqueue_pipeline(ex, batch, ex->d_kps, ex->d_desc, ex->d_counts, s);
+    if (rc) return rc;
+    const int ncopy = std::min(cap, P.nfeatures);
+    CU_TRY(cudaMemcpyAsync(ex->h_counts, ex->d_counts, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(ex->h_err, ex->work.err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (ncopy > 0) {
+        CU_TRY(cudaMemcpy2DAsync(kps, sizeof(OrbfeKeyPoint) * cap, ex->d_kps, sizeof(OrbfeKeyPoint) * P.nfeatures,
+                                 sizeof(OrbfeKeyPoint) * ncopy, batch, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaMemcpy2DAsync(desc, (size_t)32 * cap, ex->d_desc, (size_t)32 * P.nfeatures, (size_t)32 * ncopy, batch,
+                                 cudaMemcpyDeviceToHost, s));
+    }
+    stage_mark(ex, s, "d2h");
+    CU_TRY(cudaStreamSynchronize(s));
+    profiling_end(ex);
+    if (*ex->h_err) {
+        int code = *ex->h_err;
+        cudaMemsetAsync(ex->work.err_flag, 0, sizeof(int), s);
+        return fail(ORBFE_ERR_INTERNAL, "device overflow flag %d", code);
+    }
+    int status = ORBFE_OK;
+    for (int f = 0; f < batch; f++) {
+        n_out[f] = ex->h_counts[f];
+        if (n_out[f] > cap) status = ORBFE_ERR_CAPACITY;
+    }
+    if (status) return fail(status, "caller capacity %d too small", cap);
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_extract(OrbfeExtractor *ex, const uint8_t *img, int width, int height, size_t stride,
+                             OrbfeKeyPoint *kps, uint8_t *desc, int cap, int *n_out) {
+    return orbfe_extract_batch(ex, img, width, height, stride, stride * (size_t)std::max(height, 0), 1, kps, desc, cap, n_out);
+}
+
+extern "C" int orbfe_extractor_sync(OrbfeExtractor *ex) {
+    if (!ex) return fail(ORBFE_ERR_ARG, "ex is NULL");
+    CU_TRY(cudaSetDevice(ex->device));
+    CU_TRY(cudaStreamSynchronize(ex->stream));
+    profiling_end(ex);
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_extractor_last_launches(const OrbfeExtractor *ex) { return ex ? ex->last_launches : 0; }
+
+extern "C" int orbfe_extractor_set_profiling(OrbfeExtractor *ex, int on) {
+    if (!ex) return fail(ORBFE_ERR_ARG, "ex is NULL");
+    ex->profiling = on != 0;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_extractor_stage_times(const OrbfeExtractor *ex, char (*names)[32], float *ms, int cap) {
+    if (!ex) return 0;
+    int n = (int)std::min<size_t>(ex->stage_ms.size(), (size_t)std::max(cap, 0));
+    for (int i = 0; i < n; i++) {
+        if (names) { strncpy(names[i], ex->timer.names[i].c_str(), 31); names[i][31] = 0; }
+        if (ms) ms[i] = ex->stage_ms[i];
+    }
+    return n;
+}
+
+extern "C" int orbfe_debug_level_size(const OrbfeExtractor *ex, int level, int *w, int *h) {
+    if (!ex || level < 0 || level >= ex->nlevels || !ex->Bcap) return fail(ORBFE_ERR_ARG, "no plan / bad level");
+    if (w) *w = ex->hplan.lv[level].w;
+    if (h) *h = ex->hplan.lv[level].h;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_debug_read_level(OrbfeExtractor *ex, int frame, int level, int which, uint8_t *out, size_t out_stride) {
+    if (!ex || !out || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->Bcap)
+        return fail(ORBFE_ERR_ARG, "bad arguments");
+    CU_TRY(cudaSetDevice(ex->device));
+    const LevelDev &L = ex->hplan.lv[level];
+    const uint8_t *src = (which ? L.blur : L.pyr) + (size_t)frame * L.plane;
+    CU_TRY(cudaStreamSynchronize(ex->stream));
+    CU_TRY(cudaMemcpy2D(out, out_stride, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return ORBFE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Matcher
+// ------------------------------------------------------------------------------------------------
+struct OrbfeMatcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // grow-only device scratch for the host-pointer entry points
+    void *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+};
+
+static cudaError_t mreserve(OrbfeMatcher *m, int i, size_t bytes) {
+    if (m->cap[i] >= bytes) return cudaSuccess;
+    if (m->buf[i]) cudaFree(m->buf[i]);
+    m->buf[i] = nullptr;
+    m->cap[i] = 0;
+    size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+    cudaError_t e = cudaMalloc(&m->buf[i], want);
+    if (e == cudaSuccess) m->cap[i] = want;
+    return e;
+}
+
+extern "C" int orbfe_matcher_create(int device, OrbfeMatcher **out) {
+    if (!out) return fail(ORBFE_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ORBFE_ERR_NO_DEVICE, "no CUDA device available: liborbfe has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(ORBFE_ERR_ARG, "device %d out of range", device);
+    OrbfeMatcher *m = new OrbfeMatcher();
+    m->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete m; return fail(ORBFE_ERR_CUDA, "matcher setup failed: %s", cudaGetErrorString(e)); }
+    *out = m;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_matcher_destroy(OrbfeMatcher *m) {
+    if (!m) return ORBFE_OK;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    for (int i = 0; i < 6; i++) if (m->buf[i]) cudaFree(m->buf[i]);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_matcher_sync(OrbfeMatcher *m) {
+    if (!m) return fail(ORBFE_ERR_ARG, "m is NULL");
+    CU_TRY(cudaSetDevice(m->device));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_hamming_csr_device(OrbfeMatcher *m, const uint8_t *d_q, const uint8_t *d_t, const int32_t *d_row_ptr,
+                                        const int32_t *d_cols, int nq, int npairs, uint16_t *d_out, void *stream) {
+    if (!m || (nq > 0 && (!d_q || !d_t || !d_row_ptr))) return fail(ORBFE_ERR_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(m->device));
+    if (nq <= 0 || npairs <= 0) return ORBFE_OK;
+    launch_hamming_csr(d_q, d_t, d_row_ptr, d_cols, nq, npairs, d_out, stream ? (cudaStream_t)stream : m->stream);
+    CU_TRY(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_hamming_csr(OrbfeMatcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt,
+                                 const int32_t *row_ptr, const int32_t *cols, uint16_t *out) {
+    if (!m || nq < 0 || nt < 0) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (nq == 0) return ORBFE_OK;
+    if (!q || !row_ptr) return fail(ORBFE_ERR_ARG, "NULL argument");
+    const int np = row_ptr[nq];
+    if (np == 0) return ORBFE_OK;
+    if (!t || !cols || !out || nt == 0) return fail(ORBFE_ERR_ARG, "NULL argument");
+    for (int k = 0; k < np; k++)
+        if (cols[k] < 0 || cols[k] >= nt) return fail(ORBFE_ERR_ARG, "cols[%d]=%d out of range", k, cols[k]);
+    CU_TRY(cudaSetDevice(m->device));
+    CU_TRY(mreserve(m, 0, (size_t)nq * 32));
+    CU_TRY(mreserve(m, 1, (size_t)nt * 32));
+    CU_TRY(mreserve(m, 2, sizeof(int32_t) * ((size_t)nq + 1)));
+    CU_TRY(mreserve(m, 3, sizeof(int32_t) * (size_t)np));
+    CU_TRY(mreserve(m, 4, sizeof(uint16_t) * (size_t)np));
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(m->buf[0], q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(m->buf[1], t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(m->buf[2], row_ptr, sizeof(int32_t) * ((size_t)nq + 1), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(m->buf[3], cols, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, s));
+    launch_hamming_csr((const uint8_t *)m->buf[0], (const uint8_t *)m->buf[1], (const int32_t *)m->buf[2],
+                       (const int32_t *)m->buf[3], nq, np, (uint16_t *)m->buf[4], s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, m->buf[4], sizeof(uint16_t) * (size_t)np, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_hamming_dense(OrbfeMatcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, uint16_t *out) {
+    if (!m || nq < 0 || nt < 0) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (nq == 0 || nt == 0) return ORBFE_OK;
+    if (!q || !t || !out) return fail(ORBFE_ERR_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(m->device));
+    CU_TRY(mreserve(m, 0, (size_t)nq * 32));
+    CU_TRY(mreserve(m, 1, (size_t)nt * 32));
+    CU_TRY(mreserve(m, 4, sizeof(uint16_t) * (size_t)nq * nt));
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(m->buf[0], q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(m->buf[1], t, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    launch_hamming_dense((const uint8_t *)m->buf[0], nq, (const uint8_t *)m->buf[1], nt, (uint16_t *)m->buf[4], s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, m->buf[4], sizeof(uint16_t) * (size_t)nq * nt, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_knn2_groups_device(OrbfeMatcher *m, const uint8_t *d_q, int nq, const uint8_t *d_db, int ngroups,
+                                        int group_size, uint16_t *d_best, int32_t *d_best_idx, uint16_t *d_second,
+                                        void *stream) {
+    if (!m || nq < 0 || ngroups < 0 || group_size < 0) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (nq == 0 || ngroups == 0) return ORBFE_OK;
+    if (!d_q || !d_db || !d_best || !d_best_idx || !d_second) return fail(ORBFE_ERR_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(m->device));
+    launch_knn2_groups(d_q, nq, d_db, ngroups, group_size, d_best, d_best_idx, d_second,
+                       stream ? (cudaStream_t)stream : m->stream);
+    CU_TRY(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_knn2_groups(OrbfeMatcher *m, const uint8_t *q, int nq, const uint8_t *db, int ngroups,
+                                 int group_size, uint16_t *best, int32_t *best_idx, uint16_t *second) {
+    if (!m || nq < 0 || ngroups < 0 || group_size < 0) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (nq == 0 || ngroups == 0) return ORBFE_OK;
+    if (!q || !db || !best || !best_idx || !second) return fail(ORBFE_ERR_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t ndb = (size_t)ngroups * group_size, no = (size_t)ngroups * nq;
+    CU_TRY(mreserve(m, 0, (size_t)nq * 32));
+    CU_TRY(mreserve(m, 1, ndb * 32));
+    CU_TRY(mreserve(m, 2, sizeof(uint16_t) * no));
+    CU_TRY(mreserve(m, 3, sizeof(int32_t) * no));
+    CU_TRY(mreserve(m, 4, sizeof(uint16_t) * no));
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(m->buf[0], q, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(m->buf[1], db, ndb * 32, cudaMemcpyHostToDevice, s));
+    launch_knn2_groups((const uint8_t *)m->buf[0], nq, (const uint8_t *)m->buf[1], ngroups, group_size,
+                       (uint16_t *)m->buf[2], (int32_t *)m->buf[3], (uint16_t *)m->buf[4], s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(best, m->buf[2], sizeof(uint16_t) * no, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(best_idx, m->buf[3], sizeof(int32_t) * no, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(second, m->buf[4], sizeof(uint16_t) * no, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return ORBFE_OK;
+}

@@ -1,0 +1,89 @@
+// orbfe_internal.h -- structures shared by the host plan code and the sm_100a kernels of liborbfe.so.
+// Not part of the public ABI (that is include/orbfe.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbfe.h"
+
+#define ORBFE_EDGE 16  // EDGE_THRESHOLD, reference src/ORBextractor.cc:77
+
+// FAST/NMS tile (detect-area pixels per CTA) and blur tile
+#define ORBFE_FT_W 64
+#define ORBFE_FT_H 32
+#define ORBFE_BT_W 128
+#define ORBFE_BT_H 32
+
+namespace orbfe {
+
+// One pyramid level of the current plan.  All B frames of a batch live in one allocation per level:
+// frame f of level l starts at pyr + f * plane (row pitch `pitch`, a multiple of 128 B so rows are
+// TMA-/vector-aligned).
+struct LevelDev {
+    uint8_t *pyr;   // unblurred level (level 0 = the input image)
+    uint8_t *blur;  // 7x7 Gaussian of the level (interior only; descriptor sampling outside reads pyr by reflection)
+    size_t plane;   // pitch * h
+    int w, h, pitch;
+    // cell grid (reference ORBextractor.cc:527-547); detect windows tile [16, w-16) x [16, h-16)
+    int cols, rows, cw, ch, ncells, nfc, quota;
+    int cell_base;              // global id of this level's cell 0
+    int kp_base;                // sum of quotas of lower levels = first keypoint slot of this level
+    int kept_base, kept_cap;    // region of the per-frame "kept" list
+    int ftiles_x, ftiles_y, ftile_base;  // FAST tiles
+    int btiles_x, btiles_y, btile_base;  // blur tiles
+    float scale;       // mvScaleFactor[l]
+    float patch_size;  // (float)(int)(31 * scale)
+    // bilinear tables for producing THIS level from level l-1 (OpenCV fixed-point, computed on the host)
+    const int *xofs;      // [w]  source column (already clamped)
+    const short2 *xab;    // [w]  11-bit weights (a0, a1)
+    const int2 *yrows;    // [h]  source rows (r0, r1), each clipped to [0, h_src-1]
+    const short2 *yab;    // [h]  (b0, b1)
+};
+
+struct PlanDev {
+    int nlevels, batch, nfeatures;
+    int ncells_total, nftiles_total, nbtiles_total, kept_total;
+    int t_lo, t_hi;      // min / max of (fastTh, 7)
+    int t1_is_lo;        // fastTh <= 7
+    int score_type;
+    long long cand_total;  // candidate slots per frame
+    LevelDev lv[ORBFE_MAX_LEVELS];
+};
+
+// Per-batch work buffers (device).  Index [frame] strides are in the plan.
+struct WorkDev {
+    const long long *cell_cand_base;  // [ncells_total] first candidate slot of each cell
+    const int *cell_cand_cap;         // [ncells_total]
+    uint32_t *cand_keys;              // [batch][cand_total]   (score<<24 | 0xFFFFFF - raster)
+    int *cell_cnt_lo;                 // [batch][ncells_total] candidates with m > t_lo (= all emitted)
+    int *cell_cnt_hi;                 // [batch][ncells_total] candidates with m > t_hi
+    int *cell_keep;                   // [batch][ncells_total] nToRetain
+    uint32_t *cell_min_key;           // [batch][ncells_total] eligibility threshold key, then the cut key
+    unsigned long long *kept_keys;    // [batch][kept_total]
+    int *kept_cnt;                    // [batch][nlevels]
+    int2 *kp_xy_score;                // [batch][nfeatures]  (x | y<<16, score) in level coordinates
+    int *level_cnt;                   // [batch][nlevels]
+    int *err_flag;                    // [1]
+};
+
+// ---- launchers (extract_kernels.cu) ----
+void launch_resize_level(const PlanDev *d_plan, const PlanDev &h_plan, int level, cudaStream_t s);
+void launch_fast_nms(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
+void launch_cell_quota(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
+void launch_cell_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
+void launch_level_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, size_t smem_bytes, cudaStream_t s);
+void launch_blur(const PlanDev *d_plan, const PlanDev &h_plan, cudaStream_t s);
+void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, const int8_t *d_pattern,
+                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s);
+int level_select_smem_bytes(int max_kept);
+int set_level_select_smem(int bytes);
+
+// ---- launchers (match_kernels.cu) ----
+void launch_hamming_csr(const uint8_t *q, const uint8_t *t, const int32_t *row_ptr, const int32_t *cols, int nq,
+                        int npairs, uint16_t *out, cudaStream_t s);
+void launch_hamming_dense(const uint8_t *q, int nq, const uint8_t *t, int nt, uint16_t *out, cudaStream_t s);
+void launch_knn2_groups(const uint8_t *q, int nq, const uint8_t *db, int ngroups, int group_size,
+                        uint16_t *best, int32_t *best_idx, uint16_t *second, cudaStream_t s);
+
+}  // namespace orbfe
