@@ -1,0 +1,404 @@
+#!/usr/bin/env python3
+"""bench.py -- Mkeypoints/s of the ORB front-end hot path (extract + match) on B200.
+
+Workload (BASELINE.json configs[1]): a stream of synthetic 1920x1080 u8 frames, ORBextractor(2000, 1.2, 8,
+FAST_SCORE, 20), frame-to-frame ORBmatcher(0.9, true).SearchByProjection(Current, Last, 15).
+One "step" = one batch of `--batch` consecutive frames of the stream: extract all of them, then match every
+frame against its predecessor.  Mkeypoints/s = keypoints extracted-and-matched / time.
+
+  value : inputs already resident in HBM when the timed region starts (device API of liborbfe.so),
+          results read back + matched.
+  e2e   : the reference-facing C-ABI call with HOST buffers (orbfe_extract_batch + the matcher), H2D of the
+          step's frames from pinned memory and D2H of keypoints/descriptors inside the timed region.
+
+`--impl reference` times the CPU oracle port of the reference path (oracle/) on the host cores.
+PyTorch is used only for plumbing: device buffers, pinned host memory, torch.distributed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, FAST_TH = 1920, 1080, 2000, 8, 1.2, 20
+FX = FY = 1000.0
+CX, CY = W / 2.0, H / 2.0
+DEPTH = 5.0
+MATCH_TH = 15.0  # Tracking.cc:565
+METRIC = "Mkeypoints/s extract+match"
+
+
+def level_sizes():
+    # float32 emulation of ORBextractor.cc:461-471,785-786
+    inv = np.float32(1.0) / np.float64(np.float32(SCALE))
+    inv = np.float32(inv)
+    s = np.float32(1.0)
+    out = []
+    for l in range(NLEVELS):
+        out.append((int(np.rint(np.float32(W) * s)), int(np.rint(np.float32(H) * s))))
+        s = np.float32(s * inv)
+    return out
+
+
+def algorithmic_bytes():
+    """per-frame algorithmic bytes of extract (reads, writes, gathers, outputs)."""
+    ls = level_sizes()
+    P = sum(w * h for w, h in ls)
+    reads = sum(w * h for w, h in ls[:-1]) + 2 * P
+    writes = (P - W * H) + P
+    gathers = NFEAT * (749 + 512)
+    outputs = NFEAT * 60
+    return {"P": P, "total": reads + writes + gathers + outputs, "fast_read": P, "blur": 2 * P,
+            "resize": sum(w * h for w, h in ls[:-1]) + (P - W * H)}
+
+
+def make_stream(batch, seed):
+    """`batch` consecutive frames: a few base textures, each followed by small translations of itself."""
+    from orb_slam_b200.synth import textured_frame, shifted_frame
+    frames = np.empty((batch, H, W), np.uint8)
+    shifts = np.zeros((batch, 2), np.int32)  # shift of frame i relative to frame i-1 (dx, dy)
+    rng = np.random.default_rng(seed)
+    nbase = max(1, min(4, batch // 4))
+    per = (batch + nbase - 1) // nbase
+    i = 0
+    for b in range(nbase):
+        base = textured_frame(W, H, seed=seed * 100 + b)
+        cur = base
+        for k in range(per):
+            if i >= batch:
+                break
+            if k > 0:
+                dx, dy = int(rng.integers(-6, 7)), int(rng.integers(-4, 5))
+                cur = shifted_frame(cur, dx, dy, seed=seed * 1000 + i)
+                shifts[i] = (dx, dy)
+            frames[i] = cur
+            i += 1
+    return frames, shifts
+
+
+def tcw_for_shift(dx, dy):
+    """Camera translation that moves every point at depth DEPTH by (dx, dy) pixels."""
+    T = np.zeros((3, 4), np.float32)
+    T[0, 0] = T[1, 1] = T[2, 2] = 1.0
+    T[0, 3] = dx * DEPTH / FX
+    T[1, 3] = dy * DEPTH / FY
+    return T
+
+
+def backproject(kps):
+    w = np.empty((len(kps), 3), np.float32)
+    w[:, 0] = (kps["x"] - np.float32(CX)) / np.float32(FX) * np.float32(DEPTH)
+    w[:, 1] = (kps["y"] - np.float32(CY)) / np.float32(FY) * np.float32(DEPTH)
+    w[:, 2] = DEPTH
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (oracle port of the reference path): the only place bench.py executes oracle/
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(frames, shifts, threads):
+    """Oracle extract + SearchByProjection over consecutive frames with `threads` host threads.
+    Returns (keypoints processed, seconds)."""
+    import oracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(frames)
+
+    def extract_one(i):
+        p = O.make_params(NFEAT, SCALE, NLEVELS, 1, FAST_TH)
+        rc, k, d, _ = O.extract(p, frames[i])
+        assert rc == 0
+        return k, d
+
+    def match_one(i, feats):
+        (kl, dl), (kc, dc) = feats[i - 1], feats[i]
+        fl = O.OracleFrame(kl, dl, W, H, SCALE, NLEVELS)
+        fc = O.OracleFrame(kc, dc, W, H, SCALE, NLEVELS)
+        nm, _ = O.search_by_projection_ff(fc, fl, np.ones(fl.n, np.uint8), np.zeros(fl.n, np.uint8), backproject(kl),
+                                          tcw_for_shift(*shifts[i]), FX, FY, CX, CY, MATCH_TH, True)
+        return nm
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        feats = list(ex.map(extract_one, range(n)))
+        list(ex.map(lambda i: match_one(i, feats), range(1, n)))
+    dt = time.perf_counter() - t0
+    return sum(len(k) for k, _ in feats), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    nframes = max(2, min(cores, 32))
+    frames, shifts = make_stream(nframes, seed=7)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_pass(frames[:2], shifts[:2], cores)
+    tot_kp, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        kp, dt = cpu_reference_pass(frames, shifts, cores)
+        tot_kp += kp
+        tot_t += dt
+    val = tot_kp / tot_t / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mkeypoints/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1920x1080 u8 stream, 2000 kp, 8 levels, scale 1.2, SearchByProjection th=15",
+                       "frames_per_step": nframes},
+            "cpu_baseline": {"value": val, "unit": "Mkeypoints/s", "cores": cores, "kind": "port",
+                             "sample": "%d frames per step x %d steps, CPU oracle port (reference cannot be compiled: "
+                                       "needs OpenCV 2.4/ROS/Boost)" % (nframes, args.steps)},
+            "e2e": {"value": val, "unit": "Mkeypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="orbfe", choices=["orbfe", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import orb_slam_b200 as fe
+    from orb_slam_b200 import matching as M
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: liborbfe has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    B = args.batch
+    frames_np, shifts = make_stream(B, seed=11 + rank)
+    h_frames = torch.from_numpy(frames_np).pin_memory()                 # pinned host input (e2e path)
+    d_frames = torch.from_numpy(frames_np).to(dev)                      # resident input (value path)
+    h_kps = torch.empty((B, NFEAT, 28), dtype=torch.uint8).pin_memory()
+    h_desc = torch.empty((B, NFEAT, 32), dtype=torch.uint8).pin_memory()
+    h_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
+    d_kps = torch.empty((B, NFEAT, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((B, NFEAT, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    kps_np = h_kps.numpy().view(fe.KP_DTYPE).reshape(B, NFEAT)
+    desc_np = h_desc.numpy()
+    cnt_np = h_cnt.numpy()
+
+    ex = fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank)
+    mt = fe.ORBmatcher(0.9, True, device=local_rank)
+    ex.set_profiling(True)
+    # a dedicated (non-default) stream: the library's kernels and torch's async copies share it
+    stream = torch.cuda.Stream(device=dev)
+    Tcws = [tcw_for_shift(*shifts[i]) for i in range(B)]
+    prev = {"view": None, "kps": None}
+    stage_acc, stage_n = {}, [0]
+    kp_total = [0]
+    launches = [0]
+
+    def match_step():
+        views = [M.FrameView(kps_np[i, :cnt_np[i]], desc_np[i, :cnt_np[i]], W, H, SCALE, NLEVELS) for i in range(B)]
+        lasts = [prev["view"] if prev["view"] is not None else views[B - 1]] + views[:-1]
+        nm, _ = M.search_by_projection_frames(
+            mt, views, lasts, [np.ones(f.n, np.uint8) for f in lasts], [np.zeros(f.n, np.uint8) for f in lasts],
+            [backproject(f.kps) for f in lasts], Tcws, FX, FY, CX, CY, MATCH_TH)
+        # keep a private copy of the last frame's features for the next step
+        lk, ld = kps_np[B - 1, :cnt_np[B - 1]].copy(), desc_np[B - 1, :cnt_np[B - 1]].copy()
+        prev["view"] = M.FrameView(lk, ld, W, H, SCALE, NLEVELS)
+        return int(nm.sum())
+
+    def collect_stages():
+        for name, ms in ex.stage_times():
+            stage_acc[name] = stage_acc.get(name, 0.0) + ms
+        stage_n[0] += 1
+
+    def step_device():
+        ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(),
+                                d_cnt.data_ptr(), stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            h_cnt.copy_(d_cnt, non_blocking=True)
+            h_kps.copy_(d_kps, non_blocking=True)
+            h_desc.copy_(d_desc, non_blocking=True)
+        stream.synchronize()
+        ex.sync()
+        collect_stages()
+        launches[0] += ex.last_launches()
+        nm = match_step()
+        kp_total[0] += int(cnt_np.sum())
+        return nm
+
+    def step_e2e():
+        ex.extract_batch_ptr(h_frames.data_ptr(), W, H, W, W * H, B, h_kps.data_ptr(), h_desc.data_ptr(), NFEAT,
+                             h_cnt.data_ptr())
+        launches[0] += ex.last_launches()
+        nm = match_step()
+        kp_total[0] += int(cnt_np.sum())
+        return nm
+
+    def timed(step_fn, steps):
+        kp_total[0] = 0
+        launches[0] = 0
+        c0 = mt.counters()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        nm = 0
+        for _ in range(steps):
+            nm += step_fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        c1 = mt.counters()
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        k = torch.tensor([kp_total[0], nm], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(k, op=dist.ReduceOp.SUM)
+            dist.barrier()
+        return {"ms": float(t[0]), "wall_ms": float(t[1]), "kp": float(k[0]), "matches": float(k[1]),
+                "launches": launches[0] + (c1[2] - c0[2]), "mh2d": c1[0] - c0[0], "md2h": c1[1] - c0[1]}
+
+    for _ in range(args.warmup):
+        step_device()
+    for _ in range(args.warmup):
+        step_e2e()
+    stage_acc.clear()
+    stage_n[0] = 0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    r_dev = timed(step_device, args.steps)
+    stages = {k: v / max(stage_n[0], 1) for k, v in stage_acc.items()}
+    r_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        ab = algorithmic_bytes()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # dominant kernel of the extract pipeline by measured stage time
+        kernel_stages = {k: v for k, v in stages.items() if k not in ("ingest", "h2d", "d2h")}
+        dom = max(kernel_stages, key=kernel_stages.get) if kernel_stages else None
+        dom_bytes = {"fast_nms": ab["fast_read"], "blur7": ab["blur"], "pyramid": ab["resize"]}.get(dom, ab["total"]) * B
+        dom_ms = kernel_stages.get(dom, 0.0) if dom else 0.0
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        ext_ms = sum(kernel_stages.values())
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
+                "extract_all_kernels": {"algorithmic_bytes": ab["total"] * B, "ms": ext_ms,
+                                        "achieved": ab["total"] * B / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0},
+                "stage_ms": stages}
+        value = r_dev["kp"] / (r_dev["ms"] * 1e-3) / 1e6
+        e2e_val = r_e2e["kp"] / (r_e2e["ms"] * 1e-3) / 1e6
+        line = {"metric": METRIC, "value": value, "unit": "Mkeypoints/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r_dev["ms"] / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "configs[1]: 1920x1080 u8 stream, 2000 kp, 8 levels, scale 1.2, "
+                                       "frame-to-frame SearchByProjection th=15",
+                           "frames_per_step_per_gpu": B, "parallelism": "frames sharded one stream per GPU, no data-path collective",
+                           "l2": "inputs+pyramids per step (%.0f MB) larger than L2 (126 MB)" % (B * (W * H + 2 * ab["P"]) / 1e6)},
+                "e2e": {"value": e2e_val, "unit": "Mkeypoints/s", "ms_per_step": r_e2e["ms"] / args.steps,
+                        "h2d_bytes_per_step": B * W * H + r_e2e["mh2d"] // args.steps,
+                        "d2h_bytes_per_step": B * (NFEAT * 60 + 4) + r_e2e["md2h"] // args.steps},
+                "gpu_launches": int(r_dev["launches"]),
+                "matches_per_step": r_dev["matches"] / args.steps / world,
+                "keypoints_per_step": r_dev["kp"] / args.steps,
+                "wall_ms_per_step": r_dev["wall_ms"] / args.steps,
+                "roofline": roof, "clocks": clocks}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            nfr = max(2, min(cores, 32))
+            kp, dt = cpu_reference_pass(frames_np[:nfr], shifts[:nfr], cores)
+            line["cpu_baseline"] = {"value": kp / dt / 1e6, "unit": "Mkeypoints/s", "cores": cores, "kind": "port",
+                                    "sample": "%d of the step's frames, CPU oracle port on %d threads (%.1f s)" % (nfr, cores, dt)}
+        print(json.dumps(line))
+    ex.close()
+    mt.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,65 @@
+/*
+ * orbfe_match.h -- C-ABI of the windowed matchers of liborbfe.so on plain arrays.
+ *
+ * Each function is the array-level equivalent of one ORB_SLAM::ORBmatcher method (reference
+ * src/ORBmatcher.cc); the C++ facade orb_slam_b200/host/ORBmatcher.cc converts Frame / MapPoint objects
+ * into these views.  Candidate enumeration and the sequential accept loop run on the host exactly in the
+ * reference's order; every 256-bit Hamming distance is computed on the GPU (one launch per call).
+ */
+#ifndef ORBFE_MATCH_H
+#define ORBFE_MATCH_H
+
+#include "orbfe.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* The slice of ORB_SLAM::Frame the matchers read (include/Frame.h): mvKeysUn, mDescriptors, the image
+ * bounds mnMinX.. (Frame.cc:321-350), mfGridElementWidthInv/HeightInv (Frame.cc:77-78) and mvScaleFactors
+ * (Frame.cc:95-103).  The 64x48 lookup grid (Frame.cc:109-123) is rebuilt from keys_un on each call. */
+typedef struct {
+    int n;
+    const OrbfeKeyPoint *keys_un;
+    const uint8_t *desc; /* n x 32 */
+    float min_x, min_y, max_x, max_y;
+    float grid_inv_w, grid_inv_h;
+    int nlevels;
+    const float *scale_factors;
+} OrbfeFrameView;
+
+/* Frame::mvScaleFactors as Frame.cc:95-103 derives them from ORBextractor::GetScaleFactor() */
+void orbfe_frame_scale_factors(float scale_factor, int nlevels, float *out);
+
+/* int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, float th)
+ * (ORBmatcher.cc:1507-1620) for `npairs` independent (Current, Last) pairs per call.
+ * Per pair j: last_has_mp[j][i] != 0 <=> LastFrame.mvpMapPoints[i] != NULL; last_outlier[j][i] =
+ * LastFrame.mvbOutlier[i]; last_world[j] = 3 floats per Last feature (MapPoint::GetWorldPos);
+ * Tcw[j] = CurrentFrame.mTcw as 3x4 row-major floats; fx..cy = Frame::fx.. (static camera intrinsics).
+ * cur_mp_inout[j][i2] = index of the Last feature whose map point got assigned to Current feature i2, or -1
+ * (entries >= 0 on input are treated as already-occupied slots, CurrentFrame.mvpMapPoints[i2] != NULL).
+ * nmatches_out[j] = the method's return value. */
+int orbfe_search_by_projection_frames(OrbfeMatcher *m, int npairs, const OrbfeFrameView *cur,
+                                      const OrbfeFrameView *last, const uint8_t *const *last_has_mp,
+                                      const uint8_t *const *last_outlier, const float *const *last_world,
+                                      const float *const *Tcw, float fx, float fy, float cx, float cy, float th,
+                                      int check_orientation, int *const *cur_mp_inout, int *nmatches_out);
+
+/* int ORBmatcher::WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minOctave, maxOctave)
+ * (ORBmatcher.cc:409-516).  f1_has_mp[i1] != 0 <=> F1.mvpMapPoints[i1] && !isBad().
+ * match21_out[i2] = i1 whose map point was matched to F2 feature i2, or -1. */
+int orbfe_window_search(OrbfeMatcher *m, const OrbfeFrameView *f1, const OrbfeFrameView *f2,
+                        const uint8_t *f1_has_mp, int window, int min_level, int max_level, float nnratio,
+                        int check_orientation, int *match21_out, int *nmatches_out);
+
+/* int ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+ * (ORBmatcher.cc:598-713).  prev_matched = 2 floats per F1 feature, updated in place (:708-710).
+ * match12_out[i1] = i2 or -1. */
+int orbfe_search_for_initialization(OrbfeMatcher *m, const OrbfeFrameView *f1, const OrbfeFrameView *f2,
+                                    float *prev_matched, int window, float nnratio, int check_orientation,
+                                    int *match12_out, int *nmatches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

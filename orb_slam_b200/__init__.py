@@ -36,6 +36,10 @@ ABI_SYMBOLS = [
     "orbfe_extractor_stage_times", "orbfe_debug_level_size", "orbfe_debug_read_level",
     "orbfe_matcher_create", "orbfe_matcher_destroy", "orbfe_hamming_csr", "orbfe_hamming_dense",
     "orbfe_knn2_groups", "orbfe_knn2_groups_device", "orbfe_hamming_csr_device", "orbfe_matcher_sync",
+    "orbfe_matcher_counters",
+    # include/orbfe_match.h
+    "orbfe_frame_scale_factors", "orbfe_search_by_projection_frames", "orbfe_window_search",
+    "orbfe_search_for_initialization",
 ]
 
 
@@ -86,6 +90,7 @@ def lib():
     L.orbfe_knn2_groups_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.orbfe_hamming_csr_device.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
     L.orbfe_matcher_sync.argtypes = [vp]
+    L.orbfe_matcher_counters.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -262,3 +267,9 @@ class ORBmatcher:
 
     def sync(self):
         _check(lib().orbfe_matcher_sync(self._h))
+
+    def counters(self):
+        """(h2d_bytes, d2h_bytes, launches) accumulated by the host-pointer entry points."""
+        a, b, c = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+        _check(lib().orbfe_matcher_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value

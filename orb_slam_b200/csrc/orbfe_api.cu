@@ -552,6 +552,7 @@ struct OrbfeMatcher {
     // grow-only device scratch for the host-pointer entry points
     void *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0, launches = 0;  // cumulative, for bench.py
 };
 
 static cudaError_t mreserve(OrbfeMatcher *m, int i, size_t bytes) {
@@ -590,6 +591,15 @@ extern "C" int orbfe_matcher_destroy(OrbfeMatcher *m) {
     for (int i = 0; i < 6; i++) if (m->buf[i]) cudaFree(m->buf[i]);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_matcher_counters(const OrbfeMatcher *m, unsigned long long *h2d_bytes,
+                                      unsigned long long *d2h_bytes, unsigned long long *launches) {
+    if (!m) return fail(ORBFE_ERR_ARG, "m is NULL");
+    if (h2d_bytes) *h2d_bytes = m->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = m->d2h_bytes;
+    if (launches) *launches = m->launches;
     return ORBFE_OK;
 }
 
@@ -634,6 +644,9 @@ extern "C" int orbfe_hamming_csr(OrbfeMatcher *m, const uint8_t *q, int nq, cons
     launch_hamming_csr((const uint8_t *)m->buf[0], (const uint8_t *)m->buf[1], (const int32_t *)m->buf[2],
                        (const int32_t *)m->buf[3], nq, np, (uint16_t *)m->buf[4], s);
     CU_TRY(cudaGetLastError());
+    m->h2d_bytes += (size_t)nq * 32 + (size_t)nt * 32 + sizeof(int32_t) * ((size_t)nq + 1 + np);
+    m->d2h_bytes += sizeof(uint16_t) * (size_t)np;
+    m->launches += 1;
     CU_TRY(cudaMemcpyAsync(out, m->buf[4], sizeof(uint16_t) * (size_t)np, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     return ORBFE_OK;

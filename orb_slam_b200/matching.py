@@ -1,0 +1,112 @@
+"""ctypes views for the array-level matcher entry points (include/orbfe_match.h).
+
+`FrameView` is the slice of ORB_SLAM::Frame (reference include/Frame.h, src/Frame.cc:56-125) that
+ORBmatcher reads: undistorted keypoints, descriptors, image bounds, grid cell sizes and per-level scale
+factors.  Zero lens distortion is assumed here (mvKeysUn == mvKeys, Frame.cc:291-295), which is what the
+synthetic bench uses; the C++ facade passes whatever the real Frame holds.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import KP_DTYPE, ORBmatcher, OrbfeError, lib
+
+GRID_COLS, GRID_ROWS = 64, 48  # Frame.h:35-36
+
+
+class _FrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int), ("keys_un", C.c_void_p), ("desc", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_inv_w", C.c_float), ("grid_inv_h", C.c_float),
+                ("nlevels", C.c_int), ("scale_factors", C.c_void_p)]
+
+
+_bound = False
+
+
+def _bind():
+    global _bound
+    if _bound:
+        return lib()
+    L = lib()
+    vp = C.c_void_p
+    L.orbfe_frame_scale_factors.argtypes = [C.c_float, C.c_int, vp]
+    L.orbfe_frame_scale_factors.restype = None
+    L.orbfe_search_by_projection_frames.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
+                                                    C.c_float, C.c_float, C.c_float, C.c_int, vp, vp]
+    L.orbfe_window_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
+    L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
+    _bound = True
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class FrameView:
+    def __init__(self, kps, desc, width, height, scale_factor=1.2, nlevels=8):
+        L = _bind()
+        self.kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, dtype=np.uint8).reshape(-1, 32)
+        self.n = int(self.kps.shape[0])
+        self.sf = np.empty(nlevels, np.float32)
+        L.orbfe_frame_scale_factors(scale_factor, nlevels, _p(self.sf))
+        c = _FrameViewC()
+        c.n = self.n
+        c.keys_un = self.kps.ctypes.data
+        c.desc = self.desc.ctypes.data
+        c.min_x, c.min_y, c.max_x, c.max_y = 0.0, 0.0, float(width), float(height)  # Frame.cc:342-348
+        c.grid_inv_w = np.float32(GRID_COLS) / np.float32(width)   # Frame.cc:77
+        c.grid_inv_h = np.float32(GRID_ROWS) / np.float32(height)  # Frame.cc:78
+        c.nlevels = nlevels
+        c.scale_factors = self.sf.ctypes.data
+        self.c = c
+
+
+def _check(rc):
+    if rc != 0:
+        raise OrbfeError(rc, lib().orbfe_last_error().decode("utf-8", "replace") or "matcher call failed")
+
+
+def search_by_projection_frames(matcher: ORBmatcher, curs, lasts, last_has_mp, last_outlier, last_world, Tcws,
+                                fx, fy, cx, cy, th, cur_mp=None):
+    """Batched ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th) (ORBmatcher.cc:1507-1620).
+
+    curs/lasts: lists of FrameView; last_*: lists of arrays; Tcws: list of 3x4 float arrays.
+    Returns (nmatches[npairs], [cur_mp arrays])."""
+    L = _bind()
+    n = len(curs)
+    views_c = (_FrameViewC * n)(*[f.c for f in curs])
+    views_l = (_FrameViewC * n)(*[f.c for f in lasts])
+    has = [np.ascontiguousarray(a, np.uint8) for a in last_has_mp]
+    outl = [np.ascontiguousarray(a, np.uint8) for a in last_outlier]
+    world = [np.ascontiguousarray(a, np.float32) for a in last_world]
+    T = [np.ascontiguousarray(a, np.float32) for a in Tcws]
+    mp = [np.full(f.n, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp[i], np.int32).copy()
+          for i, f in enumerate(curs)]
+    arr = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+    nm = np.zeros(n, np.int32)
+    _check(L.orbfe_search_by_projection_frames(matcher.handle, n, views_c, views_l, arr(has), arr(outl), arr(world),
+                                               arr(T), fx, fy, cx, cy, th, int(matcher.mbCheckOrientation), arr(mp), _p(nm)))
+    return nm, mp
+
+
+def window_search(matcher: ORBmatcher, f1, f2, f1_has_mp, window, min_level=-1, max_level=2 ** 31 - 1):
+    L = _bind()
+    has = np.ascontiguousarray(f1_has_mp, np.uint8)
+    m21 = np.full(max(f2.n, 1), -1, np.int32)
+    nm = C.c_int(0)
+    _check(L.orbfe_window_search(matcher.handle, C.byref(f1.c), C.byref(f2.c), _p(has), window, min_level, max_level,
+                                 float(matcher.mfNNratio), int(matcher.mbCheckOrientation), _p(m21), C.byref(nm)))
+    return nm.value, m21[:f2.n]
+
+
+def search_for_initialization(matcher: ORBmatcher, f1, f2, prev_matched, window):
+    L = _bind()
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.full(max(f1.n, 1), -1, np.int32)
+    nm = C.c_int(0)
+    _check(L.orbfe_search_for_initialization(matcher.handle, C.byref(f1.c), C.byref(f2.c), _p(prev), window,
+                                             float(matcher.mfNNratio), int(matcher.mbCheckOrientation), _p(m12), C.byref(nm)))
+    return nm.value, m12[:f1.n], prev
