@@ -1,0 +1,170 @@
+"""CPU tests: the matcher half of the oracle against brute-force Python restatements written directly from
+the reference loops (ORBmatcher.cc, Frame.cc), on small random frames."""
+import numpy as np
+
+import oracle as O
+from orb_slam_b200.synth import random_descriptors, noisy_copies
+
+W, H = 640, 480
+
+
+def _rand_frame(n, seed, desc=None):
+    rng = np.random.default_rng(seed)
+    k = np.zeros(n, O.KP_DTYPE)
+    k["octave"] = rng.integers(0, 4, n)
+    k["x"] = rng.uniform(0, W, n).astype(np.float32)
+    k["y"] = rng.uniform(0, H, n).astype(np.float32)
+    k["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    d = random_descriptors(n, seed) if desc is None else desc
+    return k, d
+
+
+def _ham(a, b):
+    return int(np.unpackbits(a ^ b).sum())
+
+
+def test_hamming():
+    d = random_descriptors(50, 3)
+    for i in range(49):
+        assert O.hamming(d[i], d[i + 1]) == _ham(d[i], d[i + 1])
+    assert O.hamming(d[0], d[0]) == 0 and O.hamming(d[0], ~d[0]) == 256
+
+
+def _grid_py(k):
+    gx, gy = np.float32(64) / np.float32(W), np.float32(48) / np.float32(H)
+    cells = {}
+    for i in range(len(k)):
+        vx, vy = np.float32(k["x"][i]) * gx, np.float32(k["y"][i]) * gy
+        px = int(np.floor(vx + np.float32(0.5))) if vx >= 0 else int(np.ceil(vx - np.float32(0.5)))   # round(): half away
+        py = int(np.floor(vy + np.float32(0.5))) if vy >= 0 else int(np.ceil(vy - np.float32(0.5)))
+        if 0 <= px < 64 and 0 <= py < 48:
+            cells.setdefault((px, py), []).append(i)
+    return cells, gx, gy
+
+
+def _area_py(k, cells, gx, gy, x, y, r, lo, hi):
+    x, y, r = np.float32(x), np.float32(y), np.float32(r)
+    x0 = max(0, int(np.floor((x - r) * gx)))
+    x1 = min(63, int(np.ceil((x + r) * gx)))
+    y0 = max(0, int(np.floor((y - r) * gy)))
+    y1 = min(47, int(np.ceil((y + r) * gy)))
+    if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+        return []
+    out = []
+    for ix in range(x0, x1 + 1):
+        for iy in range(y0, y1 + 1):
+            for i in cells.get((ix, iy), []):
+                o = k["octave"][i]
+                if not (lo == -1 and hi == -1):
+                    if lo == hi:
+                        if o != lo:
+                            continue
+                    elif o < lo or o > hi:
+                        continue
+                if abs(np.float32(k["x"][i]) - x) > r or abs(np.float32(k["y"][i]) - y) > r:
+                    continue
+                out.append(i)
+    return out
+
+
+def test_features_in_area_order_and_filters():
+    k, d = _rand_frame(800, 1)
+    f = O.OracleFrame(k, d, W, H)
+    cells, gx, gy = _grid_py(k)
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        x, y, r = rng.uniform(-20, W + 20), rng.uniform(-20, H + 20), rng.uniform(1, 120)
+        lo = int(rng.integers(-1, 3))
+        hi = lo if rng.random() < 0.4 else (-1 if lo == -1 else lo + int(rng.integers(0, 3)))
+        got = f.features_in_area(np.float32(x), np.float32(y), np.float32(r), lo, hi).tolist()
+        assert got == _area_py(k, cells, gx, gy, x, y, r, lo, hi)
+
+
+def _three_max_py(counts):
+    m = [0, 0, 0]
+    ind = [-1, -1, -1]
+    for i, s in enumerate(counts):
+        if s > m[0]:
+            m, ind = [s, m[0], m[1]], [i, ind[0], ind[1]]
+        elif s > m[1]:
+            m, ind = [m[0], s, m[1]], [ind[0], i, ind[1]]
+        elif s > m[2]:
+            m[2], ind[2] = s, i
+    if m[1] < np.float32(0.1) * np.float32(m[0]):
+        ind[1] = ind[2] = -1
+    elif m[2] < np.float32(0.1) * np.float32(m[0]):
+        ind[2] = -1
+    return ind
+
+
+def _bin(a1, a2):
+    rot = np.float32(a1) - np.float32(a2)
+    if rot < 0:
+        rot = np.float32(rot + np.float32(360.0))
+    v = np.float32(rot * (np.float32(1.0) / np.float32(30)))
+    b = int(np.floor(v + np.float32(0.5)))
+    return 0 if b == 30 else b
+
+
+def test_window_search_against_python_loop():
+    k1, d1 = _rand_frame(400, 5)
+    k2 = k1.copy()
+    rng = np.random.default_rng(6)
+    k2["x"] = (k1["x"] + rng.uniform(-8, 8, 400)).astype(np.float32)
+    k2["y"] = (k1["y"] + rng.uniform(-8, 8, 400)).astype(np.float32)
+    k2["angle"] = ((k1["angle"] + rng.uniform(-10, 10, 400)) % 360).astype(np.float32)
+    d2 = noisy_copies(d1, 0.06, 7)
+    perm = rng.permutation(400)
+    k2, d2 = k2[perm], d2[perm]
+    f1, f2 = O.OracleFrame(k1, d1, W, H), O.OracleFrame(k2, d2, W, H)
+    has = (rng.random(400) < 0.85).astype(np.uint8)
+    nnr = np.float32(0.8)
+    n, m21 = O.window_search(f1, f2, has, 30, nnratio=0.8, check_orientation=True)
+    # python restatement of ORBmatcher.cc:409-516
+    cells, gx, gy = _grid_py(k2)
+    exp = np.full(400, -1, np.int64)
+    hist = [[] for _ in range(30)]
+    for i1 in range(400):
+        if not has[i1]:
+            continue
+        cand = _area_py(k2, cells, gx, gy, k1["x"][i1], k1["y"][i1], 30, k1["octave"][i1], k1["octave"][i1])
+        b1 = b2 = 2 ** 31 - 1
+        bi = -1
+        for i2 in cand:
+            if exp[i2] >= 0:
+                continue
+            dd = _ham(d1[i1], d2[i2])
+            if dd < b1:
+                b2, b1, bi = b1, dd, i2
+            elif dd < b2:
+                b2 = dd
+        if np.float32(b1) <= np.float32(b2) * nnr and b1 <= 100:
+            exp[bi] = i1
+            hist[_bin(k1["angle"][i1], k2["angle"][bi])].append(bi)
+    keep = _three_max_py([len(h) for h in hist])
+    for b in range(30):
+        if b not in keep:
+            for i2 in hist[b]:
+                exp[i2] = -1
+    assert np.array_equal(m21, exp) and n == int((exp >= 0).sum()) and n > 150
+
+
+def test_three_maxima_edge_cases():
+    import ctypes as C
+    for counts in ([0] * 30, [5] + [0] * 29, [10, 1, 0] + [0] * 27, [10, 10, 10] + [0] * 27, list(range(30)), [3, 3, 2, 2] + [0] * 26):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        arr = np.array(counts, np.int32)
+        O.lib().orb_oracle_three_maxima(arr.ctypes.data_as(C.c_void_p), 30, C.byref(a), C.byref(b), C.byref(c))
+        assert [a.value, b.value, c.value] == _three_max_py(counts)
+
+
+def test_knn2_first_minimum_and_second():
+    q = random_descriptors(20, 1)
+    db = random_descriptors(300, 2)
+    db[17] = q[3]
+    db[200] = q[3]  # duplicate minimum: the first one must win, second-best = 0
+    bd, bi, sd = O.knn2(q, db)
+    assert bi[3] == 17 and bd[3] == 0 and sd[3] == 0
+    for i in range(20):
+        ds = sorted((_ham(q[i], db[j]), j) for j in range(300))
+        assert bd[i] == ds[0][0] and bi[i] == ds[0][1] and sd[i] == ds[1][0]

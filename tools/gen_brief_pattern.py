@@ -13,7 +13,7 @@ assert len(nums) == 1024, len(nums)
 h = hashlib.sha256(','.join(map(str, nums)).encode()).hexdigest()
 assert h == '88df8ca875cc8db56799edd57bb914edad8acb2d48c202b7a464a575b55dbdb8', h
 out = open('include/orbfe_brief_pattern.inc', 'w')
-out.write("/* rBRIEF-256 learned sampling pattern: 256 point pairs, 1024 signed offsets in [-13,13],\n"
+out.write("/* rBRIEF-256 learned sampling pattern: 256 point pairs, 1024 signed offsets in [-13,12],\n"
           "   order x0,y0,x1,y1 per pair. DATA extracted by tools/gen_brief_pattern.py from the table at\n"
           "   reference src/ORBextractor.cc:197-455 (bit_pattern_31_).\n"
           "   sha256 of the comma-joined decimal values: %s */\n" % h)
