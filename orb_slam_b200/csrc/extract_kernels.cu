@@ -82,135 +82,317 @@ void launch_resize_level(const PlanDev *d_plan, const PlanDev &hp, int level, cu
 // on t: one pass emits every local maximum with m > min(fastTh,7) and the per-cell threshold
 // (fastTh, or 7 when fastTh yields <= 3 keypoints, :609-614) is applied later as a key threshold.
 // ------------------------------------------------------------------------------------------------
-#define FPW (ORBFE_FT_W + 8)  // pixel tile width  (72)
-#define FPH (ORBFE_FT_H + 8)  // pixel tile height (40)
-#define FMW (ORBFE_FT_W + 2)  // m tile width (66)
-#define FMH (ORBFE_FT_H + 2)  // m tile height (34)
-#define FPS 80                // pixel tile row stride in smem (bytes, multiple of 4)
-#define FMS 68                // m tile row stride
+// Geometry of one CTA: detect tile 120 x 62 px.  m is needed on a 1-px apron (122 x 64); it is computed for
+// 32 column groups of 4 px (x0-4 .. x0+123) x 64 rows (y0-1 .. y0+62): lane = column group, warp = 8-row
+// segment.  Each thread slides a 7-row register window down its 4-px column: per new row 3 LDS.32 + 10 PRMT
+// build the eight packed pixel pairs P_j = (b_j, b_{j+2}) as u16x2; every ring pixel of the two pixel pairs
+// A = (x, x+2) and B = (x+1, x+3) is then one of those registers, and the 16 arc minima / maxima are
+// VIMNMX3.U16x2 (two pixels per instruction, no divergence):
+//     t_k = min3(r_k, r_k+1, r_k+2) ; w_k = min3(t_k, t_k+3, t_k+6) = min of the 9-arc starting at k
+//     m   = max( max_k w_k - v , v - min_k W_k , 0 )          (W_k likewise with max3)
+#define F2_W ORBFE_FT_W            // 120
+#define F2_H ORBFE_FT_H            // 62
+#define F2_PW 144                  // staged pixel row stride (bytes): cols x0-8 .. x0+135
+#define F2_PWORDS 35               // words actually loaded per row (x0-8 .. x0+131)
+#define F2_PH (F2_H + 8)           // 70 staged rows: y0-4 .. y0+65
+#define F2_MS 128                  // m tile row stride (32 groups x 4)
+#define F2_MH (F2_H + 2)           // 64 m rows
 
-__device__ __forceinline__ int fast_m_at(const uint8_t *c /* smem centre */, int tlo) {
-    // ring offsets, radius-3 Bresenham circle, clockwise from (0,+3)
-    const int v = c[0];
-    int d[16];
-    d[0] = c[3 * FPS + 0];
-    d[8] = c[-3 * FPS + 0];
-    // early reject: any 9-arc contains one pixel of every opposite pair
-    {
-        const int a0 = d[0] - v, a8 = d[8] - v;
-        if (abs(a0) <= tlo && abs(a8) <= tlo) return 0;
-    }
-    d[4] = c[0 * FPS + 3];
-    d[12] = c[0 * FPS - 3];
-    {
-        const int a4 = d[4] - v, a12 = d[12] - v;
-        if (abs(a4) <= tlo && abs(a12) <= tlo) return 0;
-    }
-    d[1] = c[3 * FPS + 1];
-    d[2] = c[2 * FPS + 2];
-    d[3] = c[1 * FPS + 3];
-    d[5] = c[-1 * FPS + 3];
-    d[6] = c[-2 * FPS + 2];
-    d[7] = c[-3 * FPS + 1];
-    d[9] = c[-3 * FPS - 1];
-    d[10] = c[-2 * FPS - 2];
-    d[11] = c[-1 * FPS - 3];
-    d[13] = c[1 * FPS - 3];
-    d[14] = c[2 * FPS - 2];
-    d[15] = c[3 * FPS - 1];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] -= v;
-    int tmin[16], tmax[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        tmin[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        tmax[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    }
-    int mb = 0, md = 0;  // bright: max of window-min ; dark: max of -(window-max)
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int wmin = __vimin3_s32(tmin[k], tmin[(k + 3) & 15], tmin[(k + 6) & 15]);
-        const int wmax = __vimax3_s32(tmax[k], tmax[(k + 3) & 15], tmax[(k + 6) & 15]);
-        mb = max(mb, wmin);
-        md = max(md, -wmax);
-    }
-    return max(mb, md);
+__device__ __forceinline__ uint32_t max16_u16x2(const uint32_t *w) {
+    const uint32_t a0 = __vimax3_u16x2(w[0], w[1], w[2]), a1 = __vimax3_u16x2(w[3], w[4], w[5]);
+    const uint32_t a2 = __vimax3_u16x2(w[6], w[7], w[8]), a3 = __vimax3_u16x2(w[9], w[10], w[11]);
+    const uint32_t a4 = __vimax3_u16x2(w[12], w[13], w[14]);
+    return __vmaxu2(__vimax3_u16x2(a0, a1, a2), __vimax3_u16x2(a3, a4, w[15]));
+}
+__device__ __forceinline__ uint32_t min16_u16x2(const uint32_t *w) {
+    const uint32_t a0 = __vimin3_u16x2(w[0], w[1], w[2]), a1 = __vimin3_u16x2(w[3], w[4], w[5]);
+    const uint32_t a2 = __vimin3_u16x2(w[6], w[7], w[8]), a3 = __vimin3_u16x2(w[9], w[10], w[11]);
+    const uint32_t a4 = __vimin3_u16x2(w[12], w[13], w[14]);
+    return __vminu2(__vimin3_u16x2(a0, a1, a2), __vimin3_u16x2(a3, a4, w[15]));
 }
 
-__global__ void __launch_bounds__(256) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
-    __shared__ __align__(16) uint8_t pix[FPH * FPS];
-    __shared__ __align__(16) uint8_t mm[FMH * FMS];
+// r[16]: ring pixels (two pixels per register, values 0..255 in each 16-bit half), c: the two centres
+__device__ __forceinline__ uint32_t fast_m_u16x2(const uint32_t (&r)[16], uint32_t c) {
+    uint32_t tmin[16], tmax[16], w[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        tmin[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        tmax[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = __vimin3_u16x2(tmin[k], tmin[(k + 3) & 15], tmin[(k + 6) & 15]);
+    const uint32_t mb = max16_u16x2(w);  // brightest guaranteed level of some 9-arc
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = __vimax3_u16x2(tmax[k], tmax[(k + 3) & 15], tmax[(k + 6) & 15]);
+    const uint32_t md = min16_u16x2(w);  // darkest guaranteed level of some 9-arc
+    const uint32_t bright = __vmaxu2(mb, c) - c;  // per half >= 0: no borrow across halves
+    const uint32_t dark = c - __vminu2(md, c);
+    return __vmaxu2(bright, dark);
+}
+
+__device__ __forceinline__ void fast_load_row(const uint8_t *row /* smem, word aligned at the group's b0 */, uint32_t (&P)[8]) {
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row);
+    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(row + 4);
+    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(row + 8);
+    const uint32_t E0 = __byte_perm(w0, 0, 0x4240), O0 = __byte_perm(w0, 0, 0x4341);
+    const uint32_t E1 = __byte_perm(w1, 0, 0x4240), O1 = __byte_perm(w1, 0, 0x4341);
+    const uint32_t E2 = __byte_perm(w2, 0, 0x4240), O2 = __byte_perm(w2, 0, 0x4341);
+    P[0] = O0;                             // P_1 = (b1, b3)
+    P[1] = __byte_perm(E0, E1, 0x5412);    // P_2 = (b2, b4)
+    P[2] = __byte_perm(O0, O1, 0x5412);    // P_3 = (b3, b5)
+    P[3] = E1;                             // P_4 = (b4, b6)   centre of pair A
+    P[4] = O1;                             // P_5 = (b5, b7)   centre of pair B
+    P[5] = __byte_perm(E1, E2, 0x5412);    // P_6 = (b6, b8)
+    P[6] = __byte_perm(O1, O2, 0x5412);    // P_7 = (b7, b9)
+    P[7] = E2;                             // P_8 = (b8, b10)
+}
+
+// m tile in shared memory, u16x2 pairs exactly as produced: row r, group g -> [mA, mB] (8 bytes) with
+// mA = (m[x], m[x+2]), mB = (m[x+1], m[x+3]), x = x0-4+4g.
+__device__ __forceinline__ int m_at(const uint32_t *mt, int r, int c /* tile column, 0 <-> x0-4 */) {
+    const int g = c >> 2, k = c & 3;
+    const uint32_t wv = mt[(r * 32 + g) * 2 + (k & 1)];
+    return (k & 2) ? (int)(wv >> 16) : (int)(wv & 0xFFFF);
+}
+
+// candidates per tile: strict 8-neighbour maxima (<= one per 2x2 block) + cell-boundary pixels of pass 2
+#define F2_MAXC ((F2_W / 2) * (F2_H / 2) + 4 * (F2_W + F2_H))
+#define F2_MAXCELLS 16                    // cells a tile can overlap (cells are never smaller than ~1/3 tile)
+
+struct FastEmitCtx {
+    const LevelDev *L;
+    int xmax, ymax, thi;
+    int cj0, ci0, ncj;       // first cell column/row overlapped by the tile, number of cell columns
+    uint2 *s_cand;           // staged candidates: (key, local cell << 16 | slot inside (tile, cell))
+    int *s_n, *s_cnt_lo, *s_cnt_hi;
+};
+
+// cell of (x, y) and its detect window [xa, xb] x [ya, yb]  (ORBextractor.cc:560-599)
+__device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int ymax, int x, int y, int &ci, int &cj, int &xa,
+                                            int &xb, int &ya, int &yb) {
+    cj = min((x - ORBFE_EDGE) / L.cw, L.cols - 1);
+    ci = min((y - ORBFE_EDGE) / L.ch, L.rows - 1);
+    xa = ORBFE_EDGE + cj * L.cw;
+    ya = ORBFE_EDGE + ci * L.ch;
+    xb = (cj == L.cols - 1) ? xmax - 1 : xa + L.cw - 1;
+    yb = (ci == L.rows - 1) ? ymax - 1 : ya + L.ch - 1;
+}
+
+// stage one keypoint candidate in shared memory (global counters are touched once per (tile, cell) later)
+__device__ __forceinline__ void fast_emit(const FastEmitCtx &E, int x, int y, int m, int ci, int cj, int xa, int ya) {
+    const int lc = (ci - E.ci0) * E.ncj + (cj - E.cj0);
+    const int slot = atomicAdd(&E.s_cnt_lo[lc], 1);
+    if (m > E.thi) atomicAdd(&E.s_cnt_hi[lc], 1);
+    const int n = atomicAdd(E.s_n, 1);
+    const uint32_t raster = (uint32_t)((y - ya) * E.L->cw + (x - xa));
+    E.s_cand[n] = make_uint2(((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster), ((uint32_t)lc << 16) | (uint32_t)slot);
+}
+
+__global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+    // one buffer, two lives: the staged pixel tile (until m is computed), then the candidate list
+    __shared__ __align__(16) uint8_t sbuf[(F2_MAXC * 8 > F2_PH * F2_PW) ? F2_MAXC * 8 : F2_PH * F2_PW];
+    __shared__ __align__(16) uint32_t mt[F2_MH * 32 * 2];  // 16 KB
+    uint8_t *pix = sbuf;
+    uint2 *s_cand = reinterpret_cast<uint2 *>(sbuf);
+    __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
 
     const int f = blockIdx.y;
     const int l = find_level_by(plan, blockIdx.x, 0);
     const LevelDev &L = plan->lv[l];
     const int tile = blockIdx.x - L.ftile_base;
     const int ty = tile / L.ftiles_x, tx = tile - ty * L.ftiles_x;
-    const int x0 = ORBFE_EDGE + tx * ORBFE_FT_W, y0 = ORBFE_EDGE + ty * ORBFE_FT_H;
+    const int x0 = ORBFE_EDGE + tx * F2_W, y0 = ORBFE_EDGE + ty * F2_H;
     const int w = L.w, h = L.h, pitch = L.pitch;
     const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
-    const int tlo = plan->t_lo, thi = plan->t_hi;
+    const int tlo = plan->t_lo;
 
-    // ---- stage the pixel tile: rows y0-4 .. y0+FT_H+3, cols x0-4 .. x0+FT_W+3 (x0-4 is 4-byte aligned) ----
+    if (threadIdx.x < F2_MAXCELLS) { s_cnt_lo[threadIdx.x] = 0; s_cnt_hi[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_n = 0;
+    // ---- stage pixel rows y0-4 .. y0+65, cols x0-8 .. x0+131 (x0 is a multiple of 4) ----
     {
-        const int words_per_row = FPW / 4;  // 18
         const int max_word = pitch / 4 - 1;
-        const int wx0 = (x0 - 4) >> 2;
-        for (int i = threadIdx.x; i < FPH * words_per_row; i += blockDim.x) {
-            const int r = i / words_per_row, c = i - r * words_per_row;
+        const int wx0 = (x0 - 8) >> 2;
+        for (int i = threadIdx.x; i < F2_PH * F2_PWORDS; i += blockDim.x) {
+            const int r = i / F2_PWORDS, c = i - r * F2_PWORDS;
             const int gy = min(y0 - 4 + r, h - 1);
             const int gw = min(wx0 + c, max_word);
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gy * pitch) + gw);
-            *reinterpret_cast<uint32_t *>(&pix[r * FPS + c * 4]) = v;
+            *reinterpret_cast<uint32_t *>(&pix[r * F2_PW + c * 4]) =
+                __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gy * pitch) + gw);
         }
     }
     __syncthreads();
 
-    // ---- m for the (FT_H+2) x (FT_W+2) tile (1-px apron for the NMS) ----
     const int xmax = w - ORBFE_EDGE, ymax = h - ORBFE_EDGE;  // detect area is [16, xmax) x [16, ymax)
-    for (int i = threadIdx.x; i < FMH * FMW; i += blockDim.x) {
-        const int my = i / FMW, mx = i - my * FMW;
-        const int x = x0 - 1 + mx, y = y0 - 1 + my;
-        int m = 0;
-        if (x >= ORBFE_EDGE && x < xmax && y >= ORBFE_EDGE && y < ymax) m = fast_m_at(&pix[(my + 3) * FPS + (mx + 3)], tlo);
-        mm[my * FMS + mx] = (uint8_t)m;
+    const int g = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int gx = x0 - 4 + 4 * g;  // image x of the group's first pixel
+    // ---- m for 32 groups x 64 rows; lane = group, warp = 8-row segment ----
+    {
+        // halves of (mA, mB) that lie inside the detect area: A = (gx, gx+2), B = (gx+1, gx+3)
+        uint32_t maskA = 0, maskB = 0;
+        if (gx >= ORBFE_EDGE && gx < xmax) maskA |= 0x0000FFFFu;
+        if (gx + 2 >= ORBFE_EDGE && gx + 2 < xmax) maskA |= 0xFFFF0000u;
+        if (gx + 1 >= ORBFE_EDGE && gx + 1 < xmax) maskB |= 0x0000FFFFu;
+        if (gx + 3 >= ORBFE_EDGE && gx + 3 < xmax) maskB |= 0xFFFF0000u;
+        const uint8_t *base = &pix[(seg * 8) * F2_PW + 4 * g];  // b0 of the group = tile col 4g  (image x gx-4)
+        uint32_t P[7][8];
+#pragma unroll
+        for (int r = 0; r < 6; r++) fast_load_row(base + r * F2_PW, P[r]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            fast_load_row(base + (6 + i) * F2_PW, P[(6 + i) % 7]);
+#define FROW(dy) P[(i + (dy) + 3) % 7]
+            // ring in circular order, (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+            // pair A uses P_{4+dx} = index 3+dx ; pair B uses P_{5+dx} = index 4+dx
+            uint32_t mA, mB;
+            {
+                const uint32_t r[16] = {FROW(3)[3], FROW(3)[4], FROW(2)[5], FROW(1)[6], FROW(0)[6], FROW(-1)[6], FROW(-2)[5], FROW(-3)[4],
+                                        FROW(-3)[3], FROW(-3)[2], FROW(-2)[1], FROW(-1)[0], FROW(0)[0], FROW(1)[0], FROW(2)[1], FROW(3)[2]};
+                mA = fast_m_u16x2(r, FROW(0)[3]);
+            }
+            {
+                const uint32_t r[16] = {FROW(3)[4], FROW(3)[5], FROW(2)[6], FROW(1)[7], FROW(0)[7], FROW(-1)[7], FROW(-2)[6], FROW(-3)[5],
+                                        FROW(-3)[4], FROW(-3)[3], FROW(-2)[2], FROW(-1)[1], FROW(0)[1], FROW(1)[1], FROW(2)[2], FROW(3)[3]};
+                mB = fast_m_u16x2(r, FROW(0)[4]);
+            }
+#undef FROW
+            const int mr = seg * 8 + i;
+            const int y = y0 - 1 + mr;
+            const bool yin = (y >= ORBFE_EDGE && y < ymax);
+            uint2 o;
+            o.x = yin ? (mA & maskA) : 0u;
+            o.y = yin ? (mB & maskB) : 0u;
+            *reinterpret_cast<uint2 *>(&mt[(mr * 32 + g) * 2]) = o;
+        }
     }
     __syncthreads();
 
-    // ---- windowed NMS + emission ----
-    const int cw = L.cw, ch = L.ch, cols = L.cols, rows = L.rows;
-    for (int i = threadIdx.x; i < ORBFE_FT_H * ORBFE_FT_W; i += blockDim.x) {
-        const int iy = i / ORBFE_FT_W, ix = i - iy * ORBFE_FT_W;
-        const int x = x0 + ix, y = y0 + iy;
-        const uint8_t *c = &mm[(iy + 1) * FMS + (ix + 1)];
-        const int m = c[0];
-        if (m <= tlo || x >= xmax || y >= ymax) continue;
-        const int cj = min((x - ORBFE_EDGE) / cw, cols - 1), ci = min((y - ORBFE_EDGE) / ch, rows - 1);
-        const int xa = ORBFE_EDGE + cj * cw, ya = ORBFE_EDGE + ci * ch;
-        const int xb = (cj == cols - 1) ? xmax - 1 : xa + cw - 1;
-        const int yb = (ci == rows - 1) ? ymax - 1 : ya + ch - 1;
-        const bool L_ = x > xa, R_ = x < xb, U_ = y > ya, D_ = y < yb;
-        bool keep = true;
-        keep &= !(L_) || m > c[-1];
-        keep &= !(R_) || m > c[+1];
-        keep &= !(U_) || m > c[-FMS];
-        keep &= !(D_) || m > c[+FMS];
-        keep &= !(L_ && U_) || m > c[-FMS - 1];
-        keep &= !(R_ && U_) || m > c[-FMS + 1];
-        keep &= !(L_ && D_) || m > c[+FMS - 1];
-        keep &= !(R_ && D_) || m > c[+FMS + 1];
-        if (!keep) continue;
-        const int gcell = L.cell_base + ci * cols + cj;
-        const size_t fc = (size_t)f * plan->ncells_total + gcell;
-        const int slot = atomicAdd(&wk.cell_cnt_lo[fc], 1);
-        if (m > thi) atomicAdd(&wk.cell_cnt_hi[fc], 1);
-        if (slot < wk.cell_cand_cap[gcell]) {
-            const uint32_t raster = (uint32_t)((y - ya) * cw + (x - xa));
-            wk.cand_keys[(size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + slot] =
-                ((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster);
-        } else {
-            atomicExch(wk.err_flag, 1);
+    FastEmitCtx E;
+    E.L = &L; E.xmax = xmax; E.ymax = ymax; E.thi = plan->t_hi;
+    E.cj0 = min((x0 - ORBFE_EDGE) / L.cw, L.cols - 1);
+    E.ci0 = min((y0 - ORBFE_EDGE) / L.ch, L.rows - 1);
+    const int cj1 = min((min(x0 + F2_W, xmax) - 1 - ORBFE_EDGE) / L.cw, L.cols - 1);
+    const int ci1 = min((min(y0 + F2_H, ymax) - 1 - ORBFE_EDGE) / L.ch, L.rows - 1);
+    E.ncj = cj1 - E.cj0 + 1;
+    const int ncell_loc = E.ncj * (ci1 - E.ci0 + 1);  // <= F2_MAXCELLS (checked on the host)
+    E.s_cand = s_cand; E.s_n = &s_n; E.s_cnt_lo = s_cnt_lo; E.s_cnt_hi = s_cnt_hi;
+
+    // ---- pass 1: strict maximum over ALL 8 neighbours, two pixels per instruction.  Such a pixel is a
+    //      strict maximum over any subset of its neighbours too, so it is a keypoint whatever the cell
+    //      window is.  Rows 1..62 and groups 1..30 are the detect tile.
+    if (g >= 1 && g <= 30) {
+        uint32_t A[3], B[3], lrA[3], lrB[3], fullA[3], fullB[3];
+        const int r0 = seg * 8;  // first centre row handled = max(r0, 1)
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            // load tile row r0 - 1 + j into slot j % 3
+            const int rr = min(max(r0 - 1 + j, 0), F2_MH - 1);
+            const uint32_t *rowp = &mt[(rr * 32 + g) * 2];
+            const uint2 own = *reinterpret_cast<const uint2 *>(rowp);
+            const uint32_t pB = rowp[-1], nA = rowp[2];
+            const int sl = j % 3;
+            A[sl] = own.x;
+            B[sl] = own.y;
+            const uint32_t leftA = __byte_perm(pB, own.y, 0x5432);   // (m[x-1], m[x+1])
+            const uint32_t rightB = __byte_perm(own.x, nA, 0x5432);  // (m[x+2], m[x+4])
+            lrA[sl] = __vmaxu2(leftA, own.y);
+            fullA[sl] = __vmaxu2(lrA[sl], own.x);
+            lrB[sl] = __vmaxu2(own.x, rightB);
+            fullB[sl] = __vmaxu2(lrB[sl], own.y);
+            if (j >= 2) {
+                const int cr = r0 + j - 2;  // centre row (slot (j-1)%3), above = (j-2)%3, below = j%3
+                const int c = (j - 1) % 3, u = (j - 2) % 3, d = j % 3;
+                const uint32_t nbA = __vimax3_u16x2(fullA[u], fullA[d], lrA[c]);
+                const uint32_t nbB = __vimax3_u16x2(fullB[u], fullB[d], lrB[c]);
+                const uint32_t tA = __vmaxu2(A[c], nbA) ^ nbA;  // half != 0  <=>  m > every neighbour
+                const uint32_t tB = __vmaxu2(B[c], nbB) ^ nbB;
+                if (((tA | tB) != 0) && cr >= 1 && cr <= F2_H) {
+                    const int y = y0 - 1 + cr;
+#pragma unroll 1
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t tv = (k & 1) ? tB : tA, mv = (k & 1) ? B[c] : A[c];
+                        const int sh = (k & 2) ? 16 : 0;
+                        if (((tv >> sh) & 0xFFFF) == 0) continue;
+                        const int m = (int)((mv >> sh) & 0xFFFF);
+                        if (m <= tlo) continue;
+                        const int x = gx + k;
+                        int ci, cj, xa, xb, ya, yb;
+                        cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
+                        fast_emit(E, x, y, m, ci, cj, xa, ya);
+                    }
+                }
+            }
         }
+    }
+
+    // ---- pass 2: pixels on an interior cell boundary see only the neighbours inside their own cell
+    //      (cv::FAST ran per cell image): re-test them against the window and emit those that pass but
+    //      were not already emitted by pass 1.
+    {
+        const int cw = L.cw, ch = L.ch;
+        // vertical boundaries: columns xa-1 (right edge of cell cj-1) and xa (left edge of cell cj)
+        const int cj_lo = max(1, (x0 - ORBFE_EDGE + cw - 1) / cw), cj_hi = min(L.cols - 1, (x0 + F2_W - ORBFE_EDGE) / cw);
+        const int ci_lo = max(1, (y0 - ORBFE_EDGE + ch - 1) / ch), ci_hi = min(L.rows - 1, (y0 + F2_H - ORBFE_EDGE) / ch);
+        const int nv = max(0, cj_hi - cj_lo + 1), nh = max(0, ci_hi - ci_lo + 1);
+        const int items_v = nv * 2 * F2_H, items_h = nh * 2 * F2_W;
+        for (int it = threadIdx.x; it < items_v + items_h; it += blockDim.x) {
+            int x, y;
+            if (it < items_v) {
+                const int b = it / (2 * F2_H), rem = it - b * 2 * F2_H;
+                x = ORBFE_EDGE + (cj_lo + b) * cw - 1 + (rem & 1);
+                y = y0 + (rem >> 1);
+            } else {
+                const int it2 = it - items_v;
+                const int b = it2 / (2 * F2_W), rem = it2 - b * 2 * F2_W;
+                y = ORBFE_EDGE + (ci_lo + b) * ch - 1 + (rem & 1);
+                x = x0 + (rem >> 1);
+            }
+            if (x < x0 || x >= x0 + F2_W || y < y0 || y >= y0 + F2_H || x >= xmax || y >= ymax) continue;
+            int ci, cj, xa, xb, ya, yb;
+            cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
+            if (it >= items_v && (x == xa || x == xb) && cj_hi >= cj_lo &&
+                ((x == xa && cj >= 1) || (x == xb && cj < L.cols - 1)))
+                continue;  // on a vertical boundary too: handled by the vertical items
+            const int r = y - (y0 - 1), c = x - (x0 - 4);
+            const int m = m_at(mt, r, c);
+            if (m <= tlo) continue;
+            const bool L_ = x > xa, R_ = x < xb, U_ = y > ya, D_ = y < yb;
+            bool win = true, all8 = true;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (dx == 0 && dy == 0) continue;
+                    const bool gt = m > m_at(mt, r + dy, c + dx);
+                    const bool inside = (dx < 0 ? L_ : dx > 0 ? R_ : true) && (dy < 0 ? U_ : dy > 0 ? D_ : true);
+                    all8 &= gt;
+                    win &= (!inside) || gt;
+                }
+            if (win && !all8) fast_emit(E, x, y, m, ci, cj, xa, ya);
+        }
+    }
+    // ---- flush: one global atomic per (tile, cell) reserves the range, then the keys are written ----
+    __syncthreads();
+    if ((int)threadIdx.x < ncell_loc) {
+        const int lc = threadIdx.x;
+        const int gcell = L.cell_base + (E.ci0 + lc / E.ncj) * L.cols + (E.cj0 + lc % E.ncj);
+        const size_t fc = (size_t)f * plan->ncells_total + gcell;
+        int base = 0;
+        if (s_cnt_lo[lc] > 0) {
+            base = atomicAdd(&wk.cell_cnt_lo[fc], s_cnt_lo[lc]);
+            if (s_cnt_hi[lc] > 0) atomicAdd(&wk.cell_cnt_hi[fc], s_cnt_hi[lc]);
+            if (base + s_cnt_lo[lc] > wk.cell_cand_cap[gcell]) atomicExch(wk.err_flag, 1);
+        }
+        s_base[lc] = base;
+    }
+    __syncthreads();
+    const int ncand = s_n;
+    for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+        const uint2 cnd = s_cand[i];
+        const int lc = (int)(cnd.y >> 16), slot = (int)(cnd.y & 0xFFFF);
+        const int gcell = L.cell_base + (E.ci0 + lc / E.ncj) * L.cols + (E.cj0 + lc % E.ncj);
+        const int pos = s_base[lc] + slot;
+        if (pos < wk.cell_cand_cap[gcell])
+            wk.cand_keys[(size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + pos] = cnd.x;
     }
 }
 

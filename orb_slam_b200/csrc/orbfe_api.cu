@@ -175,6 +175,9 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         L.nfc = (int)std::ceil((float)L.quota / (float)L.ncells);
         if ((L.cols - 1) * L.cw > Wd || (L.rows - 1) * L.ch > Hd)
             return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cell grid does not tile the detect area (image too small)", l);
+        // a FAST tile (ORBFE_FT_W x ORBFE_FT_H) may overlap at most 16 cells (shared-memory counters)
+        if (((ORBFE_FT_W + L.cw - 2) / L.cw + 1) * ((ORBFE_FT_H + L.ch - 2) / L.ch + 1) > 16)
+            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cells of %dx%d are too small for the FAST tile", l, L.cw, L.ch);
         if (L.ncells > 4096 || (long long)L.cw * L.ch > (1 << 24))
             return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %d cells of %dx%d exceed the key layout", l, L.ncells, L.cw, L.ch);
         L.cell_base = cell_base;

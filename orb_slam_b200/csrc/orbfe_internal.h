@@ -10,8 +10,8 @@
 #define ORBFE_EDGE 16  // EDGE_THRESHOLD, reference src/ORBextractor.cc:77
 
 // FAST/NMS tile (detect-area pixels per CTA) and blur tile
-#define ORBFE_FT_W 64
-#define ORBFE_FT_H 32
+#define ORBFE_FT_W 120
+#define ORBFE_FT_H 62
 #define ORBFE_BT_W 128
 #define ORBFE_BT_H 32
 
