@@ -159,13 +159,11 @@ __device__ __forceinline__ int m_at(const uint32_t *mt, int r, int c /* tile col
 #define F2_MAXC ((F2_W / 2) * (F2_H / 2) + 4 * (F2_W + F2_H))
 #define F2_MAXCELLS 16                    // cells a tile can overlap (cells are never smaller than ~1/3 tile)
 
-struct FastEmitCtx {
-    const LevelDev *L;
-    int xmax, ymax, thi;
-    int cj0, ci0, ncj;       // first cell column/row overlapped by the tile, number of cell columns
-    uint2 *s_cand;           // staged candidates: (key, local cell << 16 | slot inside (tile, cell))
-    int *s_n, *s_cnt_lo, *s_cnt_hi;
-};
+// raw candidate queue entry: (x | y << 16, m); converted in place to (key, local cell << 16 | slot) later
+__device__ __forceinline__ void fast_push(uint2 *q, int *q_n, int x, int y, int m) {
+    const int n = atomicAdd(q_n, 1);
+    q[n] = make_uint2((uint32_t)x | ((uint32_t)y << 16), (uint32_t)m);
+}
 
 // cell of (x, y) and its detect window [xa, xb] x [ya, yb]  (ORBextractor.cc:560-599)
 __device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int ymax, int x, int y, int &ci, int &cj, int &xa,
@@ -176,16 +174,6 @@ __device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int yma
     ya = ORBFE_EDGE + ci * L.ch;
     xb = (cj == L.cols - 1) ? xmax - 1 : xa + L.cw - 1;
     yb = (ci == L.rows - 1) ? ymax - 1 : ya + L.ch - 1;
-}
-
-// stage one keypoint candidate in shared memory (global counters are touched once per (tile, cell) later)
-__device__ __forceinline__ void fast_emit(const FastEmitCtx &E, int x, int y, int m, int ci, int cj, int xa, int ya) {
-    const int lc = (ci - E.ci0) * E.ncj + (cj - E.cj0);
-    const int slot = atomicAdd(&E.s_cnt_lo[lc], 1);
-    if (m > E.thi) atomicAdd(&E.s_cnt_hi[lc], 1);
-    const int n = atomicAdd(E.s_n, 1);
-    const uint32_t raster = (uint32_t)((y - ya) * E.L->cw + (x - xa));
-    E.s_cand[n] = make_uint2(((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster), ((uint32_t)lc << 16) | (uint32_t)slot);
 }
 
 __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
@@ -266,16 +254,10 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
     }
     __syncthreads();
 
-    FastEmitCtx E;
-    E.L = &L; E.xmax = xmax; E.ymax = ymax; E.thi = plan->t_hi;
-    E.cj0 = min((x0 - ORBFE_EDGE) / L.cw, L.cols - 1);
-    E.ci0 = min((y0 - ORBFE_EDGE) / L.ch, L.rows - 1);
-    const int cj1 = min((min(x0 + F2_W, xmax) - 1 - ORBFE_EDGE) / L.cw, L.cols - 1);
-    const int ci1 = min((min(y0 + F2_H, ymax) - 1 - ORBFE_EDGE) / L.ch, L.rows - 1);
-    E.ncj = cj1 - E.cj0 + 1;
-    const int ncell_loc = E.ncj * (ci1 - E.ci0 + 1);  // <= F2_MAXCELLS (checked on the host)
-    E.s_cand = s_cand; E.s_n = &s_n; E.s_cnt_lo = s_cnt_lo; E.s_cnt_hi = s_cnt_hi;
-
+    // per-tile cell geometry, precomputed on the host (no integer divisions on the common path)
+    const FTileInfo ti = wk.ftile_info[blockIdx.x];
+    const int thi = plan->t_hi;
+    const uint32_t tlo2 = (uint32_t)tlo * 0x00010001u;
     // ---- pass 1: strict maximum over ALL 8 neighbours, two pixels per instruction.  Such a pixel is a
     //      strict maximum over any subset of its neighbours too, so it is a keypoint whatever the cell
     //      window is.  Rows 1..62 and groups 1..30 are the detect tile.
@@ -301,60 +283,48 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
             if (j >= 2) {
                 const int cr = r0 + j - 2;  // centre row (slot (j-1)%3), above = (j-2)%3, below = j%3
                 const int c = (j - 1) % 3, u = (j - 2) % 3, d = j % 3;
-                const uint32_t nbA = __vimax3_u16x2(fullA[u], fullA[d], lrA[c]);
-                const uint32_t nbB = __vimax3_u16x2(fullB[u], fullB[d], lrB[c]);
-                const uint32_t tA = __vmaxu2(A[c], nbA) ^ nbA;  // half != 0  <=>  m > every neighbour
+                // neighbour maximum, floored at t_lo: m must exceed both to be a candidate
+                const uint32_t nbA = __vmaxu2(__vimax3_u16x2(fullA[u], fullA[d], lrA[c]), tlo2);
+                const uint32_t nbB = __vmaxu2(__vimax3_u16x2(fullB[u], fullB[d], lrB[c]), tlo2);
+                const uint32_t tA = __vmaxu2(A[c], nbA) ^ nbA;  // half != 0  <=>  m > t_lo and m > every neighbour
                 const uint32_t tB = __vmaxu2(B[c], nbB) ^ nbB;
                 if (((tA | tB) != 0) && cr >= 1 && cr <= F2_H) {
                     const int y = y0 - 1 + cr;
-#pragma unroll 1
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t tv = (k & 1) ? tB : tA, mv = (k & 1) ? B[c] : A[c];
-                        const int sh = (k & 2) ? 16 : 0;
-                        if (((tv >> sh) & 0xFFFF) == 0) continue;
-                        const int m = (int)((mv >> sh) & 0xFFFF);
-                        if (m <= tlo) continue;
-                        const int x = gx + k;
-                        int ci, cj, xa, xb, ya, yb;
-                        cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
-                        fast_emit(E, x, y, m, ci, cj, xa, ya);
-                    }
+                    if (tA & 0x0000FFFFu) fast_push(s_cand, &s_n, gx + 0, y, (int)(A[c] & 0xFFFF));
+                    if (tB & 0x0000FFFFu) fast_push(s_cand, &s_n, gx + 1, y, (int)(B[c] & 0xFFFF));
+                    if (tA & 0xFFFF0000u) fast_push(s_cand, &s_n, gx + 2, y, (int)(A[c] >> 16));
+                    if (tB & 0xFFFF0000u) fast_push(s_cand, &s_n, gx + 3, y, (int)(B[c] >> 16));
                 }
             }
         }
     }
 
     // ---- pass 2: pixels on an interior cell boundary see only the neighbours inside their own cell
-    //      (cv::FAST ran per cell image): re-test them against the window and emit those that pass but
-    //      were not already emitted by pass 1.
+    //      (cv::FAST ran per cell image): re-test them against the window and queue those that pass but
+    //      were not already queued by pass 1.
     {
         const int cw = L.cw, ch = L.ch;
-        // vertical boundaries: columns xa-1 (right edge of cell cj-1) and xa (left edge of cell cj)
-        const int cj_lo = max(1, (x0 - ORBFE_EDGE + cw - 1) / cw), cj_hi = min(L.cols - 1, (x0 + F2_W - ORBFE_EDGE) / cw);
-        const int ci_lo = max(1, (y0 - ORBFE_EDGE + ch - 1) / ch), ci_hi = min(L.rows - 1, (y0 + F2_H - ORBFE_EDGE) / ch);
-        const int nv = max(0, cj_hi - cj_lo + 1), nh = max(0, ci_hi - ci_lo + 1);
-        const int items_v = nv * 2 * F2_H, items_h = nh * 2 * F2_W;
+        const int items_v = ti.nv * 2 * F2_H, items_h = ti.nh * 2 * F2_W;
         for (int it = threadIdx.x; it < items_v + items_h; it += blockDim.x) {
             int x, y;
             if (it < items_v) {
                 const int b = it / (2 * F2_H), rem = it - b * 2 * F2_H;
-                x = ORBFE_EDGE + (cj_lo + b) * cw - 1 + (rem & 1);
+                x = ORBFE_EDGE + (ti.cj_lo + b) * cw - 1 + (rem & 1);
                 y = y0 + (rem >> 1);
             } else {
                 const int it2 = it - items_v;
                 const int b = it2 / (2 * F2_W), rem = it2 - b * 2 * F2_W;
-                y = ORBFE_EDGE + (ci_lo + b) * ch - 1 + (rem & 1);
+                y = ORBFE_EDGE + (ti.ci_lo + b) * ch - 1 + (rem & 1);
                 x = x0 + (rem >> 1);
             }
             if (x < x0 || x >= x0 + F2_W || y < y0 || y >= y0 + F2_H || x >= xmax || y >= ymax) continue;
-            int ci, cj, xa, xb, ya, yb;
-            cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
-            if (it >= items_v && (x == xa || x == xb) && cj_hi >= cj_lo &&
-                ((x == xa && cj >= 1) || (x == xb && cj < L.cols - 1)))
-                continue;  // on a vertical boundary too: handled by the vertical items
             const int r = y - (y0 - 1), c = x - (x0 - 4);
             const int m = m_at(mt, r, c);
             if (m <= tlo) continue;
+            int ci, cj, xa, xb, ya, yb;
+            cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
+            if (it >= items_v && ((x == xa && cj >= 1) || (x == xb && cj < L.cols - 1)))
+                continue;  // on a vertical boundary too: handled by the vertical items
             const bool L_ = x > xa, R_ = x < xb, U_ = y > ya, D_ = y < yb;
             bool win = true, all8 = true;
 #pragma unroll
@@ -367,14 +337,29 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
                     all8 &= gt;
                     win &= (!inside) || gt;
                 }
-            if (win && !all8) fast_emit(E, x, y, m, ci, cj, xa, ya);
+            if (win && !all8) fast_push(s_cand, &s_n, x, y, m);
         }
+    }
+    __syncthreads();
+    // ---- dense conversion of the queue: cell lookup, per-(tile, cell) slot, selection key ----
+    const int ncand = s_n;
+    const int ncell_loc = ti.ncj * ti.nci;
+    for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+        const uint2 q = s_cand[i];
+        const int x = (int)(q.x & 0xFFFF), y = (int)(q.x >> 16), m = (int)q.y;
+        int ci, cj, xa, xb, ya, yb;
+        cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
+        const int lc = (ci - ti.ci0) * ti.ncj + (cj - ti.cj0);
+        const int slot = atomicAdd(&s_cnt_lo[lc], 1);
+        if (m > thi) atomicAdd(&s_cnt_hi[lc], 1);
+        const uint32_t raster = (uint32_t)((y - ya) * L.cw + (x - xa));
+        s_cand[i] = make_uint2(((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster), ((uint32_t)lc << 16) | (uint32_t)slot);
     }
     // ---- flush: one global atomic per (tile, cell) reserves the range, then the keys are written ----
     __syncthreads();
     if ((int)threadIdx.x < ncell_loc) {
         const int lc = threadIdx.x;
-        const int gcell = L.cell_base + (E.ci0 + lc / E.ncj) * L.cols + (E.cj0 + lc % E.ncj);
+        const int gcell = L.cell_base + (ti.ci0 + lc / ti.ncj) * L.cols + (ti.cj0 + lc % ti.ncj);
         const size_t fc = (size_t)f * plan->ncells_total + gcell;
         int base = 0;
         if (s_cnt_lo[lc] > 0) {
@@ -385,11 +370,10 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
         s_base[lc] = base;
     }
     __syncthreads();
-    const int ncand = s_n;
     for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
         const uint2 cnd = s_cand[i];
         const int lc = (int)(cnd.y >> 16), slot = (int)(cnd.y & 0xFFFF);
-        const int gcell = L.cell_base + (E.ci0 + lc / E.ncj) * L.cols + (E.cj0 + lc % E.ncj);
+        const int gcell = L.cell_base + (ti.ci0 + lc / ti.ncj) * L.cols + (ti.cj0 + lc % ti.ncj);
         const int pos = s_base[lc] + slot;
         if (pos < wk.cell_cand_cap[gcell])
             wk.cand_keys[(size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + pos] = cnd.x;

@@ -255,6 +255,34 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     }
     WorkDev &Wk = ex->work;
     memset(&Wk, 0, sizeof(Wk));
+    {   // per-tile cell geometry for the FAST kernel
+        std::vector<FTileInfo> info((size_t)P.nftiles_total);
+        for (int l = 0; l < ex->nlevels; l++) {
+            const LevelDev &L = P.lv[l];
+            const int xmax = L.w - ORBFE_EDGE, ymax = L.h - ORBFE_EDGE;
+            for (int ty = 0; ty < L.ftiles_y; ty++)
+                for (int tx = 0; tx < L.ftiles_x; tx++) {
+                    FTileInfo &T = info[(size_t)L.ftile_base + ty * L.ftiles_x + tx];
+                    const int x0 = ORBFE_EDGE + tx * ORBFE_FT_W, y0 = ORBFE_EDGE + ty * ORBFE_FT_H;
+                    const int x1 = std::min(x0 + ORBFE_FT_W, xmax) - 1, y1 = std::min(y0 + ORBFE_FT_H, ymax) - 1;
+                    const int cj0 = std::min((x0 - ORBFE_EDGE) / L.cw, L.cols - 1), cj1 = std::min((x1 - ORBFE_EDGE) / L.cw, L.cols - 1);
+                    const int ci0 = std::min((y0 - ORBFE_EDGE) / L.ch, L.rows - 1), ci1 = std::min((y1 - ORBFE_EDGE) / L.ch, L.rows - 1);
+                    T.cj0 = (short)cj0; T.ci0 = (short)ci0; T.ncj = (short)(cj1 - cj0 + 1); T.nci = (short)(ci1 - ci0 + 1);
+                    // interior boundaries X = 16 + cj*cw (cj >= 1) with x0 <= X <= x0 + FT_W (columns X-1 and X)
+                    const int cj_lo = std::max(1, (x0 - ORBFE_EDGE + L.cw - 1) / L.cw);
+                    const int cj_hi = std::min(L.cols - 1, (x0 + ORBFE_FT_W - ORBFE_EDGE) / L.cw);
+                    const int ci_lo = std::max(1, (y0 - ORBFE_EDGE + L.ch - 1) / L.ch);
+                    const int ci_hi = std::min(L.rows - 1, (y0 + ORBFE_FT_H - ORBFE_EDGE) / L.ch);
+                    T.cj_lo = (short)cj_lo; T.nv = (short)std::max(0, cj_hi - cj_lo + 1);
+                    T.ci_lo = (short)ci_lo; T.nh = (short)std::max(0, ci_hi - ci_lo + 1);
+                    if (T.ncj * T.nci > 16) return fail(ORBFE_ERR_UNSUPPORTED, "level %d: a FAST tile overlaps %d cells", l, T.ncj * T.nci);
+                }
+        }
+        FTileInfo *d_info;
+        CU_TRY(dmalloc(ex, &d_info, info.size()));
+        CU_TRY(cudaMemcpy(d_info, info.data(), sizeof(FTileInfo) * info.size(), cudaMemcpyHostToDevice));
+        Wk.ftile_info = d_info;
+    }
     long long *d_cb; int *d_cc;
     CU_TRY(dmalloc(ex, &d_cb, cand_base.size()));
     CU_TRY(dmalloc(ex, &d_cc, cand_cap.size()));

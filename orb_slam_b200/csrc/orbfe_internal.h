@@ -51,10 +51,17 @@ struct PlanDev {
     LevelDev lv[ORBFE_MAX_LEVELS];
 };
 
+// Cell geometry of one FAST tile (host-precomputed): cells overlapped and interior cell boundaries inside it
+struct FTileInfo {
+    short cj0, ci0, ncj, nci;    // first cell col/row overlapped, number of cell cols/rows overlapped
+    short cj_lo, nv, ci_lo, nh;  // interior vertical boundaries cj_lo .. cj_lo+nv-1 (x = 16 + cj*cw), horizontal likewise
+};
+
 // Per-batch work buffers (device).  Index [frame] strides are in the plan.
 struct WorkDev {
     const long long *cell_cand_base;  // [ncells_total] first candidate slot of each cell
     const int *cell_cand_cap;         // [ncells_total]
+    const FTileInfo *ftile_info;      // [nftiles_total]
     uint32_t *cand_keys;              // [batch][cand_total]   (score<<24 | 0xFFFFFF - raster)
     int *cell_cnt_lo;                 // [batch][ncells_total] candidates with m > t_lo (= all emitted)
     int *cell_cnt_hi;                 // [batch][ncells_total] candidates with m > t_hi
