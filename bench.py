@@ -265,13 +265,21 @@ def main():
     stage_acc, stage_n = {}, [0]
     kp_total = [0]
     launches = [0]
+    host_t = {"extract_call": 0.0, "match_call": 0.0, "views": 0.0, "n": 0}
 
     def match_step():
+        t0 = time.perf_counter()
         views = [M.FrameView(kps_np[i, :cnt_np[i]], desc_np[i, :cnt_np[i]], W, H, SCALE, NLEVELS) for i in range(B)]
         lasts = [prev["view"] if prev["view"] is not None else views[B - 1]] + views[:-1]
-        nm, _ = M.search_by_projection_frames(
-            mt, views, lasts, [np.ones(f.n, np.uint8) for f in lasts], [np.zeros(f.n, np.uint8) for f in lasts],
-            [backproject(f.kps) for f in lasts], Tcws, FX, FY, CX, CY, MATCH_TH)
+        has = [np.ones(f.n, np.uint8) for f in lasts]
+        outl = [np.zeros(f.n, np.uint8) for f in lasts]
+        world = [backproject(f.kps) for f in lasts]
+        t1 = time.perf_counter()
+        nm, _ = M.search_by_projection_frames(mt, views, lasts, has, outl, world, Tcws, FX, FY, CX, CY, MATCH_TH)
+        t2 = time.perf_counter()
+        host_t["views"] += t1 - t0
+        host_t["match_call"] += t2 - t1
+        host_t["n"] += 1
         # keep a private copy of the last frame's features for the next step
         lk, ld = kps_np[B - 1, :cnt_np[B - 1]].copy(), desc_np[B - 1, :cnt_np[B - 1]].copy()
         prev["view"] = M.FrameView(lk, ld, W, H, SCALE, NLEVELS)
@@ -283,6 +291,7 @@ def main():
         stage_n[0] += 1
 
     def step_device():
+        t0 = time.perf_counter()
         ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(),
                                 d_cnt.data_ptr(), stream.cuda_stream)
         with torch.cuda.stream(stream):
@@ -292,6 +301,7 @@ def main():
         stream.synchronize()
         ex.sync()
         collect_stages()
+        host_t["extract_call"] += time.perf_counter() - t0
         launches[0] += ex.last_launches()
         nm = match_step()
         kp_total[0] += int(cnt_np.sum())
@@ -385,6 +395,7 @@ def main():
                 "matches_per_step": r_dev["matches"] / args.steps / world,
                 "keypoints_per_step": r_dev["kp"] / args.steps,
                 "wall_ms_per_step": r_dev["wall_ms"] / args.steps,
+                "host_ms_per_step": {k: 1e3 * v / max(host_t["n"], 1) for k, v in host_t.items() if k != "n"},
                 "roofline": roof, "clocks": clocks}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
