@@ -45,6 +45,23 @@ int orbfe_search_by_projection_frames(OrbfeMatcher *m, int npairs, const OrbfeFr
                                       const float *const *Tcw, float fx, float fy, float cx, float cy, float th,
                                       int check_orientation, int *const *cur_mp_inout, int *nmatches_out);
 
+/* The same routine with EVERYTHING device-resident (no host round trip between extract and match):
+ * d_kps / d_desc / d_counts are the outputs of orbfe_extract_batch_device (frame f at f*cap); pair j matches
+ * frame d_cur_idx[j] (Current) against frame d_last_idx[j] (Last).  d_world = 3 floats per feature of every
+ * frame (position of the feature's map point), d_flags[f*cap+i] != 0 <=> feature i of frame f has a map point and is
+ * not an outlier, d_Tcw = 12 floats per pair.  d_cur_mp (npairs x cap ints) must be initialised by the caller
+ * (-1 = free slot, >= 0 = occupied) and receives the Last index matched to each Current feature; d_nmatches[j] =
+ * return value (-1 if the pair overflowed the candidate scratch: orbfe_matcher_sync then reports ORBFE_ERR_CAPACITY).
+ * Frame's 64x48 grid, GetFeaturesInArea order, the greedy accept loop and the rotation histogram all run in one
+ * kernel (one CTA per pair) with results identical to orbfe_search_by_projection_frames.  Enqueued on `stream`
+ * (NULL = the matcher's stream), not synchronised. */
+int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                      const int *d_counts, int cap, const int *d_cur_idx, const int *d_last_idx,
+                                      const float *d_world, const uint8_t *d_flags, const float *d_Tcw,
+                                      float min_x, float min_y, float max_x, float max_y, float scale_factor, int nlevels,
+                                      float fx, float fy, float cx, float cy, float th, int check_orientation,
+                                      int *d_cur_mp, int *d_nmatches, void *stream);
+
 /* int ORBmatcher::WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minOctave, maxOctave)
  * (ORBmatcher.cc:409-516).  f1_has_mp[i1] != 0 <=> F1.mvpMapPoints[i1] && !isBad().
  * match21_out[i2] = i1 whose map point was matched to F2 feature i2, or -1. */

@@ -38,7 +38,8 @@ ABI_SYMBOLS = [
     "orbfe_knn2_groups", "orbfe_knn2_groups_device", "orbfe_hamming_csr_device", "orbfe_matcher_sync",
     "orbfe_matcher_counters",
     # include/orbfe_match.h
-    "orbfe_frame_scale_factors", "orbfe_search_by_projection_frames", "orbfe_window_search",
+    "orbfe_frame_scale_factors", "orbfe_search_by_projection_frames", "orbfe_search_by_projection_device",
+    "orbfe_window_search",
     "orbfe_search_for_initialization",
 ]
 

@@ -157,7 +157,7 @@ __device__ __forceinline__ int m_at(const uint32_t *mt, int r, int c /* tile col
 
 // candidates per tile: strict 8-neighbour maxima (<= one per 2x2 block) + cell-boundary pixels of pass 2
 #define F2_MAXC ((F2_W / 2) * (F2_H / 2) + 4 * (F2_W + F2_H))
-#define F2_MAXCELLS 16                    // cells a tile can overlap (cells are never smaller than ~1/3 tile)
+#define F2_MAXCELLS 64                    // cells a tile can overlap (host-checked)
 
 // raw candidate queue entry: (x | y << 16, m); converted in place to (key, local cell << 16 | slot) later
 __device__ __forceinline__ void fast_push(uint2 *q, int *q_n, int x, int y, int m) {

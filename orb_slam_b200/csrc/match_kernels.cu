@@ -105,3 +105,307 @@ void launch_knn2_groups(const uint8_t *q, int nq, const uint8_t *db, int ngroups
 }
 
 }  // namespace orbfe
+
+// ================================================================================================
+// Device-resident frame-to-frame matcher: ORBmatcher::SearchByProjection(Frame &Cur, const Frame &Last, th)
+// (reference src/ORBmatcher.cc:1507-1620) with Frame's lookup grid (src/Frame.cc:109-123,200-277) rebuilt on
+// the device.  One CTA per (Current, Last) pair:
+//   A  grid of the Current frame: counting sort of the keypoints into the 64x48 cells, ascending index
+//      inside a cell (= push_back order, Frame.cc:116-123; PosInGrid rounds with round(), :269-270);
+//   B  one thread per Last feature: project its map point with Tcw (double accumulation like cv::gemm),
+//      enumerate the candidates exactly in GetFeaturesInArea order (ix outer, iy inner, cell order; octave
+//      and |dx|,|dy| <= r filters) and compute every 256-bit Hamming distance (XOR + POPC);
+//   C  the sequential accept loop, replayed by one warp over the precomputed (candidate, distance) lists:
+//      strict-< argmin over the candidates whose Current slot is still free, accept if <= TH_HIGH;
+//   D  rotation histogram + ComputeThreeMaxima (:1748-1789) and removal of the inconsistent matches.
+// Bit-exact with the host replay (orbfe_search_by_projection_frames) and with the oracle.
+// ================================================================================================
+namespace orbfe {
+
+#define SBP_GCOLS 64
+#define SBP_GROWS 48
+#define SBP_NCELL (SBP_GCOLS * SBP_GROWS)
+
+__device__ __forceinline__ int block_excl_scan_256(int v, int *s_warp /*[8]*/, int *total) {
+    // exclusive scan of one value per thread over a 256-thread CTA
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < wid; k++) base += s_warp[k];
+    int tot = 0;
+    for (int k = 0; k < 8; k++) tot += s_warp[k];
+    *total = tot;
+    __syncthreads();
+    return base + x - v;
+}
+
+struct SbpQuery {
+    float u, v, r;
+    int oct, x0, x1, y0, y1;
+    bool ok;
+};
+
+__device__ __forceinline__ SbpQuery sbp_project(const SbpParams &P, const OrbfeKeyPoint &kl, const float *X, const float *T) {
+    SbpQuery q;
+    q.ok = false;
+    float xc3[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)T[4 * k], (double)X[0]), __dmul_rn((double)T[4 * k + 1], (double)X[1])),
+                                   __dmul_rn((double)T[4 * k + 2], (double)X[2]));
+        xc3[k] = (float)__dadd_rn(s, (double)T[4 * k + 3]);
+    }
+    const float invzc = (float)(1.0 / (double)xc3[2]);
+    q.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, xc3[0]), invzc), P.cx);
+    q.v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, xc3[1]), invzc), P.cy);
+    if (q.u < P.min_x || q.u > P.max_x) return q;
+    if (q.v < P.min_y || q.v > P.max_y) return q;
+    q.oct = kl.octave;
+    q.r = __fmul_rn(P.th, P.scale[q.oct]);
+    int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.u, P.min_x), q.r), P.gw));
+    x0 = max(0, x0);
+    if (x0 >= SBP_GCOLS) return q;
+    int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.u, P.min_x), q.r), P.gw));
+    x1 = min(SBP_GCOLS - 1, x1);
+    if (x1 < 0) return q;
+    int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.v, P.min_y), q.r), P.gh));
+    y0 = max(0, y0);
+    if (y0 >= SBP_GROWS) return q;
+    int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.v, P.min_y), q.r), P.gh));
+    y1 = min(SBP_GROWS - 1, y1);
+    if (y1 < 0) return q;
+    q.x0 = x0; q.x1 = x1; q.y0 = y0; q.y1 = y1;
+    q.ok = true;
+    return q;
+}
+
+__global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const OrbfeKeyPoint *__restrict__ kps,
+                                                         const uint8_t *__restrict__ desc, const int *__restrict__ counts,
+                                                         const int *__restrict__ cur_idx, const int *__restrict__ last_idx,
+                                                         const float *__restrict__ world, const uint8_t *__restrict__ flags,
+                                                         const float *__restrict__ Tcw, uint32_t *__restrict__ scratch,
+                                                         int *__restrict__ cur_mp, int *__restrict__ nmatches,
+                                                         int *__restrict__ err) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int cap = P.cap;
+    int *cell_start = reinterpret_cast<int *>(smem);                 // [NCELL + 1]
+    int *cell_cur = cell_start + SBP_NCELL + 1;                      // [NCELL]
+    int *q_off = cell_cur + SBP_NCELL;                               // [cap + 1]
+    uint32_t *taken = reinterpret_cast<uint32_t *>(q_off + cap + 1); // [(cap + 31) / 32]
+    uint16_t *items = reinterpret_cast<uint16_t *>(taken + (cap + 31) / 32);  // [cap]
+    uint8_t *newbin = reinterpret_cast<uint8_t *>(items + cap);      // [cap]
+    __shared__ int s_warp[8], s_hist[32], s_keep[3], s_removed, s_nm;
+    // entry staging area (the rest of the dynamic shared memory)
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem + P.smem_fixed);
+
+    const int pair = blockIdx.x;
+    const int fc = cur_idx[pair], fl = last_idx[pair];
+    const int nc = min(counts[fc], cap), nl = min(counts[fl], cap);
+    const OrbfeKeyPoint *__restrict__ kc = kps + (size_t)fc * cap;
+    const OrbfeKeyPoint *__restrict__ kl = kps + (size_t)fl * cap;
+    const uint4 *__restrict__ dc = reinterpret_cast<const uint4 *>(desc + (size_t)fc * cap * 32);
+    const uint4 *__restrict__ dl = reinterpret_cast<const uint4 *>(desc + (size_t)fl * cap * 32);
+    const float *__restrict__ wl = world + (size_t)fl * cap * 3;
+    const uint8_t *__restrict__ fll = flags + (size_t)fl * cap;
+    const float *__restrict__ T = Tcw + (size_t)pair * 12;
+    int *__restrict__ mp = cur_mp + (size_t)pair * cap;
+    const int tid = threadIdx.x;
+
+    // ---- A: grid of the Current frame ----
+    for (int i = tid; i < SBP_NCELL; i += 256) cell_cur[i] = 0;
+    for (int i = tid; i < (cap + 31) / 32; i += 256) taken[i] = 0;
+    if (tid < 32) s_hist[tid] = 0;
+    if (tid == 0) { s_removed = 0; s_nm = 0; }
+    __syncthreads();
+    for (int i = tid; i < nc; i += 256) {
+        const float px = roundf(__fmul_rn(__fsub_rn(kc[i].x, P.min_x), P.gw));
+        const float py = roundf(__fmul_rn(__fsub_rn(kc[i].y, P.min_y), P.gh));
+        int cell = -1;
+        if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS) cell = (int)px * SBP_GROWS + (int)py;
+        newbin[i] = 0xFF;
+        if (cell >= 0) atomicAdd(&cell_cur[cell], 1);
+        if (mp[i] >= 0) atomicOr(&taken[i >> 5], 1u << (i & 31));  // slot occupied on entry (:1562)
+    }
+    __syncthreads();
+    {   // exclusive scan of the 3072 cell counts: 12 cells per thread
+        int loc[12], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { loc[k] = cell_cur[tid * 12 + k]; sum += loc[k]; }
+        int tot;
+        int base = block_excl_scan_256(sum, s_warp, &tot);
+#pragma unroll
+        for (int k = 0; k < 12; k++) { cell_start[tid * 12 + k] = base; cell_cur[tid * 12 + k] = base; base += loc[k]; }
+        if (tid == 255) cell_start[SBP_NCELL] = base;
+    }
+    __syncthreads();
+    for (int i = tid; i < nc; i += 256) {
+        const float px = roundf(__fmul_rn(__fsub_rn(kc[i].x, P.min_x), P.gw));
+        const float py = roundf(__fmul_rn(__fsub_rn(kc[i].y, P.min_y), P.gh));
+        if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS) {
+            const int cell = (int)px * SBP_GROWS + (int)py;
+            items[atomicAdd(&cell_cur[cell], 1)] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < SBP_NCELL; c += 256) {  // ascending index inside each cell (insertion sort, cells are tiny)
+        const int b = cell_start[c], e = cell_start[c + 1];
+        for (int i = b + 1; i < e; i++) {
+            const uint16_t v = items[i];
+            int j = i - 1;
+            while (j >= b && items[j] > v) { items[j + 1] = items[j]; j--; }
+            items[j + 1] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- B1: candidate counts per Last feature ----
+    const int nq_iter = (nl + 255) / 256;
+    int run_total = 0;
+    for (int it = 0; it < nq_iter; it++) {
+        const int q = it * 256 + tid;
+        int cnt = 0;
+        if (q < nl && fll[q]) {
+            const SbpQuery Q = sbp_project(P, kl[q], wl + 3 * q, T);
+            if (Q.ok) {
+                for (int ix = Q.x0; ix <= Q.x1; ix++)
+                    for (int iy = Q.y0; iy <= Q.y1; iy++) {
+                        const int c = ix * SBP_GROWS + iy;
+                        for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
+                            const OrbfeKeyPoint &kp = kc[items[k]];
+                            if (kp.octave < Q.oct - 1 || kp.octave > Q.oct + 1) continue;
+                            if (fabsf(__fsub_rn(kp.x, Q.u)) > Q.r || fabsf(__fsub_rn(kp.y, Q.v)) > Q.r) continue;
+                            cnt++;
+                        }
+                    }
+            }
+        }
+        int tot;
+        const int off = block_excl_scan_256(cnt, s_warp, &tot);
+        if (q < nl) q_off[q] = run_total + off;
+        run_total += tot;
+    }
+    if (tid == 0) q_off[nl] = run_total;
+    __syncthreads();
+    const int T_total = run_total;
+    if (T_total > P.scratch_per_pair) {
+        if (tid == 0) { atomicExch(err, 1); nmatches[pair] = -1; }
+        return;
+    }
+    uint32_t *ent = (T_total <= P.smem_entries) ? s_ent : scratch + (size_t)pair * P.scratch_per_pair;
+
+    // ---- B2: fill (candidate index | distance << 16) in enumeration order ----
+    for (int q = tid; q < nl; q += 256) {
+        int o = q_off[q];
+        if (q_off[q + 1] == o) continue;
+        const SbpQuery Q = sbp_project(P, kl[q], wl + 3 * q, T);
+        const uint4 a0 = __ldg(&dl[2 * q]), a1 = __ldg(&dl[2 * q + 1]);
+        for (int ix = Q.x0; ix <= Q.x1; ix++)
+            for (int iy = Q.y0; iy <= Q.y1; iy++) {
+                const int c = ix * SBP_GROWS + iy;
+                for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
+                    const int i2 = items[k];
+                    const OrbfeKeyPoint &kp = kc[i2];
+                    if (kp.octave < Q.oct - 1 || kp.octave > Q.oct + 1) continue;
+                    if (fabsf(__fsub_rn(kp.x, Q.u)) > Q.r || fabsf(__fsub_rn(kp.y, Q.v)) > Q.r) continue;
+                    const int d = ham256(a0, a1, __ldg(&dc[2 * i2]), __ldg(&dc[2 * i2 + 1]));
+                    ent[o++] = (uint32_t)i2 | ((uint32_t)d << 16);
+                }
+            }
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- C: sequential accept loop (one warp) ----
+    if (tid < 32) {
+        const int lane = tid;
+        int nm = 0;
+        for (int q = 0; q < nl; q++) {
+            const int b = q_off[q], e = q_off[q + 1];
+            if (b == e) continue;
+            uint32_t best = 0xFFFFFFFFu;  // dist << 16 | position: strict-< argmin, first minimum wins
+            for (int p0 = b; p0 < e; p0 += 32) {
+                const int p = p0 + lane;
+                uint32_t key = 0xFFFFFFFFu;
+                if (p < e) {
+                    const uint32_t en = ent[p];
+                    const int i2 = (int)(en & 0xFFFF);
+                    if (!((taken[i2 >> 5] >> (i2 & 31)) & 1u)) key = ((en >> 16) << 16) | (uint32_t)min(p - b, 0xFFFF);
+                }
+                best = min(best, __reduce_min_sync(0xffffffffu, key));
+            }
+            if (best != 0xFFFFFFFFu && (int)(best >> 16) <= 100 /* TH_HIGH */) {
+                const int i2 = (int)(ent[b + (int)(best & 0xFFFF)] & 0xFFFF);
+                if (lane == 0) {
+                    taken[i2 >> 5] |= 1u << (i2 & 31);
+                    mp[i2] = q;
+                    if (P.check_ori) {
+                        float rot = __fsub_rn(kl[q].angle, kc[i2].angle);
+                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                        int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+                        if (bin == 30) bin = 0;
+                        newbin[i2] = (uint8_t)bin;
+                        s_hist[bin]++;
+                    }
+                }
+                nm++;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) s_nm = nm;
+    }
+    __syncthreads();
+
+    // ---- D: rotation consistency ----
+    if (P.check_ori) {
+        if (tid == 0) {
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < 30; i++) {
+                const int s = s_hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+            s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+        }
+        __syncthreads();
+        int removed = 0;
+        for (int i = tid; i < nc; i += 256) {
+            const int b = newbin[i];
+            if (b != 0xFF && b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { mp[i] = -1; removed++; }
+        }
+        if (removed) atomicAdd(&s_removed, removed);
+        __syncthreads();
+    }
+    if (tid == 0) nmatches[pair] = s_nm - s_removed;
+}
+
+size_t sbp_smem_fixed_bytes(int cap) {
+    size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)cap + 1) +
+               sizeof(uint32_t) * (((size_t)cap + 31) / 32) + sizeof(uint16_t) * (size_t)cap + (size_t)cap;
+    return (b + 15) / 16 * 16;
+}
+
+int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const OrbfeKeyPoint *kps, const uint8_t *desc,
+                      const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
+                      const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem_bytes;
+    }
+    sbp_device_kernel<<<npairs, 256, smem_bytes, s>>>(P, kps, desc, counts, cur_idx, last_idx, world, flags, Tcw, scratch,
+                                                      cur_mp, nmatches, err);
+    return 0;
+}
+
+}  // namespace orbfe

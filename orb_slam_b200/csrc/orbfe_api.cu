@@ -175,8 +175,8 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         L.nfc = (int)std::ceil((float)L.quota / (float)L.ncells);
         if ((L.cols - 1) * L.cw > Wd || (L.rows - 1) * L.ch > Hd)
             return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cell grid does not tile the detect area (image too small)", l);
-        // a FAST tile (ORBFE_FT_W x ORBFE_FT_H) may overlap at most 16 cells (shared-memory counters)
-        if (((ORBFE_FT_W + L.cw - 2) / L.cw + 1) * ((ORBFE_FT_H + L.ch - 2) / L.ch + 1) > 16)
+        // a FAST tile (ORBFE_FT_W x ORBFE_FT_H) may overlap at most 64 cells (shared-memory counters)
+        if (((ORBFE_FT_W + L.cw - 2) / L.cw + 1) * ((ORBFE_FT_H + L.ch - 2) / L.ch + 1) > 64)
             return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cells of %dx%d are too small for the FAST tile", l, L.cw, L.ch);
         if (L.ncells > 4096 || (long long)L.cw * L.ch > (1 << 24))
             return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %d cells of %dx%d exceed the key layout", l, L.ncells, L.cw, L.ch);
@@ -275,7 +275,7 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
                     const int ci_hi = std::min(L.rows - 1, (y0 + ORBFE_FT_H - ORBFE_EDGE) / L.ch);
                     T.cj_lo = (short)cj_lo; T.nv = (short)std::max(0, cj_hi - cj_lo + 1);
                     T.ci_lo = (short)ci_lo; T.nh = (short)std::max(0, ci_hi - ci_lo + 1);
-                    if (T.ncj * T.nci > 16) return fail(ORBFE_ERR_UNSUPPORTED, "level %d: a FAST tile overlaps %d cells", l, T.ncj * T.nci);
+                    if (T.ncj * T.nci > 64) return fail(ORBFE_ERR_UNSUPPORTED, "level %d: a FAST tile overlaps %d cells", l, T.ncj * T.nci);
                 }
         }
         FTileInfo *d_info;
@@ -584,6 +584,10 @@ struct OrbfeMatcher {
     void *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long h2d_bytes = 0, d2h_bytes = 0, launches = 0;  // cumulative, for bench.py
+    uint32_t *scratch = nullptr;  // candidate entries of the device-resident matcher
+    size_t scratch_entries = 0;
+    int *d_err = nullptr;
+    int *h_err = nullptr;  // pinned
 };
 
 static cudaError_t mreserve(OrbfeMatcher *m, int i, size_t bytes) {
@@ -610,6 +614,9 @@ extern "C" int orbfe_matcher_create(int device, OrbfeMatcher **out) {
     m->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(m->d_err, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_err, sizeof(int), cudaHostAllocDefault);
     if (e != cudaSuccess) { delete m; return fail(ORBFE_ERR_CUDA, "matcher setup failed: %s", cudaGetErrorString(e)); }
     *out = m;
     return ORBFE_OK;
@@ -620,6 +627,9 @@ extern "C" int orbfe_matcher_destroy(OrbfeMatcher *m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (int i = 0; i < 6; i++) if (m->buf[i]) cudaFree(m->buf[i]);
+    if (m->scratch) cudaFree(m->scratch);
+    if (m->d_err) cudaFree(m->d_err);
+    if (m->h_err) cudaFreeHost(m->h_err);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return ORBFE_OK;
@@ -637,7 +647,57 @@ extern "C" int orbfe_matcher_counters(const OrbfeMatcher *m, unsigned long long 
 extern "C" int orbfe_matcher_sync(OrbfeMatcher *m) {
     if (!m) return fail(ORBFE_ERR_ARG, "m is NULL");
     CU_TRY(cudaSetDevice(m->device));
+    CU_TRY(cudaMemcpyAsync(m->h_err, m->d_err, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
+    if (*m->h_err) {
+        CU_TRY(cudaMemsetAsync(m->d_err, 0, sizeof(int), m->stream));
+        return fail(ORBFE_ERR_CAPACITY, "device matcher: a pair exceeded the candidate scratch budget (its nmatches is -1); "
+                                        "use orbfe_search_by_projection_frames for that pair");
+    }
+    return ORBFE_OK;
+}
+
+// SearchByProjection(Frame &Current, const Frame &Last, th) for `npairs` pairs, everything device-resident.
+extern "C" int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                                 const int *d_counts, int cap, const int *d_cur_idx, const int *d_last_idx,
+                                                 const float *d_world, const uint8_t *d_flags, const float *d_Tcw,
+                                                 float min_x, float min_y, float max_x, float max_y, float scale_factor,
+                                                 int nlevels, float fx, float fy, float cx, float cy, float th,
+                                                 int check_orientation, int *d_cur_mp, int *d_nmatches, void *stream) {
+    if (!m || npairs < 0 || cap < 1 || cap > 65535 || nlevels < 1 || nlevels > ORBFE_MAX_LEVELS) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (npairs == 0) return ORBFE_OK;
+    if (!d_kps || !d_desc || !d_counts || !d_cur_idx || !d_last_idx || !d_world || !d_flags || !d_Tcw || !d_cur_mp || !d_nmatches)
+        return fail(ORBFE_ERR_ARG, "NULL argument");
+    if (!(max_x > min_x) || !(max_y > min_y)) return fail(ORBFE_ERR_ARG, "bad image bounds");
+    CU_TRY(cudaSetDevice(m->device));
+    SbpParams P;
+    memset(&P, 0, sizeof(P));
+    P.min_x = min_x; P.min_y = min_y; P.max_x = max_x; P.max_y = max_y;
+    P.gw = (float)64 / (float)(max_x - min_x);   // Frame.cc:77
+    P.gh = (float)48 / (float)(max_y - min_y);   // Frame.cc:78
+    P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy; P.th = th;
+    P.scale[0] = 1.0f;                           // Frame.cc:95-103
+    for (int i = 1; i < nlevels; i++) P.scale[i] = P.scale[i - 1] * scale_factor;
+    P.nlevels = nlevels; P.cap = cap; P.check_ori = check_orientation ? 1 : 0;
+    P.scratch_per_pair = 64 * cap;
+    const size_t fixed = sbp_smem_fixed_bytes(cap);
+    const size_t total = std::max<size_t>(fixed + 16 * 1024, 100 * 1024);
+    if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large for the device matcher", cap);
+    P.smem_fixed = (int)fixed;
+    P.smem_entries = (int)((total - fixed) / sizeof(uint32_t));
+    const size_t need = (size_t)npairs * P.scratch_per_pair;
+    if (m->scratch_entries < need) {
+        if (m->scratch) cudaFree(m->scratch);
+        m->scratch = nullptr; m->scratch_entries = 0;
+        CU_TRY(cudaMalloc((void **)&m->scratch, need * sizeof(uint32_t)));
+        m->scratch_entries = need;
+    }
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    int rc = launch_sbp_device(P, total, npairs, d_kps, d_desc, d_counts, d_cur_idx, d_last_idx, d_world, d_flags, d_Tcw,
+                               m->scratch, d_cur_mp, d_nmatches, m->d_err, s);
+    if (rc) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)rc));
+    CU_TRY(cudaGetLastError());
+    m->launches += 1;
     return ORBFE_OK;
 }
 

@@ -86,6 +86,21 @@ void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, co
 int level_select_smem_bytes(int max_kept);
 int set_level_select_smem(int bytes);
 
+// parameters of the device-resident SearchByProjection(Frame,Frame) kernel
+struct SbpParams {
+    float min_x, min_y, max_x, max_y, gw, gh;  // Frame::mnMinX.., mfGridElementWidthInv/HeightInv
+    float fx, fy, cx, cy, th;
+    float scale[ORBFE_MAX_LEVELS];             // Frame::mvScaleFactors
+    int nlevels, cap, check_ori;
+    int scratch_per_pair;                      // global scratch entries per pair
+    int smem_entries;                          // entries that fit in the dynamic shared-memory staging area
+    int smem_fixed;                            // bytes of the fixed shared-memory part
+};
+size_t sbp_smem_fixed_bytes(int cap);
+int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const OrbfeKeyPoint *kps, const uint8_t *desc,
+                      const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
+                      const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s);
+
 // ---- launchers (match_kernels.cu) ----
 void launch_hamming_csr(const uint8_t *q, const uint8_t *t, const int32_t *row_ptr, const int32_t *cols, int nq,
                         int npairs, uint16_t *out, cudaStream_t s);

@@ -34,6 +34,9 @@ def _bind():
     L.orbfe_frame_scale_factors.restype = None
     L.orbfe_search_by_projection_frames.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
                                                     C.c_float, C.c_float, C.c_float, C.c_int, vp, vp]
+    L.orbfe_search_by_projection_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp,
+                                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp]
     L.orbfe_window_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
     _bound = True
@@ -110,3 +113,17 @@ def search_for_initialization(matcher: ORBmatcher, f1, f2, prev_matched, window)
     _check(L.orbfe_search_for_initialization(matcher.handle, C.byref(f1.c), C.byref(f2.c), _p(prev), window,
                                              float(matcher.mfNNratio), int(matcher.mbCheckOrientation), _p(m12), C.byref(nm)))
     return nm.value, m12[:f1.n], prev
+
+
+def search_by_projection_device(matcher: ORBmatcher, npairs, d_kps, d_desc, d_counts, cap, d_cur_idx, d_last_idx, d_world,
+                                d_flags, d_Tcw, width, height, scale_factor, nlevels, fx, fy, cx, cy, th, d_cur_mp,
+                                d_nmatches, stream=0):
+    """Device-pointer form (ints = raw device addresses) of SearchByProjection(Current, Last, th); see
+    include/orbfe_match.h.  Zero distortion image bounds (0, 0, width, height) as in Frame.cc:342-348."""
+    L = _bind()
+    vp = C.c_void_p
+    _check(L.orbfe_search_by_projection_device(matcher.handle, npairs, vp(d_kps), vp(d_desc), vp(d_counts), cap,
+                                               vp(d_cur_idx), vp(d_last_idx), vp(d_world), vp(d_flags), vp(d_Tcw),
+                                               0.0, 0.0, float(width), float(height), scale_factor, nlevels,
+                                               fx, fy, cx, cy, th, int(matcher.mbCheckOrientation), vp(d_cur_mp),
+                                               vp(d_nmatches), vp(stream)))

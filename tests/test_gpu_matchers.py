@@ -97,3 +97,70 @@ def test_window_search_and_initialization(gpu_required):
     n2_o, m12b_o, _ = O.search_for_initialization(o1, o2, prev_o, 100, nnratio=0.9, check_orientation=True)
     assert n2 == n2_o and np.array_equal(m12b, m12b_o)
     m.close()
+
+
+def test_device_resident_search_by_projection(gpu_required):
+    """The fused device kernel (grid + candidates + distances + greedy + rotation filter) vs the oracle."""
+    import torch
+    feats, shifts = _features(5)
+    cap = 1000
+    nfr = len(feats)
+    kps_all = np.zeros((nfr, cap), fe.KP_DTYPE)
+    desc_all = np.zeros((nfr, cap, 32), np.uint8)
+    counts = np.zeros(nfr, np.int32)
+    world = np.zeros((nfr, cap, 3), np.float32)
+    flags = np.zeros((nfr, cap), np.uint8)
+    rng = np.random.default_rng(11)
+    for f, (k, d) in enumerate(feats):
+        n = len(k) - 37 * f  # different counts per frame
+        counts[f] = n
+        kps_all[f, :n], desc_all[f, :n] = k[:n], d[:n]
+        world[f, :n] = _world(k[:n])
+        flags[f, :n] = (rng.random(n) < 0.92)
+    pairs = [(1, 0), (2, 1), (3, 2), (4, 3), (4, 0), (2, 2)]
+    npairs = len(pairs)
+    T = np.stack([_tcw(*shifts[c]) if c == l + 1 else _tcw(0, 0) for c, l in pairs]).astype(np.float32)
+    pre = np.full((npairs, cap), -1, np.int32)
+    pre[rng.random((npairs, cap)) < 0.02] = 7
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_kps, d_desc, d_cnt = t(kps_all.view(np.uint8).reshape(nfr, cap, 28)), t(desc_all), t(counts)
+    d_world, d_flags, d_T = t(world), t(flags), t(T.reshape(npairs, 12))
+    d_cur = t(np.array([p[0] for p in pairs], np.int32))
+    d_last = t(np.array([p[1] for p in pairs], np.int32))
+    d_mp, d_nm = t(pre), torch.zeros(npairs, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    m = fe.ORBmatcher(0.9, True)
+    M.search_by_projection_device(m, npairs, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, d_cur.data_ptr(),
+                                  d_last.data_ptr(), d_world.data_ptr(), d_flags.data_ptr(), d_T.data_ptr(), W, H, 1.2, 8,
+                                  FX, FY, CX, CY, 15.0, d_mp.data_ptr(), d_nm.data_ptr())
+    m.sync()
+    mp, nm = d_mp.cpu().numpy(), d_nm.cpu().numpy()
+    tot = 0
+    for j, (c, l) in enumerate(pairs):
+        nc, nl = counts[c], counts[l]
+        fc = O.OracleFrame(kps_all[c, :nc], desc_all[c, :nc], W, H)
+        fl = O.OracleFrame(kps_all[l, :nl], desc_all[l, :nl], W, H)
+        n_o, mp_o = O.search_by_projection_ff(fc, fl, flags[l, :nl], np.zeros(nl, np.uint8), world[l, :nl], T[j], FX, FY, CX, CY,
+                                              15.0, True, cur_mp=pre[j, :nc])
+        assert nm[j] == n_o, (j, nm[j], n_o)
+        assert np.array_equal(mp[j, :nc], mp_o), j
+        tot += n_o
+    assert tot > 1000
+    # without the orientation check
+    m2 = fe.ORBmatcher(0.9, False)
+    d_mp2 = t(pre)
+    M.search_by_projection_device(m2, npairs, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, d_cur.data_ptr(),
+                                  d_last.data_ptr(), d_world.data_ptr(), d_flags.data_ptr(), d_T.data_ptr(), W, H, 1.2, 8,
+                                  FX, FY, CX, CY, 15.0, d_mp2.data_ptr(), d_nm.data_ptr())
+    m2.sync()
+    mp2, nm2 = d_mp2.cpu().numpy(), d_nm.cpu().numpy()
+    for j, (c, l) in enumerate(pairs):
+        nc, nl = counts[c], counts[l]
+        fc = O.OracleFrame(kps_all[c, :nc], desc_all[c, :nc], W, H)
+        fl = O.OracleFrame(kps_all[l, :nl], desc_all[l, :nl], W, H)
+        n_o, mp_o = O.search_by_projection_ff(fc, fl, flags[l, :nl], np.zeros(nl, np.uint8), world[l, :nl], T[j], FX, FY, CX, CY,
+                                              15.0, False, cur_mp=pre[j, :nc])
+        assert nm2[j] == n_o and np.array_equal(mp2[j, :nc], mp_o)
+    m.close()
+    m2.close()
