@@ -290,22 +290,51 @@ def main():
             stage_acc[name] = stage_acc.get(name, 0.0) + ms
         stage_n[0] += 1
 
+    # ---- device-resident pipeline state (value path): slot B holds the previous step's last frame ----
+    d_kps_all = torch.zeros((B + 1, NFEAT, 28), dtype=torch.uint8, device=dev)
+    d_desc_all = torch.zeros((B + 1, NFEAT, 32), dtype=torch.uint8, device=dev)
+    d_cnt_all = torch.zeros((B + 1,), dtype=torch.int32, device=dev)
+    d_world = torch.zeros((B + 1, NFEAT, 3), dtype=torch.float32, device=dev)
+    d_flags = torch.ones((B + 1, NFEAT), dtype=torch.uint8, device=dev)   # every feature carries a map point
+    d_T = torch.from_numpy(np.stack(Tcws).reshape(B, 12)).to(dev)
+    d_cur = torch.arange(0, B, dtype=torch.int32, device=dev)
+    d_last = torch.tensor([B] + list(range(0, B - 1)), dtype=torch.int32, device=dev)
+    d_mp = torch.empty((B, NFEAT), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros((B,), dtype=torch.int32, device=dev)
+    h_mp = torch.empty((B, NFEAT), dtype=torch.int32).pin_memory()
+    h_nm = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    kxy = d_kps_all.view(torch.float32).view(B + 1, NFEAT, 7)
+
     def step_device():
         t0 = time.perf_counter()
-        ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(),
-                                d_cnt.data_ptr(), stream.cuda_stream)
         with torch.cuda.stream(stream):
-            h_cnt.copy_(d_cnt, non_blocking=True)
-            h_kps.copy_(d_kps, non_blocking=True)
-            h_desc.copy_(d_desc, non_blocking=True)
+            ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps_all.data_ptr(), d_desc_all.data_ptr(),
+                                    d_cnt_all.data_ptr(), stream.cuda_stream)
+            # synthetic map points: back-project every keypoint at depth DEPTH (same float32 ops as backproject())
+            d_world[:B, :, 0] = (kxy[:B, :, 0] - CX) / FX * DEPTH
+            d_world[:B, :, 1] = (kxy[:B, :, 1] - CY) / FY * DEPTH
+            d_world[:B, :, 2] = DEPTH
+            d_mp.fill_(-1)
+            M.search_by_projection_device(mt, B, d_kps_all.data_ptr(), d_desc_all.data_ptr(), d_cnt_all.data_ptr(), NFEAT,
+                                          d_cur.data_ptr(), d_last.data_ptr(), d_world.data_ptr(), d_flags.data_ptr(),
+                                          d_T.data_ptr(), W, H, SCALE, NLEVELS, FX, FY, CX, CY, MATCH_TH,
+                                          d_mp.data_ptr(), d_nm.data_ptr(), stream.cuda_stream)
+            h_cnt.copy_(d_cnt_all[:B], non_blocking=True)
+            h_nm.copy_(d_nm, non_blocking=True)
+            h_kps.copy_(d_kps_all[:B], non_blocking=True)
+            h_desc.copy_(d_desc_all[:B], non_blocking=True)
+            h_mp.copy_(d_mp, non_blocking=True)
+            # carry the last frame over to slot B for the next step
+            d_kps_all[B].copy_(d_kps_all[B - 1]); d_desc_all[B].copy_(d_desc_all[B - 1])
+            d_cnt_all[B:B + 1].copy_(d_cnt_all[B - 1:B]); d_world[B].copy_(d_world[B - 1])
         stream.synchronize()
         ex.sync()
         collect_stages()
         host_t["extract_call"] += time.perf_counter() - t0
-        launches[0] += ex.last_launches()
-        nm = match_step()
+        host_t["n"] += 1
+        launches[0] += ex.last_launches() + 1
         kp_total[0] += int(cnt_np.sum())
-        return nm
+        return int(h_nm.numpy().sum())
 
     def step_e2e():
         ex.extract_batch_ptr(h_frames.data_ptr(), W, H, W, W * H, B, h_kps.data_ptr(), h_desc.data_ptr(), NFEAT,

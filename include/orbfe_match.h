@@ -45,6 +45,10 @@ int orbfe_search_by_projection_frames(OrbfeMatcher *m, int npairs, const OrbfeFr
                                       const float *const *Tcw, float fx, float fy, float cx, float cy, float th,
                                       int check_orientation, int *const *cur_mp_inout, int *nmatches_out);
 
+/* Test / debugging hook: 1 = orbfe_search_by_projection_frames always takes the host-replay path (host candidate
+ * lists + device distances + host greedy loop) instead of the fused device kernel.  Results are identical. */
+void orbfe_matcher_force_host_replay(int on);
+
 /* The same routine with EVERYTHING device-resident (no host round trip between extract and match):
  * d_kps / d_desc / d_counts are the outputs of orbfe_extract_batch_device (frame f at f*cap); pair j matches
  * frame d_cur_idx[j] (Current) against frame d_last_idx[j] (Last).  d_world = 3 floats per feature of every

@@ -39,6 +39,7 @@ ABI_SYMBOLS = [
     "orbfe_matcher_counters",
     # include/orbfe_match.h
     "orbfe_frame_scale_factors", "orbfe_search_by_projection_frames", "orbfe_search_by_projection_device",
+    "orbfe_matcher_force_host_replay",
     "orbfe_window_search",
     "orbfe_search_for_initialization",
 ]

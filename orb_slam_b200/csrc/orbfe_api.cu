@@ -588,6 +588,10 @@ struct OrbfeMatcher {
     size_t scratch_entries = 0;
     int *d_err = nullptr;
     int *h_err = nullptr;  // pinned
+    // staging of the host-view entry point that runs on the fused device kernel
+    unsigned char *h_stage = nullptr;  // pinned
+    unsigned char *d_stage = nullptr;
+    size_t stage_cap = 0;
 };
 
 static cudaError_t mreserve(OrbfeMatcher *m, int i, size_t bytes) {
@@ -628,6 +632,8 @@ extern "C" int orbfe_matcher_destroy(OrbfeMatcher *m) {
     if (m->stream) cudaStreamSynchronize(m->stream);
     for (int i = 0; i < 6; i++) if (m->buf[i]) cudaFree(m->buf[i]);
     if (m->scratch) cudaFree(m->scratch);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->d_stage) cudaFree(m->d_stage);
     if (m->d_err) cudaFree(m->d_err);
     if (m->h_err) cudaFreeHost(m->h_err);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -796,5 +802,102 @@ extern "C" int orbfe_knn2_groups(OrbfeMatcher *m, const uint8_t *q, int nq, cons
     CU_TRY(cudaMemcpyAsync(best_idx, m->buf[3], sizeof(int32_t) * no, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(second, m->buf[4], sizeof(uint16_t) * no, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
+    return ORBFE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-view SearchByProjection(Frame,Frame) on the fused device kernel: pack the views into one pinned
+// staging block, one H2D, one launch, one D2H.  Returns 1 when the call has to take the host-replay path
+// (mixed geometries, > 65535 features, or a pair overflowed the candidate scratch).
+// ------------------------------------------------------------------------------------------------
+#include "../../include/orbfe_match.h"
+extern "C" int orbfe_sbp_frames_via_device(OrbfeMatcher *m, int npairs, const OrbfeFrameView *cur, const OrbfeFrameView *last,
+                                           const uint8_t *const *last_has_mp, const uint8_t *const *last_outlier,
+                                           const float *const *last_world, const float *const *Tcw, float fx, float fy,
+                                           float cx, float cy, float th, int check_orientation, int *const *cur_mp_inout,
+                                           int *nmatches_out) {
+    if (npairs <= 0) return ORBFE_OK;
+    const OrbfeFrameView &R = cur[0];
+    if (R.nlevels < 1 || R.nlevels > ORBFE_MAX_LEVELS || !R.scale_factors) return 1;
+    int cap = 1;
+    for (int j = 0; j < npairs; j++) {
+        const OrbfeFrameView *v[2] = {&cur[j], &last[j]};
+        for (int k = 0; k < 2; k++) {
+            if (v[k]->min_x != R.min_x || v[k]->min_y != R.min_y || v[k]->max_x != R.max_x || v[k]->max_y != R.max_y ||
+                v[k]->grid_inv_w != R.grid_inv_w || v[k]->grid_inv_h != R.grid_inv_h || v[k]->nlevels != R.nlevels)
+                return 1;
+            for (int l = 0; l < R.nlevels; l++)
+                if (v[k]->scale_factors[l] != R.scale_factors[l]) return 1;
+            cap = std::max(cap, v[k]->n);
+        }
+    }
+    if (cap > 65535) return 1;
+    // the kernel derives the grid cell sizes and scale factors itself: make sure they are the Frame.cc values
+    if (R.grid_inv_w != (float)64 / (float)(R.max_x - R.min_x) || R.grid_inv_h != (float)48 / (float)(R.max_y - R.min_y)) return 1;
+    const float sf = R.nlevels > 1 ? R.scale_factors[1] : 1.2f;
+    {
+        float s = 1.0f;
+        for (int l = 1; l < R.nlevels; l++) { s = s * sf; if (s != R.scale_factors[l]) return 1; }
+    }
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t nf = (size_t)2 * npairs;  // frame slot 2j = Current of pair j, 2j+1 = Last of pair j
+    // layout of the staging block
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_kps = take(nf * cap * sizeof(OrbfeKeyPoint)), o_desc = take(nf * cap * 32), o_cnt = take(nf * sizeof(int));
+    const size_t o_world = take(nf * cap * 3 * sizeof(float)), o_flags = take(nf * cap), o_T = take((size_t)npairs * 12 * sizeof(float));
+    const size_t o_ci = take((size_t)npairs * sizeof(int)), o_li = take((size_t)npairs * sizeof(int));
+    const size_t in_bytes = off;
+    const size_t o_mp = take((size_t)npairs * cap * sizeof(int)), o_nm = take((size_t)npairs * sizeof(int));
+    const size_t total = off;
+    if (m->stage_cap < total) {
+        if (m->h_stage) cudaFreeHost(m->h_stage);
+        if (m->d_stage) cudaFree(m->d_stage);
+        m->h_stage = nullptr; m->d_stage = nullptr; m->stage_cap = 0;
+        const size_t want = total + total / 4;
+        CU_TRY(cudaHostAlloc((void **)&m->h_stage, want, cudaHostAllocDefault));
+        CU_TRY(cudaMalloc((void **)&m->d_stage, want));
+        m->stage_cap = want;
+    }
+    unsigned char *H = m->h_stage, *D = m->d_stage;
+    int *h_cnt = (int *)(H + o_cnt), *h_ci = (int *)(H + o_ci), *h_li = (int *)(H + o_li);
+    for (int j = 0; j < npairs; j++) {
+        const OrbfeFrameView &C = cur[j], &L = last[j];
+        h_cnt[2 * j] = C.n; h_cnt[2 * j + 1] = L.n;
+        h_ci[j] = 2 * j; h_li[j] = 2 * j + 1;
+        if (C.n) {
+            memcpy(H + o_kps + (size_t)(2 * j) * cap * sizeof(OrbfeKeyPoint), C.keys_un, (size_t)C.n * sizeof(OrbfeKeyPoint));
+            memcpy(H + o_desc + (size_t)(2 * j) * cap * 32, C.desc, (size_t)C.n * 32);
+            memcpy(H + o_mp + (size_t)j * cap * sizeof(int), cur_mp_inout[j], (size_t)C.n * sizeof(int));
+        }
+        if (L.n) {
+            memcpy(H + o_kps + (size_t)(2 * j + 1) * cap * sizeof(OrbfeKeyPoint), L.keys_un, (size_t)L.n * sizeof(OrbfeKeyPoint));
+            memcpy(H + o_desc + (size_t)(2 * j + 1) * cap * 32, L.desc, (size_t)L.n * 32);
+            memcpy(H + o_world + (size_t)(2 * j + 1) * cap * 3 * sizeof(float), last_world[j], (size_t)L.n * 3 * sizeof(float));
+            unsigned char *fl = H + o_flags + (size_t)(2 * j + 1) * cap;
+            for (int i = 0; i < L.n; i++) fl[i] = (last_has_mp[j][i] && !last_outlier[j][i]) ? 1 : 0;
+        }
+        memcpy(H + o_T + (size_t)j * 12 * sizeof(float), Tcw[j], 12 * sizeof(float));
+    }
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(D, H, in_bytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(D + o_mp, H + o_mp, (size_t)npairs * cap * sizeof(int), cudaMemcpyHostToDevice, s));
+    int rc = orbfe_search_by_projection_device(m, npairs, (const OrbfeKeyPoint *)(D + o_kps), D + o_desc, (const int *)(D + o_cnt), cap,
+                                               (const int *)(D + o_ci), (const int *)(D + o_li), (const float *)(D + o_world),
+                                               D + o_flags, (const float *)(D + o_T), R.min_x, R.min_y, R.max_x, R.max_y, sf,
+                                               R.nlevels, fx, fy, cx, cy, th, check_orientation, (int *)(D + o_mp),
+                                               (int *)(D + o_nm), s);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(H + o_mp, D + o_mp, total - o_mp, cudaMemcpyDeviceToHost, s));
+    rc = orbfe_matcher_sync(m);
+    if (rc == ORBFE_ERR_CAPACITY) return 1;  // some pair overflowed the scratch: take the exact host-replay path
+    if (rc) return rc;
+    m->h2d_bytes += in_bytes + (size_t)npairs * cap * sizeof(int);
+    m->d2h_bytes += total - o_mp;
+    const int *h_nm = (const int *)(H + o_nm);
+    for (int j = 0; j < npairs; j++) {
+        if (cur[j].n) memcpy(cur_mp_inout[j], H + o_mp + (size_t)j * cap * sizeof(int), (size_t)cur[j].n * sizeof(int));
+        nmatches_out[j] = h_nm[j];
+    }
     return ORBFE_OK;
 }

@@ -23,6 +23,15 @@
 #include "../../include/orbfe.h"
 #include "../../include/orbfe_match.h"
 
+extern "C" int orbfe_sbp_frames_via_device(OrbfeMatcher *m, int npairs, const OrbfeFrameView *cur, const OrbfeFrameView *last,
+                                           const uint8_t *const *last_has_mp, const uint8_t *const *last_outlier,
+                                           const float *const *last_world, const float *const *Tcw, float fx, float fy,
+                                           float cx, float cy, float th, int check_orientation, int *const *cur_mp_inout,
+                                           int *nmatches_out);
+static bool g_force_host_replay = false;
+// test hook: 1 = always use host candidate lists + device distances + host greedy replay
+extern "C" void orbfe_matcher_force_host_replay(int on) { g_force_host_replay = on != 0; }
+
 namespace {
 
 constexpr int kGridCols = 64;  // FRAME_GRID_COLS, Frame.h:36
@@ -168,6 +177,12 @@ extern "C" int orbfe_search_by_projection_frames(OrbfeMatcher *m, int npairs, co
     if (!m || npairs < 0 || (npairs > 0 && (!cur || !last || !last_has_mp || !last_outlier || !last_world || !Tcw ||
                                             !cur_mp_inout || !nmatches_out)))
         return ORBFE_ERR_ARG;
+    // fast path: everything (grid, candidates, distances, greedy, rotation filter) in ONE device kernel
+    if (!g_force_host_replay) {
+        const int rc = orbfe_sbp_frames_via_device(m, npairs, cur, last, last_has_mp, last_outlier, last_world, Tcw, fx, fy, cx,
+                                                   cy, th, check_orientation, cur_mp_inout, nmatches_out);
+        if (rc != 1) return rc;  // 1 = not applicable (mixed geometry / overflow): exact host replay below
+    }
     std::vector<Job> jobs(npairs);
     std::vector<const OrbfeFrameView *> qf(npairs), tf(npairs);
     parallel_for(npairs, [&](int j) {

@@ -62,6 +62,11 @@ def test_search_by_projection_pairs(gpu_required):
         occ[rng.random(len(kc)) < 0.03] = 5  # a few already-occupied slots
         pre.append(occ)
     nm, mp = M.search_by_projection_frames(m, curs, lasts, has, outl, world, T, FX, FY, CX, CY, 15.0, cur_mp=pre)
+    # the same call through the host-replay path (host candidate lists + device distances + host greedy loop)
+    fe.lib().orbfe_matcher_force_host_replay(1)
+    nm_h, mp_h = M.search_by_projection_frames(m, curs, lasts, has, outl, world, T, FX, FY, CX, CY, 15.0, cur_mp=pre)
+    fe.lib().orbfe_matcher_force_host_replay(0)
+    assert np.array_equal(nm, nm_h) and all(np.array_equal(a, b) for a, b in zip(mp, mp_h))
     total = 0
     for j in range(3):
         fc = O.OracleFrame(curs[j].kps, curs[j].desc, W, H)
