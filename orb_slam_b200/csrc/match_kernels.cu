@@ -126,8 +126,11 @@ namespace orbfe {
 #define SBP_GROWS 48
 #define SBP_NCELL (SBP_GCOLS * SBP_GROWS)
 
-__device__ __forceinline__ int block_excl_scan_256(int v, int *s_warp /*[8]*/, int *total) {
-    // exclusive scan of one value per thread over a 256-thread CTA
+#define SBP_THREADS 1024
+#define SBP_WARPS (SBP_THREADS / 32)
+
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp /*[SBP_WARPS]*/, int *total) {
+    // exclusive scan of one value per thread over the CTA
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int x = v;
 #pragma unroll
@@ -137,11 +140,15 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int *s_warp /*[8]*/, i
     }
     if (lane == 31) s_warp[wid] = x;
     __syncthreads();
-    int base = 0;
-    for (int k = 0; k < wid; k++) base += s_warp[k];
-    int tot = 0;
-    for (int k = 0; k < 8; k++) tot += s_warp[k];
-    *total = tot;
+    const int wv = s_warp[lane];  // SBP_WARPS == 32: one partial per lane
+    int incl = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int base = __shfl_sync(0xffffffffu, incl - wv, wid);
+    *total = __shfl_sync(0xffffffffu, incl, 31);
     __syncthreads();
     return base + x - v;
 }
@@ -186,24 +193,26 @@ __device__ __forceinline__ SbpQuery sbp_project(const SbpParams &P, const OrbfeK
     return q;
 }
 
-__global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const OrbfeKeyPoint *__restrict__ kps,
-                                                         const uint8_t *__restrict__ desc, const int *__restrict__ counts,
-                                                         const int *__restrict__ cur_idx, const int *__restrict__ last_idx,
-                                                         const float *__restrict__ world, const uint8_t *__restrict__ flags,
-                                                         const float *__restrict__ Tcw, uint32_t *__restrict__ scratch,
-                                                         int *__restrict__ cur_mp, int *__restrict__ nmatches,
-                                                         int *__restrict__ err) {
+__global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, const OrbfeKeyPoint *__restrict__ kps,
+                                                                 const uint8_t *__restrict__ desc, const int *__restrict__ counts,
+                                                                 const int *__restrict__ cur_idx, const int *__restrict__ last_idx,
+                                                                 const float *__restrict__ world, const uint8_t *__restrict__ flags,
+                                                                 const float *__restrict__ Tcw, uint32_t *__restrict__ scratch,
+                                                                 int *__restrict__ cur_mp, int *__restrict__ nmatches,
+                                                                 int *__restrict__ err) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int cap = P.cap;
     int *cell_start = reinterpret_cast<int *>(smem);                 // [NCELL + 1]
     int *cell_cur = cell_start + SBP_NCELL + 1;                      // [NCELL]
     int *q_off = cell_cur + SBP_NCELL;                               // [cap + 1]
-    uint32_t *taken = reinterpret_cast<uint32_t *>(q_off + cap + 1); // [(cap + 31) / 32]
+    float *kx = reinterpret_cast<float *>(q_off + cap + 1);          // [cap] Current keypoint x
+    float *ky = kx + cap;                                            // [cap]
+    uint32_t *taken = reinterpret_cast<uint32_t *>(ky + cap);        // [(cap + 31) / 32]
     uint16_t *items = reinterpret_cast<uint16_t *>(taken + (cap + 31) / 32);  // [cap]
     uint8_t *newbin = reinterpret_cast<uint8_t *>(items + cap);      // [cap]
-    __shared__ int s_warp[8], s_hist[32], s_keep[3], s_removed, s_nm;
-    // entry staging area (the rest of the dynamic shared memory)
-    uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem + P.smem_fixed);
+    uint8_t *koct = newbin + cap;                                    // [cap] Current keypoint octave
+    __shared__ int s_warp[SBP_WARPS], s_hist[32], s_keep[3], s_removed, s_nm;
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem + P.smem_fixed);  // entry staging area
 
     const int pair = blockIdx.x;
     const int fc = cur_idx[pair], fl = last_idx[pair];
@@ -219,14 +228,16 @@ __global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const Orbf
     const int tid = threadIdx.x;
 
     // ---- A: grid of the Current frame ----
-    for (int i = tid; i < SBP_NCELL; i += 256) cell_cur[i] = 0;
-    for (int i = tid; i < (cap + 31) / 32; i += 256) taken[i] = 0;
+    for (int i = tid; i < SBP_NCELL; i += SBP_THREADS) cell_cur[i] = 0;
+    for (int i = tid; i < (cap + 31) / 32; i += SBP_THREADS) taken[i] = 0;
     if (tid < 32) s_hist[tid] = 0;
     if (tid == 0) { s_removed = 0; s_nm = 0; }
     __syncthreads();
-    for (int i = tid; i < nc; i += 256) {
-        const float px = roundf(__fmul_rn(__fsub_rn(kc[i].x, P.min_x), P.gw));
-        const float py = roundf(__fmul_rn(__fsub_rn(kc[i].y, P.min_y), P.gh));
+    for (int i = tid; i < nc; i += SBP_THREADS) {
+        const OrbfeKeyPoint k = kc[i];
+        kx[i] = k.x; ky[i] = k.y; koct[i] = (uint8_t)k.octave;
+        const float px = roundf(__fmul_rn(__fsub_rn(k.x, P.min_x), P.gw));
+        const float py = roundf(__fmul_rn(__fsub_rn(k.y, P.min_y), P.gh));
         int cell = -1;
         if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS) cell = (int)px * SBP_GROWS + (int)py;
         newbin[i] = 0xFF;
@@ -234,27 +245,27 @@ __global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const Orbf
         if (mp[i] >= 0) atomicOr(&taken[i >> 5], 1u << (i & 31));  // slot occupied on entry (:1562)
     }
     __syncthreads();
-    {   // exclusive scan of the 3072 cell counts: 12 cells per thread
-        int loc[12], sum = 0;
+    {   // exclusive scan of the 3072 cell counts: 3 cells per thread
+        int loc[3], sum = 0;
 #pragma unroll
-        for (int k = 0; k < 12; k++) { loc[k] = cell_cur[tid * 12 + k]; sum += loc[k]; }
+        for (int k = 0; k < 3; k++) { loc[k] = cell_cur[tid * 3 + k]; sum += loc[k]; }
         int tot;
-        int base = block_excl_scan_256(sum, s_warp, &tot);
+        int base = block_excl_scan(sum, s_warp, &tot);
 #pragma unroll
-        for (int k = 0; k < 12; k++) { cell_start[tid * 12 + k] = base; cell_cur[tid * 12 + k] = base; base += loc[k]; }
-        if (tid == 255) cell_start[SBP_NCELL] = base;
+        for (int k = 0; k < 3; k++) { cell_start[tid * 3 + k] = base; cell_cur[tid * 3 + k] = base; base += loc[k]; }
+        if (tid == SBP_THREADS - 1) cell_start[SBP_NCELL] = base;
     }
     __syncthreads();
-    for (int i = tid; i < nc; i += 256) {
-        const float px = roundf(__fmul_rn(__fsub_rn(kc[i].x, P.min_x), P.gw));
-        const float py = roundf(__fmul_rn(__fsub_rn(kc[i].y, P.min_y), P.gh));
+    for (int i = tid; i < nc; i += SBP_THREADS) {
+        const float px = roundf(__fmul_rn(__fsub_rn(kx[i], P.min_x), P.gw));
+        const float py = roundf(__fmul_rn(__fsub_rn(ky[i], P.min_y), P.gh));
         if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS) {
             const int cell = (int)px * SBP_GROWS + (int)py;
             items[atomicAdd(&cell_cur[cell], 1)] = (uint16_t)i;
         }
     }
     __syncthreads();
-    for (int c = tid; c < SBP_NCELL; c += 256) {  // ascending index inside each cell (insertion sort, cells are tiny)
+    for (int c = tid; c < SBP_NCELL; c += SBP_THREADS) {  // ascending index inside each cell (cells are tiny)
         const int b = cell_start[c], e = cell_start[c + 1];
         for (int i = b + 1; i < e; i++) {
             const uint16_t v = items[i];
@@ -266,28 +277,29 @@ __global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const Orbf
     __syncthreads();
 
     // ---- B1: candidate counts per Last feature ----
-    const int nq_iter = (nl + 255) / 256;
+    const int nq_iter = (nl + SBP_THREADS - 1) / SBP_THREADS;
     int run_total = 0;
     for (int it = 0; it < nq_iter; it++) {
-        const int q = it * 256 + tid;
+        const int q = it * SBP_THREADS + tid;
         int cnt = 0;
         if (q < nl && fll[q]) {
             const SbpQuery Q = sbp_project(P, kl[q], wl + 3 * q, T);
             if (Q.ok) {
-                for (int ix = Q.x0; ix <= Q.x1; ix++)
-                    for (int iy = Q.y0; iy <= Q.y1; iy++) {
-                        const int c = ix * SBP_GROWS + iy;
-                        for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
-                            const OrbfeKeyPoint &kp = kc[items[k]];
-                            if (kp.octave < Q.oct - 1 || kp.octave > Q.oct + 1) continue;
-                            if (fabsf(__fsub_rn(kp.x, Q.u)) > Q.r || fabsf(__fsub_rn(kp.y, Q.v)) > Q.r) continue;
-                            cnt++;
-                        }
+                for (int ix = Q.x0; ix <= Q.x1; ix++) {
+                    // cells (ix, y0..y1) are contiguous in the cell-major layout: one item range per column
+                    const int kb = cell_start[ix * SBP_GROWS + Q.y0], ke = cell_start[ix * SBP_GROWS + Q.y1 + 1];
+                    for (int k = kb; k < ke; k++) {
+                        const int i2 = items[k];
+                        const int o = koct[i2];
+                        if (o < Q.oct - 1 || o > Q.oct + 1) continue;
+                        if (fabsf(__fsub_rn(kx[i2], Q.u)) > Q.r || fabsf(__fsub_rn(ky[i2], Q.v)) > Q.r) continue;
+                        cnt++;
                     }
+                }
             }
         }
         int tot;
-        const int off = block_excl_scan_256(cnt, s_warp, &tot);
+        const int off = block_excl_scan(cnt, s_warp, &tot);
         if (q < nl) q_off[q] = run_total + off;
         run_total += tot;
     }
@@ -301,62 +313,62 @@ __global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const Orbf
     uint32_t *ent = (T_total <= P.smem_entries) ? s_ent : scratch + (size_t)pair * P.scratch_per_pair;
 
     // ---- B2: fill (candidate index | distance << 16) in enumeration order ----
-    for (int q = tid; q < nl; q += 256) {
+    for (int q = tid; q < nl; q += SBP_THREADS) {
         int o = q_off[q];
         if (q_off[q + 1] == o) continue;
         const SbpQuery Q = sbp_project(P, kl[q], wl + 3 * q, T);
         const uint4 a0 = __ldg(&dl[2 * q]), a1 = __ldg(&dl[2 * q + 1]);
-        for (int ix = Q.x0; ix <= Q.x1; ix++)
-            for (int iy = Q.y0; iy <= Q.y1; iy++) {
-                const int c = ix * SBP_GROWS + iy;
-                for (int k = cell_start[c]; k < cell_start[c + 1]; k++) {
-                    const int i2 = items[k];
-                    const OrbfeKeyPoint &kp = kc[i2];
-                    if (kp.octave < Q.oct - 1 || kp.octave > Q.oct + 1) continue;
-                    if (fabsf(__fsub_rn(kp.x, Q.u)) > Q.r || fabsf(__fsub_rn(kp.y, Q.v)) > Q.r) continue;
-                    const int d = ham256(a0, a1, __ldg(&dc[2 * i2]), __ldg(&dc[2 * i2 + 1]));
-                    ent[o++] = (uint32_t)i2 | ((uint32_t)d << 16);
-                }
+        for (int ix = Q.x0; ix <= Q.x1; ix++) {
+            const int kb = cell_start[ix * SBP_GROWS + Q.y0], ke = cell_start[ix * SBP_GROWS + Q.y1 + 1];
+            for (int k = kb; k < ke; k++) {
+                const int i2 = items[k];
+                const int oc = koct[i2];
+                if (oc < Q.oct - 1 || oc > Q.oct + 1) continue;
+                if (fabsf(__fsub_rn(kx[i2], Q.u)) > Q.r || fabsf(__fsub_rn(ky[i2], Q.v)) > Q.r) continue;
+                const int d = ham256(a0, a1, __ldg(&dc[2 * i2]), __ldg(&dc[2 * i2 + 1]));
+                ent[o++] = (uint32_t)i2 | ((uint32_t)d << 16);
             }
+        }
     }
     __threadfence_block();
     __syncthreads();
 
-    // ---- C: sequential accept loop (one warp) ----
+    // ---- C: sequential accept loop (one warp); the next query's entries are prefetched while the
+    //         current one is resolved (only the `taken` test depends on earlier queries) ----
     if (tid < 32) {
         const int lane = tid;
         int nm = 0;
+        int b = q_off[0], e = (nl > 0) ? q_off[1] : 0;
+        uint32_t en = (nl > 0 && b + lane < e) ? ent[b + lane] : 0xFFFFFFFFu;
         for (int q = 0; q < nl; q++) {
-            const int b = q_off[q], e = q_off[q + 1];
-            if (b == e) continue;
-            uint32_t best = 0xFFFFFFFFu;  // dist << 16 | position: strict-< argmin, first minimum wins
-            for (int p0 = b; p0 < e; p0 += 32) {
-                const int p = p0 + lane;
-                uint32_t key = 0xFFFFFFFFu;
-                if (p < e) {
-                    const uint32_t en = ent[p];
-                    const int i2 = (int)(en & 0xFFFF);
-                    if (!((taken[i2 >> 5] >> (i2 & 31)) & 1u)) key = ((en >> 16) << 16) | (uint32_t)min(p - b, 0xFFFF);
-                }
-                best = min(best, __reduce_min_sync(0xffffffffu, key));
-            }
-            if (best != 0xFFFFFFFFu && (int)(best >> 16) <= 100 /* TH_HIGH */) {
-                const int i2 = (int)(ent[b + (int)(best & 0xFFFF)] & 0xFFFF);
-                if (lane == 0) {
-                    taken[i2 >> 5] |= 1u << (i2 & 31);
-                    mp[i2] = q;
-                    if (P.check_ori) {
-                        float rot = __fsub_rn(kl[q].angle, kc[i2].angle);
-                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                        int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
-                        if (bin == 30) bin = 0;
-                        newbin[i2] = (uint8_t)bin;
-                        s_hist[bin]++;
+            // prefetch query q+1
+            const int nb = e, ne = (q + 1 < nl) ? q_off[q + 2] : e;
+            const uint32_t nen = (q + 1 < nl && nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
+            if (b != e) {
+                uint32_t best = 0xFFFFFFFFu;  // dist << 16 | position: strict-< argmin, first minimum wins
+                uint32_t cur = en;
+                for (int p0 = b; p0 < e; p0 += 32) {
+                    const int p = p0 + lane;
+                    if (p0 != b) cur = (p < e) ? ent[p] : 0xFFFFFFFFu;
+                    uint32_t key = 0xFFFFFFFFu;
+                    if (p < e) {
+                        const int i2 = (int)(cur & 0xFFFF);
+                        if (!((taken[i2 >> 5] >> (i2 & 31)) & 1u)) key = (cur & 0xFFFF0000u) | (uint32_t)(p - b);
                     }
+                    best = min(best, __reduce_min_sync(0xffffffffu, key));
                 }
-                nm++;
-                __syncwarp();
+                if (best != 0xFFFFFFFFu && (int)(best >> 16) <= 100 /* TH_HIGH */) {
+                    const int i2 = (int)(ent[b + (int)(best & 0xFFFF)] & 0xFFFF);
+                    if (lane == 0) {
+                        taken[i2 >> 5] |= 1u << (i2 & 31);
+                        mp[i2] = q;
+                        newbin[i2] = 0xFE;  // matched in this call; the rotation bin is filled in phase D
+                    }
+                    nm++;
+                    __syncwarp();
+                }
             }
+            b = nb; e = ne; en = nen;
         }
         if (lane == 0) s_nm = nm;
     }
@@ -364,6 +376,17 @@ __global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const Orbf
 
     // ---- D: rotation consistency ----
     if (P.check_ori) {
+        // rotation histogram of the new matches (:1583-1590), in parallel: bin = round((aLast - aCur [+360]) / 30)
+        for (int i = tid; i < nc; i += SBP_THREADS) {
+            if (newbin[i] != 0xFE) continue;
+            float rot = __fsub_rn(kl[mp[i]].angle, kc[i].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+            if (bin == 30) bin = 0;
+            newbin[i] = (uint8_t)bin;
+            atomicAdd(&s_hist[bin], 1);
+        }
+        __syncthreads();
         if (tid == 0) {
             int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
             for (int i = 0; i < 30; i++) {
@@ -378,9 +401,9 @@ __global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const Orbf
         }
         __syncthreads();
         int removed = 0;
-        for (int i = tid; i < nc; i += 256) {
-            const int b = newbin[i];
-            if (b != 0xFF && b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { mp[i] = -1; removed++; }
+        for (int i = tid; i < nc; i += SBP_THREADS) {
+            const int bb = newbin[i];
+            if (bb != 0xFF && bb != s_keep[0] && bb != s_keep[1] && bb != s_keep[2]) { mp[i] = -1; removed++; }
         }
         if (removed) atomicAdd(&s_removed, removed);
         __syncthreads();
@@ -390,7 +413,8 @@ __global__ void __launch_bounds__(256) sbp_device_kernel(SbpParams P, const Orbf
 
 size_t sbp_smem_fixed_bytes(int cap) {
     size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)cap + 1) +
-               sizeof(uint32_t) * (((size_t)cap + 31) / 32) + sizeof(uint16_t) * (size_t)cap + (size_t)cap;
+               2 * sizeof(float) * (size_t)cap + sizeof(uint32_t) * (((size_t)cap + 31) / 32) + sizeof(uint16_t) * (size_t)cap +
+               2 * (size_t)cap;
     return (b + 15) / 16 * 16;
 }
 
@@ -403,7 +427,7 @@ int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const O
         if (e != cudaSuccess) return (int)e;
         configured = smem_bytes;
     }
-    sbp_device_kernel<<<npairs, 256, smem_bytes, s>>>(P, kps, desc, counts, cur_idx, last_idx, world, flags, Tcw, scratch,
+    sbp_device_kernel<<<npairs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, cur_idx, last_idx, world, flags, Tcw, scratch,
                                                       cur_mp, nmatches, err);
     return 0;
 }
