@@ -185,11 +185,10 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
     __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
 
     const int f = blockIdx.y;
-    const int l = find_level_by(plan, blockIdx.x, 0);
-    const LevelDev &L = plan->lv[l];
-    const int tile = blockIdx.x - L.ftile_base;
-    const int ty = tile / L.ftiles_x, tx = tile - ty * L.ftiles_x;
-    const int x0 = ORBFE_EDGE + tx * F2_W, y0 = ORBFE_EDGE + ty * F2_H;
+    // per-tile geometry, precomputed on the host (no dependent scan of the plan, no integer divisions)
+    const FTileInfo ti = wk.ftile_info[blockIdx.x];
+    const LevelDev &L = plan->lv[ti.level];
+    const int x0 = ORBFE_EDGE + ti.tx * F2_W, y0 = ORBFE_EDGE + ti.ty * F2_H;
     const int w = L.w, h = L.h, pitch = L.pitch;
     const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
     const int tlo = plan->t_lo;
@@ -254,8 +253,6 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
     }
     __syncthreads();
 
-    // per-tile cell geometry, precomputed on the host (no integer divisions on the common path)
-    const FTileInfo ti = wk.ftile_info[blockIdx.x];
     const int thi = plan->t_hi;
     const uint32_t tlo2 = (uint32_t)tlo * 0x00010001u;
     // ---- pass 1: strict maximum over ALL 8 neighbours, two pixels per instruction.  Such a pixel is a
@@ -619,16 +616,14 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ plan) {
+__global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ plan, const BTileInfo *__restrict__ btiles) {
     __shared__ __align__(16) uint8_t pix[BPH * BPW];
     __shared__ __align__(16) uint16_t rowsum[BPH * ORBFE_BT_W];
 
     const int f = blockIdx.y;
-    const int l = find_level_by(plan, blockIdx.x, 1);
-    const LevelDev &L = plan->lv[l];
-    const int tile = blockIdx.x - L.btile_base;
-    const int ty = tile / L.btiles_x, tx = tile - ty * L.btiles_x;
-    const int x0 = tx * ORBFE_BT_W, y0 = ty * ORBFE_BT_H;
+    const BTileInfo bt = btiles[blockIdx.x];
+    const LevelDev &L = plan->lv[bt.level];
+    const int x0 = bt.tx * ORBFE_BT_W, y0 = bt.ty * ORBFE_BT_H;
     const int w = L.w, h = L.h, pitch = L.pitch;
     const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
 
@@ -680,9 +675,9 @@ __global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ 
     }
 }
 
-void launch_blur(const PlanDev *d_plan, const PlanDev &hp, cudaStream_t s) {
+void launch_blur(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
     dim3 grid(hp.nbtiles_total, hp.batch);
-    blur7_kernel<<<grid, 256, 0, s>>>(d_plan);
+    blur7_kernel<<<grid, 256, 0, s>>>(d_plan, w.btile_info);
 }
 
 // ------------------------------------------------------------------------------------------------

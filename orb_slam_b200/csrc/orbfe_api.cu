@@ -273,6 +273,7 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
                     const int cj_hi = std::min(L.cols - 1, (x0 + ORBFE_FT_W - ORBFE_EDGE) / L.cw);
                     const int ci_lo = std::max(1, (y0 - ORBFE_EDGE + L.ch - 1) / L.ch);
                     const int ci_hi = std::min(L.rows - 1, (y0 + ORBFE_FT_H - ORBFE_EDGE) / L.ch);
+                    T.level = (short)l; T.tx = (short)tx; T.ty = (short)ty; T.pad = 0;
                     T.cj_lo = (short)cj_lo; T.nv = (short)std::max(0, cj_hi - cj_lo + 1);
                     T.ci_lo = (short)ci_lo; T.nh = (short)std::max(0, ci_hi - ci_lo + 1);
                     if (T.ncj * T.nci > 64) return fail(ORBFE_ERR_UNSUPPORTED, "level %d: a FAST tile overlaps %d cells", l, T.ncj * T.nci);
@@ -282,6 +283,19 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         CU_TRY(dmalloc(ex, &d_info, info.size()));
         CU_TRY(cudaMemcpy(d_info, info.data(), sizeof(FTileInfo) * info.size(), cudaMemcpyHostToDevice));
         Wk.ftile_info = d_info;
+        std::vector<BTileInfo> binfo((size_t)P.nbtiles_total);
+        for (int l = 0; l < ex->nlevels; l++) {
+            const LevelDev &L = P.lv[l];
+            for (int ty = 0; ty < L.btiles_y; ty++)
+                for (int tx = 0; tx < L.btiles_x; tx++) {
+                    BTileInfo &T = binfo[(size_t)L.btile_base + ty * L.btiles_x + tx];
+                    T.level = (short)l; T.tx = (short)tx; T.ty = (short)ty; T.pad = 0;
+                }
+        }
+        BTileInfo *d_binfo;
+        CU_TRY(dmalloc(ex, &d_binfo, binfo.size()));
+        CU_TRY(cudaMemcpy(d_binfo, binfo.data(), sizeof(BTileInfo) * binfo.size(), cudaMemcpyHostToDevice));
+        Wk.btile_info = d_binfo;
     }
     long long *d_cb; int *d_cc;
     CU_TRY(dmalloc(ex, &d_cb, cand_base.size()));
@@ -430,7 +444,7 @@ static int enqueue_pipeline(OrbfeExtractor *ex, int B, OrbfeKeyPoint *d_kps, uin
     stage_mark(ex, s, "cell_select");
     launch_level_select(ex->dplan, hp, ex->work, ex->ls_smem, s); launches++;
     stage_mark(ex, s, "level_select");
-    launch_blur(ex->dplan, hp, s); launches++;
+    launch_blur(ex->dplan, hp, ex->work, s); launches++;
     stage_mark(ex, s, "blur7");
     launch_describe(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, s); launches++;
     stage_mark(ex, s, "describe");

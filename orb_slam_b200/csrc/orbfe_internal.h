@@ -55,13 +55,16 @@ struct PlanDev {
 struct FTileInfo {
     short cj0, ci0, ncj, nci;    // first cell col/row overlapped, number of cell cols/rows overlapped
     short cj_lo, nv, ci_lo, nh;  // interior vertical boundaries cj_lo .. cj_lo+nv-1 (x = 16 + cj*cw), horizontal likewise
+    short level, tx, ty, pad;    // which level / tile this is (saves a dependent scan of the plan at CTA start)
 };
+struct BTileInfo { short level, tx, ty, pad; };  // blur tiles
 
 // Per-batch work buffers (device).  Index [frame] strides are in the plan.
 struct WorkDev {
     const long long *cell_cand_base;  // [ncells_total] first candidate slot of each cell
     const int *cell_cand_cap;         // [ncells_total]
     const FTileInfo *ftile_info;      // [nftiles_total]
+    const BTileInfo *btile_info;      // [nbtiles_total]
     uint32_t *cand_keys;              // [batch][cand_total]   (score<<24 | 0xFFFFFF - raster)
     int *cell_cnt_lo;                 // [batch][ncells_total] candidates with m > t_lo (= all emitted)
     int *cell_cnt_hi;                 // [batch][ncells_total] candidates with m > t_hi
@@ -80,7 +83,7 @@ void launch_fast_nms(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cu
 void launch_cell_quota(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
 void launch_cell_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
 void launch_level_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, size_t smem_bytes, cudaStream_t s);
-void launch_blur(const PlanDev *d_plan, const PlanDev &h_plan, cudaStream_t s);
+void launch_blur(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
 void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, const int8_t *d_pattern,
                      OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s);
 int level_select_smem_bytes(int max_kept);
