@@ -34,10 +34,10 @@ __device__ __forceinline__ int find_level_by(const PlanDev *plan, int idx, int w
 // Horizontal/vertical tap tables were computed on the host exactly as OpenCV computes them, so the
 // device part is pure integer: r = S[x0]*a0 + S[x1]*a1 ; v = (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__restrict__ plan, int level) {
+__global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__restrict__ plan, int level, int f0) {
     const LevelDev &D = plan->lv[level];
     const LevelDev &S = plan->lv[level - 1];
-    const int f = blockIdx.z;
+    const int f = blockIdx.z + f0;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int dw = D.w, dh = D.h;
@@ -64,11 +64,11 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
     *reinterpret_cast<uint32_t *>(D.pyr + (size_t)f * D.plane + (size_t)y * D.pitch + x4) = out;
 }
 
-void launch_resize_level(const PlanDev *d_plan, const PlanDev &hp, int level, cudaStream_t s) {
+void launch_resize_level(const PlanDev *d_plan, const PlanDev &hp, int level, int f0, int nf, cudaStream_t s) {
     const LevelDev &D = hp.lv[level];
     dim3 block(64, 4);
-    dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, hp.batch);
-    resize_level_kernel<<<grid, block, 0, s>>>(d_plan, level);
+    dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, nf);
+    resize_level_kernel<<<grid, block, 0, s>>>(d_plan, level, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,7 +176,7 @@ __device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int yma
     yb = (ci == L.rows - 1) ? ymax - 1 : ya + L.ch - 1;
 }
 
-__global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+__global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
     // one buffer, two lives: the staged pixel tile (until m is computed), then the candidate list
     __shared__ __align__(16) uint8_t sbuf[(F2_MAXC * 8 > F2_PH * F2_PW) ? F2_MAXC * 8 : F2_PH * F2_PW];
     __shared__ __align__(16) uint32_t mt[F2_MH * 32 * 2];  // 16 KB
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
     uint2 *s_cand = reinterpret_cast<uint2 *>(sbuf);
     __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
 
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + f0;
     // per-tile geometry, precomputed on the host (no dependent scan of the plan, no integer divisions)
     const FTileInfo ti = wk.ftile_info[blockIdx.x];
     const LevelDev &L = plan->lv[ti.level];
@@ -377,9 +377,9 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
     }
 }
 
-void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
-    dim3 grid(hp.nftiles_total, hp.batch);
-    fast_nms_kernel<<<grid, 256, 0, s>>>(d_plan, w);
+void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+    dim3 grid(hp.nftiles_total, nf);
+    fast_nms_kernel<<<grid, 256, 0, s>>>(d_plan, w, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -391,9 +391,9 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
-__global__ void __launch_bounds__(32) cell_quota_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+__global__ void __launch_bounds__(32) cell_quota_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
     __shared__ uint32_t no_more[128];  // bitmap, up to 4096 cells per level
-    const int l = blockIdx.x, f = blockIdx.y;
+    const int l = blockIdx.x, f = blockIdx.y + f0;
     const LevelDev &L = plan->lv[l];
     const int lane = threadIdx.x;
     const int nCells = L.ncells, nfc = L.nfc;
@@ -443,9 +443,9 @@ __global__ void __launch_bounds__(32) cell_quota_kernel(const PlanDev *__restric
     }
 }
 
-void launch_cell_quota(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
-    dim3 grid(hp.nlevels, hp.batch);
-    cell_quota_kernel<<<grid, 32, 0, s>>>(d_plan, w);
+void launch_cell_quota(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+    dim3 grid(hp.nlevels, nf);
+    cell_quota_kernel<<<grid, 32, 0, s>>>(d_plan, w, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -455,12 +455,12 @@ void launch_cell_quota(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cuda
 // Survivors are appended (order irrelevant) to the level's kept list as 64-bit selection keys
 //   score(8) << 36 | (4095 - cell)(12) << 24 | (0xFFFFFF - raster)(24).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+__global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix, s_mask;
     __shared__ int s_k, s_base, s_fill;
 
-    const int gcell = blockIdx.x, f = blockIdx.y;
+    const int gcell = blockIdx.x, f = blockIdx.y + f0;
     const size_t fc = (size_t)f * plan->ncells_total + gcell;
     const int keep = wk.cell_keep[fc];
     if (keep <= 0) return;
@@ -523,9 +523,9 @@ __global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restr
     }
 }
 
-void launch_cell_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
-    dim3 grid(hp.ncells_total, hp.batch);
-    cell_select_kernel<<<grid, 128, 0, s>>>(d_plan, w);
+void launch_cell_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+    dim3 grid(hp.ncells_total, nf);
+    cell_select_kernel<<<grid, 128, 0, s>>>(d_plan, w, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -547,9 +547,9 @@ __device__ void bitonic_sort_desc(unsigned long long *a, int n2) {
     }
 }
 
-__global__ void __launch_bounds__(512) level_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk) {
+__global__ void __launch_bounds__(512) level_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
     extern __shared__ unsigned long long skeys[];
-    const int l = blockIdx.x, f = blockIdx.y;
+    const int l = blockIdx.x, f = blockIdx.y + f0;
     const LevelDev &L = plan->lv[l];
     int n = min(wk.kept_cnt[(size_t)f * plan->nlevels + l], L.kept_cap);
     int n2 = 1;
@@ -597,9 +597,9 @@ int set_level_select_smem(int bytes) {
     return (int)cudaFuncSetAttribute(level_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-void launch_level_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, size_t smem_bytes, cudaStream_t s) {
-    dim3 grid(hp.nlevels, hp.batch);
-    level_select_kernel<<<grid, 512, smem_bytes, s>>>(d_plan, w);
+void launch_level_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, size_t smem_bytes, int f0, int nf, cudaStream_t s) {
+    dim3 grid(hp.nlevels, nf);
+    level_select_kernel<<<grid, 512, smem_bytes, s>>>(d_plan, w, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -607,8 +607,14 @@ void launch_level_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, si
 // int accumulation, (sum)/65536 rounded half-to-even, saturated.  BORDER_REFLECT_101 by index reflection.
 // Row sums fit u16 exactly (255*257 = 65535).
 // ------------------------------------------------------------------------------------------------
-#define BPW (ORBFE_BT_W + 8)  // staged width: x0-4 .. x0+BT_W+3 (word aligned; the taps use x0-3 .. x0+BT_W+2)
-#define BPH (ORBFE_BT_H + 6)
+// Tile = 120 x 64 output pixels per CTA.  lane = 4-px column group (lanes 0 and 31 are halo columns), warp =
+// 8-row segment.  Vertical pass FIRST, on packed pixel pairs (b0,b2)/(b1,b3) of the thread's own word, in a 7-row
+// register window: column sums fit u16, so one IMAD/IADD handles two pixels.  The horizontal pass takes the
+// three neighbours on each side from the adjacent lanes (4 shuffles) and finishes in 32-bit.
+#define B2_W ORBFE_BT_W           // 120
+#define B2_H ORBFE_BT_H           // 64
+#define B2_PH (B2_H + 6)          // staged rows y0-3 .. y0+66
+#define B2_PS 128                 // staged row stride: cols x0-4 .. x0+123
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -616,68 +622,80 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ plan, const BTileInfo *__restrict__ btiles) {
-    __shared__ __align__(16) uint8_t pix[BPH * BPW];
-    __shared__ __align__(16) uint16_t rowsum[BPH * ORBFE_BT_W];
+__device__ __forceinline__ uint32_t blur_round_u8(int s) {
+    int q = (s + 0x7FFF + ((s >> 16) & 1)) >> 16;  // round half to even of s / 65536
+    return (uint32_t)min(q, 255);
+}
 
-    const int f = blockIdx.y;
+__global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ plan, const BTileInfo *__restrict__ btiles, int f0) {
+    __shared__ __align__(16) uint8_t pix[B2_PH * B2_PS];
+
+    const int f = blockIdx.y + f0;
     const BTileInfo bt = btiles[blockIdx.x];
     const LevelDev &L = plan->lv[bt.level];
-    const int x0 = bt.tx * ORBFE_BT_W, y0 = bt.ty * ORBFE_BT_H;
+    const int x0 = bt.tx * B2_W, y0 = bt.ty * B2_H;
     const int w = L.w, h = L.h, pitch = L.pitch;
     const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
 
-    const bool interior = (x0 >= 4) && (x0 + ORBFE_BT_W + 4 <= w) && (y0 >= 3) && (y0 + ORBFE_BT_H + 3 <= h);
+    const bool interior = (x0 >= 4) && (x0 + B2_W + 4 <= w) && (y0 >= 3) && (y0 + B2_H + 3 <= h);
     if (interior) {
-        const int wpr = BPW / 4;  // 34 words per staged row
-        for (int i = threadIdx.x; i < BPH * wpr; i += blockDim.x) {
-            const int r = i / wpr, c = i - r * wpr;
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)(y0 - 3 + r) * pitch + (x0 - 4)) + c);
-            *reinterpret_cast<uint32_t *>(&pix[r * BPW + c * 4]) = v;
+        for (int i = threadIdx.x; i < B2_PH * 32; i += blockDim.x) {
+            const int r = i >> 5, c = i & 31;
+            reinterpret_cast<uint32_t *>(pix)[i] =
+                __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)(y0 - 3 + r) * pitch + (x0 - 4)) + c);
         }
     } else {
-        for (int i = threadIdx.x; i < BPH * BPW; i += blockDim.x) {
-            const int r = i / BPW, c = i - r * BPW;
+        for (int i = threadIdx.x; i < B2_PH * B2_PS; i += blockDim.x) {
+            const int r = i >> 7, c = i & 127;
             const int gy = reflect101(y0 - 3 + r, h);
             const int gx = reflect101(x0 - 4 + c, w);
             pix[i] = __ldg(img + (size_t)gy * pitch + gx);
         }
     }
     __syncthreads();
-    // horizontal pass: rowsum[r][x] for r in [0,BPH), x in [0,BT_W): centre column = x + 4 in pix
-    for (int i = threadIdx.x; i < BPH * ORBFE_BT_W; i += blockDim.x) {
-        const int r = i / ORBFE_BT_W, x = i - r * ORBFE_BT_W;
-        const uint8_t *p = &pix[r * BPW + x + 4];
-        const int s = 55 * p[0] + 49 * (p[-1] + p[1]) + 34 * (p[-2] + p[2]) + 18 * (p[-3] + p[3]);
-        rowsum[i] = (uint16_t)s;
-    }
-    __syncthreads();
-    // vertical pass, 4 pixels per thread, one 32-bit store
-    uint8_t *__restrict__ dst = L.blur + (size_t)f * L.plane;
-    for (int i = threadIdx.x; i < ORBFE_BT_H * (ORBFE_BT_W / 4); i += blockDim.x) {
-        const int y = i / (ORBFE_BT_W / 4), xq = (i - y * (ORBFE_BT_W / 4)) * 4;
-        const int gy = y0 + y, gx = x0 + xq;
-        if (gy >= h || gx >= w) continue;
-        uint32_t out = 0;
+
+    const int g = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const uint32_t *col = reinterpret_cast<const uint32_t *>(pix) + (seg * 8) * 32 + g;
+    uint32_t A[7], B[7];  // packed (b0,b2) and (b1,b3) of rows r-3 .. r+3
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint16_t *q = &rowsum[(y + 3) * ORBFE_BT_W + xq + k];
-            const int s = 55 * (int)q[0] + 49 * ((int)q[-ORBFE_BT_W] + (int)q[ORBFE_BT_W]) +
-                          34 * ((int)q[-2 * ORBFE_BT_W] + (int)q[2 * ORBFE_BT_W]) +
-                          18 * ((int)q[-3 * ORBFE_BT_W] + (int)q[3 * ORBFE_BT_W]);
-            int v = s >> 16;
-            const int r = s & 0xFFFF;
-            v += (r > 0x8000) | ((r == 0x8000) & (v & 1));
-            v = min(v, 255);
-            out |= (uint32_t)v << (8 * k);
+    for (int r = 0; r < 6; r++) {
+        const uint32_t wv = col[r * 32];
+        A[r] = __byte_perm(wv, 0, 0x4240);
+        B[r] = __byte_perm(wv, 0, 0x4341);
+    }
+    uint8_t *__restrict__ dst = L.blur + (size_t)f * L.plane;
+    const int gx = x0 - 4 + 4 * g;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        {
+            const uint32_t wv = col[(6 + i) * 32];
+            A[(6 + i) % 7] = __byte_perm(wv, 0, 0x4240);
+            B[(6 + i) % 7] = __byte_perm(wv, 0, 0x4341);
         }
-        *reinterpret_cast<uint32_t *>(dst + (size_t)gy * pitch + gx) = out;
+#define WR(k) ((i + (k)) % 7)
+        // vertical 7-tap on packed pairs (each half <= 65535: no carry between halves)
+        const uint32_t VA = 55u * A[WR(3)] + 49u * (A[WR(2)] + A[WR(4)]) + 34u * (A[WR(1)] + A[WR(5)]) + 18u * (A[WR(0)] + A[WR(6)]);
+        const uint32_t VB = 55u * B[WR(3)] + 49u * (B[WR(2)] + B[WR(4)]) + 34u * (B[WR(1)] + B[WR(5)]) + 18u * (B[WR(0)] + B[WR(6)]);
+#undef WR
+        const uint32_t LA = __shfl_up_sync(0xffffffffu, VA, 1), LB = __shfl_up_sync(0xffffffffu, VB, 1);
+        const uint32_t RA = __shfl_down_sync(0xffffffffu, VA, 1), RB = __shfl_down_sync(0xffffffffu, VB, 1);
+        // column sums v[-3..6] around the group's 4 pixels
+        const int vm3 = (int)(LB & 0xFFFF), vm2 = (int)(LA >> 16), vm1 = (int)(LB >> 16);
+        const int v0 = (int)(VA & 0xFFFF), v1 = (int)(VB & 0xFFFF), v2 = (int)(VA >> 16), v3 = (int)(VB >> 16);
+        const int v4 = (int)(RA & 0xFFFF), v5 = (int)(RB & 0xFFFF), v6 = (int)(RA >> 16);
+        const int s0 = 55 * v0 + 49 * (vm1 + v1) + 34 * (vm2 + v2) + 18 * (vm3 + v3);
+        const int s1 = 55 * v1 + 49 * (v0 + v2) + 34 * (vm1 + v3) + 18 * (vm2 + v4);
+        const int s2 = 55 * v2 + 49 * (v1 + v3) + 34 * (v0 + v4) + 18 * (vm1 + v5);
+        const int s3 = 55 * v3 + 49 * (v2 + v4) + 34 * (v1 + v5) + 18 * (v0 + v6);
+        const uint32_t out = blur_round_u8(s0) | (blur_round_u8(s1) << 8) | (blur_round_u8(s2) << 16) | (blur_round_u8(s3) << 24);
+        const int gy = y0 + seg * 8 + i;
+        if (g >= 1 && g <= 30 && gy < h && gx < w) *reinterpret_cast<uint32_t *>(dst + (size_t)gy * pitch + gx) = out;
     }
 }
 
-void launch_blur(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, cudaStream_t s) {
-    dim3 grid(hp.nbtiles_total, hp.batch);
-    blur7_kernel<<<grid, 256, 0, s>>>(d_plan, w.btile_info);
+void launch_blur(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+    dim3 grid(hp.nbtiles_total, nf);
+    blur7_kernel<<<grid, 256, 0, s>>>(d_plan, w.btile_info, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -710,13 +728,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 __global__ void __launch_bounds__(256) describe_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
                                                        const int8_t *__restrict__ g_pattern,
                                                        OrbfeKeyPoint *__restrict__ out_kps,
-                                                       uint8_t *__restrict__ out_desc, int *__restrict__ out_counts) {
+                                                       uint8_t *__restrict__ out_desc, int *__restrict__ out_counts, int f0) {
     __shared__ __align__(16) int8_t pat[1024];
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         reinterpret_cast<uint32_t *>(pat)[i] = __ldg(reinterpret_cast<const uint32_t *>(g_pattern) + i);
     __syncthreads();
 
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + f0;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nlev = plan->nlevels;
@@ -802,10 +820,10 @@ __global__ void __launch_bounds__(256) describe_kernel(const PlanDev *__restrict
 }
 
 void launch_describe(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, const int8_t *d_pattern,
-                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s) {
-    dim3 grid((hp.nfeatures + 7) / 8, hp.batch);
+                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s) {
+    dim3 grid((hp.nfeatures + 7) / 8, nf);
     if (grid.x == 0) grid.x = 1;
-    describe_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, d_kps, d_desc, d_counts);
+    describe_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, d_kps, d_desc, d_counts, f0);
 }
 
 }  // namespace orbfe

@@ -89,6 +89,8 @@ struct OrbfeExtractor {
     size_t h_counts_cap = 0;
 
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
     int last_launches = 0;
     bool profiling = false;
     StageTimer timer;
@@ -398,6 +400,8 @@ extern "C" int orbfe_extractor_destroy(OrbfeExtractor *ex) {
     if (ex->h_counts) cudaFreeHost(ex->h_counts);
     if (ex->h_err) cudaFreeHost(ex->h_err);
     for (cudaEvent_t ev : ex->timer.ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ex->chunk_ev) cudaEventDestroy(ev);
+    if (ex->copy_stream) cudaStreamDestroy(ex->copy_stream);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
     return ORBFE_OK;
@@ -427,29 +431,33 @@ static void stage_mark(OrbfeExtractor *ex, cudaStream_t s, const char *name) {
     cudaEventRecord(T.ev[i + 1], s);
 }
 
-// Enqueue the whole device pipeline for `B` frames whose level-0 images are already in lv[0].pyr.
-static int enqueue_pipeline(OrbfeExtractor *ex, int B, OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts,
-                            cudaStream_t s) {
-    PlanDev hp = ex->hplan;
-    hp.batch = B;
-    int launches = 0;
+// Enqueue the device pipeline for frames [f0, f0+nf) whose level-0 images are already in lv[0].pyr.
+// The per-call counters must have been zeroed (zero_counters) before the first chunk.
+static int zero_counters(OrbfeExtractor *ex, cudaStream_t s) {
     CU_TRY(cudaMemsetAsync(ex->counters, 0, ex->counters_bytes, s));
-    for (int l = 1; l < hp.nlevels; l++) { launch_resize_level(ex->dplan, hp, l, s); launches++; }
+    return ORBFE_OK;
+}
+
+static int enqueue_pipeline(OrbfeExtractor *ex, int f0, int nf, OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts,
+                            cudaStream_t s) {
+    const PlanDev &hp = ex->hplan;
+    int launches = 0;
+    for (int l = 1; l < hp.nlevels; l++) { launch_resize_level(ex->dplan, hp, l, f0, nf, s); launches++; }
     stage_mark(ex, s, "pyramid");
-    launch_fast_nms(ex->dplan, hp, ex->work, s); launches++;
+    launch_fast_nms(ex->dplan, hp, ex->work, f0, nf, s); launches++;
     stage_mark(ex, s, "fast_nms");
-    launch_cell_quota(ex->dplan, hp, ex->work, s); launches++;
+    launch_cell_quota(ex->dplan, hp, ex->work, f0, nf, s); launches++;
     stage_mark(ex, s, "cell_quota");
-    launch_cell_select(ex->dplan, hp, ex->work, s); launches++;
+    launch_cell_select(ex->dplan, hp, ex->work, f0, nf, s); launches++;
     stage_mark(ex, s, "cell_select");
-    launch_level_select(ex->dplan, hp, ex->work, ex->ls_smem, s); launches++;
+    launch_level_select(ex->dplan, hp, ex->work, ex->ls_smem, f0, nf, s); launches++;
     stage_mark(ex, s, "level_select");
-    launch_blur(ex->dplan, hp, ex->work, s); launches++;
+    launch_blur(ex->dplan, hp, ex->work, f0, nf, s); launches++;
     stage_mark(ex, s, "blur7");
-    launch_describe(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, s); launches++;
+    launch_describe(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, f0, nf, s); launches++;
     stage_mark(ex, s, "describe");
     CU_TRY(cudaGetLastError());
-    ex->last_launches = launches;
+    ex->last_launches += launches;
     return ORBFE_OK;
 }
 
@@ -486,7 +494,10 @@ extern "C" int orbfe_extract_batch_device(OrbfeExtractor *ex, const uint8_t *d_i
                                      cudaMemcpyDeviceToDevice, s));
     }
     stage_mark(ex, s, "ingest");
-    return enqueue_pipeline(ex, batch, d_kps, d_desc, d_counts, s);
+    ex->last_launches = 0;
+    rc = zero_counters(ex, s);
+    if (rc) return rc;
+    return enqueue_pipeline(ex, 0, batch, d_kps, d_desc, d_counts, s);
 }
 
 extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int width, int height, size_t stride,
@@ -503,16 +514,36 @@ extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int 
     const PlanDev &P = ex->hplan;
     const LevelDev &L0 = P.lv[0];
     profiling_begin(ex, s);
-    if (frame_stride == stride * (size_t)height) {
-        CU_TRY(cudaMemcpy2DAsync(L0.pyr, L0.pitch, imgs, stride, width, (size_t)height * batch, cudaMemcpyHostToDevice, s));
-    } else {
-        for (int f = 0; f < batch; f++)
-            CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, width, height,
-                                     cudaMemcpyHostToDevice, s));
-    }
-    stage_mark(ex, s, "h2d");
-    rc = enqueue_pipeline(ex, batch, ex->d_kps, ex->d_desc, ex->d_counts, s);
+    ex->last_launches = 0;
+    rc = zero_counters(ex, s);
     if (rc) return rc;
+    // H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream)
+    const int nchunks = batch >= 8 ? 4 : 1;
+    if (!ex->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&ex->copy_stream, cudaStreamNonBlocking));
+    while ((int)ex->chunk_ev.size() < nchunks + 1) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ex->chunk_ev.push_back(e);
+    }
+    // the copy stream must not overwrite level 0 before earlier work of this handle has drained
+    CU_TRY(cudaEventRecord(ex->chunk_ev[nchunks], s));
+    CU_TRY(cudaStreamWaitEvent(ex->copy_stream, ex->chunk_ev[nchunks], 0));
+    for (int k = 0; k < nchunks; k++) {
+        const int f0 = (int)((long long)batch * k / nchunks), f1 = (int)((long long)batch * (k + 1) / nchunks);
+        if (f1 <= f0) continue;
+        if (frame_stride == stride * (size_t)height) {
+            CU_TRY(cudaMemcpy2DAsync(L0.pyr + (size_t)f0 * L0.plane, L0.pitch, imgs + (size_t)f0 * frame_stride, stride, width,
+                                     (size_t)height * (f1 - f0), cudaMemcpyHostToDevice, ex->copy_stream));
+        } else {
+            for (int f = f0; f < f1; f++)
+                CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, imgs + f * frame_stride, stride, width, height,
+                                         cudaMemcpyHostToDevice, ex->copy_stream));
+        }
+        CU_TRY(cudaEventRecord(ex->chunk_ev[k], ex->copy_stream));
+        CU_TRY(cudaStreamWaitEvent(s, ex->chunk_ev[k], 0));
+        rc = enqueue_pipeline(ex, f0, f1 - f0, ex->d_kps, ex->d_desc, ex->d_counts, s);
+        if (rc) return rc;
+    }
     const int ncopy = std::min(cap, P.nfeatures);
     CU_TRY(cudaMemcpyAsync(ex->h_counts, ex->d_counts, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(ex->h_err, ex->work.err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -12,8 +12,8 @@
 // FAST/NMS tile (detect-area pixels per CTA) and blur tile
 #define ORBFE_FT_W 120
 #define ORBFE_FT_H 62
-#define ORBFE_BT_W 128
-#define ORBFE_BT_H 32
+#define ORBFE_BT_W 120
+#define ORBFE_BT_H 64
 
 namespace orbfe {
 
@@ -77,15 +77,15 @@ struct WorkDev {
     int *err_flag;                    // [1]
 };
 
-// ---- launchers (extract_kernels.cu) ----
-void launch_resize_level(const PlanDev *d_plan, const PlanDev &h_plan, int level, cudaStream_t s);
-void launch_fast_nms(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
-void launch_cell_quota(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
-void launch_cell_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
-void launch_level_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, size_t smem_bytes, cudaStream_t s);
-void launch_blur(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, cudaStream_t s);
+// ---- launchers (extract_kernels.cu): every launch covers frames [f0, f0 + nf) of the batch ----
+void launch_resize_level(const PlanDev *d_plan, const PlanDev &h_plan, int level, int f0, int nf, cudaStream_t s);
+void launch_fast_nms(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, int f0, int nf, cudaStream_t s);
+void launch_cell_quota(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, int f0, int nf, cudaStream_t s);
+void launch_cell_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, int f0, int nf, cudaStream_t s);
+void launch_level_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, size_t smem_bytes, int f0, int nf, cudaStream_t s);
+void launch_blur(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, int f0, int nf, cudaStream_t s);
 void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, const int8_t *d_pattern,
-                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s);
+                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s);
 int level_select_smem_bytes(int max_kept);
 int set_level_select_smem(int bytes);
 
