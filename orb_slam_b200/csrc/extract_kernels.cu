@@ -176,39 +176,14 @@ __device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int yma
     yb = (ci == L.rows - 1) ? ymax - 1 : ya + L.ch - 1;
 }
 
-__global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
-    // one buffer, two lives: the staged pixel tile (until m is computed), then the candidate list
-    __shared__ __align__(16) uint8_t sbuf[(F2_MAXC * 8 > F2_PH * F2_PW) ? F2_MAXC * 8 : F2_PH * F2_PW];
-    __shared__ __align__(16) uint32_t mt[F2_MH * 32 * 2];  // 16 KB
-    uint8_t *pix = sbuf;
-    uint2 *s_cand = reinterpret_cast<uint2 *>(sbuf);
-    __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
-
-    const int f = blockIdx.y + f0;
-    // per-tile geometry, precomputed on the host (no dependent scan of the plan, no integer divisions)
-    const FTileInfo ti = wk.ftile_info[blockIdx.x];
-    const LevelDev &L = plan->lv[ti.level];
-    const int x0 = ORBFE_EDGE + ti.tx * F2_W, y0 = ORBFE_EDGE + ti.ty * F2_H;
-    const int w = L.w, h = L.h, pitch = L.pitch;
-    const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
+// Everything after the pixel tile is staged: m map, NMS passes, candidate conversion and flush.
+// pix: staged pixel rows (stride F2_PW); mt: 16 KB m tile; s_cand: candidate list (F2_MAXC entries).
+template <int PSTRIDE>
+__device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ plan, const WorkDev &wk, const LevelDev &L,
+                                                  const FTileInfo &ti, int f, int x0, int y0, const uint8_t *pix, uint32_t *mt,
+                                                  uint2 *s_cand, int &s_n, int *s_cnt_lo, int *s_cnt_hi, int *s_base) {
+    const int w = L.w, h = L.h;
     const int tlo = plan->t_lo;
-
-    if (threadIdx.x < F2_MAXCELLS) { s_cnt_lo[threadIdx.x] = 0; s_cnt_hi[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) s_n = 0;
-    // ---- stage pixel rows y0-4 .. y0+65, cols x0-8 .. x0+131 (x0 is a multiple of 4) ----
-    {
-        const int max_word = pitch / 4 - 1;
-        const int wx0 = (x0 - 8) >> 2;
-        for (int i = threadIdx.x; i < F2_PH * F2_PWORDS; i += blockDim.x) {
-            const int r = i / F2_PWORDS, c = i - r * F2_PWORDS;
-            const int gy = min(y0 - 4 + r, h - 1);
-            const int gw = min(wx0 + c, max_word);
-            *reinterpret_cast<uint32_t *>(&pix[r * F2_PW + c * 4]) =
-                __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gy * pitch) + gw);
-        }
-    }
-    __syncthreads();
-
     const int xmax = w - ORBFE_EDGE, ymax = h - ORBFE_EDGE;  // detect area is [16, xmax) x [16, ymax)
     const int g = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int gx = x0 - 4 + 4 * g;  // image x of the group's first pixel
@@ -220,13 +195,13 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
         if (gx + 2 >= ORBFE_EDGE && gx + 2 < xmax) maskA |= 0xFFFF0000u;
         if (gx + 1 >= ORBFE_EDGE && gx + 1 < xmax) maskB |= 0x0000FFFFu;
         if (gx + 3 >= ORBFE_EDGE && gx + 3 < xmax) maskB |= 0xFFFF0000u;
-        const uint8_t *base = &pix[(seg * 8) * F2_PW + 4 * g];  // b0 of the group = tile col 4g  (image x gx-4)
+        const uint8_t *base = &pix[(seg * 8) * PSTRIDE + 4 * g];  // b0 of the group = tile col 4g  (image x gx-4)
         uint32_t P[7][8];
 #pragma unroll
-        for (int r = 0; r < 6; r++) fast_load_row(base + r * F2_PW, P[r]);
+        for (int r = 0; r < 6; r++) fast_load_row(base + r * PSTRIDE, P[r]);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            fast_load_row(base + (6 + i) * F2_PW, P[(6 + i) % 7]);
+            fast_load_row(base + (6 + i) * PSTRIDE, P[(6 + i) % 7]);
 #define FROW(dy) P[(i + (dy) + 3) % 7]
             // ring in circular order, (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
             // pair A uses P_{4+dx} = index 3+dx ; pair B uses P_{5+dx} = index 4+dx
@@ -377,7 +352,132 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
     }
 }
 
+__global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
+    // one buffer, two lives: the staged pixel tile (until m is computed), then the candidate list
+    __shared__ __align__(16) uint8_t sbuf[(F2_MAXC * 8 > F2_PH * F2_PW) ? F2_MAXC * 8 : F2_PH * F2_PW];
+    __shared__ __align__(16) uint32_t mt[F2_MH * 32 * 2];  // 16 KB
+    __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
+    uint8_t *pix = sbuf;
+    uint2 *s_cand = reinterpret_cast<uint2 *>(sbuf);
+
+    const int f = blockIdx.y + f0;
+    const FTileInfo ti = wk.ftile_info[blockIdx.x];
+    const LevelDev &L = plan->lv[ti.level];
+    const int x0 = ORBFE_EDGE + ti.tx * F2_W, y0 = ORBFE_EDGE + ti.ty * F2_H;
+    const int h = L.h, pitch = L.pitch;
+    const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
+
+    if (threadIdx.x < F2_MAXCELLS) { s_cnt_lo[threadIdx.x] = 0; s_cnt_hi[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_n = 0;
+    // ---- stage pixel rows y0-4 .. y0+65, cols x0-8 .. x0+131 (x0 is a multiple of 4) ----
+    {
+        const int max_word = pitch / 4 - 1;
+        const int wx0 = (x0 - 8) >> 2;
+        for (int i = threadIdx.x; i < F2_PH * F2_PWORDS; i += blockDim.x) {
+            const int r = i / F2_PWORDS, c = i - r * F2_PWORDS;
+            const int gy = min(y0 - 4 + r, h - 1);
+            const int gw = min(wx0 + c, max_word);
+            *reinterpret_cast<uint32_t *>(&pix[r * F2_PW + c * 4]) =
+                __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gy * pitch) + gw);
+        }
+    }
+    __syncthreads();
+    fast_tile_compute<F2_PW>(plan, wk, L, ti, f, x0, y0, pix, mt, s_cand, s_n, s_cnt_lo, s_cnt_hi, s_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA variant (default): persistent CTAs, the pixel tile of work item i+1 is fetched by the Tensor
+// Memory Accelerator (cp.async.bulk.tensor.3d -> UTMALDG) into the second buffer while item i is
+// being computed; completion is signalled on an mbarrier.  One 3-D tensor map (x, y, frame) per level;
+// out-of-image parts of the box are zero-filled by the hardware (they only feed masked m positions).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// TMA needs the innermost box coordinate 16-byte aligned (measured: a misaligned start traps as an illegal
+// instruction): the box starts at (x0-8) & ~15 and is 160 wide; the tile's own columns begin dx = (x0-8) & 15 in.
+#define F2_TW 160
+#define F2_PIXBYTES (F2_PH * F2_TW)                       // 11200 = TMA box 160 x 70 x 1
+#define F2_PIXSLOT ((F2_PIXBYTES + 127) / 128 * 128)      // 11264
+#define F2_TMA_SMEM (2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4 + F2_MAXC * 8 + 128)
+
+__global__ void __launch_bounds__(256, 2) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint8_t *pixbuf0 = dsm, *pixbuf1 = dsm + F2_PIXSLOT;
+    uint32_t *mt = reinterpret_cast<uint32_t *>(dsm + 2 * F2_PIXSLOT);
+    uint2 *s_cand = reinterpret_cast<uint2 *>(dsm + 2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4);
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
+
+    const int ntiles = plan->nftiles_total;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int wi = blockIdx.x;
+    if (wi < nwork && threadIdx.x == 0) {
+        const FTileInfo t0 = wk.ftile_info[wi % ntiles];
+        mbar_expect_tx(&bar[0], F2_PIXBYTES);
+        tma_load_3d(pixbuf0, &wk.tmaps[t0.level], &bar[0], (ORBFE_EDGE + t0.tx * F2_W - 8) & ~15, ORBFE_EDGE + t0.ty * F2_H - 4, f0 + wi / ntiles);
+    }
+    for (int it = 0; wi < nwork; it++, wi += gridDim.x) {
+        const int cur = it & 1;
+        const int nxt = wi + gridDim.x;
+        if (nxt < nwork && threadIdx.x == 0) {  // prefetch the next tile into the other buffer
+            const FTileInfo tn = wk.ftile_info[nxt % ntiles];
+            mbar_expect_tx(&bar[cur ^ 1], F2_PIXBYTES);
+            tma_load_3d(cur ? pixbuf0 : pixbuf1, &wk.tmaps[tn.level], &bar[cur ^ 1], (ORBFE_EDGE + tn.tx * F2_W - 8) & ~15,
+                        ORBFE_EDGE + tn.ty * F2_H - 4, f0 + nxt / ntiles);
+        }
+        const FTileInfo ti = wk.ftile_info[wi % ntiles];
+        const int f = f0 + wi / ntiles;
+        const LevelDev &L = plan->lv[ti.level];
+        const int x0 = ORBFE_EDGE + ti.tx * F2_W, y0 = ORBFE_EDGE + ti.ty * F2_H;
+        if (threadIdx.x < F2_MAXCELLS) { s_cnt_lo[threadIdx.x] = 0; s_cnt_hi[threadIdx.x] = 0; }
+        if (threadIdx.x == 0) s_n = 0;
+        mbar_wait(&bar[cur], (it >> 1) & 1);
+        __syncthreads();
+        fast_tile_compute<F2_TW>(plan, wk, L, ti, f, x0, y0, (cur ? pixbuf1 : pixbuf0) + ((x0 - 8) & 15), mt, s_cand, s_n,
+                                 s_cnt_lo, s_cnt_hi, s_base);
+        __syncthreads();  // mt / s_cand / counters and the pixel buffer are reused by the next item
+    }
+}
+
+int fast_tma_setup() {
+    return (int)cudaFuncSetAttribute(fast_nms_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_TMA_SMEM);
+}
+
 void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+    if (w.tmaps) {
+        const int nwork = hp.nftiles_total * nf;
+        const int grid = min(nwork, w.fast_grid);
+        fast_nms_tma_kernel<<<grid, 256, F2_TMA_SMEM, s>>>(d_plan, w, f0, nwork);
+        return;
+    }
     dim3 grid(hp.nftiles_total, nf);
     fast_nms_kernel<<<grid, 256, 0, s>>>(d_plan, w, f0);
 }

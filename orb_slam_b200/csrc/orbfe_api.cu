@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -306,6 +307,40 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     CU_TRY(cudaMemcpy(d_cc, cand_cap.data(), sizeof(int) * cand_cap.size(), cudaMemcpyHostToDevice));
     Wk.cell_cand_base = d_cb;
     Wk.cell_cand_cap = d_cc;
+    // ---- TMA tensor maps (one per level: x, y, frame) for the FAST kernel's pixel tiles ----
+    Wk.tmaps = nullptr;
+    Wk.fast_grid = 0;
+    if (!getenv("ORBFE_FAST_NO_TMA")) {
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess)
+            return fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        std::vector<CUtensorMap> maps(ex->nlevels);
+        for (int l = 0; l < ex->nlevels; l++) {
+            const LevelDev &L = P.lv[l];
+            const cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)B};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)L.plane};  // bytes, dims 1 and 2
+            const cuuint32_t box[3] = {160, ORBFE_FT_H + 8, 1};  // F2_TW x F2_PH x 1
+            const cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = ((EncodeFn)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, L.pyr, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled(level %d) failed: %d", l, (int)r);
+        }
+        CUtensorMap *d_maps;
+        CU_TRY(dmalloc(ex, &d_maps, maps.size()));
+        CU_TRY(cudaMemcpy(d_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice));
+        Wk.tmaps = d_maps;
+        cudaError_t e = (cudaError_t)fast_tma_setup();
+        if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(fast_nms_tma_kernel): %s", cudaGetErrorString(e));
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ex->device);
+        Wk.fast_grid = 2 * nsm;  // two resident CTAs per SM (register-limited), persistent
+    }
     CU_TRY(dmalloc(ex, &Wk.cand_keys, (size_t)cand_total * B));
     const size_t nc = (size_t)P.ncells_total * B, nl = (size_t)P.nlevels * B;
     int *cnt;

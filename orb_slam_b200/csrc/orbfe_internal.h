@@ -2,6 +2,7 @@
 // Not part of the public ABI (that is include/orbfe.h).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -65,6 +66,8 @@ struct WorkDev {
     const int *cell_cand_cap;         // [ncells_total]
     const FTileInfo *ftile_info;      // [nftiles_total]
     const BTileInfo *btile_info;      // [nbtiles_total]
+    const CUtensorMap *tmaps;         // [nlevels] 3-D (x, y, frame) tensor maps of the unblurred levels; NULL = no TMA
+    int fast_grid;                    // persistent CTAs of the TMA FAST kernel
     uint32_t *cand_keys;              // [batch][cand_total]   (score<<24 | 0xFFFFFF - raster)
     int *cell_cnt_lo;                 // [batch][ncells_total] candidates with m > t_lo (= all emitted)
     int *cell_cnt_hi;                 // [batch][ncells_total] candidates with m > t_hi
@@ -86,6 +89,7 @@ void launch_level_select(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w
 void launch_blur(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, int f0, int nf, cudaStream_t s);
 void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, const int8_t *d_pattern,
                      OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s);
+int fast_tma_setup();
 int level_select_smem_bytes(int max_kept);
 int set_level_select_smem(int bytes);
 
