@@ -90,8 +90,10 @@ int orbfe_extract_batch_device(OrbfeExtractor *ex, const uint8_t *d_imgs, int wi
 int orbfe_extractor_sync(OrbfeExtractor *ex);
 /* number of kernels the last extract call launched (for bench.py's gpu_launches) */
 int orbfe_extractor_last_launches(const OrbfeExtractor *ex);
-/* name + average device time (ms, CUDA events on the launching stream) of each stage of the last call made
- * with profiling enabled; returns the number of stages written (<= cap) */
+/* With profiling on, every extract call records CUDA events around its stages on the launching stream.
+ * orbfe_extractor_stage_times returns (name, ms) of every stage interval recorded since the previous read --
+ * possibly from several calls -- and clears the list; the caller must have synchronised any external stream it
+ * passed to orbfe_extract_batch_device.  Returns the number of intervals written (<= cap). */
 int orbfe_extractor_set_profiling(OrbfeExtractor *ex, int on);
 int orbfe_extractor_stage_times(const OrbfeExtractor *ex, char (*names)[32], float *ms, int cap);
 

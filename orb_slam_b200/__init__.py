@@ -197,9 +197,10 @@ class ORBextractor:
         _check(lib().orbfe_extractor_set_profiling(self._h, int(on)))
 
     def stage_times(self):
-        names = (C.c_char * 32 * 32)()
-        ms = (C.c_float * 32)()
-        n = lib().orbfe_extractor_stage_times(self._h, names, ms, 32)
+        cap = 1024
+        names = (C.c_char * 32 * cap)()
+        ms = (C.c_float * cap)()
+        n = lib().orbfe_extractor_stage_times(self._h, names, ms, cap)
         return [(names[i].value.decode(), ms[i]) for i in range(n)]
 
     def debug_level(self, frame, level, blurred=False):

@@ -230,12 +230,26 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
 
     const int thi = plan->t_hi;
     const uint32_t tlo2 = (uint32_t)tlo * 0x00010001u;
-    // ---- pass 1: strict maximum over ALL 8 neighbours, two pixels per instruction.  Such a pixel is a
-    //      strict maximum over any subset of its neighbours too, so it is a keypoint whatever the cell
-    //      window is.  Rows 1..62 and groups 1..30 are the detect tile.
+    // ---- windowed 3x3 NMS, two pixels per instruction.  A pixel only competes with the neighbours inside
+    //      its own cell's detect window (cv::FAST ran per cell image): neighbour relations that cross an
+    //      interior cell boundary are masked to 0 -- per-lane u16x2 masks for vertical boundaries (they kill
+    //      the left/right/diagonal terms), per-row flags for horizontal ones (they kill the row above/below).
+    //      Rows 1..62 and groups 1..30 are the detect tile.
     if (g >= 1 && g <= 30) {
+        // relation (gx+d-1 <-> gx+d), d = 0..4, crosses a boundary at X = 16 + cj*cw  <=>  X == gx + d
+        uint32_t mLA = 0xFFFFFFFFu, mRA = 0xFFFFFFFFu, mLB = 0xFFFFFFFFu, mRB = 0xFFFFFFFFu;
+        for (int bnd = 0; bnd < ti.nv; bnd++) {
+            const int d = ORBFE_EDGE + (ti.cj_lo + bnd) * L.cw - gx;
+            if (d == 0) mLA &= 0xFFFF0000u;
+            else if (d == 1) { mRA &= 0xFFFF0000u; mLB &= 0xFFFF0000u; }
+            else if (d == 2) { mLA &= 0x0000FFFFu; mRB &= 0xFFFF0000u; }
+            else if (d == 3) { mRA &= 0x0000FFFFu; mLB &= 0x0000FFFFu; }
+            else if (d == 4) mRB &= 0x0000FFFFu;
+        }
+        // ti.hmask bit r: tile row r (image y0-1+r) is the top row of a cell (interior horizontal boundary above it)
+        const unsigned long long hmask = ti.hmask;
         uint32_t A[3], B[3], lrA[3], lrB[3], fullA[3], fullB[3];
-        const int r0 = seg * 8;  // first centre row handled = max(r0, 1)
+        const int r0 = seg * 8;
 #pragma unroll
         for (int j = 0; j < 10; j++) {
             // load tile row r0 - 1 + j into slot j % 3
@@ -246,19 +260,22 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
             const int sl = j % 3;
             A[sl] = own.x;
             B[sl] = own.y;
-            const uint32_t leftA = __byte_perm(pB, own.y, 0x5432);   // (m[x-1], m[x+1])
-            const uint32_t rightB = __byte_perm(own.x, nA, 0x5432);  // (m[x+2], m[x+4])
-            lrA[sl] = __vmaxu2(leftA, own.y);
+            const uint32_t leftA = __byte_perm(pB, own.y, 0x5432) & mLA;   // (m[x-1], m[x+1])
+            const uint32_t rightB = __byte_perm(own.x, nA, 0x5432) & mRB;  // (m[x+2], m[x+4])
+            lrA[sl] = __vmaxu2(leftA, own.y & mRA);
             fullA[sl] = __vmaxu2(lrA[sl], own.x);
-            lrB[sl] = __vmaxu2(own.x, rightB);
+            lrB[sl] = __vmaxu2(own.x & mLB, rightB);
             fullB[sl] = __vmaxu2(lrB[sl], own.y);
             if (j >= 2) {
                 const int cr = r0 + j - 2;  // centre row (slot (j-1)%3), above = (j-2)%3, below = j%3
                 const int c = (j - 1) % 3, u = (j - 2) % 3, d = j % 3;
+                const bool no_up = (hmask >> cr) & 1ull, no_dn = (hmask >> (cr + 1)) & 1ull;
+                const uint32_t upA = no_up ? 0u : fullA[u], dnA = no_dn ? 0u : fullA[d];
+                const uint32_t upB = no_up ? 0u : fullB[u], dnB = no_dn ? 0u : fullB[d];
                 // neighbour maximum, floored at t_lo: m must exceed both to be a candidate
-                const uint32_t nbA = __vmaxu2(__vimax3_u16x2(fullA[u], fullA[d], lrA[c]), tlo2);
-                const uint32_t nbB = __vmaxu2(__vimax3_u16x2(fullB[u], fullB[d], lrB[c]), tlo2);
-                const uint32_t tA = __vmaxu2(A[c], nbA) ^ nbA;  // half != 0  <=>  m > t_lo and m > every neighbour
+                const uint32_t nbA = __vmaxu2(__vimax3_u16x2(upA, dnA, lrA[c]), tlo2);
+                const uint32_t nbB = __vmaxu2(__vimax3_u16x2(upB, dnB, lrB[c]), tlo2);
+                const uint32_t tA = __vmaxu2(A[c], nbA) ^ nbA;  // half != 0  <=>  m > t_lo and m > every window neighbour
                 const uint32_t tB = __vmaxu2(B[c], nbB) ^ nbB;
                 if (((tA | tB) != 0) && cr >= 1 && cr <= F2_H) {
                     const int y = y0 - 1 + cr;
@@ -268,48 +285,6 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
                     if (tB & 0xFFFF0000u) fast_push(s_cand, &s_n, gx + 3, y, (int)(B[c] >> 16));
                 }
             }
-        }
-    }
-
-    // ---- pass 2: pixels on an interior cell boundary see only the neighbours inside their own cell
-    //      (cv::FAST ran per cell image): re-test them against the window and queue those that pass but
-    //      were not already queued by pass 1.
-    {
-        const int cw = L.cw, ch = L.ch;
-        const int items_v = ti.nv * 2 * F2_H, items_h = ti.nh * 2 * F2_W;
-        for (int it = threadIdx.x; it < items_v + items_h; it += blockDim.x) {
-            int x, y;
-            if (it < items_v) {
-                const int b = it / (2 * F2_H), rem = it - b * 2 * F2_H;
-                x = ORBFE_EDGE + (ti.cj_lo + b) * cw - 1 + (rem & 1);
-                y = y0 + (rem >> 1);
-            } else {
-                const int it2 = it - items_v;
-                const int b = it2 / (2 * F2_W), rem = it2 - b * 2 * F2_W;
-                y = ORBFE_EDGE + (ti.ci_lo + b) * ch - 1 + (rem & 1);
-                x = x0 + (rem >> 1);
-            }
-            if (x < x0 || x >= x0 + F2_W || y < y0 || y >= y0 + F2_H || x >= xmax || y >= ymax) continue;
-            const int r = y - (y0 - 1), c = x - (x0 - 4);
-            const int m = m_at(mt, r, c);
-            if (m <= tlo) continue;
-            int ci, cj, xa, xb, ya, yb;
-            cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
-            if (it >= items_v && ((x == xa && cj >= 1) || (x == xb && cj < L.cols - 1)))
-                continue;  // on a vertical boundary too: handled by the vertical items
-            const bool L_ = x > xa, R_ = x < xb, U_ = y > ya, D_ = y < yb;
-            bool win = true, all8 = true;
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (dx == 0 && dy == 0) continue;
-                    const bool gt = m > m_at(mt, r + dy, c + dx);
-                    const bool inside = (dx < 0 ? L_ : dx > 0 ? R_ : true) && (dy < 0 ? U_ : dy > 0 ? D_ : true);
-                    all8 &= gt;
-                    win &= (!inside) || gt;
-                }
-            if (win && !all8) fast_push(s_cand, &s_n, x, y, m);
         }
     }
     __syncthreads();

@@ -63,6 +63,7 @@ static inline int cv_floor(double v) { int i = (int)v; return i - (i > v); }
 struct StageTimer {
     std::vector<std::string> names;
     std::vector<cudaEvent_t> ev;  // names.size()+1 events
+    bool origin_pending = true;
 };
 
 struct OrbfeExtractor {
@@ -96,6 +97,7 @@ struct OrbfeExtractor {
     bool profiling = false;
     StageTimer timer;
     std::vector<float> stage_ms;
+    std::vector<std::string> stage_names;
 };
 
 static void free_plan(OrbfeExtractor *ex) {
@@ -279,6 +281,12 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
                     T.level = (short)l; T.tx = (short)tx; T.ty = (short)ty; T.pad = 0;
                     T.cj_lo = (short)cj_lo; T.nv = (short)std::max(0, cj_hi - cj_lo + 1);
                     T.ci_lo = (short)ci_lo; T.nh = (short)std::max(0, ci_hi - ci_lo + 1);
+                    T.hmask = 0;
+                    for (int r = 0; r < ORBFE_FT_H + 2; r++) {
+                        const int y = y0 - 1 + r;
+                        const int d = y - ORBFE_EDGE;
+                        if (d >= L.ch && d % L.ch == 0 && d / L.ch <= L.rows - 1) T.hmask |= 1ull << r;
+                    }
                     if (T.ncj * T.nci > 64) return fail(ORBFE_ERR_UNSUPPORTED, "level %d: a FAST tile overlaps %d cells", l, T.ncj * T.nci);
                 }
         }
@@ -454,15 +462,17 @@ extern "C" int orbfe_extractor_tables(const OrbfeExtractor *ex, float *scale, fl
     return ORBFE_OK;
 }
 
+// Stage timing: a flat list of events; entry i of `names` labels the interval ev[i] -> ev[i+1]; the marker
+// name "" opens a new call (its interval, the gap since the previous call, is dropped when reading).
+// The list accumulates over calls until orbfe_extractor_stage_times() is read, so several calls can be in
+// flight on the stream (chunked pipelines) without a host synchronisation in between.
 static void stage_mark(OrbfeExtractor *ex, cudaStream_t s, const char *name) {
     if (!ex->profiling) return;
     StageTimer &T = ex->timer;
-    const size_t i = T.names.size();
-    if (T.ev.size() < i + 2) {
-        while (T.ev.size() < i + 2) { cudaEvent_t e; cudaEventCreate(&e); T.ev.push_back(e); }
-    }
-    if (i == 0 && name == nullptr) { cudaEventRecord(T.ev[0], s); return; }
-    T.names.push_back(name);
+    const size_t i = T.names.size();  // ev[0] is the origin; names[i] labels ev[i] -> ev[i+1]
+    while (T.ev.size() < i + 2) { cudaEvent_t e; cudaEventCreate(&e); T.ev.push_back(e); }
+    if (i == 0 && T.origin_pending) { cudaEventRecord(T.ev[0], s); T.origin_pending = false; }
+    T.names.push_back(name ? name : "");
     cudaEventRecord(T.ev[i + 1], s);
 }
 
@@ -498,16 +508,27 @@ static int enqueue_pipeline(OrbfeExtractor *ex, int f0, int nf, OrbfeKeyPoint *d
 
 static void profiling_begin(OrbfeExtractor *ex, cudaStream_t s) {
     if (!ex->profiling) return;
-    ex->timer.names.clear();
-    stage_mark(ex, s, nullptr);
+    if (ex->timer.names.size() > 4096) { ex->timer.names.clear(); ex->timer.origin_pending = true; }  // never read: recycle
+    stage_mark(ex, s, nullptr);  // call marker (its interval is ignored)
 }
 
-static void profiling_end(OrbfeExtractor *ex) {
-    if (!ex->profiling) return;
-    ex->stage_ms.assign(ex->timer.names.size(), 0.f);
-    for (size_t i = 0; i < ex->timer.names.size(); i++)
-        cudaEventElapsedTime(&ex->stage_ms[i], ex->timer.ev[i], ex->timer.ev[i + 1]);
+// reads and clears the accumulated list; the caller must have synchronised the stream(s) used
+static void profiling_collect(OrbfeExtractor *ex) {
+    ex->stage_names.clear();
+    ex->stage_ms.clear();
+    StageTimer &T = ex->timer;
+    for (size_t i = 0; i < T.names.size(); i++) {
+        if (T.names[i].empty()) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, T.ev[i], T.ev[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        ex->stage_names.push_back(T.names[i]);
+        ex->stage_ms.push_back(ms);
+    }
+    T.names.clear();
+    T.origin_pending = true;
 }
+
+static void profiling_end(OrbfeExtractor *) {}
 
 extern "C" int orbfe_extract_batch_device(OrbfeExtractor *ex, const uint8_t *d_imgs, int width, int height,
                                           size_t stride, size_t frame_stride, int batch, OrbfeKeyPoint *d_kps,
@@ -626,11 +647,16 @@ extern "C" int orbfe_extractor_set_profiling(OrbfeExtractor *ex, int on) {
     return ORBFE_OK;
 }
 
-extern "C" int orbfe_extractor_stage_times(const OrbfeExtractor *ex, char (*names)[32], float *ms, int cap) {
-    if (!ex) return 0;
+extern "C" int orbfe_extractor_stage_times(const OrbfeExtractor *ex_c, char (*names)[32], float *ms, int cap) {
+    if (!ex_c) return 0;
+    OrbfeExtractor *ex = const_cast<OrbfeExtractor *>(ex_c);
+    if (!ex->profiling) return 0;
+    cudaSetDevice(ex->device);
+    cudaStreamSynchronize(ex->stream);
+    profiling_collect(ex);
     int n = (int)std::min<size_t>(ex->stage_ms.size(), (size_t)std::max(cap, 0));
     for (int i = 0; i < n; i++) {
-        if (names) { strncpy(names[i], ex->timer.names[i].c_str(), 31); names[i][31] = 0; }
+        if (names) { strncpy(names[i], ex->stage_names[i].c_str(), 31); names[i][31] = 0; }
         if (ms) ms[i] = ex->stage_ms[i];
     }
     return n;

@@ -47,7 +47,8 @@ def test_1080p_2000(gpu_required):
 
 
 @pytest.mark.parametrize("W,H,nf,nl,th", [(752, 480, 1000, 8, 20), (641, 479, 500, 5, 20), (1280, 720, 2000, 8, 20),
-                                            (640, 480, 1000, 8, 7), (640, 480, 1000, 8, 5), (333, 257, 300, 4, 20)])
+                                            (640, 480, 1000, 8, 7), (640, 480, 1000, 8, 5), (333, 257, 300, 4, 20),
+                                            (640, 480, 2000, 8, 20), (752, 480, 4000, 8, 20)])
 def test_geometries(gpu_required, W, H, nf, nl, th):
     _compare(textured_frame(W, H, seed=W + H), nf, nl, fast_th=th)
 
