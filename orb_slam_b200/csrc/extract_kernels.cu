@@ -249,6 +249,7 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
         // ti.hmask bit r: tile row r (image y0-1+r) is the top row of a cell (interior horizontal boundary above it)
         const unsigned long long hmask = ti.hmask;
         uint32_t A[3], B[3], lrA[3], lrB[3], fullA[3], fullB[3];
+        uint32_t fbits = 0;  // 4 flag bits per row x 8 rows
         const int r0 = seg * 8;
 #pragma unroll
         for (int j = 0; j < 10; j++) {
@@ -277,14 +278,19 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
                 const uint32_t nbB = __vmaxu2(__vimax3_u16x2(upB, dnB, lrB[c]), tlo2);
                 const uint32_t tA = __vmaxu2(A[c], nbA) ^ nbA;  // half != 0  <=>  m > t_lo and m > every window neighbour
                 const uint32_t tB = __vmaxu2(B[c], nbB) ^ nbB;
-                if (((tA | tB) != 0) && cr >= 1 && cr <= F2_H) {
-                    const int y = y0 - 1 + cr;
-                    if (tA & 0x0000FFFFu) fast_push(s_cand, &s_n, gx + 0, y, (int)(A[c] & 0xFFFF));
-                    if (tB & 0x0000FFFFu) fast_push(s_cand, &s_n, gx + 1, y, (int)(B[c] & 0xFFFF));
-                    if (tA & 0xFFFF0000u) fast_push(s_cand, &s_n, gx + 2, y, (int)(A[c] >> 16));
-                    if (tB & 0xFFFF0000u) fast_push(s_cand, &s_n, gx + 3, y, (int)(B[c] >> 16));
+                // one flag bit per pixel; the (rare) candidates are pushed after the loop, outside the unrolled code
+                if (cr >= 1 && cr <= F2_H) {
+                    const uint32_t f4 = ((tA & 0x0000FFFFu) ? 1u : 0u) | ((tB & 0x0000FFFFu) ? 2u : 0u) |
+                                        ((tA & 0xFFFF0000u) ? 4u : 0u) | ((tB & 0xFFFF0000u) ? 8u : 0u);
+                    fbits |= f4 << (4 * (j - 2));
                 }
             }
+        }
+        while (fbits) {
+            const int b = __ffs(fbits) - 1;
+            fbits &= fbits - 1;
+            const int cr = r0 + (b >> 2), k = b & 3;
+            fast_push(s_cand, &s_n, gx + k, y0 - 1 + cr, m_at(mt, cr, 4 * g + k));
         }
     }
     __syncthreads();
@@ -398,7 +404,7 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, ui
 #define F2_PIXSLOT ((F2_PIXBYTES + 127) / 128 * 128)      // 11264
 #define F2_TMA_SMEM (2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4 + F2_MAXC * 8 + 128)
 
-__global__ void __launch_bounds__(256, 2) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
+__global__ void __launch_bounds__(256, 3) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint8_t *pixbuf0 = dsm, *pixbuf1 = dsm + F2_PIXSLOT;
     uint32_t *mt = reinterpret_cast<uint32_t *>(dsm + 2 * F2_PIXSLOT);
