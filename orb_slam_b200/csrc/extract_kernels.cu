@@ -34,40 +34,85 @@ __device__ __forceinline__ int find_level_by(const PlanDev *plan, int idx, int w
 // Horizontal/vertical tap tables were computed on the host exactly as OpenCV computes them, so the
 // device part is pure integer: r = S[x0]*a0 + S[x1]*a1 ; v = (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
 // ------------------------------------------------------------------------------------------------
+#define RZ_ROWS 4  // destination rows per thread (the horizontal taps are loaded once and reused)
+
 __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__restrict__ plan, int level, int f0) {
     const LevelDev &D = plan->lv[level];
     const LevelDev &S = plan->lv[level - 1];
     const int f = blockIdx.z + f0;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ybase = (blockIdx.y * blockDim.y + threadIdx.y) * RZ_ROWS;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int dw = D.w, dh = D.h;
-    if (y >= dh || x4 >= dw) return;
-    const int2 rr = __ldg(&D.yrows[y]);
-    const short2 bb = __ldg(&D.yab[y]);
-    const uint8_t *__restrict__ s0 = S.pyr + (size_t)f * S.plane + (size_t)rr.x * S.pitch;
-    const uint8_t *__restrict__ s1 = S.pyr + (size_t)f * S.plane + (size_t)rr.y * S.pitch;
-    const int swm1 = S.w - 1;
-    uint32_t out = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int x = min(x4 + i, dw - 1);
-        const int xo = __ldg(&D.xofs[x]);
-        const short2 ab = __ldg(&D.xab[x]);
-        const int x1 = min(xo + 1, swm1);
-        const int r0 = (int)__ldg(s0 + xo) * ab.x + (int)__ldg(s0 + x1) * ab.y;
-        const int r1 = (int)__ldg(s1 + xo) * ab.x + (int)__ldg(s1 + x1) * ab.y;
-        int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
-        out |= (uint32_t)v << (8 * i);
+    if (ybase >= dh || x4 >= dw) return;
+    // taps of the thread's 4 destination columns (tables are padded to a multiple of 4 entries)
+    const int4 xo = __ldg(reinterpret_cast<const int4 *>(D.xofs + x4));
+    const uint4 ab = __ldg(reinterpret_cast<const uint4 *>(D.xab + x4));  // (a0 | a1 << 16) per column
+    // the 4 source columns and their right neighbours lie within 9 bytes of sbase: three aligned words
+    const int sbase = xo.x & ~3;
+    const int o0 = xo.x - sbase, o1 = xo.y - sbase, o2 = xo.z - sbase, o3 = xo.w - sbase;
+    const uint8_t *__restrict__ src = S.pyr + (size_t)f * S.plane + sbase;
+    uint8_t *__restrict__ dst = D.pyr + (size_t)f * D.plane + x4;
+    const int spitch = S.pitch;
+    if (!D.rz_fast) {
+        // generic path (scale factors > 4/3: the four source columns do not fit three words): byte loads
+        const uint8_t *__restrict__ sb = S.pyr + (size_t)f * S.plane;
+        const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
+        const uint32_t as[4] = {ab.x, ab.y, ab.z, ab.w};
+        for (int ry = 0; ry < RZ_ROWS; ry++) {
+            const int y = ybase + ry;
+            if (y >= dh) break;
+            const int2 rr = __ldg(&D.yrows[y]);
+            const short2 bb = __ldg(&D.yab[y]);
+            const uint8_t *s0 = sb + (size_t)rr.x * spitch, *s1 = sb + (size_t)rr.y * spitch;
+            uint32_t out = 0;
+            for (int i = 0; i < 4; i++) {
+                const int a0 = (int)(as[i] & 0xFFFF), a1 = (int)(as[i] >> 16);
+                const int r0 = (int)__ldg(s0 + xs[i]) * a0 + (int)__ldg(s0 + xs[i] + 1) * a1;
+                const int r1 = (int)__ldg(s1 + xs[i]) * a0 + (int)__ldg(s1 + xs[i] + 1) * a1;
+                int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
+                out |= (uint32_t)min(max(v, 0), 255) << (8 * i);
+            }
+            *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch) = out;
+        }
+        return;
     }
-    // pitch is a multiple of 128 and x4 a multiple of 4: aligned 32-bit store (bytes beyond w land in row padding)
-    *reinterpret_cast<uint32_t *>(D.pyr + (size_t)f * D.plane + (size_t)y * D.pitch + x4) = out;
+#pragma unroll
+    for (int ry = 0; ry < RZ_ROWS; ry++) {
+        const int y = ybase + ry;
+        if (y >= dh) break;
+        const int2 rr = __ldg(&D.yrows[y]);
+        const short2 bb = __ldg(&D.yab[y]);
+        const uint32_t *p0 = reinterpret_cast<const uint32_t *>(src + (size_t)rr.x * spitch);
+        const uint32_t *p1 = reinterpret_cast<const uint32_t *>(src + (size_t)rr.y * spitch);
+        const uint32_t u0 = __ldg(p0), u1 = __ldg(p0 + 1), u2 = __ldg(p0 + 2);
+        const uint32_t v0 = __ldg(p1), v1 = __ldg(p1 + 1), v2 = __ldg(p1 + 2);
+        uint32_t out = 0;
+#define RZ_PIX(i, o, abv)                                                                                   \
+        {                                                                                                   \
+            const int sh = 8 * ((o) & 3);                                                                   \
+            const bool hiw = (o) >= 4;                                                                      \
+            const uint32_t pu = __funnelshift_r(hiw ? u1 : u0, hiw ? u2 : u1, sh);  /* bytes S[s], S[s+1] */ \
+            const uint32_t pv = __funnelshift_r(hiw ? v1 : v0, hiw ? v2 : v1, sh);                          \
+            const int r0 = (int)__dp2a_lo((abv), pu, 0u);  /* S[s]*a0 + S[s+1]*a1 */                        \
+            const int r1 = (int)__dp2a_lo((abv), pv, 0u);                                                   \
+            int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;           \
+            v = min(max(v, 0), 255);                                                                        \
+            out |= (uint32_t)v << (8 * (i));                                                                \
+        }
+        RZ_PIX(0, o0, ab.x)
+        RZ_PIX(1, o1, ab.y)
+        RZ_PIX(2, o2, ab.z)
+        RZ_PIX(3, o3, ab.w)
+#undef RZ_PIX
+        // pitch is a multiple of 128 and x4 a multiple of 4: aligned 32-bit store (bytes beyond w land in row padding)
+        *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch) = out;
+    }
 }
 
 void launch_resize_level(const PlanDev *d_plan, const PlanDev &hp, int level, int f0, int nf, cudaStream_t s) {
     const LevelDev &D = hp.lv[level];
     dim3 block(64, 4);
-    dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, nf);
+    dim3 grid((D.w + 255) / 256, (D.h + 4 * RZ_ROWS - 1) / (4 * RZ_ROWS), nf);
     resize_level_kernel<<<grid, block, 0, s>>>(d_plan, level, f0);
 }
 

@@ -246,13 +246,18 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
                 yr[y].x = std::min(std::max(yo[y], 0), S.h - 1);
                 yr[y].y = std::min(std::max(yo[y] + 1, 0), S.h - 1);
             }
+            // the kernel reads the x tables four entries at a time: pad with copies of the last entry
+            while (xo.size() % 4 || xo.size() < (size_t)L.w + 4) { xo.push_back(xo[L.w - 1]); xab.push_back(xab[L.w - 1]); }
+            L.rz_fast = 1;
+            for (size_t x4 = 0; x4 + 3 < xo.size(); x4 += 4)
+                if (xo[x4 + 3] - (xo[x4] & ~3) > 7) L.rz_fast = 0;
             int *dxo; short2 *dxab; int2 *dyr; short2 *dyab;
-            CU_TRY(dmalloc(ex, &dxo, (size_t)L.w));
-            CU_TRY(dmalloc(ex, &dxab, (size_t)L.w));
+            CU_TRY(dmalloc(ex, &dxo, xo.size()));
+            CU_TRY(dmalloc(ex, &dxab, xab.size()));
             CU_TRY(dmalloc(ex, &dyr, (size_t)L.h));
             CU_TRY(dmalloc(ex, &dyab, (size_t)L.h));
-            CU_TRY(cudaMemcpy(dxo, xo.data(), sizeof(int) * L.w, cudaMemcpyHostToDevice));
-            CU_TRY(cudaMemcpy(dxab, xab.data(), sizeof(short2) * L.w, cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(dxo, xo.data(), sizeof(int) * xo.size(), cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(dxab, xab.data(), sizeof(short2) * xab.size(), cudaMemcpyHostToDevice));
             CU_TRY(cudaMemcpy(dyr, yr.data(), sizeof(int2) * L.h, cudaMemcpyHostToDevice));
             CU_TRY(cudaMemcpy(dyab, yab.data(), sizeof(short2) * L.h, cudaMemcpyHostToDevice));
             L.xofs = dxo; L.xab = dxab; L.yrows = dyr; L.yab = dyab;

@@ -40,6 +40,7 @@ struct LevelDev {
     const short2 *xab;    // [w]  11-bit weights (a0, a1)
     const int2 *yrows;    // [h]  source rows (r0, r1), each clipped to [0, h_src-1]
     const short2 *yab;    // [h]  (b0, b1)
+    int rz_fast;          // the 4 source columns of every aligned destination quad fit three aligned words
 };
 
 struct PlanDev {

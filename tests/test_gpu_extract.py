@@ -53,6 +53,13 @@ def test_geometries(gpu_required, W, H, nf, nl, th):
     _compare(textured_frame(W, H, seed=W + H), nf, nl, fast_th=th)
 
 
+def test_other_scale_factors(gpu_required):
+    """scale factors on both sides of the resize kernel's fast-path limit (4/3)"""
+    _compare(textured_frame(640, 480, seed=12), 800, 5, sf=1.1)
+    _compare(textured_frame(640, 480, seed=13), 600, 4, sf=1.5)
+    _compare(textured_frame(800, 600, seed=14), 500, 3, sf=1.7)
+
+
 def test_flat_and_noise(gpu_required):
     flat = np.full((480, 640), 77, np.uint8)
     assert _compare(flat, 1000, 8) == 0
