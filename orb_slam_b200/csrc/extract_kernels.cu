@@ -204,10 +204,10 @@ __device__ __forceinline__ int m_at(const uint32_t *mt, int r, int c /* tile col
 #define F2_MAXC ((F2_W / 2) * (F2_H / 2) + 4 * (F2_W + F2_H))
 #define F2_MAXCELLS 64                    // cells a tile can overlap (host-checked)
 
-// raw candidate queue entry: (x | y << 16, m); converted in place to (key, local cell << 16 | slot) later
-__device__ __forceinline__ void fast_push(uint2 *q, int *q_n, int x, int y, int m) {
+// candidate queue entry (u32): x - x0 (7 bits) | y - y0 (6 bits) << 7 | m (8 bits) << 13 | slot inside (tile, cell) (11 bits) << 21
+__device__ __forceinline__ void fast_push(uint32_t *q, int *q_n, int xl, int yl, int m) {
     const int n = atomicAdd(q_n, 1);
-    q[n] = make_uint2((uint32_t)x | ((uint32_t)y << 16), (uint32_t)m);
+    q[n] = (uint32_t)xl | ((uint32_t)yl << 7) | ((uint32_t)m << 13);
 }
 
 // cell of (x, y) and its detect window [xa, xb] x [ya, yb]  (ORBextractor.cc:560-599)
@@ -226,7 +226,7 @@ __device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int yma
 template <int PSTRIDE>
 __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ plan, const WorkDev &wk, const LevelDev &L,
                                                   const FTileInfo &ti, int f, int x0, int y0, const uint8_t *pix, uint32_t *mt,
-                                                  uint2 *s_cand, int &s_n, int *s_cnt_lo, int *s_cnt_hi, int *s_base) {
+                                                  uint32_t *s_cand, int &s_n, int *s_cnt_lo, int *s_cnt_hi, int *s_base) {
     const int w = L.w, h = L.h;
     const int tlo = plan->t_lo;
     const int xmax = w - ORBFE_EDGE, ymax = h - ORBFE_EDGE;  // detect area is [16, xmax) x [16, ymax)
@@ -335,23 +335,23 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
             const int b = __ffs(fbits) - 1;
             fbits &= fbits - 1;
             const int cr = r0 + (b >> 2), k = b & 3;
-            fast_push(s_cand, &s_n, gx + k, y0 - 1 + cr, m_at(mt, cr, 4 * g + k));
+            fast_push(s_cand, &s_n, gx + k - x0, cr - 1, m_at(mt, cr, 4 * g + k));
         }
     }
     __syncthreads();
-    // ---- dense conversion of the queue: cell lookup, per-(tile, cell) slot, selection key ----
+    // ---- per-(tile, cell) slots: each candidate takes a slot in its cell's local counter ----
     const int ncand = s_n;
     const int ncell_loc = ti.ncj * ti.nci;
     for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
-        const uint2 q = s_cand[i];
-        const int x = (int)(q.x & 0xFFFF), y = (int)(q.x >> 16), m = (int)q.y;
+        const uint32_t q = s_cand[i];
+        const int x = x0 + (int)(q & 127), y = y0 + (int)((q >> 7) & 63), m = (int)((q >> 13) & 255);
         int ci, cj, xa, xb, ya, yb;
         cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
         const int lc = (ci - ti.ci0) * ti.ncj + (cj - ti.cj0);
         const int slot = atomicAdd(&s_cnt_lo[lc], 1);
         if (m > thi) atomicAdd(&s_cnt_hi[lc], 1);
-        const uint32_t raster = (uint32_t)((y - ya) * L.cw + (x - xa));
-        s_cand[i] = make_uint2(((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster), ((uint32_t)lc << 16) | (uint32_t)slot);
+        if (slot >= 2048) atomicExch(wk.err_flag, 3);  // 11-bit slot field (unreachable: <= 1860 maxima per tile)
+        s_cand[i] = q | ((uint32_t)slot << 21);
     }
     // ---- flush: one global atomic per (tile, cell) reserves the range, then the keys are written ----
     __syncthreads();
@@ -369,22 +369,27 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
     }
     __syncthreads();
     for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
-        const uint2 cnd = s_cand[i];
-        const int lc = (int)(cnd.y >> 16), slot = (int)(cnd.y & 0xFFFF);
-        const int gcell = L.cell_base + (ti.ci0 + lc / ti.ncj) * L.cols + (ti.cj0 + lc % ti.ncj);
+        const uint32_t q = s_cand[i];
+        const int x = x0 + (int)(q & 127), y = y0 + (int)((q >> 7) & 63), m = (int)((q >> 13) & 255), slot = (int)(q >> 21);
+        int ci, cj, xa, xb, ya, yb;
+        cell_window(L, xmax, ymax, x, y, ci, cj, xa, xb, ya, yb);
+        const int lc = (ci - ti.ci0) * ti.ncj + (cj - ti.cj0);
+        const int gcell = L.cell_base + ci * L.cols + cj;
         const int pos = s_base[lc] + slot;
+        const uint32_t raster = (uint32_t)((y - ya) * L.cw + (x - xa));
         if (pos < wk.cell_cand_cap[gcell])
-            wk.cand_keys[(size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + pos] = cnd.x;
+            wk.cand_keys[(size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + pos] =
+                ((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster);
     }
 }
 
 __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
     // one buffer, two lives: the staged pixel tile (until m is computed), then the candidate list
-    __shared__ __align__(16) uint8_t sbuf[(F2_MAXC * 8 > F2_PH * F2_PW) ? F2_MAXC * 8 : F2_PH * F2_PW];
+    __shared__ __align__(16) uint8_t sbuf[(F2_MAXC * 4 > F2_PH * F2_PW) ? F2_MAXC * 4 : F2_PH * F2_PW];
     __shared__ __align__(16) uint32_t mt[F2_MH * 32 * 2];  // 16 KB
     __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
     uint8_t *pix = sbuf;
-    uint2 *s_cand = reinterpret_cast<uint2 *>(sbuf);
+    uint32_t *s_cand = reinterpret_cast<uint32_t *>(sbuf);
 
     const int f = blockIdx.y + f0;
     const FTileInfo ti = wk.ftile_info[blockIdx.x];
@@ -447,13 +452,13 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, ui
 #define F2_TW 160
 #define F2_PIXBYTES (F2_PH * F2_TW)                       // 11200 = TMA box 160 x 70 x 1
 #define F2_PIXSLOT ((F2_PIXBYTES + 127) / 128 * 128)      // 11264
-#define F2_TMA_SMEM (2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4 + F2_MAXC * 8 + 128)
+#define F2_TMA_SMEM (2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4 + 128)
+static_assert(F2_MAXC * 4 <= F2_PIXSLOT, "the candidate queue lives in the pixel slot that was just consumed");
 
-__global__ void __launch_bounds__(256, 3) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
+__global__ void __launch_bounds__(256, 4) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint8_t *pixbuf0 = dsm, *pixbuf1 = dsm + F2_PIXSLOT;
     uint32_t *mt = reinterpret_cast<uint32_t *>(dsm + 2 * F2_PIXSLOT);
-    uint2 *s_cand = reinterpret_cast<uint2 *>(dsm + 2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4);
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ int s_n, s_cnt_lo[F2_MAXCELLS], s_cnt_hi[F2_MAXCELLS], s_base[F2_MAXCELLS];
 
@@ -487,8 +492,11 @@ __global__ void __launch_bounds__(256, 3) fast_nms_tma_kernel(const PlanDev *__r
         if (threadIdx.x == 0) s_n = 0;
         mbar_wait(&bar[cur], (it >> 1) & 1);
         __syncthreads();
-        fast_tile_compute<F2_TW>(plan, wk, L, ti, f, x0, y0, (cur ? pixbuf1 : pixbuf0) + ((x0 - 8) & 15), mt, s_cand, s_n,
-                                 s_cnt_lo, s_cnt_hi, s_base);
+        // the candidate queue reuses the current pixel slot (dead once m is computed; the next TMA into it is
+        // only issued after the __syncthreads that ends this iteration)
+        uint8_t *slot_cur = cur ? pixbuf1 : pixbuf0;
+        fast_tile_compute<F2_TW>(plan, wk, L, ti, f, x0, y0, slot_cur + ((x0 - 8) & 15), mt, reinterpret_cast<uint32_t *>(slot_cur),
+                                 s_n, s_cnt_lo, s_cnt_hi, s_base);
         __syncthreads();  // mt / s_cand / counters and the pixel buffer are reused by the next item
     }
 }
@@ -891,14 +899,15 @@ __global__ void __launch_bounds__(256) describe_kernel(const PlanDev *__restrict
         const int au = abs(u);
         if (lane < 31) {
             const uint8_t *c = img + (size_t)y * pitch + x + u;
-#pragma unroll 1
+            // all 31 row loads are independent: issue them back to back (fully unrolled), then reduce
+            int colsum = 0;
+#pragma unroll
             for (int v = -15; v <= 15; v++) {
-                if (au <= c_umax[abs(v)]) {
-                    const int val = __ldg(c + (ptrdiff_t)v * pitch);
-                    m10 += u * val;
-                    m01 += v * val;
-                }
+                const int val = (au <= c_umax[v < 0 ? -v : v]) ? (int)__ldg(c + (ptrdiff_t)v * pitch) : 0;
+                colsum += val;
+                m01 += v * val;
             }
+            m10 = u * colsum;
         }
         m10 = warp_sum(m10);
         m01 = warp_sum(m01);

@@ -352,7 +352,7 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(fast_nms_tma_kernel): %s", cudaGetErrorString(e));
         int nsm = 148;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ex->device);
-        Wk.fast_grid = 3 * nsm;  // three resident CTAs per SM (80 registers, 60 KB smem each), persistent
+        Wk.fast_grid = (getenv("ORBFE_FAST_CTAS") ? atoi(getenv("ORBFE_FAST_CTAS")) : 4) * nsm;  // resident persistent CTAs per SM (64 registers, 39 KB smem each)
     }
     CU_TRY(dmalloc(ex, &Wk.cand_keys, (size_t)cand_total * B));
     const size_t nc = (size_t)P.ncells_total * B, nl = (size_t)P.nlevels * B;
