@@ -579,7 +579,7 @@ extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int 
     rc = zero_counters(ex, s);
     if (rc) return rc;
     // H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream)
-    const int nchunks = batch >= 8 ? 4 : 1;
+    const int nchunks = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
     if (!ex->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&ex->copy_stream, cudaStreamNonBlocking));
     while ((int)ex->chunk_ev.size() < nchunks + 1) {
         cudaEvent_t e;
