@@ -302,63 +302,85 @@ def main():
             stage_acc[name] = stage_acc.get(name, 0.0) + ms
         stage_n[0] += 1
 
-    # ---- device-resident pipeline state (value path): slot B holds the previous step's last frame ----
-    d_kps_all = torch.zeros((B + 1, NFEAT, 28), dtype=torch.uint8, device=dev)
-    d_desc_all = torch.zeros((B + 1, NFEAT, 32), dtype=torch.uint8, device=dev)
-    d_cnt_all = torch.zeros((B + 1,), dtype=torch.int32, device=dev)
-    d_world = torch.zeros((B + 1, NFEAT, 3), dtype=torch.float32, device=dev)
+    # ---- device-resident pipeline (value path).  Two buffer sets: while step t is matched and read back on
+    # stream_m, step t+1 is already being extracted on stream_x.  Slot B of a set holds the previous step's last frame.
+    def make_set():
+        S = {}
+        S["kps"] = torch.zeros((B + 1, NFEAT, 28), dtype=torch.uint8, device=dev)
+        S["desc"] = torch.zeros((B + 1, NFEAT, 32), dtype=torch.uint8, device=dev)
+        S["cnt"] = torch.zeros((B + 1,), dtype=torch.int32, device=dev)
+        S["world"] = torch.zeros((B + 1, NFEAT, 3), dtype=torch.float32, device=dev)
+        S["mp"] = torch.empty((B, NFEAT), dtype=torch.int32, device=dev)
+        S["nm"] = torch.zeros((B,), dtype=torch.int32, device=dev)
+        S["kxy"] = S["kps"].view(torch.float32).view(B + 1, NFEAT, 7)
+        S["h_kps"] = torch.empty((B, NFEAT, 28), dtype=torch.uint8).pin_memory()
+        S["h_desc"] = torch.empty((B, NFEAT, 32), dtype=torch.uint8).pin_memory()
+        S["h_cnt"] = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        S["h_mp"] = torch.empty((B, NFEAT), dtype=torch.int32).pin_memory()
+        S["h_nm"] = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        S["ev_x"] = torch.cuda.Event()
+        S["ev_done"] = torch.cuda.Event()
+        return S
+
+    dsets = [make_set(), make_set()]
     d_flags = torch.ones((B + 1, NFEAT), dtype=torch.uint8, device=dev)   # every feature carries a map point
     d_T = torch.from_numpy(np.stack(Tcws).reshape(B, 12)).to(dev)
     d_cur = torch.arange(0, B, dtype=torch.int32, device=dev)
     d_last = torch.tensor([B] + list(range(0, B - 1)), dtype=torch.int32, device=dev)
-    d_mp = torch.empty((B, NFEAT), dtype=torch.int32, device=dev)
-    d_nm = torch.zeros((B,), dtype=torch.int32, device=dev)
-    h_mp = torch.empty((B, NFEAT), dtype=torch.int32).pin_memory()
-    h_nm = torch.zeros((B,), dtype=torch.int32).pin_memory()
-    kxy = d_kps_all.view(torch.float32).view(B + 1, NFEAT, 7)
+    stream_m = torch.cuda.Stream(device=dev)
+    stream_b = stream_m
+    dev_state = {"step": 0}
 
-    # extraction of chunk k+1 (stream A) overlaps the matching of chunk k (stream B)
-    NCH = args.chunks if (args.chunks >= 1 and B % args.chunks == 0) else 1
-    CB = B // NCH
-    stream_b = torch.cuda.Stream(device=dev)
-    ev_chunk = [torch.cuda.Event() for _ in range(NCH)]
+    def enqueue_device_step():
+        st = dev_state["step"]
+        S, Pv = dsets[st & 1], dsets[(st - 1) & 1]
+        with torch.cuda.stream(stream):
+            stream.wait_event(S["ev_done"])          # the set's previous results have left the device
+            ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, S["kps"].data_ptr(), S["desc"].data_ptr(),
+                                    S["cnt"].data_ptr(), stream.cuda_stream)
+            # synthetic map points: back-project every keypoint at depth DEPTH (same float32 ops as backproject())
+            S["world"][:B, :, 0] = (S["kxy"][:B, :, 0] - CX) / FX * DEPTH
+            S["world"][:B, :, 1] = (S["kxy"][:B, :, 1] - CY) / FY * DEPTH
+            S["world"][:B, :, 2] = DEPTH
+            S["ev_x"].record(stream)
+        with torch.cuda.stream(stream_m):
+            stream_m.wait_event(S["ev_x"])
+            # slot B <- last frame of the previous step (extracted earlier on `stream`, matched earlier on stream_m)
+            S["kps"][B].copy_(Pv["kps"][B - 1]); S["desc"][B].copy_(Pv["desc"][B - 1])
+            S["cnt"][B:B + 1].copy_(Pv["cnt"][B - 1:B]); S["world"][B].copy_(Pv["world"][B - 1])
+            S["mp"].fill_(-1)
+            M.search_by_projection_device(mt, B, S["kps"].data_ptr(), S["desc"].data_ptr(), S["cnt"].data_ptr(), NFEAT,
+                                          d_cur.data_ptr(), d_last.data_ptr(), S["world"].data_ptr(), d_flags.data_ptr(),
+                                          d_T.data_ptr(), W, H, SCALE, NLEVELS, FX, FY, CX, CY, MATCH_TH,
+                                          S["mp"].data_ptr(), S["nm"].data_ptr(), stream_m.cuda_stream)
+            S["h_cnt"].copy_(S["cnt"][:B], non_blocking=True)
+            S["h_nm"].copy_(S["nm"], non_blocking=True)
+            S["h_kps"].copy_(S["kps"][:B], non_blocking=True)
+            S["h_desc"].copy_(S["desc"][:B], non_blocking=True)
+            S["h_mp"].copy_(S["mp"], non_blocking=True)
+            S["ev_done"].record(stream_m)
+        launches[0] += ex.last_launches() + 1
+        dev_state["step"] = st + 1
+        return S
 
-    def step_device():
+    def finish_device_step(S):
+        S["ev_done"].synchronize()
+        kp_total[0] += int(S["h_cnt"].numpy().sum())
+        return int(S["h_nm"].numpy().sum())
+
+    def run_device(steps):
         t0 = time.perf_counter()
-        for k in range(NCH):
-            lo, hi = k * CB, (k + 1) * CB
-            with torch.cuda.stream(stream):
-                ex.extract_batch_device(d_frames[lo].data_ptr(), W, H, W, W * H, CB, d_kps_all[lo].data_ptr(),
-                                        d_desc_all[lo].data_ptr(), d_cnt_all[lo:].data_ptr(), stream.cuda_stream)
-                # synthetic map points: back-project every keypoint at depth DEPTH (same float32 ops as backproject())
-                d_world[lo:hi, :, 0] = (kxy[lo:hi, :, 0] - CX) / FX * DEPTH
-                d_world[lo:hi, :, 1] = (kxy[lo:hi, :, 1] - CY) / FY * DEPTH
-                d_world[lo:hi, :, 2] = DEPTH
-                ev_chunk[k].record(stream)
-            with torch.cuda.stream(stream_b):
-                stream_b.wait_event(ev_chunk[k])
-                d_mp[lo:hi].fill_(-1)
-                M.search_by_projection_device(mt, CB, d_kps_all.data_ptr(), d_desc_all.data_ptr(), d_cnt_all.data_ptr(), NFEAT,
-                                              d_cur[lo:].data_ptr(), d_last[lo:].data_ptr(), d_world.data_ptr(),
-                                              d_flags.data_ptr(), d_T[lo].data_ptr(), W, H, SCALE, NLEVELS, FX, FY, CX, CY,
-                                              MATCH_TH, d_mp[lo].data_ptr(), d_nm[lo:].data_ptr(), stream_b.cuda_stream)
-        with torch.cuda.stream(stream_b):
-            h_cnt.copy_(d_cnt_all[:B], non_blocking=True)
-            h_nm.copy_(d_nm, non_blocking=True)
-            h_kps.copy_(d_kps_all[:B], non_blocking=True)
-            h_desc.copy_(d_desc_all[:B], non_blocking=True)
-            h_mp.copy_(d_mp, non_blocking=True)
-            # carry the last frame over to slot B for the next step
-            d_kps_all[B].copy_(d_kps_all[B - 1]); d_desc_all[B].copy_(d_desc_all[B - 1])
-            d_cnt_all[B:B + 1].copy_(d_cnt_all[B - 1:B]); d_world[B].copy_(d_world[B - 1])
-        stream_b.synchronize()
+        nm, pending = 0, None
+        for _ in range(steps):
+            S = enqueue_device_step()
+            if pending is not None:
+                nm += finish_device_step(pending)
+            pending = S
+        nm += finish_device_step(pending)
         stream.synchronize()
         collect_stages()
         host_t["extract_call"] += time.perf_counter() - t0
-        host_t["n"] += 1
-        launches[0] += (ex.last_launches() + 1) * NCH
-        kp_total[0] += int(cnt_np.sum())
-        return int(h_nm.numpy().sum())
+        return nm
 
     # ---- e2e: host buffers in, host results out.  A stream of frames is processed as a two-stage pipeline:
     # while step t is being matched (worker thread: orbfe_search_by_projection_frames), step t+1 is already being
@@ -385,9 +407,6 @@ def main():
         if fut is not None:
             nm += fut.result()
         return nm
-
-    def run_device(steps):
-        return sum(step_device() for _ in range(steps))
 
     def timed(run_fn, steps):
         kp_total[0] = 0
@@ -418,8 +437,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        step_device()
+    run_device(args.warmup)
     ex.set_profiling(False)          # stage events only during the device-resident timed region
     run_e2e(args.warmup)
     ex.set_profiling(True)
@@ -429,7 +447,7 @@ def main():
 
     sampler.t_begin = time.perf_counter()
     r_dev = timed(run_device, args.steps)
-    stages = {k: v / max(stage_n[0], 1) for k, v in stage_acc.items()}   # ms per step (summed over the step's chunks)
+    stages = {k: v / max(args.steps, 1) for k, v in stage_acc.items()}   # ms per step
     ex.set_profiling(False)
     r_e2e = timed(run_e2e, args.steps)
     sampler.t_end = time.perf_counter()
