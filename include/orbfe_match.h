@@ -66,6 +66,30 @@ int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, const OrbfeKe
                                       float fx, float fy, float cx, float cy, float th, int check_orientation,
                                       int *d_cur_mp, int *d_nmatches, void *stream);
 
+/* int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, float th) (ORBmatcher.cc:49-125), local-map
+ * tracking.  Per map point: in_view = mbTrackInView && !isBad(); proj_xy = (mTrackProjX, mTrackProjY); level =
+ * mnTrackScaleLevel; view_cos = mTrackViewCos; desc = GetDescriptor().  f_mp_inout[i2] >= 0 <=> F.mvpMapPoints[i2] set
+ * on entry; on exit it holds the index of the map point assigned to feature i2. */
+int orbfe_search_local_points(OrbfeMatcher *m, const OrbfeFrameView *f, int npts, const uint8_t *in_view,
+                              const float *proj_xy, const int *level, const float *view_cos, const uint8_t *desc, float th,
+                              float nnratio, int *f_mp_inout, int *nmatches_out);
+
+/* int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, float th,
+ * int ORBdist) (ORBmatcher.cc:1622-1746), relocalisation refinement.  Per keyframe feature i: valid[i] = has a map point,
+ * not bad, not in sAlreadyFound; world / min_dist (GetMinDistanceInvariance) / desc of that point; kf_angle[i] =
+ * pKF->GetKeyPointUn(i).angle.  Tcw = CurrentFrame.mTcw (3x4). */
+int orbfe_search_by_projection_kf(OrbfeMatcher *m, const OrbfeFrameView *cur, int npts, const uint8_t *valid, const float *world,
+                                  const float *min_dist, const uint8_t *desc, const float *kf_angle, const float *Tcw, float fx,
+                                  float fy, float cx, float cy, float th, int orb_dist, int check_orientation, int *cur_mp_inout,
+                                  int *nmatches_out);
+
+/* int ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, int windowSize, vector<MapPoint*> &vpMapPointMatches2)
+ * (ORBmatcher.cc:519-594).  valid1[i1] = F1 has a map point there, not bad, not already among F2's matches (:533-537);
+ * world1 = its position; Tc2w = F2.mTcw; f2_mp_inout = F2's slots (>= 0 occupied), receives i1 for new matches. */
+int orbfe_search_by_projection_f1f2(OrbfeMatcher *m, const OrbfeFrameView *f1, const OrbfeFrameView *f2, const uint8_t *valid1,
+                                    const float *world1, const float *Tc2w, float fx, float fy, float cx, float cy, int window,
+                                    float nnratio, int *f2_mp_inout, int *nmatches_out);
+
 /* int ORBmatcher::WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minOctave, maxOctave)
  * (ORBmatcher.cc:409-516).  f1_has_mp[i1] != 0 <=> F1.mvpMapPoints[i1] && !isBad().
  * match21_out[i2] = i1 whose map point was matched to F2 feature i2, or -1. */

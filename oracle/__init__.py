@@ -106,6 +106,11 @@ def lib():
         L.orb_oracle_window_search.argtypes = [C.POINTER(Frame), C.POINTER(Frame), u8p, C.c_int, C.c_int, C.c_int,
                                                C.c_float, C.c_int, i32p]
         L.orb_oracle_search_for_initialization.argtypes = [C.POINTER(Frame), C.POINTER(Frame), f32p, C.c_int, C.c_float, C.c_int, i32p]
+        L.orb_oracle_search_local_points.argtypes = [C.POINTER(Frame), C.c_int, u8p, f32p, i32p, f32p, u8p, C.c_float, C.c_float, i32p]
+        L.orb_oracle_search_by_projection_kf.argtypes = [C.POINTER(Frame), C.c_int, u8p, f32p, f32p, u8p, f32p, f32p, C.c_float,
+                                                         C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, i32p]
+        L.orb_oracle_search_by_projection_f1f2.argtypes = [C.POINTER(Frame), C.POINTER(Frame), u8p, f32p, f32p, C.c_float, C.c_float,
+                                                           C.c_float, C.c_float, C.c_int, C.c_float, i32p]
         L.orb_oracle_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p, i32p]
         L.orb_oracle_knn2.restype = None
         _lib = L
@@ -312,3 +317,30 @@ def search_for_initialization(f1, f2, prev_matched, window, nnratio=0.9, check_o
     n = lib().orb_oracle_search_for_initialization(C.byref(f1.c), C.byref(f2.c), _p(prev), window, nnratio,
                                                    int(check_orientation), _p(m12))
     return n, m12[:f1.n], prev
+
+
+def _a(x, t):
+    return np.ascontiguousarray(x, t)
+
+
+def search_local_points(f, in_view, proj_xy, level, view_cos, desc, th, nnratio=0.8, f_mp=None):
+    mp = np.full(max(f.n, 1), -1, np.int32) if f_mp is None else _a(f_mp, np.int32).copy()
+    iv, pj, lv, vc, ds = _a(in_view, np.uint8), _a(proj_xy, np.float32), _a(level, np.int32), _a(view_cos, np.float32), _a(desc, np.uint8)
+    n = lib().orb_oracle_search_local_points(C.byref(f.c), len(iv), _p(iv), _p(pj), _p(lv), _p(vc), _p(ds), th, nnratio, _p(mp))
+    return n, mp[:f.n]
+
+
+def search_by_projection_kf(cur, valid, world, min_dist, desc, kf_angle, Tcw, fx, fy, cx, cy, th, orb_dist, check_orientation=True,
+                            cur_mp=None):
+    mp = np.full(max(cur.n, 1), -1, np.int32) if cur_mp is None else _a(cur_mp, np.int32).copy()
+    v, w, md, ds, ka, T = _a(valid, np.uint8), _a(world, np.float32), _a(min_dist, np.float32), _a(desc, np.uint8), _a(kf_angle, np.float32), _a(Tcw, np.float32)
+    n = lib().orb_oracle_search_by_projection_kf(C.byref(cur.c), len(v), _p(v), _p(w), _p(md), _p(ds), _p(ka), _p(T), fx, fy, cx, cy,
+                                                 th, orb_dist, int(check_orientation), _p(mp))
+    return n, mp[:cur.n]
+
+
+def search_by_projection_f1f2(f1, f2, valid1, world1, Tc2w, fx, fy, cx, cy, window, nnratio=0.9, f2_mp=None):
+    mp = np.full(max(f2.n, 1), -1, np.int32) if f2_mp is None else _a(f2_mp, np.int32).copy()
+    v, w, T = _a(valid1, np.uint8), _a(world1, np.float32), _a(Tc2w, np.float32)
+    n = lib().orb_oracle_search_by_projection_f1f2(C.byref(f1.c), C.byref(f2.c), _p(v), _p(w), _p(T), fx, fy, cx, cy, window, nnratio, _p(mp))
+    return n, mp[:f2.n]

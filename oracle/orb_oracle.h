@@ -170,6 +170,19 @@ int orb_oracle_window_search(const OrbOracleFrame *f1, const OrbOracleFrame *f2,
 int orb_oracle_search_for_initialization(const OrbOracleFrame *f1, const OrbOracleFrame *f2,
                                          float *prev_matched, int window, float nnratio,
                                          int check_orientation, int *out_match12);
+/* SearchByProjection(Frame&, const vector<MapPoint*>&, th), ORBmatcher.cc:49-125 (local-map tracking) */
+int orb_oracle_search_local_points(const OrbOracleFrame *f, int npts, const uint8_t *in_view, const float *proj_xy,
+                                   const int *level, const float *view_cos, const uint8_t *desc, float th,
+                                   float nnratio, int *f_mp);
+/* SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), ORBmatcher.cc:1622-1746 (relocalisation) */
+int orb_oracle_search_by_projection_kf(const OrbOracleFrame *cur, int npts, const uint8_t *valid, const float *world,
+                                       const float *min_dist, const uint8_t *desc, const float *kf_angle,
+                                       const float *Tcw, float fx, float fy, float cx, float cy, float th, int orb_dist,
+                                       int check_orientation, int *cur_mp);
+/* SearchByProjection(Frame &F1, Frame &F2, windowSize, matches2), ORBmatcher.cc:519-594 */
+int orb_oracle_search_by_projection_f1f2(const OrbOracleFrame *f1, const OrbOracleFrame *f2, const uint8_t *valid1,
+                                         const float *world1, const float *Tc2w, float fx, float fy, float cx, float cy,
+                                         int window, float nnratio, int *f2_mp);
 /* brute-force best/second-best of each query against a database (BASELINE config 5 primitive;
  * same strict-< update rule as every best/second loop in ORBmatcher.cc, e.g. :456-466) */
 void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,

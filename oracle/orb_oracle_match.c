@@ -328,3 +328,160 @@ void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,
         best_dist[i] = b1; best_idx[i] = bi; second_dist[i] = b2;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * cv::Mat float algebra used by the projecting matchers (OpenCV 2.4 core semantics):
+ *   A*x + t  (MatExpr -> one cv::gemm, CV_32F): every output element is accumulated in double,
+ *            the addend joins in double, then one rounding to float;
+ *   -R.t()*t (gemm with alpha = -1 on the transposed left operand): double accumulate, * alpha, round;
+ *   cv::norm(v) for CV_32F: sqrt of the double sum of squares.
+ * ---------------------------------------------------------------------------------------------- */
+static void cv_Rx_plus_t(const float *T /*3x4 row-major [R|t]*/, const float *X, float out[3]) {
+    for (int k = 0; k < 3; k++) {
+        double s = (double)T[4 * k + 0] * (double)X[0] + (double)T[4 * k + 1] * (double)X[1] + (double)T[4 * k + 2] * (double)X[2];
+        out[k] = (float)(s + (double)T[4 * k + 3]);
+    }
+}
+static void cv_camera_centre(const float *T, float Ow[3]) { /* Ow = -Rcw.t()*tcw */
+    for (int k = 0; k < 3; k++) {
+        double s = (double)T[0 * 4 + k] * (double)T[3] + (double)T[1 * 4 + k] * (double)T[7] + (double)T[2 * 4 + k] * (double)T[11];
+        Ow[k] = (float)(s * -1.0);
+    }
+}
+static float cv_norm3(const float *v) {
+    return (float)sqrt((double)v[0] * (double)v[0] + (double)v[1] * (double)v[1] + (double)v[2] * (double)v[2]);
+}
+
+/* SearchByProjection(Frame &F, const vector<MapPoint*>&, th), ORBmatcher.cc:49-125.
+ * Per map point: in_view = mbTrackInView && !isBad(); proj = (mTrackProjX, mTrackProjY); level = mnTrackScaleLevel;
+ * view_cos = mTrackViewCos; desc = GetDescriptor().  f_mp[i2] >= 0 <=> F.mvpMapPoints[i2] != NULL on entry;
+ * on exit f_mp[i2] = index of the map point assigned.  Returns nmatches. */
+int orb_oracle_search_local_points(const OrbOracleFrame *f, int npts, const uint8_t *in_view, const float *proj_xy,
+                                   const int *level, const float *view_cos, const uint8_t *desc, float th,
+                                   float nnratio, int *f_mp) {
+    int nmatches = 0;
+    const int bFactor = th != 1.0f;
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(f->n > 0 ? f->n : 1));
+    for (int iMP = 0; iMP < npts; iMP++) {
+        if (!in_view[iMP]) continue;
+        const int nPredictedLevel = level[iMP];
+        float r = view_cos[iMP] > 0.998 ? 2.5f : 4.0f; /* RadiusByViewingCos :127-133 (float compared to a double literal) */
+        if (bFactor) r *= th;
+        const int nc = orb_oracle_features_in_area(f, proj_xy[2 * iMP], proj_xy[2 * iMP + 1], r * f->scale_factors[nPredictedLevel],
+                                                   nPredictedLevel - 1, nPredictedLevel, cand, f->n);
+        if (nc == 0) continue;
+        const uint8_t *d = desc + (size_t)iMP * 32;
+        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            if (f_mp[idx] >= 0) continue;
+            const int dist = orb_oracle_hamming(d, f->desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = f->keys_un[idx].octave; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = f->keys_un[idx].octave; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+            f_mp[bestIdx] = iMP;
+            nmatches++;
+        }
+    }
+    free(cand);
+    return nmatches;
+}
+
+/* SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist), ORBmatcher.cc:1622-1746.
+ * Per keyframe feature i: valid[i] = has a map point && !isBad() && not in sAlreadyFound; world/min_dist/desc of that
+ * point; kf_angle[i] = pKF->GetKeyPointUn(i).angle.  cur_mp as in orb_oracle_search_by_projection_ff. */
+int orb_oracle_search_by_projection_kf(const OrbOracleFrame *cur, int npts, const uint8_t *valid, const float *world,
+                                       const float *min_dist, const uint8_t *desc, const float *kf_angle,
+                                       const float *Tcw, float fx, float fy, float cx, float cy, float th, int orb_dist,
+                                       int check_orientation, int *cur_mp) {
+    int nmatches = 0;
+    IVec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    float Ow[3];
+    cv_camera_centre(Tcw, Ow); /* :1628 */
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(cur->n > 0 ? cur->n : 1));
+    for (int i = 0; i < npts; i++) {
+        if (!valid[i]) continue;
+        const float *X = world + 3 * i;
+        float xc3[3];
+        cv_Rx_plus_t(Tcw, X, xc3);
+        const float invzc = (float)(1.0 / (double)xc3[2]);
+        const float u = fx * xc3[0] * invzc + cx;
+        const float v = fy * xc3[1] * invzc + cy;
+        if (u < cur->min_x || u > cur->max_x) continue;
+        if (v < cur->min_y || v > cur->max_y) continue;
+        /* :1664-1670 predicted scale level */
+        const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+        const float dist3D = cv_norm3(PO);
+        const float ratio = dist3D / min_dist[i];
+        int it = 0; /* lower_bound: first scale factor >= ratio */
+        while (it < cur->nlevels && cur->scale_factors[it] < ratio) it++;
+        const int nPredictedLevel = it < cur->nlevels - 1 ? it : cur->nlevels - 1;
+        const float radius = th * cur->scale_factors[nPredictedLevel];
+        const int nc = orb_oracle_features_in_area(cur, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, cand, cur->n);
+        if (nc == 0) continue;
+        const uint8_t *dMP = desc + (size_t)i * 32;
+        int bestDist = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (cur_mp[i2] >= 0) continue;
+            const int dist = orb_oracle_hamming(dMP, cur->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= orb_dist) {
+            cur_mp[bestIdx2] = i;
+            nmatches++;
+            if (check_orientation) ivec_push(&hist[rot_bin(kf_angle[i], cur->keys_un[bestIdx2].angle)], bestIdx2);
+        }
+    }
+    if (check_orientation) {
+        int counts[HISTO_LENGTH], i1, i2, i3;
+        for (int b = 0; b < HISTO_LENGTH; b++) counts[b] = hist[b].n;
+        orb_oracle_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int b = 0; b < HISTO_LENGTH; b++) {
+            if (b == i1 || b == i2 || b == i3) continue;
+            for (int j = 0; j < hist[b].n; j++) { cur_mp[hist[b].v[j]] = -1; nmatches--; }
+        }
+    }
+    for (int b = 0; b < HISTO_LENGTH; b++) free(hist[b].v);
+    free(cand);
+    return nmatches;
+}
+
+/* SearchByProjection(Frame &F1, Frame &F2, int windowSize, vpMapPointMatches2), ORBmatcher.cc:519-594.
+ * valid1[i1] = F1 has a map point there && !isBad() && the point is not already among F2's matches (:533-537).
+ * f2_mp: copy of F2.mvpMapPoints occupancy on entry (>=0 occupied), on exit index i1 for new matches. */
+int orb_oracle_search_by_projection_f1f2(const OrbOracleFrame *f1, const OrbOracleFrame *f2, const uint8_t *valid1,
+                                         const float *world1, const float *Tc2w, float fx, float fy, float cx, float cy,
+                                         int window, float nnratio, int *f2_mp) {
+    int nmatches = 0;
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(f2->n > 0 ? f2->n : 1));
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        if (!valid1[i1]) continue;
+        const int level1 = f1->keys_un[i1].octave;
+        float xc3[3];
+        cv_Rx_plus_t(Tc2w, world1 + 3 * i1, xc3);
+        const float invzc2 = (float)(1.0 / (double)xc3[2]);
+        const float u2 = fx * xc3[0] * invzc2 + cx;
+        const float v2 = fy * xc3[1] * invzc2 + cy;
+        const int nc = orb_oracle_features_in_area(f2, u2, v2, (float)window, level1, level1, cand, f2->n);
+        if (nc == 0) continue;
+        const uint8_t *d1 = f1->desc + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (f2_mp[i2] >= 0) continue;
+            const int dist = orb_oracle_hamming(d1, f2->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if ((float)bestDist <= (float)bestDist2 * nnratio && bestDist <= TH_HIGH) { /* :586 */
+            f2_mp[bestIdx2] = i1;
+            nmatches++;
+        }
+    }
+    free(cand);
+    return nmatches;
+}

@@ -5,8 +5,9 @@
 // (2) one GPU launch computes all 256-bit Hamming distances of the call; (3) replay -- the reference's
 // sequential accept/skip loop runs over those distances, so results (incl. tie-breaks) are unchanged.
 //
-// Implemented: DescriptorDistance and the Frame-level routines of the Tracking thread.
-// Not yet implemented (declared in the header, open work in DESIGN.md): the KeyFrame-level routines
+// Implemented: DescriptorDistance and the Frame-level routines of the Tracking thread; the array-level
+// form of SearchByProjection(Frame,KeyFrame*,...) exists in the C-ABI (orbfe_search_by_projection_kf).
+// Not yet implemented here (declared in the header, open work in DESIGN.md): the KeyFrame-typed routines
 // SearchByProjection(Frame,KeyFrame*), SearchByProjection(KeyFrame*,Scw), SearchByBoW x2,
 // SearchForTriangulation, SearchBySim3, Fuse x2.
 #include "ORBmatcher.h"
@@ -184,48 +185,32 @@ int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Po
 }
 
 // ---- Tracking::SearchReferencePointsInFrustum (Tracking.cc:724) -----------------------------------------
-// queries = local map points with their cached projection; candidates through Frame::GetFeaturesInArea.
 int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th)
 {
-    const bool bFactor = th != 1.0;
     const DescBuf df(F.mDescriptors);
-    std::vector<int> row_ptr(1, 0), cols, qmp;
-    std::vector<unsigned char> qdesc;
-    for (size_t iMP = 0; iMP < vpMapPoints.size(); iMP++) {
-        MapPoint *pMP = vpMapPoints[iMP];
-        if (!pMP->mbTrackInView) continue;
-        if (pMP->isBad()) continue;
-        const int nPredictedLevel = pMP->mnTrackScaleLevel;
-        float r = RadiusByViewingCos(pMP->mTrackViewCos);
-        if (bFactor) r *= th;
-        const std::vector<size_t> vNear = F.GetFeaturesInArea(pMP->mTrackProjX, pMP->mTrackProjY,
-                                                              r * F.mvScaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel);
-        if (vNear.empty()) continue;
+    const OrbfeFrameView fv = make_view(F, df);
+    const int np = (int)vpMapPoints.size();
+    std::vector<unsigned char> in_view(np, 0), desc((size_t)np * 32 + 1, 0);
+    std::vector<float> proj((size_t)np * 2 + 1, 0.f), vcos(np + 1, 0.f);
+    std::vector<int> level(np + 1, 0);
+    for (int i = 0; i < np; i++) {
+        MapPoint *pMP = vpMapPoints[i];
+        if (!pMP->mbTrackInView || pMP->isBad()) continue;  // :57-61
+        in_view[i] = 1;
+        proj[2 * i] = pMP->mTrackProjX; proj[2 * i + 1] = pMP->mTrackProjY;
+        level[i] = pMP->mnTrackScaleLevel;
+        vcos[i] = pMP->mTrackViewCos;
         const cv::Mat d = pMP->GetDescriptor();
-        qdesc.insert(qdesc.end(), d.ptr(0), d.ptr(0) + 32);
-        for (size_t k = 0; k < vNear.size(); k++) cols.push_back((int)vNear[k]);
-        row_ptr.push_back((int)cols.size());
-        qmp.push_back((int)iMP);
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(0), 32);
     }
-    std::vector<unsigned short> dist(cols.size() ? cols.size() : 1);
-    if (!cols.empty())
-        check(orbfe_hamming_csr(thread_matcher(), &qdesc[0], (int)qmp.size(), df.ptr, F.mDescriptors.rows, &row_ptr[0], &cols[0], &dist[0]));
+    std::vector<int> mp(fv.n > 0 ? fv.n : 1, -1);
+    for (int i = 0; i < fv.n; i++)
+        if (F.mvpMapPoints[i]) mp[i] = INT_MAX;
     int nmatches = 0;
-    for (size_t q = 0; q < qmp.size(); q++) {  // :82-121
-        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
-        for (int c = row_ptr[q]; c < row_ptr[q + 1]; c++) {
-            const int idx = cols[c];
-            if (F.mvpMapPoints[idx]) continue;
-            const int d = dist[c];
-            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = F.mvKeysUn[idx].octave; bestIdx = idx; }
-            else if (d < bestDist2) { bestLevel2 = F.mvKeysUn[idx].octave; bestDist2 = d; }
-        }
-        if (bestDist <= TH_HIGH) {
-            if (bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2) continue;
-            F.mvpMapPoints[bestIdx] = vpMapPoints[qmp[q]];
-            nmatches++;
-        }
-    }
+    check(orbfe_search_local_points(thread_matcher(), &fv, np, np ? &in_view[0] : NULL, &proj[0], &level[0], &vcos[0], &desc[0], th,
+                                    mfNNratio, &mp[0], &nmatches));
+    for (int i = 0; i < fv.n; i++)
+        if (mp[i] >= 0 && mp[i] != INT_MAX) F.mvpMapPoints[i] = vpMapPoints[mp[i]];
     return nmatches;
 }
 
@@ -235,50 +220,27 @@ int ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, int windowSize, std::ve
     vpMapPointMatches2 = F2.mvpMapPoints;  // :521
     const std::set<MapPoint *> found(vpMapPointMatches2.begin(), vpMapPointMatches2.end());
     const DescBuf d1(F1.mDescriptors), d2(F2.mDescriptors);
-    std::vector<int> row_ptr(1, 0), cols, q1;
-    for (size_t i1 = 0; i1 < F1.mvpMapPoints.size(); i1++) {
-        MapPoint *pMP1 = F1.mvpMapPoints[i1];
-        if (!pMP1) continue;
-        if (pMP1->isBad() || found.count(pMP1)) continue;
-        const int level1 = F1.mvKeysUn[i1].octave;
-        // x3Dc2 = Rc2w*x3Dw + tc2w: cv::gemm on CV_32F accumulates and adds in double (:540-541)
-        const cv::Mat X = pMP1->GetWorldPos();
-        float xc[3];
-        for (int k = 0; k < 3; k++) {
-            const double s = (double)F2.mTcw.at<float>(k, 0) * (double)X.at<float>(0, 0) + (double)F2.mTcw.at<float>(k, 1) * (double)X.at<float>(1, 0) +
-                             (double)F2.mTcw.at<float>(k, 2) * (double)X.at<float>(2, 0);
-            xc[k] = (float)(s + (double)F2.mTcw.at<float>(k, 3));
-        }
-        const float invz = 1.0 / xc[2];
-        const float u2 = Frame::fx * xc[0] * invz + Frame::cx;
-        const float v2 = Frame::fy * xc[1] * invz + Frame::cy;
-        const std::vector<size_t> vIdx = F2.GetFeaturesInArea(u2, v2, windowSize, level1, level1);
-        if (vIdx.empty()) continue;
-        for (size_t k = 0; k < vIdx.size(); k++) cols.push_back((int)vIdx[k]);
-        row_ptr.push_back((int)cols.size());
-        q1.push_back((int)i1);
+    const OrbfeFrameView v1 = make_view(F1, d1), v2 = make_view(F2, d2);
+    std::vector<unsigned char> valid(v1.n + 1, 0);
+    std::vector<float> world((size_t)v1.n * 3 + 1, 0.f);
+    for (int i1 = 0; i1 < v1.n; i1++) {
+        MapPoint *p = F1.mvpMapPoints[i1];
+        if (!p || p->isBad() || found.count(p)) continue;  // :533-537
+        valid[i1] = 1;
+        const cv::Mat X = p->GetWorldPos();
+        for (int k = 0; k < 3; k++) world[(size_t)i1 * 3 + k] = X.at<float>(k, 0);
     }
-    // distances: queries are rows of F1's descriptor matrix -> gather them contiguously
-    std::vector<unsigned char> qd(q1.size() * 32 + 1);
-    for (size_t q = 0; q < q1.size(); q++) std::memcpy(&qd[q * 32], d1.ptr + (size_t)q1[q] * 32, 32);
-    std::vector<unsigned short> dist(cols.size() ? cols.size() : 1);
-    if (!cols.empty())
-        check(orbfe_hamming_csr(thread_matcher(), &qd[0], (int)q1.size(), d2.ptr, F2.mDescriptors.rows, &row_ptr[0], &cols[0], &dist[0]));
+    float T[12];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[4 * r + c] = F2.mTcw.at<float>(r, c);
+    std::vector<int> mp(v2.n > 0 ? v2.n : 1, -1);
+    for (int i = 0; i < v2.n; i++)
+        if (vpMapPointMatches2[i]) mp[i] = INT_MAX;
     int nmatches = 0;
-    for (size_t q = 0; q < q1.size(); q++) {  // :561-590
-        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
-        for (int c = row_ptr[q]; c < row_ptr[q + 1]; c++) {
-            const int i2 = cols[c];
-            if (vpMapPointMatches2[i2]) continue;
-            const int d = dist[c];
-            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
-            else if (d < bestDist2) bestDist2 = d;
-        }
-        if (static_cast<float>(bestDist) <= static_cast<float>(bestDist2) * mfNNratio && bestDist <= TH_HIGH) {
-            vpMapPointMatches2[bestIdx2] = F1.mvpMapPoints[q1[q]];
-            nmatches++;
-        }
-    }
+    check(orbfe_search_by_projection_f1f2(thread_matcher(), &v1, &v2, &valid[0], &world[0], T, Frame::fx, Frame::fy, Frame::cx,
+                                          Frame::cy, windowSize, mfNNratio, &mp[0], &nmatches));
+    for (int i = 0; i < v2.n; i++)
+        if (mp[i] >= 0 && mp[i] != INT_MAX) vpMapPointMatches2[i] = F1.mvpMapPoints[mp[i]];
     return nmatches;
 }
 

@@ -382,3 +382,157 @@ extern "C" void orbfe_frame_scale_factors(float scale_factor, int nlevels, float
     out[0] = 1.0f;
     for (int i = 1; i < nlevels; i++) out[i] = out[i - 1] * scale_factor;
 }
+
+// ================================================================================================
+// Generic guided search: the common skeleton of ORBmatcher's projection/window routines.
+//   for each query q (ascending): candidates = GetFeaturesInArea(u_q, v_q, r_q, lo_q, hi_q) on frame `f`;
+//   best (and second best) distance over the candidates whose slot is still free; accept by `rule`;
+//   optional rotation histogram.  Candidate lists on the host, ALL distances in one GPU launch, replay on the host.
+// rule 0: best <= th_dist                                   (ORBmatcher.cc:1576, :1693)
+// rule 1: best <= second*nnratio && best <= TH_HIGH          (:469, :586)
+// rule 2: best <= TH_HIGH && !(bestLevel==secondLevel && best > nnratio*second)   (:113-121)
+// hist 0: none; 1: push + filter (checkOrientation); 2: push only
+// ================================================================================================
+namespace {
+
+struct GuidedQuery { float u, v, r; int lo, hi; const uint8_t *desc; float angle; };
+
+int guided_search(OrbfeMatcher *m, const OrbfeFrameView &f, const std::vector<GuidedQuery> &Q, int rule, float nnratio,
+                  int th_dist, int hist_mode, int *slot_owner, const std::vector<int> &owner_id, int *nmatches_out) {
+    std::vector<Job> jobs(1);
+    Job &J = jobs[0];
+    build_grid(f, J.grid);
+    J.row_ptr.push_back(0);
+    std::vector<uint8_t> qd;
+    for (size_t q = 0; q < Q.size(); q++) {
+        const size_t before = J.cols.size();
+        features_in_area(f, J.grid, Q[q].u, Q[q].v, Q[q].r, Q[q].lo, Q[q].hi, J.cols);
+        if (J.cols.size() == before) continue;
+        J.qidx.push_back((int)q);
+        J.row_ptr.push_back((int)J.cols.size());
+        qd.insert(qd.end(), Q[q].desc, Q[q].desc + 32);
+    }
+    std::vector<uint16_t> dist(std::max<size_t>(J.cols.size(), 1));
+    if (!J.cols.empty()) {
+        const int rc = orbfe_hamming_csr(m, qd.data(), (int)J.qidx.size(), f.desc, f.n, J.row_ptr.data(), J.cols.data(), dist.data());
+        if (rc) return rc;
+    }
+    int nmatches = 0;
+    std::vector<int> rotHist[kHisto];
+    for (size_t k = 0; k < J.qidx.size(); k++) {
+        const int q = J.qidx[k];
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx = -1, bestLevel = -1, bestLevel2 = -1;
+        for (int c = J.row_ptr[k]; c < J.row_ptr[k + 1]; c++) {
+            const int i2 = J.cols[c];
+            if (slot_owner[i2] >= 0) continue;
+            const int d = dist[c];
+            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = f.keys_un[i2].octave; bestIdx = i2; }
+            else if (d < bestDist2) { bestLevel2 = f.keys_un[i2].octave; bestDist2 = d; }
+        }
+        bool accept;
+        if (rule == 0) accept = bestDist <= th_dist;
+        else if (rule == 1) accept = (float)bestDist <= (float)bestDist2 * nnratio && bestDist <= kThHigh;
+        else accept = bestDist <= kThHigh && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2);
+        if (!accept) continue;
+        slot_owner[bestIdx] = owner_id[q];
+        nmatches++;
+        if (hist_mode) rotHist[rot_bin(Q[q].angle, f.keys_un[bestIdx].angle)].push_back(bestIdx);
+    }
+    if (hist_mode == 1) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, kHisto, i1, i2, i3);
+        for (int b = 0; b < kHisto; b++) {
+            if (b == i1 || b == i2 || b == i3) continue;
+            for (int idx : rotHist[b]) { slot_owner[idx] = -1; nmatches--; }
+        }
+    }
+    *nmatches_out = nmatches;
+    return ORBFE_OK;
+}
+
+// cv::Mat float algebra of the reference's projections (OpenCV 2.4 gemm on CV_32F accumulates in double)
+inline void Rx_plus_t(const float *T, const float *X, float out[3]) {
+    for (int k = 0; k < 3; k++) {
+        const double s = (double)T[4 * k] * (double)X[0] + (double)T[4 * k + 1] * (double)X[1] + (double)T[4 * k + 2] * (double)X[2];
+        out[k] = (float)(s + (double)T[4 * k + 3]);
+    }
+}
+
+}  // namespace
+
+// SearchByProjection(Frame &F, const vector<MapPoint*>&, th), ORBmatcher.cc:49-125
+extern "C" int orbfe_search_local_points(OrbfeMatcher *m, const OrbfeFrameView *f, int npts, const uint8_t *in_view,
+                                         const float *proj_xy, const int *level, const float *view_cos, const uint8_t *desc,
+                                         float th, float nnratio, int *f_mp_inout, int *nmatches_out) {
+    if (!m || !f || npts < 0 || !f_mp_inout || !nmatches_out || (npts > 0 && (!in_view || !proj_xy || !level || !view_cos || !desc)))
+        return ORBFE_ERR_ARG;
+    const bool bFactor = th != 1.0f;
+    std::vector<GuidedQuery> Q;
+    std::vector<int> id;
+    for (int i = 0; i < npts; i++) {
+        if (!in_view[i]) continue;
+        float r = view_cos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos :127-133
+        if (bFactor) r *= th;
+        const int lv = level[i];
+        Q.push_back({proj_xy[2 * i], proj_xy[2 * i + 1], r * f->scale_factors[lv], lv - 1, lv, desc + (size_t)i * 32, 0.f});
+        id.push_back(i);
+    }
+    std::vector<int> owner(Q.size());
+    for (size_t q = 0; q < Q.size(); q++) owner[q] = id[q];
+    return guided_search(m, *f, Q, 2, nnratio, kThHigh, 0, f_mp_inout, owner, nmatches_out);
+}
+
+// SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist), ORBmatcher.cc:1622-1746
+extern "C" int orbfe_search_by_projection_kf(OrbfeMatcher *m, const OrbfeFrameView *cur, int npts, const uint8_t *valid,
+                                             const float *world, const float *min_dist, const uint8_t *desc,
+                                             const float *kf_angle, const float *Tcw, float fx, float fy, float cx, float cy,
+                                             float th, int orb_dist, int check_orientation, int *cur_mp_inout, int *nmatches_out) {
+    if (!m || !cur || npts < 0 || !Tcw || !cur_mp_inout || !nmatches_out ||
+        (npts > 0 && (!valid || !world || !min_dist || !desc || !kf_angle)))
+        return ORBFE_ERR_ARG;
+    float Ow[3];  // Ow = -Rcw.t()*tcw (:1628): gemm, double accumulation, alpha = -1
+    for (int k = 0; k < 3; k++) {
+        const double s = (double)Tcw[k] * (double)Tcw[3] + (double)Tcw[4 + k] * (double)Tcw[7] + (double)Tcw[8 + k] * (double)Tcw[11];
+        Ow[k] = (float)(s * -1.0);
+    }
+    std::vector<GuidedQuery> Q;
+    std::vector<int> id;
+    for (int i = 0; i < npts; i++) {
+        if (!valid[i]) continue;
+        const float *X = world + 3 * (size_t)i;
+        float xc[3];
+        Rx_plus_t(Tcw, X, xc);
+        const float invzc = (float)(1.0 / (double)xc[2]);
+        const float u = fx * xc[0] * invzc + cx, v = fy * xc[1] * invzc + cy;
+        if (u < cur->min_x || u > cur->max_x) continue;
+        if (v < cur->min_y || v > cur->max_y) continue;
+        const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+        const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);  // cv::norm
+        const float ratio = dist3D / min_dist[i];
+        const float *sf = cur->scale_factors;
+        const int it = (int)(std::lower_bound(sf, sf + cur->nlevels, ratio) - sf);
+        const int lv = std::min(it, cur->nlevels - 1);
+        Q.push_back({u, v, th * sf[lv], lv - 1, lv + 1, desc + (size_t)i * 32, kf_angle[i]});
+        id.push_back(i);
+    }
+    return guided_search(m, *cur, Q, 0, 0.f, orb_dist, check_orientation ? 1 : 0, cur_mp_inout, id, nmatches_out);
+}
+
+// SearchByProjection(Frame &F1, Frame &F2, int windowSize, vpMapPointMatches2), ORBmatcher.cc:519-594
+extern "C" int orbfe_search_by_projection_f1f2(OrbfeMatcher *m, const OrbfeFrameView *f1, const OrbfeFrameView *f2,
+                                               const uint8_t *valid1, const float *world1, const float *Tc2w, float fx, float fy,
+                                               float cx, float cy, int window, float nnratio, int *f2_mp_inout, int *nmatches_out) {
+    if (!m || !f1 || !f2 || !Tc2w || !f2_mp_inout || !nmatches_out || (f1->n > 0 && (!valid1 || !world1))) return ORBFE_ERR_ARG;
+    std::vector<GuidedQuery> Q;
+    std::vector<int> id;
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        if (!valid1[i1]) continue;
+        const int level1 = f1->keys_un[i1].octave;
+        float xc[3];
+        Rx_plus_t(Tc2w, world1 + 3 * (size_t)i1, xc);
+        const float invz = (float)(1.0 / (double)xc[2]);
+        Q.push_back({fx * xc[0] * invz + cx, fy * xc[1] * invz + cy, (float)window, level1, level1, f1->desc + (size_t)i1 * 32, 0.f});
+        id.push_back(i1);
+    }
+    return guided_search(m, *f2, Q, 1, nnratio, kThHigh, 0, f2_mp_inout, id, nmatches_out);
+}

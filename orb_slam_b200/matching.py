@@ -37,6 +37,11 @@ def _bind():
     L.orbfe_search_by_projection_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp,
                                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp]
+    L.orbfe_search_local_points.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]
+    L.orbfe_search_by_projection_kf.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float,
+                                                C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
+    L.orbfe_search_by_projection_f1f2.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                                  C.c_float, vp, vp]
     L.orbfe_window_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
     _bound = True
@@ -127,3 +132,41 @@ def search_by_projection_device(matcher: ORBmatcher, npairs, d_kps, d_desc, d_co
                                                0.0, 0.0, float(width), float(height), scale_factor, nlevels,
                                                fx, fy, cx, cy, th, int(matcher.mbCheckOrientation), vp(d_cur_mp),
                                                vp(d_nmatches), vp(stream)))
+
+
+def search_local_points(matcher: ORBmatcher, f, in_view, proj_xy, level, view_cos, desc, th, f_mp=None):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) on arrays (ORBmatcher.cc:49-125)."""
+    L = _bind()
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    in_view, proj_xy, level, view_cos, desc = a(in_view, np.uint8), a(proj_xy, np.float32), a(level, np.int32), a(view_cos, np.float32), a(desc, np.uint8)
+    mp = np.full(max(f.n, 1), -1, np.int32) if f_mp is None else a(f_mp, np.int32).copy()
+    nm = C.c_int(0)
+    _check(L.orbfe_search_local_points(matcher.handle, C.byref(f.c), len(in_view), _p(in_view), _p(proj_xy), _p(level), _p(view_cos),
+                                       _p(desc), th, float(matcher.mfNNratio), _p(mp), C.byref(nm)))
+    return nm.value, mp[:f.n]
+
+
+def search_by_projection_kf(matcher: ORBmatcher, cur, valid, world, min_dist, desc, kf_angle, Tcw, fx, fy, cx, cy, th, orb_dist,
+                            cur_mp=None):
+    """ORBmatcher::SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) on arrays (ORBmatcher.cc:1622-1746)."""
+    L = _bind()
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    valid, world, min_dist, desc, kf_angle, Tcw = a(valid, np.uint8), a(world, np.float32), a(min_dist, np.float32), a(desc, np.uint8), a(kf_angle, np.float32), a(Tcw, np.float32)
+    mp = np.full(max(cur.n, 1), -1, np.int32) if cur_mp is None else a(cur_mp, np.int32).copy()
+    nm = C.c_int(0)
+    _check(L.orbfe_search_by_projection_kf(matcher.handle, C.byref(cur.c), len(valid), _p(valid), _p(world), _p(min_dist), _p(desc),
+                                           _p(kf_angle), _p(Tcw), fx, fy, cx, cy, th, orb_dist, int(matcher.mbCheckOrientation),
+                                           _p(mp), C.byref(nm)))
+    return nm.value, mp[:cur.n]
+
+
+def search_by_projection_f1f2(matcher: ORBmatcher, f1, f2, valid1, world1, Tc2w, fx, fy, cx, cy, window, f2_mp=None):
+    """ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, windowSize, matches2) on arrays (ORBmatcher.cc:519-594)."""
+    L = _bind()
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    valid1, world1, Tc2w = a(valid1, np.uint8), a(world1, np.float32), a(Tc2w, np.float32)
+    mp = np.full(max(f2.n, 1), -1, np.int32) if f2_mp is None else a(f2_mp, np.int32).copy()
+    nm = C.c_int(0)
+    _check(L.orbfe_search_by_projection_f1f2(matcher.handle, C.byref(f1.c), C.byref(f2.c), _p(valid1), _p(world1), _p(Tc2w), fx, fy,
+                                             cx, cy, window, float(matcher.mfNNratio), _p(mp), C.byref(nm)))
+    return nm.value, mp[:f2.n]

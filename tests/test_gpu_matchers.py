@@ -169,3 +169,54 @@ def test_device_resident_search_by_projection(gpu_required):
         assert nm2[j] == n_o and np.array_equal(mp2[j, :nc], mp_o)
     m.close()
     m2.close()
+
+
+def test_local_points_reloc_and_f1f2_projection(gpu_required):
+    """M3 (local-map points), M4 (Frame vs KeyFrame, relocalisation) and M6 (F1->F2 projection window): array-level
+    C-ABI (host candidates + device distances + host replay) against the oracle's restatement."""
+    feats, shifts = _features(2)
+    (k1, d1), (k2, d2) = feats
+    n1 = len(k1)
+    rng = np.random.default_rng(5)
+    f2v, o2 = M.FrameView(k2, d2, W, H), O.OracleFrame(k2, d2, W, H)
+    f1v, o1 = M.FrameView(k1, d1, W, H), O.OracleFrame(k1, d1, W, H)
+    dx, dy = shifts[1]
+    occupied = np.full(len(k2), -1, np.int32)
+    occupied[rng.random(len(k2)) < 0.03] = 3
+
+    # ---- M3: map points with cached projections (Frame::isInFrustum fills them) ----
+    in_view = (rng.random(n1) < 0.9).astype(np.uint8)
+    proj = np.stack([k1["x"] + np.float32(dx) + rng.normal(0, 1.0, n1).astype(np.float32),
+                     k1["y"] + np.float32(dy) + rng.normal(0, 1.0, n1).astype(np.float32)], axis=1).astype(np.float32)
+    level = k1["octave"].astype(np.int32)
+    view_cos = np.where(rng.random(n1) < 0.5, 0.9995, 0.95).astype(np.float32)
+    for th, nnr in ((1.0, 0.8), (3.0, 0.8), (5.0, 0.6)):
+        m = fe.ORBmatcher(nnr, True)
+        n, mp = M.search_local_points(m, f2v, in_view, proj, level, view_cos, d1, th, f_mp=occupied)
+        n_o, mp_o = O.search_local_points(o2, in_view, proj, level, view_cos, d1, th, nnratio=nnr, f_mp=occupied)
+        assert n == n_o and np.array_equal(mp, mp_o)
+        m.close()
+    assert n > 200
+
+    # ---- M4: keyframe map points projected with the current pose, predicted level from the distance ----
+    world = _world(k1)
+    min_dist = (DEPTH / np.float32(1.2) ** k1["octave"].astype(np.float32) * rng.uniform(0.8, 1.1, n1)).astype(np.float32)
+    valid = (rng.random(n1) < 0.85).astype(np.uint8)
+    T = _tcw(dx, dy)
+    T[2, 3] = 0.3  # a little forward motion so that predicted levels vary
+    for th, od, ori in ((10.0, 100, True), (3.0, 64, True), (10.0, 100, False)):
+        m = fe.ORBmatcher(0.9, ori)
+        n, mp = M.search_by_projection_kf(m, f2v, valid, world, min_dist, d1, k1["angle"], T, FX, FY, CX, CY, th, od, cur_mp=occupied)
+        n_o, mp_o = O.search_by_projection_kf(o2, valid, world, min_dist, d1, k1["angle"], T, FX, FY, CX, CY, th, od, ori, cur_mp=occupied)
+        assert n == n_o and np.array_equal(mp, mp_o)
+        m.close()
+
+    # ---- M6: F1 map points projected into F2 with F2's pose, same-octave window ----
+    T2 = _tcw(dx, dy)
+    for win, nnr in ((15, 0.9), (50, 0.7)):
+        m = fe.ORBmatcher(nnr, True)
+        n, mp = M.search_by_projection_f1f2(m, f1v, f2v, valid, world, T2, FX, FY, CX, CY, win, f2_mp=occupied)
+        n_o, mp_o = O.search_by_projection_f1f2(o1, o2, valid, world, T2, FX, FY, CX, CY, win, nnratio=nnr, f2_mp=occupied)
+        assert n == n_o and np.array_equal(mp, mp_o)
+        m.close()
+    assert n > 100
