@@ -90,6 +90,17 @@ int orbfe_search_by_projection_f1f2(OrbfeMatcher *m, const OrbfeFrameView *f1, c
                                     const float *world1, const float *Tc2w, float fx, float fy, float cx, float cy, int window,
                                     float nnratio, int *f2_mp_inout, int *nmatches_out);
 
+/* int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches) (variant 0, ORBmatcher.cc:155-284) and
+ * SearchByBoW(KeyFrame*, KeyFrame*, matches12) (variant 1, :715-850): brute force inside equal vocabulary nodes.
+ * A DBoW2::FeatureVector is passed as ascending node ids + CSR (ptr, items = feature indices in insertion order).
+ * valid1[i] / valid2[i]: the feature has a map point that is not bad (valid2 is ignored by variant 0).
+ * angle1 / angle2: mvKeysUn[i].angle of each side.  variant 0: out has n2 entries, out[i2] = matched side-1 index;
+ * variant 1: out has n1 entries, out[i1] = matched side-2 index; -1 = no match. */
+int orbfe_search_by_bow(OrbfeMatcher *m, int variant, int n1, const uint8_t *desc1, const uint8_t *valid1, const float *angle1,
+                        int nn1, const int32_t *ids1, const int32_t *ptr1, const int32_t *items1, int n2, const uint8_t *desc2,
+                        const uint8_t *valid2, const float *angle2, int nn2, const int32_t *ids2, const int32_t *ptr2,
+                        const int32_t *items2, float nnratio, int check_orientation, int32_t *out, int *nmatches_out);
+
 /* int ORBmatcher::WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minOctave, maxOctave)
  * (ORBmatcher.cc:409-516).  f1_has_mp[i1] != 0 <=> F1.mvpMapPoints[i1] && !isBad().
  * match21_out[i2] = i1 whose map point was matched to F2 feature i2, or -1. */

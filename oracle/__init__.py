@@ -111,6 +111,8 @@ def lib():
                                                          C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, i32p]
         L.orb_oracle_search_by_projection_f1f2.argtypes = [C.POINTER(Frame), C.POINTER(Frame), u8p, f32p, f32p, C.c_float, C.c_float,
                                                            C.c_float, C.c_float, C.c_int, C.c_float, i32p]
+        L.orb_oracle_search_by_bow.argtypes = [C.c_int, C.c_int, u8p, u8p, f32p, C.c_int, i32p, i32p, i32p, C.c_int, u8p, u8p, f32p,
+                                               C.c_int, i32p, i32p, i32p, C.c_float, C.c_int, i32p]
         L.orb_oracle_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p, i32p]
         L.orb_oracle_knn2.restype = None
         _lib = L
@@ -344,3 +346,16 @@ def search_by_projection_f1f2(f1, f2, valid1, world1, Tc2w, fx, fy, cx, cy, wind
     v, w, T = _a(valid1, np.uint8), _a(world1, np.float32), _a(Tc2w, np.float32)
     n = lib().orb_oracle_search_by_projection_f1f2(C.byref(f1.c), C.byref(f2.c), _p(v), _p(w), _p(T), fx, fy, cx, cy, window, nnratio, _p(mp))
     return n, mp[:f2.n]
+
+
+def search_by_bow(variant, desc1, valid1, angle1, fv1, desc2, valid2, angle2, fv2, nnratio=0.75, check_orientation=True):
+    desc1, desc2 = _a(desc1, np.uint8), _a(desc2, np.uint8)
+    valid1, valid2, angle1, angle2 = _a(valid1, np.uint8), _a(valid2, np.uint8), _a(angle1, np.float32), _a(angle2, np.float32)
+    i1, p1, t1 = [_a(x, np.int32) for x in fv1]
+    i2, p2, t2 = [_a(x, np.int32) for x in fv2]
+    n1, n2 = desc1.shape[0], desc2.shape[0]
+    out = np.full(max(n2 if variant == 0 else n1, 1), -1, np.int32)
+    n = lib().orb_oracle_search_by_bow(variant, n1, _p(desc1), _p(valid1), _p(angle1), len(i1), _p(i1), _p(p1), _p(t1),
+                                       n2, _p(desc2), _p(valid2), _p(angle2), len(i2), _p(i2), _p(p2), _p(t2),
+                                       nnratio, int(check_orientation), _p(out))
+    return n, out[:(n2 if variant == 0 else n1)]

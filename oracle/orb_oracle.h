@@ -183,6 +183,12 @@ int orb_oracle_search_by_projection_kf(const OrbOracleFrame *cur, int npts, cons
 int orb_oracle_search_by_projection_f1f2(const OrbOracleFrame *f1, const OrbOracleFrame *f2, const uint8_t *valid1,
                                          const float *world1, const float *Tc2w, float fx, float fy, float cx, float cy,
                                          int window, float nnratio, int *f2_mp);
+/* SearchByBoW, ORBmatcher.cc:155-284 (variant 0: KeyFrame vs Frame) and :715-850 (variant 1: KeyFrame vs KeyFrame) */
+int orb_oracle_search_by_bow(int variant, int n1, const uint8_t *desc1, const uint8_t *valid1, const float *angle1,
+                             int nn1, const int *ids1, const int *ptr1, const int *items1,
+                             int n2, const uint8_t *desc2, const uint8_t *valid2, const float *angle2,
+                             int nn2, const int *ids2, const int *ptr2, const int *items2,
+                             float nnratio, int check_orientation, int *out);
 /* brute-force best/second-best of each query against a database (BASELINE config 5 primitive;
  * same strict-< update rule as every best/second loop in ORBmatcher.cc, e.g. :456-466) */
 void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,

@@ -485,3 +485,68 @@ int orb_oracle_search_by_projection_f1f2(const OrbOracleFrame *f1, const OrbOrac
     free(cand);
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * SearchByBoW -- brute force restricted to features of the same vocabulary node.
+ * A DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) is given as: ascending node ids, CSR pointer,
+ * feature indices in insertion order.
+ * variant 0: SearchByBoW(KeyFrame*, Frame&, matches)   ORBmatcher.cc:155-284   (out[i2] = idx1, F slots)
+ * variant 1: SearchByBoW(KeyFrame*, KeyFrame*, matches12) ORBmatcher.cc:715-850 (out[idx1] = idx2)
+ * valid1[i] = KF1 feature has a map point && !isBad(); valid2 likewise (variant 1 only; variant 0 ignores it).
+ * ---------------------------------------------------------------------------------------------- */
+int orb_oracle_search_by_bow(int variant, int n1, const uint8_t *desc1, const uint8_t *valid1, const float *angle1,
+                             int nn1, const int *ids1, const int *ptr1, const int *items1,
+                             int n2, const uint8_t *desc2, const uint8_t *valid2, const float *angle2,
+                             int nn2, const int *ids2, const int *ptr2, const int *items2,
+                             float nnratio, int check_orientation, int *out) {
+    int nmatches = 0;
+    const int nout = variant == 0 ? n2 : n1;
+    for (int i = 0; i < nout; i++) out[i] = -1;
+    uint8_t *matched2 = (uint8_t *)calloc((size_t)(n2 > 0 ? n2 : 1), 1);
+    IVec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int p1 = ptr1[a]; p1 < ptr1[a + 1]; p1++) {
+                const int idx1 = items1[p1];
+                if (!valid1[idx1]) continue;
+                const uint8_t *d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist1 = INT_MAX, bestIdx2 = -1, bestDist2 = INT_MAX;
+                for (int p2 = ptr2[b]; p2 < ptr2[b + 1]; p2++) {
+                    const int idx2 = items2[p2];
+                    if (variant == 0) { if (out[idx2] >= 0) continue; }          /* :204 */
+                    else { if (matched2[idx2] || !valid2[idx2]) continue; }      /* :773-778 */
+                    const int dist = orb_oracle_hamming(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                const int pass = variant == 0 ? (bestDist1 <= TH_LOW) : (bestDist1 < TH_LOW); /* :224 vs :797 */
+                if (pass && (float)bestDist1 < nnratio * (float)bestDist2) {
+                    if (variant == 0) out[bestIdx2] = idx1;
+                    else { out[idx1] = bestIdx2; matched2[bestIdx2] = 1; }
+                    if (check_orientation)
+                        ivec_push(&hist[rot_bin(angle1[idx1], angle2[bestIdx2])], variant == 0 ? bestIdx2 : idx1);
+                    nmatches++;
+                }
+            }
+            a++; b++;
+        } else if (ids1[a] < ids2[b]) {
+            while (a < nn1 && ids1[a] < ids2[b]) a++;   /* lower_bound */
+        } else {
+            while (b < nn2 && ids2[b] < ids1[a]) b++;
+        }
+    }
+    if (check_orientation) {
+        int counts[HISTO_LENGTH], i1, i2, i3;
+        for (int k = 0; k < HISTO_LENGTH; k++) counts[k] = hist[k].n;
+        orb_oracle_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int k = 0; k < HISTO_LENGTH; k++) {
+            if (k == i1 || k == i2 || k == i3) continue;
+            for (int j = 0; j < hist[k].n; j++) { out[hist[k].v[j]] = -1; nmatches--; }
+        }
+    }
+    for (int k = 0; k < HISTO_LENGTH; k++) free(hist[k].v);
+    free(matched2);
+    return nmatches;
+}

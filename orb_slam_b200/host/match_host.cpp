@@ -536,3 +536,85 @@ extern "C" int orbfe_search_by_projection_f1f2(OrbfeMatcher *m, const OrbfeFrame
     }
     return guided_search(m, *f2, Q, 1, nnratio, kThHigh, 0, f2_mp_inout, id, nmatches_out);
 }
+
+// ================================================================================================
+// SearchByBoW (both overloads): brute force inside equal vocabulary nodes.  The merge-walk over the two
+// FeatureVectors builds one CSR row per valid keyframe-1 feature (candidates = the other side's features of
+// the same node, in list order); all distances in one launch; the accept loop is replayed on the host.
+// variant 0: SearchByBoW(KeyFrame*, Frame&, ...)  ORBmatcher.cc:155-284;  variant 1: (KeyFrame*, KeyFrame*, ...) :715-850
+// ================================================================================================
+extern "C" int orbfe_search_by_bow(OrbfeMatcher *m, int variant, int n1, const uint8_t *desc1, const uint8_t *valid1,
+                                   const float *angle1, int nn1, const int32_t *ids1, const int32_t *ptr1, const int32_t *items1,
+                                   int n2, const uint8_t *desc2, const uint8_t *valid2, const float *angle2, int nn2,
+                                   const int32_t *ids2, const int32_t *ptr2, const int32_t *items2, float nnratio,
+                                   int check_orientation, int32_t *out, int *nmatches_out) {
+    if (!m || (variant != 0 && variant != 1) || n1 < 0 || n2 < 0 || nn1 < 0 || nn2 < 0 || !out || !nmatches_out) return ORBFE_ERR_ARG;
+    if ((n1 > 0 && (!desc1 || !valid1 || !angle1)) || (n2 > 0 && (!desc2 || !angle2 || (variant == 1 && !valid2)))) return ORBFE_ERR_ARG;
+    if ((nn1 > 0 && (!ids1 || !ptr1 || !items1)) || (nn2 > 0 && (!ids2 || !ptr2 || !items2))) return ORBFE_ERR_ARG;
+    const int nout = variant == 0 ? n2 : n1;
+    for (int i = 0; i < nout; i++) out[i] = -1;
+    // gather
+    std::vector<int32_t> row_ptr(1, 0), cols, q1;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int p1 = ptr1[a]; p1 < ptr1[a + 1]; p1++) {
+                const int idx1 = items1[p1];
+                if (idx1 < 0 || idx1 >= n1) return ORBFE_ERR_ARG;
+                if (!valid1[idx1]) continue;
+                if (ptr2[b + 1] == ptr2[b]) { q1.push_back(idx1); row_ptr.push_back((int32_t)cols.size()); continue; }
+                for (int p2 = ptr2[b]; p2 < ptr2[b + 1]; p2++) {
+                    if (items2[p2] < 0 || items2[p2] >= n2) return ORBFE_ERR_ARG;
+                    cols.push_back(items2[p2]);
+                }
+                q1.push_back(idx1);
+                row_ptr.push_back((int32_t)cols.size());
+            }
+            a++; b++;
+        } else if (ids1[a] < ids2[b]) {
+            a = (int)(std::lower_bound(ids1 + a, ids1 + nn1, ids2[b]) - ids1);
+        } else {
+            b = (int)(std::lower_bound(ids2 + b, ids2 + nn2, ids1[a]) - ids2);
+        }
+    }
+    std::vector<uint8_t> qd(q1.size() * 32 + 1);
+    for (size_t k = 0; k < q1.size(); k++) memcpy(&qd[k * 32], desc1 + (size_t)q1[k] * 32, 32);
+    std::vector<uint16_t> dist(std::max<size_t>(cols.size(), 1));
+    if (!cols.empty()) {
+        const int rc = orbfe_hamming_csr(m, qd.data(), (int)q1.size(), desc2, n2, row_ptr.data(), cols.data(), dist.data());
+        if (rc) return rc;
+    }
+    // replay
+    std::vector<uint8_t> matched2(std::max(n2, 1), 0);
+    std::vector<int> rotHist[kHisto];
+    int nmatches = 0;
+    for (size_t k = 0; k < q1.size(); k++) {
+        const int idx1 = q1[k];
+        int bestDist1 = INT_MAX, bestIdx2 = -1, bestDist2 = INT_MAX;
+        for (int c = row_ptr[k]; c < row_ptr[k + 1]; c++) {
+            const int idx2 = cols[c];
+            if (variant == 0) { if (out[idx2] >= 0) continue; }
+            else { if (matched2[idx2] || !valid2[idx2]) continue; }
+            const int d = dist[c];
+            if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdx2 = idx2; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        const bool pass = variant == 0 ? (bestDist1 <= kThLow) : (bestDist1 < kThLow);
+        if (pass && (float)bestDist1 < nnratio * (float)bestDist2) {
+            if (variant == 0) out[bestIdx2] = idx1;
+            else { out[idx1] = bestIdx2; matched2[bestIdx2] = 1; }
+            if (check_orientation) rotHist[rot_bin(angle1[idx1], angle2[bestIdx2])].push_back(variant == 0 ? bestIdx2 : idx1);
+            nmatches++;
+        }
+    }
+    if (check_orientation) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, kHisto, i1, i2, i3);
+        for (int k = 0; k < kHisto; k++) {
+            if (k == i1 || k == i2 || k == i3) continue;
+            for (int idx : rotHist[k]) { out[idx] = -1; nmatches--; }
+        }
+    }
+    *nmatches_out = nmatches;
+    return ORBFE_OK;
+}

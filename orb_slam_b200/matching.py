@@ -42,6 +42,8 @@ def _bind():
                                                 C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
     L.orbfe_search_by_projection_f1f2.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                                   C.c_float, vp, vp]
+    L.orbfe_search_by_bow.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
+                                      C.c_float, C.c_int, vp, vp]
     L.orbfe_window_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
     _bound = True
@@ -170,3 +172,30 @@ def search_by_projection_f1f2(matcher: ORBmatcher, f1, f2, valid1, world1, Tc2w,
     _check(L.orbfe_search_by_projection_f1f2(matcher.handle, C.byref(f1.c), C.byref(f2.c), _p(valid1), _p(world1), _p(Tc2w), fx, fy,
                                              cx, cy, window, float(matcher.mfNNratio), _p(mp), C.byref(nm)))
     return nm.value, mp[:f2.n]
+
+
+def feature_vector(node_of_feature):
+    """DBoW2::FeatureVector of a frame as (ids, ptr, items): ascending node ids, features in index order inside a node."""
+    node_of_feature = np.asarray(node_of_feature)
+    order = np.argsort(node_of_feature, kind="stable")
+    ids, counts = np.unique(node_of_feature, return_counts=True)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return ids.astype(np.int32), ptr, order.astype(np.int32)
+
+
+def search_by_bow(matcher: ORBmatcher, variant, desc1, valid1, angle1, fv1, desc2, valid2, angle2, fv2):
+    """ORBmatcher::SearchByBoW on arrays (variant 0: KeyFrame vs Frame, 1: KeyFrame vs KeyFrame)."""
+    L = _bind()
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    desc1, desc2 = a(desc1, np.uint8), a(desc2, np.uint8)
+    valid1, valid2 = a(valid1, np.uint8), a(valid2, np.uint8)
+    angle1, angle2 = a(angle1, np.float32), a(angle2, np.float32)
+    i1, p1, t1 = [a(x, np.int32) for x in fv1]
+    i2, p2, t2 = [a(x, np.int32) for x in fv2]
+    n1, n2 = desc1.shape[0], desc2.shape[0]
+    out = np.full(max(n2 if variant == 0 else n1, 1), -1, np.int32)
+    nm = C.c_int(0)
+    _check(L.orbfe_search_by_bow(matcher.handle, variant, n1, _p(desc1), _p(valid1), _p(angle1), len(i1), _p(i1), _p(p1), _p(t1),
+                                 n2, _p(desc2), _p(valid2), _p(angle2), len(i2), _p(i2), _p(p2), _p(t2),
+                                 float(matcher.mfNNratio), int(matcher.mbCheckOrientation), _p(out), C.byref(nm)))
+    return nm.value, out[:(n2 if variant == 0 else n1)]

@@ -220,3 +220,31 @@ def test_local_points_reloc_and_f1f2_projection(gpu_required):
         assert n == n_o and np.array_equal(mp, mp_o)
         m.close()
     assert n > 100
+
+
+def test_search_by_bow_both_overloads(gpu_required):
+    """M9: brute force inside equal vocabulary nodes (FeatureVectors as CSR), both overloads, against the oracle."""
+    rng = np.random.default_rng(21)
+    n1, n2 = 1500, 1400
+    d1 = M.np.zeros((0, 32), np.uint8)
+    from orb_slam_b200.synth import random_descriptors, noisy_copies
+    d1 = random_descriptors(n1, 5)
+    perm = rng.permutation(n1)[:n2]
+    d2 = noisy_copies(d1[perm], 0.05, 6)
+    a1 = rng.uniform(0, 360, n1).astype(np.float32)
+    a2 = ((a1[perm] + rng.normal(7, 4, n2)) % 360).astype(np.float32)
+    # vocabulary node of a feature: a coarse function of a few descriptor bits (noisy copies mostly land in the same node)
+    node1 = (d1[:, 0].astype(np.int32) >> 3) * 3 + 11
+    node2 = (d2[:, 0].astype(np.int32) >> 3) * 3 + 11
+    node2[rng.random(n2) < 0.05] = 9999  # a node that only one side has
+    fv1, fv2 = M.feature_vector(node1), M.feature_vector(node2)
+    valid1 = (rng.random(n1) < 0.8).astype(np.uint8)
+    valid2 = (rng.random(n2) < 0.9).astype(np.uint8)
+    for variant in (0, 1):
+        for nnr, ori in ((0.75, True), (0.6, False)):
+            m = fe.ORBmatcher(nnr, ori)
+            n, out = M.search_by_bow(m, variant, d1, valid1, a1, fv1, d2, valid2, a2, fv2)
+            n_o, out_o = O.search_by_bow(variant, d1, valid1, a1, fv1, d2, valid2, a2, fv2, nnratio=nnr, check_orientation=ori)
+            assert n == n_o and np.array_equal(out, out_o), (variant, nnr, ori)
+            assert n > 300
+            m.close()
