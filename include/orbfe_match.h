@@ -90,6 +90,17 @@ int orbfe_search_by_projection_f1f2(OrbfeMatcher *m, const OrbfeFrameView *f1, c
                                     const float *world1, const float *Tc2w, float fx, float fy, float cx, float cy, int window,
                                     float nnratio, int *f2_mp_inout, int *nmatches_out);
 
+/* The skeleton shared by ORBmatcher's projection routines, for callers that project themselves (the facade's
+ * KeyFrame-level methods: SearchByProjection(KeyFrame*,Scw,...) :286-407, SearchBySim3 :1267-1505, Fuse :1016-1265).
+ * Query q searches window (qu,qv) +- qr with octave filter [qlo,qhi] (-1,-1 = none, like KeyFrame::GetFeaturesInArea)
+ * among the features of `f` whose slot is still free; rule 0: best <= th_dist; rule 1: best <= second*nnratio and best <=
+ * TH_HIGH; rule 2: best <= TH_HIGH unless best and second are on the same level and best > nnratio*second.
+ * hist_mode 0: none, 1: rotation histogram + three-maxima filter (qangle needed), 2: filled but not applied.
+ * slot_owner_inout[i2] >= 0 = occupied on entry; accepted queries store their index q there. */
+int orbfe_guided_search(OrbfeMatcher *m, const OrbfeFrameView *f, int nq, const float *qu, const float *qv, const float *qr,
+                        const int32_t *qlo, const int32_t *qhi, const uint8_t *qdesc, const float *qangle, int rule,
+                        float nnratio, int th_dist, int hist_mode, int32_t *slot_owner_inout, int *nmatches_out);
+
 /* int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches) (variant 0, ORBmatcher.cc:155-284) and
  * SearchByBoW(KeyFrame*, KeyFrame*, matches12) (variant 1, :715-850): brute force inside equal vocabulary nodes.
  * A DBoW2::FeatureVector is passed as ascending node ids + CSR (ptr, items = feature indices in insertion order).

@@ -111,6 +111,8 @@ def lib():
                                                          C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, i32p]
         L.orb_oracle_search_by_projection_f1f2.argtypes = [C.POINTER(Frame), C.POINTER(Frame), u8p, f32p, f32p, C.c_float, C.c_float,
                                                            C.c_float, C.c_float, C.c_int, C.c_float, i32p]
+        L.orb_oracle_guided_search.argtypes = [C.POINTER(Frame), C.c_int, f32p, f32p, f32p, i32p, i32p, u8p, f32p, C.c_int, C.c_float,
+                                               C.c_int, C.c_int, i32p]
         L.orb_oracle_search_by_bow.argtypes = [C.c_int, C.c_int, u8p, u8p, f32p, C.c_int, i32p, i32p, i32p, C.c_int, u8p, u8p, f32p,
                                                C.c_int, i32p, i32p, i32p, C.c_float, C.c_int, i32p]
         L.orb_oracle_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p, i32p]
@@ -359,3 +361,11 @@ def search_by_bow(variant, desc1, valid1, angle1, fv1, desc2, valid2, angle2, fv
                                        n2, _p(desc2), _p(valid2), _p(angle2), len(i2), _p(i2), _p(p2), _p(t2),
                                        nnratio, int(check_orientation), _p(out))
     return n, out[:(n2 if variant == 0 else n1)]
+
+
+def guided_search(f, qu, qv, qr, qlo, qhi, qdesc, qangle, rule, nnratio, th_dist, hist_mode, slot_owner=None):
+    qu, qv, qr, qlo, qhi, qdesc, qangle = _a(qu, np.float32), _a(qv, np.float32), _a(qr, np.float32), _a(qlo, np.int32), _a(qhi, np.int32), _a(qdesc, np.uint8), _a(qangle, np.float32)
+    so = np.full(max(f.n, 1), -1, np.int32) if slot_owner is None else _a(slot_owner, np.int32).copy()
+    n = lib().orb_oracle_guided_search(C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), _p(qangle), rule,
+                                       nnratio, th_dist, hist_mode, _p(so))
+    return n, so[:f.n]

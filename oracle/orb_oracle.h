@@ -183,6 +183,10 @@ int orb_oracle_search_by_projection_kf(const OrbOracleFrame *cur, int npts, cons
 int orb_oracle_search_by_projection_f1f2(const OrbOracleFrame *f1, const OrbOracleFrame *f2, const uint8_t *valid1,
                                          const float *world1, const float *Tc2w, float fx, float fy, float cx, float cy,
                                          int window, float nnratio, int *f2_mp);
+/* the guided-search skeleton on explicit queries (rules: see orb_oracle_match.c) */
+int orb_oracle_guided_search(const OrbOracleFrame *f, int nq, const float *qu, const float *qv, const float *qr,
+                             const int *qlo, const int *qhi, const uint8_t *qdesc, const float *qangle, int rule,
+                             float nnratio, int th_dist, int hist_mode, int *slot_owner);
 /* SearchByBoW, ORBmatcher.cc:155-284 (variant 0: KeyFrame vs Frame) and :715-850 (variant 1: KeyFrame vs KeyFrame) */
 int orb_oracle_search_by_bow(int variant, int n1, const uint8_t *desc1, const uint8_t *valid1, const float *angle1,
                              int nn1, const int *ids1, const int *ptr1, const int *items1,

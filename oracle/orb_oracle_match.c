@@ -550,3 +550,55 @@ int orb_oracle_search_by_bow(int variant, int n1, const uint8_t *desc1, const ui
     free(matched2);
     return nmatches;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * The inner "guided search" skeleton shared by ORBmatcher's projection routines, on explicit queries:
+ * for each query q (ascending): candidates = GetFeaturesInArea(u, v, r, lo, hi); best / second best over the
+ * candidates whose slot is free; accept by rule:
+ *   0: best <= th_dist                                           (ORBmatcher.cc:394, :1107, :1239, :1576, :1693)
+ *   1: best <= second*nnratio && best <= TH_HIGH                 (:469, :586)
+ *   2: best <= TH_HIGH && !(bestLevel==secondLevel && best > nnratio*second)   (:113-121)
+ * hist_mode 0: none; 1: rotation histogram + three-maxima filter; 2: histogram filled but not applied.
+ * slot_owner[i2] >= 0 on entry = occupied; on exit = owner_id of the accepted query.
+ * ---------------------------------------------------------------------------------------------- */
+int orb_oracle_guided_search(const OrbOracleFrame *f, int nq, const float *qu, const float *qv, const float *qr,
+                             const int *qlo, const int *qhi, const uint8_t *qdesc, const float *qangle, int rule,
+                             float nnratio, int th_dist, int hist_mode, int *slot_owner) {
+    int nmatches = 0;
+    IVec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(f->n > 0 ? f->n : 1));
+    for (int q = 0; q < nq; q++) {
+        const int nc = orb_oracle_features_in_area(f, qu[q], qv[q], qr[q], qlo[q], qhi[q], cand, f->n);
+        if (nc == 0) continue;
+        const uint8_t *d = qdesc + (size_t)q * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx = -1, bestLevel = -1, bestLevel2 = -1;
+        for (int c = 0; c < nc; c++) {
+            const int i2 = cand[c];
+            if (slot_owner[i2] >= 0) continue;
+            const int dist = orb_oracle_hamming(d, f->desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = f->keys_un[i2].octave; bestIdx = i2; }
+            else if (dist < bestDist2) { bestLevel2 = f->keys_un[i2].octave; bestDist2 = dist; }
+        }
+        int accept;
+        if (rule == 0) accept = bestDist <= th_dist;
+        else if (rule == 1) accept = (float)bestDist <= (float)bestDist2 * nnratio && bestDist <= TH_HIGH;
+        else accept = bestDist <= TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2);
+        if (!accept) continue;
+        slot_owner[bestIdx] = q;
+        nmatches++;
+        if (hist_mode) ivec_push(&hist[rot_bin(qangle[q], f->keys_un[bestIdx].angle)], bestIdx);
+    }
+    if (hist_mode == 1) {
+        int counts[HISTO_LENGTH], i1, i2, i3;
+        for (int b = 0; b < HISTO_LENGTH; b++) counts[b] = hist[b].n;
+        orb_oracle_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int b = 0; b < HISTO_LENGTH; b++) {
+            if (b == i1 || b == i2 || b == i3) continue;
+            for (int j = 0; j < hist[b].n; j++) { slot_owner[hist[b].v[j]] = -1; nmatches--; }
+        }
+    }
+    for (int b = 0; b < HISTO_LENGTH; b++) free(hist[b].v);
+    free(cand);
+    return nmatches;
+}

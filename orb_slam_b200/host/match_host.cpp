@@ -618,3 +618,21 @@ extern "C" int orbfe_search_by_bow(OrbfeMatcher *m, int variant, int n1, const u
     *nmatches_out = nmatches;
     return ORBFE_OK;
 }
+
+// Exported form of the guided search for callers that do their own projection (the KeyFrame-level routines
+// of the facade: Sim3 projection :286-407, SearchBySim3 :1267-1505, Fuse :1016-1265).
+extern "C" int orbfe_guided_search(OrbfeMatcher *m, const OrbfeFrameView *f, int nq, const float *qu, const float *qv,
+                                   const float *qr, const int32_t *qlo, const int32_t *qhi, const uint8_t *qdesc,
+                                   const float *qangle, int rule, float nnratio, int th_dist, int hist_mode,
+                                   int32_t *slot_owner_inout, int *nmatches_out) {
+    if (!m || !f || nq < 0 || rule < 0 || rule > 2 || hist_mode < 0 || hist_mode > 2 || !slot_owner_inout || !nmatches_out)
+        return ORBFE_ERR_ARG;
+    if (nq > 0 && (!qu || !qv || !qr || !qlo || !qhi || !qdesc || (hist_mode && !qangle))) return ORBFE_ERR_ARG;
+    std::vector<GuidedQuery> Q(nq);
+    std::vector<int> id(nq);
+    for (int q = 0; q < nq; q++) {
+        Q[q] = {qu[q], qv[q], qr[q], qlo[q], qhi[q], qdesc + (size_t)q * 32, qangle ? qangle[q] : 0.f};
+        id[q] = q;
+    }
+    return guided_search(m, *f, Q, rule, nnratio, th_dist, hist_mode, slot_owner_inout, id, nmatches_out);
+}

@@ -44,6 +44,7 @@ def _bind():
                                                   C.c_float, vp, vp]
     L.orbfe_search_by_bow.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
                                       C.c_float, C.c_int, vp, vp]
+    L.orbfe_guided_search.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]
     L.orbfe_window_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
     _bound = True
@@ -199,3 +200,14 @@ def search_by_bow(matcher: ORBmatcher, variant, desc1, valid1, angle1, fv1, desc
                                  n2, _p(desc2), _p(valid2), _p(angle2), len(i2), _p(i2), _p(p2), _p(t2),
                                  float(matcher.mfNNratio), int(matcher.mbCheckOrientation), _p(out), C.byref(nm)))
     return nm.value, out[:(n2 if variant == 0 else n1)]
+
+
+def guided_search(matcher: ORBmatcher, f, qu, qv, qr, qlo, qhi, qdesc, qangle, rule, th_dist, hist_mode, slot_owner=None):
+    L = _bind()
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    qu, qv, qr, qlo, qhi, qdesc, qangle = a(qu, np.float32), a(qv, np.float32), a(qr, np.float32), a(qlo, np.int32), a(qhi, np.int32), a(qdesc, np.uint8), a(qangle, np.float32)
+    so = np.full(max(f.n, 1), -1, np.int32) if slot_owner is None else a(slot_owner, np.int32).copy()
+    nm = C.c_int(0)
+    _check(L.orbfe_guided_search(matcher.handle, C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), _p(qangle),
+                                 rule, float(matcher.mfNNratio), th_dist, hist_mode, _p(so), C.byref(nm)))
+    return nm.value, so[:f.n]

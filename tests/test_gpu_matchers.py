@@ -248,3 +248,28 @@ def test_search_by_bow_both_overloads(gpu_required):
             assert n == n_o and np.array_equal(out, out_o), (variant, nnr, ori)
             assert n > 300
             m.close()
+
+
+def test_guided_search_all_rules(gpu_required):
+    """The exported guided-search skeleton (used by the KeyFrame-level facade methods) against the oracle, for every
+    accept rule / histogram mode, with and without octave filters (KeyFrame::GetFeaturesInArea has none)."""
+    feats, shifts = _features(2)
+    (k1, d1), (k2, d2) = feats
+    rng = np.random.default_rng(8)
+    f2v, o2 = M.FrameView(k2, d2, W, H), O.OracleFrame(k2, d2, W, H)
+    dx, dy = shifts[1]
+    nq = len(k1)
+    qu = (k1["x"] + np.float32(dx) + rng.normal(0, 1.5, nq)).astype(np.float32)
+    qv = (k1["y"] + np.float32(dy) + rng.normal(0, 1.5, nq)).astype(np.float32)
+    qr = (np.float32(6.0) * np.float32(1.2) ** k1["octave"]).astype(np.float32)
+    occ = np.full(len(k2), -1, np.int32)
+    occ[rng.random(len(k2)) < 0.02] = 1
+    for rule, th, hist, filt in ((0, 50, 0, False), (0, 100, 1, True), (1, 0, 2, True), (2, 0, 0, True), (0, 64, 1, False)):
+        lo = (k1["octave"] - 1).astype(np.int32) if filt else np.full(nq, -1, np.int32)
+        hi = (k1["octave"]).astype(np.int32) if filt else np.full(nq, -1, np.int32)
+        m = fe.ORBmatcher(0.8, True)
+        n, so = M.guided_search(m, f2v, qu, qv, qr, lo, hi, d1, k1["angle"], rule, th, hist, slot_owner=occ)
+        n_o, so_o = O.guided_search(o2, qu, qv, qr, lo, hi, d1, k1["angle"], rule, 0.8, th, hist, slot_owner=occ)
+        assert n == n_o and np.array_equal(so, so_o), (rule, th, hist, filt)
+        assert n > 100
+        m.close()
