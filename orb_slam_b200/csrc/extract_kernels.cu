@@ -16,6 +16,9 @@
 
 namespace orbfe {
 
+__global__ void cell_select_harris_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0);
+__global__ void level_select_harris_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0);
+
 __device__ __forceinline__ int find_level_by(const PlanDev *plan, int idx, int which) {
     // which: 0 = ftile_base, 1 = btile_base, 2 = cell_base, 3 = kp_base
     int l = 0;
@@ -204,6 +207,37 @@ __device__ __forceinline__ int m_at(const uint32_t *mt, int r, int c /* tile col
 #define F2_MAXC ((F2_W / 2) * (F2_H / 2) + 4 * (F2_W + F2_H))
 #define F2_MAXCELLS 64                    // cells a tile can overlap (host-checked)
 
+// monotonic map float -> u32 (larger float <=> larger key), for selection keys
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// HarrisResponses for one keypoint (reference ORBextractor.cc:79-120, blockSize 7, k = 0.04): integer sums of the
+// 3x3 Sobel-like gradients over the 7x7 block, then a*b - c*c - k*(a+b)^2 in binary32, every operation rounded
+__device__ __forceinline__ float harris_response(const uint8_t *__restrict__ img, int pitch, int x, int y, float scale4) {
+    int a = 0, b = 0, c = 0;
+    for (int i = -3; i <= 3; i++) {
+        const uint8_t *r0 = img + (size_t)(y + i - 1) * pitch + x, *r1 = r0 + pitch, *r2 = r1 + pitch;
+        for (int j = -3; j <= 3; j++) {
+            const int Ix = ((int)__ldg(r1 + j + 1) - (int)__ldg(r1 + j - 1)) * 2 + ((int)__ldg(r0 + j + 1) - (int)__ldg(r0 + j - 1)) +
+                           ((int)__ldg(r2 + j + 1) - (int)__ldg(r2 + j - 1));
+            const int Iy = ((int)__ldg(r2 + j) - (int)__ldg(r0 + j)) * 2 + ((int)__ldg(r2 + j - 1) - (int)__ldg(r0 + j - 1)) +
+                           ((int)__ldg(r2 + j + 1) - (int)__ldg(r0 + j + 1));
+            a += Ix * Ix;
+            b += Iy * Iy;
+            c += Ix * Iy;
+        }
+    }
+    const float fa = (float)a, fb = (float)b, fc = (float)c;
+    const float s = __fadd_rn(fa, fb);
+    const float t = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, s), s));
+    return __fmul_rn(t, scale4);
+}
+
 // candidate queue entry (u32): x - x0 (7 bits) | y - y0 (6 bits) << 7 | m (8 bits) << 13 | slot inside (tile, cell) (11 bits) << 21
 __device__ __forceinline__ void fast_push(uint32_t *q, int *q_n, int xl, int yl, int m) {
     const int n = atomicAdd(q_n, 1);
@@ -377,9 +411,17 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
         const int gcell = L.cell_base + ci * L.cols + cj;
         const int pos = s_base[lc] + slot;
         const uint32_t raster = (uint32_t)((y - ya) * L.cw + (x - xa));
-        if (pos < wk.cell_cand_cap[gcell])
-            wk.cand_keys[(size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + pos] =
-                ((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster);
+        if (pos < wk.cell_cand_cap[gcell]) {
+            const size_t kidx = (size_t)f * plan->cand_total + wk.cell_cand_base[gcell] + pos;
+            if (wk.cand_keys64) {
+                // HARRIS_SCORE (:616-620): rank by the Harris response; the FAST score rides along for eligibility
+                const float resp = harris_response(L.pyr + (size_t)f * L.plane, L.pitch, x, y, plan->harris_scale4);
+                wk.cand_keys64[kidx] = ((unsigned long long)float_order_key(resp) << 32) |
+                                       ((unsigned long long)(0xFFFFFFu - raster) << 8) | (unsigned long long)(m - 1);
+            } else {
+                wk.cand_keys[kidx] = ((uint32_t)(m - 1) << 24) | (0xFFFFFFu - raster);
+            }
+        }
     }
 }
 
@@ -659,6 +701,7 @@ __global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restr
 
 void launch_cell_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
     dim3 grid(hp.ncells_total, nf);
+    if (w.cand_keys64) { cell_select_harris_kernel<<<grid, 128, 0, s>>>(d_plan, w, f0); return; }
     cell_select_kernel<<<grid, 128, 0, s>>>(d_plan, w, f0);
 }
 
@@ -721,6 +764,133 @@ __global__ void __launch_bounds__(512) level_select_kernel(const PlanDev *__rest
     if (threadIdx.x == 0) wk.level_cnt[(size_t)f * plan->nlevels + l] = n_out;
 }
 
+// ------------------------------------------------------------------------------------------------
+// HARRIS_SCORE variants (scoreType == 0, reference :616-620): candidates are ranked by the float Harris
+// response instead of the FAST score.  64-bit candidate keys  order(resp) << 32 | (0xFFFFFF - raster) << 8 | score;
+// eligibility still comes from the FAST score (low byte >= the cell's threshold).  Kept entries carry
+// (order(resp), cell, raster, score); the level trim ranks by counting (n is at most a few thousand).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cell_select_harris_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix, s_mask;
+    __shared__ int s_k, s_base, s_fill;
+
+    const int gcell = blockIdx.x, f = blockIdx.y + f0;
+    const size_t fc = (size_t)f * plan->ncells_total + gcell;
+    const int keep = wk.cell_keep[fc];
+    if (keep <= 0) return;
+    const int l = find_level_by(plan, gcell, 2);
+    const LevelDev &L = plan->lv[l];
+    const int n = min(wk.cell_cnt_lo[fc], wk.cell_cand_cap[gcell]);
+    const unsigned long long min_score = wk.cell_min_key[fc] >> 24;  // threshold t: eligible <=> score >= t
+    const unsigned long long *__restrict__ keys = wk.cand_keys64 + (size_t)f * plan->cand_total + wk.cell_cand_base[gcell];
+    const int tid = threadIdx.x;
+    const int lo = wk.cell_cnt_lo[fc], hi = wk.cell_cnt_hi[fc];
+    const int n1 = plan->t1_is_lo ? lo : hi, n2 = plan->t1_is_lo ? hi : lo;
+    const int n_elig = (n1 <= 3) ? n2 : n1;
+
+    unsigned long long cut = 0;  // rank on the upper 56 bits
+    if (n_elig > keep) {
+        if (tid == 0) { s_prefix = 0; s_mask = 0; s_k = keep; }
+        for (int shift = 56; shift >= 8; shift -= 8) {
+            for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix, mask = s_mask;
+            for (int i = tid; i < n; i += blockDim.x) {
+                const unsigned long long k = keys[i];
+                if ((k & 0xFF) >= min_score && (k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xFF)], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int k = s_k, cum = 0, b = 255;
+                for (; b >= 0; b--) {
+                    if (cum + hist[b] >= k) break;
+                    cum += hist[b];
+                }
+                s_k = k - cum;
+                s_prefix = prefix | ((unsigned long long)b << shift);
+                s_mask = mask | (0xFFull << shift);
+            }
+            __syncthreads();
+        }
+        cut = s_prefix;
+    }
+    const int nk = min(keep, n_elig);
+    if (tid == 0) {
+        s_base = atomicAdd(&wk.kept_cnt[(size_t)f * plan->nlevels + l], nk);
+        s_fill = 0;
+    }
+    __syncthreads();
+    const int base = s_base;
+    const unsigned long long cellinv = (unsigned long long)(4095 - (gcell - L.cell_base));
+    unsigned long long *__restrict__ kept = wk.kept_keys + (size_t)f * plan->kept_total + L.kept_base;
+    uint32_t *__restrict__ kept2 = wk.kept_aux + (size_t)f * plan->kept_total + L.kept_base;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        if ((k & 0xFF) >= min_score && (k & ~0xFFull) >= cut) {
+            const int p = base + atomicAdd(&s_fill, 1);
+            if (p < L.kept_cap) {
+                kept[p] = (k & 0xFFFFFFFF00000000ull) | (cellinv << 20) | ((k >> 12) & 0xFFFFFull);  // resp | ~cell | ~raster[23:4]
+                kept2[p] = (uint32_t)(((k >> 8) & 0xFull) << 8) | (uint32_t)(k & 0xFF);             // ~raster[3:0] | score
+            } else {
+                atomicExch(wk.err_flag, 2);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) level_select_harris_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
+    extern __shared__ unsigned long long skeys[];  // [n] hi keys, then [n] u32 lo keys, then [n] u8 survivor flags
+    const int l = blockIdx.x, f = blockIdx.y + f0;
+    const LevelDev &L = plan->lv[l];
+    const int n = min(wk.kept_cnt[(size_t)f * plan->nlevels + l], L.kept_cap);
+    uint32_t *slo = reinterpret_cast<uint32_t *>(skeys + L.kept_cap);
+    uint8_t *keepf = reinterpret_cast<uint8_t *>(slo + L.kept_cap);
+    const unsigned long long *__restrict__ kept = wk.kept_keys + (size_t)f * plan->kept_total + L.kept_base;
+    const uint32_t *__restrict__ kept2 = wk.kept_aux + (size_t)f * plan->kept_total + L.kept_base;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { skeys[i] = kept[i]; slo[i] = kept2[i]; }
+    __syncthreads();
+    const int quota = L.quota;
+    // rank by (resp desc, cell asc, raster asc): element i survives iff fewer than `quota` elements beat it
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long hi = skeys[i];
+        const uint32_t lo = slo[i] >> 8;
+        int rank = 0;
+        if (n > quota)
+            for (int j = 0; j < n; j++) {
+                const unsigned long long hj = skeys[j];
+                rank += (hj > hi) || (hj == hi && (slo[j] >> 8) > lo);
+            }
+        keepf[i] = rank < quota;
+    }
+    __syncthreads();
+    int2 *__restrict__ out = wk.kp_xy_score + (size_t)f * plan->nfeatures + L.kp_base;
+    const unsigned long long pos_mask = 0xFFFFFFFFull;  // ~cell (12) | ~raster[23:4] (20)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!keepf[i]) continue;
+        const unsigned long long pi = skeys[i] & pos_mask;
+        const uint32_t li = slo[i] >> 8;
+        int o = 0;  // canonical position: survivors with a smaller (cell, raster) = larger inverted fields
+        for (int j = 0; j < n; j++) {
+            if (!keepf[j]) continue;
+            const unsigned long long pj = skeys[j] & pos_mask;
+            o += (pj > pi) || (pj == pi && (slo[j] >> 8) > li);
+        }
+        const int cell = 4095 - (int)((pi >> 20) & 0xFFF);
+        const int raster = 0xFFFFFF - (int)(((pi & 0xFFFFF) << 4) | li);
+        const int ci = cell / L.cols, cj = cell - ci * L.cols;
+        const int ly = raster / L.cw, lx = raster - ly * L.cw;
+        const int x = ORBFE_EDGE + cj * L.cw + lx, y = ORBFE_EDGE + ci * L.ch + ly;
+        out[o] = make_int2(x | (y << 16), (int)__float_as_uint(float_from_order_key((uint32_t)(skeys[i] >> 32))));
+    }
+    if (threadIdx.x == 0) wk.level_cnt[(size_t)f * plan->nlevels + l] = min(n, quota);
+}
+
+int level_select_harris_smem_bytes(int max_kept) { return max_kept * (8 + 4 + 1) + 16; }
+int set_level_select_harris_smem(int bytes) {
+    return (int)cudaFuncSetAttribute(level_select_harris_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 int level_select_smem_bytes(int max_kept) {
     int n2 = 1;
     while (n2 < max_kept) n2 <<= 1;
@@ -733,6 +903,7 @@ int set_level_select_smem(int bytes) {
 
 void launch_level_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, size_t smem_bytes, int f0, int nf, cudaStream_t s) {
     dim3 grid(hp.nlevels, nf);
+    if (w.cand_keys64) { level_select_harris_kernel<<<grid, 512, smem_bytes, s>>>(d_plan, w, f0); return; }
     level_select_kernel<<<grid, 512, smem_bytes, s>>>(d_plan, w, f0);
 }
 
@@ -947,7 +1118,7 @@ __global__ void __launch_bounds__(256) describe_kernel(const PlanDev *__restrict
         r.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
         r.size = L.patch_size;
         r.angle = angle;
-        r.response = (float)kp.y;
+        r.response = wk.cand_keys64 ? __int_as_float(kp.y) : (float)kp.y;  // Harris response or FAST score
         r.octave = l;
         r.class_id = -1;
         out_kps[o] = r;

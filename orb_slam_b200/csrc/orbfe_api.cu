@@ -150,6 +150,11 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     P.t_hi = std::max(ex->fast_th, 7);
     P.t1_is_lo = ex->fast_th <= 7;
     P.score_type = ex->score_type;
+    {   // HarrisResponses scale (ORBextractor.cc:90-92)
+        float scale = (float)(1 << 2) * (float)7 * 255.0f;
+        scale = 1.0f / scale;
+        P.harris_scale4 = scale * scale * scale * scale;
+    }
 
     const float ratio = (float)W / (float)H;  // :527 (level-0 dims)
     int cell_base = 0, kp_base = 0, kept_base = 0, ft_base = 0, bt_base = 0, max_kept = 0;
@@ -220,13 +225,13 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     // max(nfeatures - sum, 0) is not clipped (:487)
     P.nfeatures = kp_base;
 
-    ex->ls_smem = (size_t)level_select_smem_bytes(max_kept);
+    ex->ls_smem = ex->score_type == 0 ? (size_t)level_select_harris_smem_bytes(max_kept) : (size_t)level_select_smem_bytes(max_kept);
     if (ex->ls_smem > 200 * 1024)
         return fail(ORBFE_ERR_UNSUPPORTED, "nfeatures too large for the level-select kernel (%zu B smem)", ex->ls_smem);
 
     CU_TRY(cudaSetDevice(ex->device));
     if (ex->ls_smem > 48 * 1024) {
-        cudaError_t e = (cudaError_t)set_level_select_smem((int)ex->ls_smem);
+        cudaError_t e = (cudaError_t)(ex->score_type == 0 ? set_level_select_harris_smem((int)ex->ls_smem) : set_level_select_smem((int)ex->ls_smem));
         if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     // ---- device memory ----
@@ -355,6 +360,10 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         Wk.fast_grid = (getenv("ORBFE_FAST_CTAS") ? atoi(getenv("ORBFE_FAST_CTAS")) : 4) * nsm;  // resident persistent CTAs per SM (64 registers, 39 KB smem each)
     }
     CU_TRY(dmalloc(ex, &Wk.cand_keys, (size_t)cand_total * B));
+    if (ex->score_type == 0) {
+        CU_TRY(dmalloc(ex, &Wk.cand_keys64, (size_t)cand_total * B));
+        CU_TRY(dmalloc(ex, &Wk.kept_aux, (size_t)P.kept_total * B));
+    }
     const size_t nc = (size_t)P.ncells_total * B, nl = (size_t)P.nlevels * B;
     int *cnt;
     ex->counters_bytes = sizeof(int) * (2 * nc + nl);
@@ -393,8 +402,6 @@ extern "C" int orbfe_extractor_create(int nfeatures, float scale_factor, int nle
         return fail(ORBFE_ERR_ARG, "bad extractor parameters (nfeatures=%d scale=%g nlevels=%d fastTh=%d)", nfeatures,
                     (double)scale_factor, nlevels, fast_th);
     if (score_type != 0 && score_type != 1) return fail(ORBFE_ERR_ARG, "score_type must be 0 (HARRIS) or 1 (FAST)");
-    if (score_type == 0)
-        return fail(ORBFE_ERR_UNSUPPORTED, "HARRIS_SCORE (ORBextractor.cc:616-620) is not implemented yet; use FAST_SCORE");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();

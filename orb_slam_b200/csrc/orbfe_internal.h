@@ -49,6 +49,7 @@ struct PlanDev {
     int t_lo, t_hi;      // min / max of (fastTh, 7)
     int t1_is_lo;        // fastTh <= 7
     int score_type;
+    float harris_scale4;   // (1 / (4 * 7 * 255))^4 as the reference computes it (ORBextractor.cc:90-92)
     long long cand_total;  // candidate slots per frame
     LevelDev lv[ORBFE_MAX_LEVELS];
 };
@@ -71,6 +72,8 @@ struct WorkDev {
     const CUtensorMap *tmaps;         // [nlevels] 3-D (x, y, frame) tensor maps of the unblurred levels; NULL = no TMA
     int fast_grid;                    // persistent CTAs of the TMA FAST kernel
     uint32_t *cand_keys;              // [batch][cand_total]   (score<<24 | 0xFFFFFF - raster)
+    unsigned long long *cand_keys64;  // HARRIS_SCORE only: order(resp)<<32 | (0xFFFFFF - raster)<<8 | score; NULL otherwise
+    uint32_t *kept_aux;               // HARRIS_SCORE only: low raster bits + score of each kept entry
     int *cell_cnt_lo;                 // [batch][ncells_total] candidates with m > t_lo (= all emitted)
     int *cell_cnt_hi;                 // [batch][ncells_total] candidates with m > t_hi
     int *cell_keep;                   // [batch][ncells_total] nToRetain
@@ -93,6 +96,8 @@ void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, co
                      OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s);
 int fast_tma_setup();
 int level_select_smem_bytes(int max_kept);
+int level_select_harris_smem_bytes(int max_kept);
+int set_level_select_harris_smem(int bytes);
 int set_level_select_smem(int bytes);
 
 // parameters of the device-resident SearchByProjection(Frame,Frame) kernel

@@ -45,9 +45,20 @@ def test_single_level_and_unsupported_geometry(gpu_required):
         ex(tiny)
     assert e.value.code == fe.ORBFE_ERR_UNSUPPORTED
     ex.close()
-    with pytest.raises(fe.OrbfeError) as e:
-        fe.ORBextractor(1000, 1.2, 8, fe.HARRIS_SCORE, 20)
-    assert e.value.code == fe.ORBFE_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("W,H,nf,nl", [(640, 480, 1000, 8), (1280, 720, 2000, 8), (641, 479, 500, 5)])
+def test_harris_score_mode(gpu_required, W, H, nf, nl):
+    """E6: scoreType == HARRIS_SCORE (ORBextractor.cc:616-620): retention ranks by the Harris response."""
+    img = textured_frame(W, H, seed=W + 7)
+    p = O.make_params(nf, 1.2, nl, 0, 20)
+    rc, ok, od, _ = O.extract(p, img)
+    assert rc == 0
+    ex = fe.ORBextractor(nf, 1.2, nl, fe.HARRIS_SCORE, 20)
+    gk, gd = ex(img)
+    _same(gk, gd, ok, od)   # response compared bit-for-bit (float Harris value)
+    assert len(gk) == nf and not np.array_equal(gk["response"], np.round(gk["response"]))
+    ex.close()
 
 
 def test_full_size_properties_1080p(gpu_required):
