@@ -112,6 +112,16 @@ int orbfe_search_by_bow(OrbfeMatcher *m, int variant, int n1, const uint8_t *des
                         const uint8_t *valid2, const float *angle2, int nn2, const int32_t *ids2, const int32_t *ptr2,
                         const int32_t *items2, float nnratio, int check_orientation, int32_t *out, int *nmatches_out);
 
+/* int ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, ...) (ORBmatcher.cc:852-1014) with CheckDistEpipolarLine
+ * (:136-153).  keys1/keys2 = GetKeyPointsUn(); has_mp1/2[i] != 0 <=> the feature already has a map point (skipped);
+ * FeatureVectors as in orbfe_search_by_bow; F12 = 3x3 row-major floats; sigma2_kf2[level] = pKF2->GetSigma2(level).
+ * match12_out[i1] = matched index in keyframe 2 or -1 (the caller builds vMatchedKeys1/2 and vMatchedPairs from it). */
+int orbfe_search_for_triangulation(OrbfeMatcher *m, int n1, const OrbfeKeyPoint *keys1, const uint8_t *desc1,
+                                   const uint8_t *has_mp1, int nn1, const int32_t *ids1, const int32_t *ptr1, const int32_t *items1,
+                                   int n2, const OrbfeKeyPoint *keys2, const uint8_t *desc2, const uint8_t *has_mp2, int nn2,
+                                   const int32_t *ids2, const int32_t *ptr2, const int32_t *items2, const float *F12,
+                                   const float *sigma2_kf2, int check_orientation, int32_t *match12_out, int *nmatches_out);
+
 /* int ORBmatcher::WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minOctave, maxOctave)
  * (ORBmatcher.cc:409-516).  f1_has_mp[i1] != 0 <=> F1.mvpMapPoints[i1] && !isBad().
  * match21_out[i2] = i1 whose map point was matched to F2 feature i2, or -1. */

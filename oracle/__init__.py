@@ -113,6 +113,8 @@ def lib():
                                                            C.c_float, C.c_float, C.c_int, C.c_float, i32p]
         L.orb_oracle_guided_search.argtypes = [C.POINTER(Frame), C.c_int, f32p, f32p, f32p, i32p, i32p, u8p, f32p, C.c_int, C.c_float,
                                                C.c_int, C.c_int, i32p]
+        L.orb_oracle_search_for_triangulation.argtypes = [C.c_int, C.c_void_p, u8p, u8p, C.c_int, i32p, i32p, i32p, C.c_int, C.c_void_p, u8p,
+                                                          u8p, C.c_int, i32p, i32p, i32p, f32p, f32p, C.c_int, i32p]
         L.orb_oracle_search_by_bow.argtypes = [C.c_int, C.c_int, u8p, u8p, f32p, C.c_int, i32p, i32p, i32p, C.c_int, u8p, u8p, f32p,
                                                C.c_int, i32p, i32p, i32p, C.c_float, C.c_int, i32p]
         L.orb_oracle_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p, i32p]
@@ -369,3 +371,16 @@ def guided_search(f, qu, qv, qr, qlo, qhi, qdesc, qangle, rule, nnratio, th_dist
     n = lib().orb_oracle_guided_search(C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), _p(qangle), rule,
                                        nnratio, th_dist, hist_mode, _p(so))
     return n, so[:f.n]
+
+
+def search_for_triangulation(keys1, desc1, has_mp1, fv1, keys2, desc2, has_mp2, fv2, F12, sigma2, check_orientation=True):
+    keys1, keys2 = _a(keys1, KP_DTYPE), _a(keys2, KP_DTYPE)
+    desc1, desc2, has_mp1, has_mp2 = _a(desc1, np.uint8), _a(desc2, np.uint8), _a(has_mp1, np.uint8), _a(has_mp2, np.uint8)
+    i1, p1, t1 = [_a(x, np.int32) for x in fv1]
+    i2, p2, t2 = [_a(x, np.int32) for x in fv2]
+    F12, sigma2 = _a(F12, np.float32), _a(sigma2, np.float32)
+    out = np.full(max(len(keys1), 1), -1, np.int32)
+    n = lib().orb_oracle_search_for_triangulation(len(keys1), _p(keys1), _p(desc1), _p(has_mp1), len(i1), _p(i1), _p(p1), _p(t1),
+                                                  len(keys2), _p(keys2), _p(desc2), _p(has_mp2), len(i2), _p(i2), _p(p2), _p(t2),
+                                                  _p(F12), _p(sigma2), int(check_orientation), _p(out))
+    return n, out[:len(keys1)]

@@ -193,6 +193,12 @@ int orb_oracle_search_by_bow(int variant, int n1, const uint8_t *desc1, const ui
                              int n2, const uint8_t *desc2, const uint8_t *valid2, const float *angle2,
                              int nn2, const int *ids2, const int *ptr2, const int *items2,
                              float nnratio, int check_orientation, int *out);
+/* SearchForTriangulation + CheckDistEpipolarLine, ORBmatcher.cc:852-1014, :136-153 */
+int orb_oracle_search_for_triangulation(int n1, const OrbOracleKeyPoint *keys1, const uint8_t *desc1, const uint8_t *has_mp1,
+                                        int nn1, const int *ids1, const int *ptr1, const int *items1,
+                                        int n2, const OrbOracleKeyPoint *keys2, const uint8_t *desc2, const uint8_t *has_mp2,
+                                        int nn2, const int *ids2, const int *ptr2, const int *items2,
+                                        const float *F12, const float *sigma2_kf2, int check_orientation, int *match12);
 /* brute-force best/second-best of each query against a database (BASELINE config 5 primitive;
  * same strict-< update rule as every best/second loop in ORBmatcher.cc, e.g. :456-466) */
 void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,

@@ -602,3 +602,87 @@ int orb_oracle_guided_search(const OrbOracleFrame *f, int nq, const float *qu, c
     free(cand);
     return nmatches;
 }
+
+/* CheckDistEpipolarLine, ORBmatcher.cc:136-153 (F12 = 3x3 row-major float; sigma2 = pKF2->GetSigma2(kp2.octave)) */
+static int check_dist_epipolar(const OrbOracleKeyPoint *kp1, const OrbOracleKeyPoint *kp2, const float *F12, const float *sigma2) {
+    const float a = kp1->x * F12[0] + kp1->y * F12[3] + F12[6];
+    const float b = kp1->x * F12[1] + kp1->y * F12[4] + F12[7];
+    const float c = kp1->x * F12[2] + kp1->y * F12[5] + F12[8];
+    const float num = a * kp2->x + b * kp2->y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return 0;
+    const float dsqr = num * num / den;
+    return (double)dsqr < 3.84 * (double)sigma2[kp2->octave];
+}
+
+typedef struct { int dist, idx; } DistIdx;
+static int cmp_distidx(const void *x, const void *y) {
+    const DistIdx *a = (const DistIdx *)x, *b = (const DistIdx *)y;
+    if (a->dist != b->dist) return a->dist < b->dist ? -1 : 1;
+    return a->idx < b->idx ? -1 : a->idx > b->idx;
+}
+
+/* SearchForTriangulation, ORBmatcher.cc:852-1014.  has_mp1/2[i] != 0 <=> the keyframe feature already has a map point.
+ * match12[i1] = i2 or -1; returns nmatches. */
+int orb_oracle_search_for_triangulation(int n1, const OrbOracleKeyPoint *keys1, const uint8_t *desc1, const uint8_t *has_mp1,
+                                        int nn1, const int *ids1, const int *ptr1, const int *items1,
+                                        int n2, const OrbOracleKeyPoint *keys2, const uint8_t *desc2, const uint8_t *has_mp2,
+                                        int nn2, const int *ids2, const int *ptr2, const int *items2,
+                                        const float *F12, const float *sigma2_kf2, int check_orientation, int *match12) {
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    uint8_t *matched2 = (uint8_t *)calloc((size_t)(n2 > 0 ? n2 : 1), 1);
+    DistIdx *vd = (DistIdx *)malloc(sizeof(DistIdx) * (size_t)(n2 > 0 ? n2 : 1));
+    IVec hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof(hist));
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int p1 = ptr1[a]; p1 < ptr1[a + 1]; p1++) {
+                const int idx1 = items1[p1];
+                if (has_mp1[idx1]) continue; /* :896-897 */
+                const OrbOracleKeyPoint *kp1 = &keys1[idx1];
+                const uint8_t *d1 = desc1 + (size_t)idx1 * 32;
+                int nv = 0;
+                for (int p2 = ptr2[b]; p2 < ptr2[b + 1]; p2++) {
+                    const int idx2 = items2[p2];
+                    if (matched2[idx2] || has_mp2[idx2]) continue;
+                    const int dist = orb_oracle_hamming(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW) continue;
+                    vd[nv].dist = dist; vd[nv].idx = idx2; nv++;
+                }
+                if (nv == 0) continue;
+                qsort(vd, (size_t)nv, sizeof(DistIdx), cmp_distidx); /* sort of pair<int,size_t> */
+                const int DistTh = (int)round(2.0 * vd[0].dist);
+                for (int id = 0; id < nv; id++) {
+                    if (vd[id].dist > DistTh) break;
+                    const int cur2 = vd[id].idx;
+                    if (check_dist_epipolar(kp1, &keys2[cur2], F12, sigma2_kf2)) {
+                        matched2[cur2] = 1;
+                        match12[idx1] = cur2;
+                        nmatches++;
+                        if (check_orientation) ivec_push(&hist[rot_bin(kp1->angle, keys2[cur2].angle)], idx1);
+                        break;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (ids1[a] < ids2[b]) {
+            while (a < nn1 && ids1[a] < ids2[b]) a++;
+        } else {
+            while (b < nn2 && ids2[b] < ids1[a]) b++;
+        }
+    }
+    if (check_orientation) {
+        int counts[HISTO_LENGTH], i1, i2, i3;
+        for (int k = 0; k < HISTO_LENGTH; k++) counts[k] = hist[k].n;
+        orb_oracle_three_maxima(counts, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int k = 0; k < HISTO_LENGTH; k++) {
+            if (k == i1 || k == i2 || k == i3) continue;
+            for (int j = 0; j < hist[k].n; j++) { match12[hist[k].v[j]] = -1; nmatches--; }
+        }
+    }
+    for (int k = 0; k < HISTO_LENGTH; k++) free(hist[k].v);
+    free(matched2); free(vd);
+    return nmatches;
+}

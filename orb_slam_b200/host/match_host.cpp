@@ -636,3 +636,97 @@ extern "C" int orbfe_guided_search(OrbfeMatcher *m, const OrbfeFrameView *f, int
     }
     return guided_search(m, *f, Q, rule, nnratio, th_dist, hist_mode, slot_owner_inout, id, nmatches_out);
 }
+
+// ================================================================================================
+// SearchForTriangulation (ORBmatcher.cc:852-1014): BoW-node brute force between the features of two keyframes
+// that have no map point yet; per query all distances <= TH_LOW are sorted, and the first candidate (up to twice
+// the best distance) that satisfies the epipolar constraint (CheckDistEpipolarLine, :136-153) wins.
+// Distances on the device, everything else replayed on the host.
+// ================================================================================================
+extern "C" int orbfe_search_for_triangulation(OrbfeMatcher *m, int n1, const OrbfeKeyPoint *keys1, const uint8_t *desc1,
+                                              const uint8_t *has_mp1, int nn1, const int32_t *ids1, const int32_t *ptr1,
+                                              const int32_t *items1, int n2, const OrbfeKeyPoint *keys2, const uint8_t *desc2,
+                                              const uint8_t *has_mp2, int nn2, const int32_t *ids2, const int32_t *ptr2,
+                                              const int32_t *items2, const float *F12, const float *sigma2_kf2,
+                                              int check_orientation, int32_t *match12_out, int *nmatches_out) {
+    if (!m || n1 < 0 || n2 < 0 || nn1 < 0 || nn2 < 0 || !F12 || !sigma2_kf2 || !match12_out || !nmatches_out) return ORBFE_ERR_ARG;
+    if ((n1 > 0 && (!keys1 || !desc1 || !has_mp1)) || (n2 > 0 && (!keys2 || !desc2 || !has_mp2))) return ORBFE_ERR_ARG;
+    if ((nn1 > 0 && (!ids1 || !ptr1 || !items1)) || (nn2 > 0 && (!ids2 || !ptr2 || !items2))) return ORBFE_ERR_ARG;
+    for (int i = 0; i < n1; i++) match12_out[i] = -1;
+    std::vector<int32_t> row_ptr(1, 0), cols, q1;
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int p1 = ptr1[a]; p1 < ptr1[a + 1]; p1++) {
+                const int idx1 = items1[p1];
+                if (idx1 < 0 || idx1 >= n1) return ORBFE_ERR_ARG;
+                if (has_mp1[idx1]) continue;
+                for (int p2 = ptr2[b]; p2 < ptr2[b + 1]; p2++) {
+                    if (items2[p2] < 0 || items2[p2] >= n2) return ORBFE_ERR_ARG;
+                    if (!has_mp2[items2[p2]]) cols.push_back(items2[p2]);  // static filter; vbMatched2 is dynamic (replay)
+                }
+                q1.push_back(idx1);
+                row_ptr.push_back((int32_t)cols.size());
+            }
+            a++; b++;
+        } else if (ids1[a] < ids2[b]) {
+            a = (int)(std::lower_bound(ids1 + a, ids1 + nn1, ids2[b]) - ids1);
+        } else {
+            b = (int)(std::lower_bound(ids2 + b, ids2 + nn2, ids1[a]) - ids2);
+        }
+    }
+    std::vector<uint8_t> qd(q1.size() * 32 + 1);
+    for (size_t k = 0; k < q1.size(); k++) memcpy(&qd[k * 32], desc1 + (size_t)q1[k] * 32, 32);
+    std::vector<uint16_t> dist(std::max<size_t>(cols.size(), 1));
+    if (!cols.empty()) {
+        const int rc = orbfe_hamming_csr(m, qd.data(), (int)q1.size(), desc2, n2, row_ptr.data(), cols.data(), dist.data());
+        if (rc) return rc;
+    }
+    std::vector<uint8_t> matched2(std::max(n2, 1), 0);
+    std::vector<int> rotHist[kHisto];
+    std::vector<std::pair<int, int> > vd;
+    int nmatches = 0;
+    for (size_t k = 0; k < q1.size(); k++) {
+        const int idx1 = q1[k];
+        const OrbfeKeyPoint &kp1 = keys1[idx1];
+        vd.clear();
+        for (int c = row_ptr[k]; c < row_ptr[k + 1]; c++) {
+            const int idx2 = cols[c];
+            if (matched2[idx2]) continue;
+            if (dist[c] > kThLow) continue;
+            vd.push_back(std::make_pair((int)dist[c], idx2));
+        }
+        if (vd.empty()) continue;
+        std::sort(vd.begin(), vd.end());
+        const int DistTh = (int)std::round(2.0 * vd.front().first);
+        // epipolar line of kp1 in image 2: l = x1' F12
+        const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+        const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+        const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+        const float den = la * la + lb * lb;
+        for (size_t id = 0; id < vd.size(); id++) {
+            if (vd[id].first > DistTh) break;
+            const int cur2 = vd[id].second;
+            const OrbfeKeyPoint &kp2 = keys2[cur2];
+            const float num = la * kp2.x + lb * kp2.y + lc;
+            if (den == 0) continue;
+            const float dsqr = num * num / den;
+            if (!((double)dsqr < 3.84 * (double)sigma2_kf2[kp2.octave])) continue;
+            matched2[cur2] = 1;
+            match12_out[idx1] = cur2;
+            nmatches++;
+            if (check_orientation) rotHist[rot_bin(kp1.angle, kp2.angle)].push_back(idx1);
+            break;
+        }
+    }
+    if (check_orientation) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rotHist, kHisto, i1, i2, i3);
+        for (int k = 0; k < kHisto; k++) {
+            if (k == i1 || k == i2 || k == i3) continue;
+            for (int idx : rotHist[k]) { match12_out[idx] = -1; nmatches--; }
+        }
+    }
+    *nmatches_out = nmatches;
+    return ORBFE_OK;
+}

@@ -45,6 +45,8 @@ def _bind():
     L.orbfe_search_by_bow.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
                                       C.c_float, C.c_int, vp, vp]
     L.orbfe_guided_search.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]
+    L.orbfe_search_for_triangulation.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
+                                                 vp, vp, C.c_int, vp, vp]
     L.orbfe_window_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
     _bound = True
@@ -211,3 +213,20 @@ def guided_search(matcher: ORBmatcher, f, qu, qv, qr, qlo, qhi, qdesc, qangle, r
     _check(L.orbfe_guided_search(matcher.handle, C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), _p(qangle),
                                  rule, float(matcher.mfNNratio), th_dist, hist_mode, _p(so), C.byref(nm)))
     return nm.value, so[:f.n]
+
+
+def search_for_triangulation(matcher: ORBmatcher, keys1, desc1, has_mp1, fv1, keys2, desc2, has_mp2, fv2, F12, sigma2):
+    """ORBmatcher::SearchForTriangulation on arrays (ORBmatcher.cc:852-1014)."""
+    L = _bind()
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    keys1, keys2 = a(keys1, KP_DTYPE), a(keys2, KP_DTYPE)
+    desc1, desc2, has_mp1, has_mp2 = a(desc1, np.uint8), a(desc2, np.uint8), a(has_mp1, np.uint8), a(has_mp2, np.uint8)
+    i1, p1, t1 = [a(x, np.int32) for x in fv1]
+    i2, p2, t2 = [a(x, np.int32) for x in fv2]
+    F12, sigma2 = a(F12, np.float32), a(sigma2, np.float32)
+    out = np.full(max(len(keys1), 1), -1, np.int32)
+    nm = C.c_int(0)
+    _check(L.orbfe_search_for_triangulation(matcher.handle, len(keys1), _p(keys1), _p(desc1), _p(has_mp1), len(i1), _p(i1), _p(p1), _p(t1),
+                                            len(keys2), _p(keys2), _p(desc2), _p(has_mp2), len(i2), _p(i2), _p(p2), _p(t2),
+                                            _p(F12), _p(sigma2), int(matcher.mbCheckOrientation), _p(out), C.byref(nm)))
+    return nm.value, out[:len(keys1)]

@@ -273,3 +273,26 @@ def test_guided_search_all_rules(gpu_required):
         assert n == n_o and np.array_equal(so, so_o), (rule, th, hist, filt)
         assert n > 100
         m.close()
+
+
+def test_search_for_triangulation(gpu_required):
+    """M10: BoW-node brute force + epipolar constraint between two keyframes (pure horizontal translation => the
+    fundamental matrix of a rectified pair), against the oracle."""
+    feats, shifts = _features(2)
+    (k1, d1), (k2, d2) = feats
+    rng = np.random.default_rng(31)
+    has1 = (rng.random(len(k1)) < 0.4).astype(np.uint8)
+    has2 = (rng.random(len(k2)) < 0.4).astype(np.uint8)
+    node1 = (d1[:, 3].astype(np.int32) >> 4) * 7 + 2
+    node2 = (d2[:, 3].astype(np.int32) >> 4) * 7 + 2
+    fv1, fv2 = M.feature_vector(node1), M.feature_vector(node2)
+    # x2' F12-style constraint used by the reference: l = x1' F12; a sideways-moving camera gives epipolar lines y = const
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, float(-shifts[1][1])]], np.float32)
+    sigma2 = (np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2
+    for ori in (True, False):
+        m = fe.ORBmatcher(0.6, ori)
+        n, m12 = M.search_for_triangulation(m, k1, d1, has1, fv1, k2, d2, has2, fv2, F12, sigma2)
+        n_o, m12_o = O.search_for_triangulation(k1, d1, has1, fv1, k2, d2, has2, fv2, F12, sigma2, check_orientation=ori)
+        assert n == n_o and np.array_equal(m12, m12_o)
+        assert n > 20
+        m.close()
