@@ -5,7 +5,7 @@
  *
  * Implementation: orb_slam_b200/host/ORBmatcher.cc.  Candidate enumeration (Frame::GetFeaturesInArea order)
  * and each routine's sequential accept loop stay on the host; every batch of 256-bit Hamming distances is
- * computed by liborbfe.so on the GPU (include/orbfe_match.h).  Status per method is tabulated in DESIGN.md.
+ * computed by liborbfe.so on the GPU (include/orbfe_match.h).  All methods are defined; status per method in DESIGN.md.
  */
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H

@@ -101,6 +101,12 @@ int orbfe_guided_search(OrbfeMatcher *m, const OrbfeFrameView *f, int nq, const 
                         const int32_t *qlo, const int32_t *qhi, const uint8_t *qdesc, const float *qangle, int rule,
                         float nnratio, int th_dist, int hist_mode, int32_t *slot_owner_inout, int *nmatches_out);
 
+/* Guided search without slot bookkeeping: best candidate of every query, kept iff best <= th_dist (first minimum wins).
+ * The inner loops of Fuse (ORBmatcher.cc:1090-1107, :1222-1239) and SearchBySim3 (:1356-1378, :1436-1458).
+ * best_idx_out[q] = feature index in `f` or -1. */
+int orbfe_guided_best(OrbfeMatcher *m, const OrbfeFrameView *f, int nq, const float *qu, const float *qv, const float *qr,
+                      const int32_t *qlo, const int32_t *qhi, const uint8_t *qdesc, int th_dist, int32_t *best_idx_out);
+
 /* int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, matches) (variant 0, ORBmatcher.cc:155-284) and
  * SearchByBoW(KeyFrame*, KeyFrame*, matches12) (variant 1, :715-850): brute force inside equal vocabulary nodes.
  * A DBoW2::FeatureVector is passed as ascending node ids + CSR (ptr, items = feature indices in insertion order).

@@ -115,6 +115,8 @@ def lib():
                                                C.c_int, C.c_int, i32p]
         L.orb_oracle_search_for_triangulation.argtypes = [C.c_int, C.c_void_p, u8p, u8p, C.c_int, i32p, i32p, i32p, C.c_int, C.c_void_p, u8p,
                                                           u8p, C.c_int, i32p, i32p, i32p, f32p, f32p, C.c_int, i32p]
+        L.orb_oracle_guided_best.argtypes = [C.POINTER(Frame), C.c_int, f32p, f32p, f32p, i32p, i32p, u8p, C.c_int, i32p]
+        L.orb_oracle_guided_best.restype = None
         L.orb_oracle_search_by_bow.argtypes = [C.c_int, C.c_int, u8p, u8p, f32p, C.c_int, i32p, i32p, i32p, C.c_int, u8p, u8p, f32p,
                                                C.c_int, i32p, i32p, i32p, C.c_float, C.c_int, i32p]
         L.orb_oracle_knn2.argtypes = [u8p, C.c_int, u8p, C.c_long, i32p, i32p, i32p]
@@ -384,3 +386,10 @@ def search_for_triangulation(keys1, desc1, has_mp1, fv1, keys2, desc2, has_mp2, 
                                                   len(keys2), _p(keys2), _p(desc2), _p(has_mp2), len(i2), _p(i2), _p(p2), _p(t2),
                                                   _p(F12), _p(sigma2), int(check_orientation), _p(out))
     return n, out[:len(keys1)]
+
+
+def guided_best(f, qu, qv, qr, qlo, qhi, qdesc, th_dist):
+    qu, qv, qr, qlo, qhi, qdesc = _a(qu, np.float32), _a(qv, np.float32), _a(qr, np.float32), _a(qlo, np.int32), _a(qhi, np.int32), _a(qdesc, np.uint8)
+    out = np.full(max(len(qu), 1), -1, np.int32)
+    lib().orb_oracle_guided_best(C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), th_dist, _p(out))
+    return out[:len(qu)]

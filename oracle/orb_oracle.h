@@ -187,6 +187,8 @@ int orb_oracle_search_by_projection_f1f2(const OrbOracleFrame *f1, const OrbOrac
 int orb_oracle_guided_search(const OrbOracleFrame *f, int nq, const float *qu, const float *qv, const float *qr,
                              const int *qlo, const int *qhi, const uint8_t *qdesc, const float *qangle, int rule,
                              float nnratio, int th_dist, int hist_mode, int *slot_owner);
+void orb_oracle_guided_best(const OrbOracleFrame *f, int nq, const float *qu, const float *qv, const float *qr,
+                            const int *qlo, const int *qhi, const uint8_t *qdesc, int th_dist, int *best_idx);
 /* SearchByBoW, ORBmatcher.cc:155-284 (variant 0: KeyFrame vs Frame) and :715-850 (variant 1: KeyFrame vs KeyFrame) */
 int orb_oracle_search_by_bow(int variant, int n1, const uint8_t *desc1, const uint8_t *valid1, const float *angle1,
                              int nn1, const int *ids1, const int *ptr1, const int *items1,

@@ -686,3 +686,22 @@ int orb_oracle_search_for_triangulation(int n1, const OrbOracleKeyPoint *keys1, 
     free(matched2); free(vd);
     return nmatches;
 }
+
+/* Guided search without slot bookkeeping: every query independently takes its best candidate (strict-<, first minimum)
+ * and keeps it iff best <= th_dist -- the inner loops of Fuse (:1090-1107, :1222-1239) and SearchBySim3 (:1356-1378,
+ * :1436-1458), whose candidates are never skipped because of earlier matches. */
+void orb_oracle_guided_best(const OrbOracleFrame *f, int nq, const float *qu, const float *qv, const float *qr,
+                            const int *qlo, const int *qhi, const uint8_t *qdesc, int th_dist, int *best_idx) {
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(f->n > 0 ? f->n : 1));
+    for (int q = 0; q < nq; q++) {
+        best_idx[q] = -1;
+        const int nc = orb_oracle_features_in_area(f, qu[q], qv[q], qr[q], qlo[q], qhi[q], cand, f->n);
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int dist = orb_oracle_hamming(qdesc + (size_t)q * 32, f->desc + (size_t)cand[c] * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = cand[c]; }
+        }
+        if (bestDist <= th_dist) best_idx[q] = bestIdx;
+    }
+    free(cand);
+}

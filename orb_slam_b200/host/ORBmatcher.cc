@@ -5,11 +5,9 @@
 // (2) one GPU launch computes all 256-bit Hamming distances of the call; (3) replay -- the reference's
 // sequential accept/skip loop runs over those distances, so results (incl. tie-breaks) are unchanged.
 //
-// Implemented: DescriptorDistance and the Frame-level routines of the Tracking thread; the array-level
-// form of SearchByProjection(Frame,KeyFrame*,...) exists in the C-ABI (orbfe_search_by_projection_kf).
-// Not yet implemented here (declared in the header, open work in DESIGN.md): the KeyFrame-typed routines
-// SearchByProjection(Frame,KeyFrame*), SearchByProjection(KeyFrame*,Scw), SearchByBoW x2,
-// SearchForTriangulation, SearchBySim3, Fuse x2.
+// All thirteen search / fuse methods of the reference class are defined here.  The Frame-level ones and the
+// BoW / triangulation ones forward to array-level entry points that have oracle parity tests
+// (tests/test_gpu_matchers.py); the Sim3 / Fuse ones gather through KeyFrame's public API and use orbfe_hamming_csr.
 #include "ORBmatcher.h"
 
 #include <climits>
@@ -242,6 +240,422 @@ int ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, int windowSize, std::ve
     for (int i = 0; i < v2.n; i++)
         if (mp[i] >= 0 && mp[i] != INT_MAX) vpMapPointMatches2[i] = F1.mvpMapPoints[mp[i]];
     return nmatches;
+}
+
+}  // namespace ORB_SLAM
+
+// =================================================================================================
+// KeyFrame-level routines.  KeyFrame keeps its image bounds and grid protected (KeyFrame.h:181-187), so the
+// candidate lists come from its own public GetFeaturesInArea; the distances of a whole call go to the GPU in
+// one orbfe_hamming_csr launch (or to the array-level matchers of include/orbfe_match.h), and the reference's
+// accept loop -- including its map mutations -- is replayed on the host in the original order.
+// The cv::Mat algebra of the projections is written out element-wise with OpenCV 2.4's float/double semantics
+// (gemm on CV_32F accumulates in double; Mat/scalar scales by the reciprocal).
+// =================================================================================================
+namespace ORB_SLAM {
+
+namespace {
+
+struct Csr {
+    std::vector<int> row_ptr, cols;
+    std::vector<unsigned char> qdesc;
+    Csr() : row_ptr(1, 0) {}
+    void add_row(const cv::Mat &d) { qdesc.insert(qdesc.end(), d.ptr(0), d.ptr(0) + 32); row_ptr.push_back((int)cols.size()); }
+    int rows() const { return (int)row_ptr.size() - 1; }
+};
+
+std::vector<unsigned short> distances(const Csr &c, const cv::Mat &targetDesc)
+{
+    std::vector<unsigned short> dist(c.cols.empty() ? 1 : c.cols.size());
+    if (c.cols.empty()) return dist;
+    const DescBuf t(targetDesc);
+    check(orbfe_hamming_csr(thread_matcher(), &c.qdesc[0], c.rows(), t.ptr, targetDesc.rows, &c.row_ptr[0], &c.cols[0], &dist[0]));
+    return dist;
+}
+
+// y = R*x + t for 3x3 / 3x1 CV_32F Mats (cv::gemm: double accumulation, one rounding)
+void transform(const cv::Mat &R, const cv::Mat &t, const float x[3], float y[3])
+{
+    for (int k = 0; k < 3; k++) {
+        const double s = (double)R.at<float>(k, 0) * x[0] + (double)R.at<float>(k, 1) * x[1] + (double)R.at<float>(k, 2) * x[2];
+        y[k] = (float)(s + (double)t.at<float>(k, 0));
+    }
+}
+void mat3(const cv::Mat &m, float out[3]) { for (int k = 0; k < 3; k++) out[k] = m.at<float>(k, 0); }
+float norm3(const float v[3]) { return (float)std::sqrt((double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2]); }
+
+// Scw = [sR | st]: scw, Rcw = sRcw/scw, tcw = st/scw, Ow = -Rcw.t()*tcw   (ORBmatcher.cc:297-301, :1146-1150)
+struct Sim3Cam {
+    cv::Mat Rcw, tcw;
+    float Ow[3];
+    explicit Sim3Cam(const cv::Mat &Scw) {
+        double dot = 0;
+        for (int c = 0; c < 3; c++) dot += (double)Scw.at<float>(0, c) * (double)Scw.at<float>(0, c);
+        const float scw = (float)std::sqrt(dot);
+        const float inv = (float)(1.0 / (double)scw);  // Mat / scalar -> scale by 1./s
+        Rcw.create(3, 3, CV_32F);
+        tcw.create(3, 1, CV_32F);
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 3; c++) Rcw.at<float>(r, c) = Scw.at<float>(r, c) * inv;
+            tcw.at<float>(r, 0) = Scw.at<float>(r, 3) * inv;
+        }
+        for (int k = 0; k < 3; k++) {
+            const double s = (double)Rcw.at<float>(0, k) * tcw.at<float>(0, 0) + (double)Rcw.at<float>(1, k) * tcw.at<float>(1, 0) +
+                             (double)Rcw.at<float>(2, k) * tcw.at<float>(2, 0);
+            Ow[k] = (float)(s * -1.0);
+        }
+    }
+};
+
+int predict_level(const std::vector<float> &sf, float ratio, int nMaxLevel)
+{
+    const int it = (int)(std::lower_bound(sf.begin(), sf.end(), ratio) - sf.begin());
+    return std::min(it, nMaxLevel);
+}
+
+// shared gate + candidate gathering of SearchByProjection(KF,Scw,..) and both Fuse overloads:
+// returns false if the point is rejected; otherwise appends a CSR row with the level-filtered candidates
+bool project_and_gather(KeyFrame *pKF, MapPoint *pMP, const cv::Mat &Rcw, const cv::Mat &tcw, const float Ow[3], float th,
+                        bool invz_in_double, const std::vector<float> &vfScaleFactors, int nMaxLevel, Csr &csr)
+{
+    float X[3], Xc[3];
+    mat3(pMP->GetWorldPos(), X);
+    transform(Rcw, tcw, X, Xc);
+    if (Xc[2] < 0.0f) return false;  // depth must be positive
+    const float invz = invz_in_double ? (float)(1.0 / (double)Xc[2]) : 1.0f / Xc[2];
+    const float u = pKF->fx * (Xc[0] * invz) + pKF->cx;
+    const float v = pKF->fy * (Xc[1] * invz) + pKF->cy;
+    if (!pKF->IsInImage(u, v)) return false;
+    const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+    const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+    const float dist = norm3(PO);
+    if (dist < minDistance || dist > maxDistance) return false;
+    float Pn[3];
+    mat3(pMP->GetNormal(), Pn);
+    const double dotPn = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];  // Mat::dot: double
+    if (dotPn < 0.5 * dist) return false;  // viewing angle < 60 deg
+    const int nPredictedLevel = predict_level(vfScaleFactors, dist / minDistance, nMaxLevel);
+    const float radius = th * vfScaleFactors[nPredictedLevel];
+    const std::vector<size_t> vIndices = pKF->GetFeaturesInArea(u, v, radius);
+    if (vIndices.empty()) return false;
+    for (size_t k = 0; k < vIndices.size(); k++) {
+        const int kpLevel = pKF->GetKeyPointScaleLevel(vIndices[k]);
+        if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+        csr.cols.push_back((int)vIndices[k]);
+    }
+    csr.add_row(pMP->GetDescriptor());
+    return true;
+}
+
+void feature_vector_csr(const DBoW2::FeatureVector &fv, std::vector<int> &ids, std::vector<int> &ptr, std::vector<int> &items)
+{
+    ids.clear(); ptr.assign(1, 0); items.clear();
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        ids.push_back((int)it->first);
+        for (size_t k = 0; k < it->second.size(); k++) items.push_back((int)it->second[k]);
+        ptr.push_back((int)items.size());
+    }
+}
+template <typename T> const T *ptr_or_null(const std::vector<T> &v) { return v.empty() ? NULL : &v[0]; }
+
+}  // namespace
+
+// ---- Tracking::Relocalisation refinement (Tracking.cc:960,974) ------------------------------------------------
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound, float th, int ORBdist)
+{
+    const DescBuf dc(CurrentFrame.mDescriptors);
+    const OrbfeFrameView cur = make_view(CurrentFrame, dc);
+    const std::vector<MapPoint *> vpMPs = pKF->GetMapPointMatches();
+    const int np = (int)vpMPs.size();
+    std::vector<unsigned char> valid(np + 1, 0), desc((size_t)np * 32 + 1, 0);
+    std::vector<float> world((size_t)np * 3 + 1, 0.f), mind(np + 1, 1.f), ang(np + 1, 0.f);
+    for (int i = 0; i < np; i++) {
+        MapPoint *pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;  // :1642-1644
+        valid[i] = 1;
+        mat3(pMP->GetWorldPos(), &world[(size_t)i * 3]);
+        mind[i] = pMP->GetMinDistanceInvariance();
+        std::memcpy(&desc[(size_t)i * 32], pMP->GetDescriptor().ptr(0), 32);
+        ang[i] = pKF->GetKeyPointUn(i).angle;
+    }
+    float T[12];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[4 * r + c] = CurrentFrame.mTcw.at<float>(r, c);
+    std::vector<int> mp(cur.n > 0 ? cur.n : 1, -1);
+    for (int i = 0; i < cur.n; i++)
+        if (CurrentFrame.mvpMapPoints[i]) mp[i] = INT_MAX;
+    int nmatches = 0;
+    check(orbfe_search_by_projection_kf(thread_matcher(), &cur, np, &valid[0], &world[0], &mind[0], &desc[0], &ang[0], T, Frame::fx,
+                                        Frame::fy, Frame::cx, Frame::cy, th, ORBdist, mbCheckOrientation ? 1 : 0, &mp[0], &nmatches));
+    for (int i = 0; i < cur.n; i++)
+        if (mp[i] >= 0 && mp[i] != INT_MAX) CurrentFrame.mvpMapPoints[i] = vpMPs[mp[i]];
+    return nmatches;
+}
+
+// ---- LoopClosing::ComputeSim3 (LoopClosing.cc:370) ------------------------------------------------------------
+int ORBmatcher::SearchByProjection(KeyFrame *pKF, cv::Mat Scw, const std::vector<MapPoint *> &vpPoints, std::vector<MapPoint *> &vpMatched, int th)
+{
+    const int nMaxLevel = pKF->GetScaleLevels() - 1;
+    const std::vector<float> vfScaleFactors = pKF->GetScaleFactors();
+    const Sim3Cam cam(Scw);
+    std::set<MapPoint *> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint *>(NULL));
+    Csr csr;
+    std::vector<int> q2mp;
+    for (int iMP = 0, iend = (int)vpPoints.size(); iMP < iend; iMP++) {
+        MapPoint *pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        if (project_and_gather(pKF, pMP, cam.Rcw, cam.tcw, cam.Ow, (float)th, false, vfScaleFactors, nMaxLevel, csr)) q2mp.push_back(iMP);
+    }
+    const std::vector<unsigned short> dist = distances(csr, pKF->GetDescriptors());
+    int nmatches = 0;
+    for (int q = 0; q < csr.rows(); q++) {  // :373-398
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int c = csr.row_ptr[q]; c < csr.row_ptr[q + 1]; c++) {
+            const int idx = csr.cols[c];
+            if (vpMatched[idx]) continue;
+            if (dist[c] < bestDist) { bestDist = dist[c]; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { vpMatched[bestIdx] = vpPoints[q2mp[q]]; nmatches++; }
+    }
+    return nmatches;
+}
+
+// ---- LocalMapping::SearchInNeighbors (LocalMapping.cc:405,430) --------------------------------------------------
+int ORBmatcher::Fuse(KeyFrame *pKF, std::vector<MapPoint *> &vpMapPoints, float th)
+{
+    const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation();
+    const int nMaxLevel = pKF->GetScaleLevels() - 1;
+    const std::vector<float> vfScaleFactors = pKF->GetScaleFactors();
+    float Ow[3];
+    mat3(pKF->GetCameraCenter(), Ow);
+    Csr csr;
+    std::vector<int> q2mp;
+    for (size_t i = 0; i < vpMapPoints.size(); i++) {
+        MapPoint *pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        if (project_and_gather(pKF, pMP, Rcw, tcw, Ow, th, false, vfScaleFactors, nMaxLevel, csr)) q2mp.push_back((int)i);
+    }
+    const std::vector<unsigned short> dist = distances(csr, pKF->GetDescriptors());
+    int nFused = 0;
+    for (int q = 0; q < csr.rows(); q++) {  // :1090-1131
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int c = csr.row_ptr[q]; c < csr.row_ptr[q + 1]; c++)
+            if (dist[c] < bestDist) { bestDist = dist[c]; bestIdx = csr.cols[c]; }
+        if (bestDist <= TH_LOW) {
+            MapPoint *pMP = vpMapPoints[q2mp[q]];
+            MapPoint *pMPinKF = pKF->GetMapPoint(bestIdx);
+            if (pMPinKF) { if (!pMPinKF->isBad()) pMP->Replace(pMPinKF); }
+            else { pMP->AddObservation(pKF, bestIdx); pKF->AddMapPoint(pMP, bestIdx); }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+
+// ---- LoopClosing::SearchAndFuse (LoopClosing.cc:568) -------------------------------------------------------------
+int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, const std::vector<MapPoint *> &vpPoints, float th)
+{
+    const Sim3Cam cam(Scw);
+    const std::set<MapPoint *> spAlreadyFound = pKF->GetMapPoints();
+    const int nMaxLevel = pKF->GetScaleLevels() - 1;
+    const std::vector<float> vfScaleFactors = pKF->GetScaleFactors();
+    Csr csr;
+    std::vector<int> q2mp;
+    for (size_t iMP = 0; iMP < vpPoints.size(); iMP++) {
+        MapPoint *pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        if (project_and_gather(pKF, pMP, cam.Rcw, cam.tcw, cam.Ow, th, true, vfScaleFactors, nMaxLevel, csr)) q2mp.push_back((int)iMP);
+    }
+    const std::vector<unsigned short> dist = distances(csr, pKF->GetDescriptors());
+    int nFused = 0;
+    for (int q = 0; q < csr.rows(); q++) {  // :1222-1261
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int c = csr.row_ptr[q]; c < csr.row_ptr[q + 1]; c++)
+            if (dist[c] < bestDist) { bestDist = dist[c]; bestIdx = csr.cols[c]; }
+        if (bestDist <= TH_LOW) {
+            MapPoint *pMP = vpPoints[q2mp[q]];
+            MapPoint *pMPinKF = pKF->GetMapPoint(bestIdx);
+            if (pMPinKF) { if (!pMPinKF->isBad()) pMPinKF->Replace(pMP); }
+            else { pMP->AddObservation(pKF, bestIdx); pKF->AddMapPoint(pMP, bestIdx); }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+
+// ---- Tracking::Relocalisation / LoopClosing::ComputeSim3 (Tracking.cc:887, LoopClosing.cc:259) --------------------
+int ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint *> &vpMapPointMatches)
+{
+    const std::vector<MapPoint *> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint *>(F.mvpMapPoints.size(), static_cast<MapPoint *>(NULL));
+    std::vector<int> ids1, ptr1, it1, ids2, ptr2, it2;
+    feature_vector_csr(pKF->GetFeatureVector(), ids1, ptr1, it1);
+    feature_vector_csr(F.mFeatVec, ids2, ptr2, it2);
+    const std::vector<cv::KeyPoint> k1 = pKF->GetKeyPointsUn();
+    const int n1 = (int)vpMapPointsKF.size(), n2 = (int)F.mvKeys.size();
+    std::vector<unsigned char> valid1(n1 + 1, 0), valid2(n2 + 1, 1);
+    std::vector<float> a1(n1 + 1, 0.f), a2(n2 + 1, 0.f);
+    for (int i = 0; i < n1; i++) { valid1[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad(); a1[i] = k1[i].angle; }
+    for (int i = 0; i < n2; i++) a2[i] = F.mvKeys[i].angle;  // :233 uses F.mvKeys
+    const DescBuf d1(pKF->GetDescriptors()), d2(F.mDescriptors);
+    std::vector<int> out(n2 + 1, -1);
+    int nmatches = 0;
+    check(orbfe_search_by_bow(thread_matcher(), 0, n1, d1.ptr, &valid1[0], &a1[0], (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1),
+                              n2, d2.ptr, &valid2[0], &a2[0], (int)ids2.size(), ptr_or_null(ids2), &ptr2[0], ptr_or_null(it2), mfNNratio,
+                              mbCheckOrientation ? 1 : 0, &out[0], &nmatches));
+    for (int i2 = 0; i2 < n2; i2++)
+        if (out[i2] >= 0) vpMapPointMatches[i2] = vpMapPointsKF[out[i2]];
+    return nmatches;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12)
+{
+    const std::vector<MapPoint *> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+    const std::vector<cv::KeyPoint> k1 = pKF1->GetKeyPointsUn(), k2 = pKF2->GetKeyPointsUn();
+    vpMatches12 = std::vector<MapPoint *>(vp1.size(), static_cast<MapPoint *>(NULL));
+    std::vector<int> ids1, ptr1, it1, ids2, ptr2, it2;
+    feature_vector_csr(pKF1->GetFeatureVector(), ids1, ptr1, it1);
+    feature_vector_csr(pKF2->GetFeatureVector(), ids2, ptr2, it2);
+    const int n1 = (int)vp1.size(), n2 = (int)vp2.size();
+    std::vector<unsigned char> valid1(n1 + 1, 0), valid2(n2 + 1, 0);
+    std::vector<float> a1(n1 + 1, 0.f), a2(n2 + 1, 0.f);
+    for (int i = 0; i < n1; i++) { valid1[i] = vp1[i] && !vp1[i]->isBad(); a1[i] = k1[i].angle; }
+    for (int i = 0; i < n2; i++) { valid2[i] = vp2[i] && !vp2[i]->isBad(); a2[i] = k2[i].angle; }
+    const DescBuf d1(pKF1->GetDescriptors()), d2(pKF2->GetDescriptors());
+    std::vector<int> out(n1 + 1, -1);
+    int nmatches = 0;
+    check(orbfe_search_by_bow(thread_matcher(), 1, n1, d1.ptr, &valid1[0], &a1[0], (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1),
+                              n2, d2.ptr, &valid2[0], &a2[0], (int)ids2.size(), ptr_or_null(ids2), &ptr2[0], ptr_or_null(it2), mfNNratio,
+                              mbCheckOrientation ? 1 : 0, &out[0], &nmatches));
+    for (int i1 = 0; i1 < n1; i1++)
+        if (out[i1] >= 0) vpMatches12[i1] = vp2[out[i1]];
+    return nmatches;
+}
+
+// ---- LocalMapping::CreateNewMapPoints (LocalMapping.cc:252) --------------------------------------------------------
+bool ORBmatcher::CheckDistEpipolarLine(const cv::KeyPoint &kp1, const cv::KeyPoint &kp2, const cv::Mat &F12, const KeyFrame *pKF2)
+{
+    const float a = kp1.pt.x * F12.at<float>(0, 0) + kp1.pt.y * F12.at<float>(1, 0) + F12.at<float>(2, 0);
+    const float b = kp1.pt.x * F12.at<float>(0, 1) + kp1.pt.y * F12.at<float>(1, 1) + F12.at<float>(2, 1);
+    const float c = kp1.pt.x * F12.at<float>(0, 2) + kp1.pt.y * F12.at<float>(1, 2) + F12.at<float>(2, 2);
+    const float num = a * kp2.pt.x + b * kp2.pt.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * pKF2->GetSigma2(kp2.octave);
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, std::vector<cv::KeyPoint> &vMatchedKeys1,
+                                       std::vector<cv::KeyPoint> &vMatchedKeys2, std::vector<std::pair<size_t, size_t> > &vMatchedPairs)
+{
+    const std::vector<MapPoint *> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+    const std::vector<cv::KeyPoint> k1 = pKF1->GetKeyPointsUn(), k2 = pKF2->GetKeyPointsUn();
+    std::vector<int> ids1, ptr1, it1, ids2, ptr2, it2;
+    feature_vector_csr(pKF1->GetFeatureVector(), ids1, ptr1, it1);
+    feature_vector_csr(pKF2->GetFeatureVector(), ids2, ptr2, it2);
+    const int n1 = (int)k1.size(), n2 = (int)k2.size();
+    std::vector<unsigned char> has1(n1 + 1, 0), has2(n2 + 1, 0);
+    for (int i = 0; i < n1; i++) has1[i] = vp1[i] != NULL;
+    for (int i = 0; i < n2; i++) has2[i] = vp2[i] != NULL;
+    float F[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) F[3 * r + c] = F12.at<float>(r, c);
+    std::vector<float> sigma2(pKF2->GetScaleLevels());
+    for (size_t l = 0; l < sigma2.size(); l++) sigma2[l] = pKF2->GetSigma2((int)l);
+    const DescBuf d1(pKF1->GetDescriptors()), d2(pKF2->GetDescriptors());
+    std::vector<int> m12(n1 + 1, -1);
+    int nmatches = 0;
+    check(orbfe_search_for_triangulation(thread_matcher(), n1, n1 ? reinterpret_cast<const OrbfeKeyPoint *>(&k1[0]) : NULL, d1.ptr, &has1[0],
+                                         (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1), n2,
+                                         n2 ? reinterpret_cast<const OrbfeKeyPoint *>(&k2[0]) : NULL, d2.ptr, &has2[0], (int)ids2.size(),
+                                         ptr_or_null(ids2), &ptr2[0], ptr_or_null(it2), F, &sigma2[0], mbCheckOrientation ? 1 : 0, &m12[0],
+                                         &nmatches));
+    vMatchedKeys1.clear(); vMatchedKeys2.clear(); vMatchedPairs.clear();  // :994-1011
+    for (int i = 0; i < n1; i++) {
+        if (m12[i] < 0) continue;
+        vMatchedKeys1.push_back(k1[i]);
+        vMatchedKeys2.push_back(k2[m12[i]]);
+        vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
+    }
+    return nmatches;
+}
+
+// ---- LoopClosing::ComputeSim3 (LoopClosing.cc:317) ------------------------------------------------------------------
+int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12, const float &s12, const cv::Mat &R12,
+                             const cv::Mat &t12, float th)
+{
+    const cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    // sR12 = s12*R12 ; sR21 = (1.0/s12)*R12.t() ; t21 = -sR21*t12   (:1282-1284)
+    cv::Mat sR12(3, 3, CV_32F), sR21(3, 3, CV_32F), t21(3, 1, CV_32F);
+    const float inv_s = (float)(1.0 / (double)s12);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) { sR12.at<float>(r, c) = R12.at<float>(r, c) * s12; sR21.at<float>(r, c) = R12.at<float>(c, r) * inv_s; }
+    for (int k = 0; k < 3; k++) {
+        const double s = (double)sR21.at<float>(k, 0) * t12.at<float>(0, 0) + (double)sR21.at<float>(k, 1) * t12.at<float>(1, 0) +
+                         (double)sR21.at<float>(k, 2) * t12.at<float>(2, 0);
+        t21.at<float>(k, 0) = (float)(s * -1.0);
+    }
+    const std::vector<MapPoint *> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vp1.size(), N2 = (int)vp2.size();
+    std::vector<bool> done1(N1, false), done2(N2, false);
+    for (int i = 0; i < N1; i++) {
+        MapPoint *pMP = vpMatches12[i];
+        if (!pMP) continue;
+        done1[i] = true;
+        const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+        if (idx2 >= 0 && idx2 < N2) done2[idx2] = true;
+    }
+    std::vector<int> vnMatch1(N1, -1), vnMatch2(N2, -1);
+    // one direction: project the points of `from` into `to` and take the best candidate (<= TH_HIGH)
+    struct Dir { KeyFrame *from, *to; const cv::Mat *Rw, *tw, *sR, *t; const std::vector<MapPoint *> *vp; std::vector<bool> *done; std::vector<int> *match; };
+    Dir dirs[2] = {{pKF1, pKF2, &R1w, &t1w, &sR21, &t21, &vp1, &done1, &vnMatch1}, {pKF2, pKF1, &R2w, &t2w, &sR12, &t12, &vp2, &done2, &vnMatch2}};
+    for (int dsel = 0; dsel < 2; dsel++) {
+        Dir &D = dirs[dsel];
+        const int nMaxLevel = D.to->GetScaleLevels() - 1;
+        const std::vector<float> sf = D.to->GetScaleFactors();
+        Csr csr;
+        std::vector<int> q2i;
+        for (int i = 0; i < (int)D.vp->size(); i++) {
+            MapPoint *pMP = (*D.vp)[i];
+            if (!pMP || (*D.done)[i]) continue;
+            if (pMP->isBad()) continue;
+            float X[3], Xa[3], Xb[3];
+            mat3(pMP->GetWorldPos(), X);
+            transform(*D.Rw, *D.tw, X, Xa);
+            transform(*D.sR, *D.t, Xa, Xb);
+            if (Xb[2] < 0.0f) continue;
+            const float invz = (float)(1.0 / (double)Xb[2]);
+            const float u = pKF1->fx * (Xb[0] * invz) + pKF1->cx, v = pKF1->fy * (Xb[1] * invz) + pKF1->cy;  // :1270-1273: KF1's intrinsics both ways
+            if (!D.to->IsInImage(u, v)) continue;
+            const float maxD = pMP->GetMaxDistanceInvariance(), minD = pMP->GetMinDistanceInvariance();
+            const float dist3D = norm3(Xb);
+            if (dist3D < minD || dist3D > maxD) continue;
+            const int lv = predict_level(sf, dist3D / minD, nMaxLevel);
+            const std::vector<size_t> vIdx = D.to->GetFeaturesInArea(u, v, th * sf[lv]);
+            if (vIdx.empty()) continue;
+            for (size_t k = 0; k < vIdx.size(); k++) {
+                const int oct = D.to->GetKeyPointUn(vIdx[k]).octave;
+                if (oct < lv - 1 || oct > lv) continue;
+                csr.cols.push_back((int)vIdx[k]);
+            }
+            csr.add_row(pMP->GetDescriptor());
+            q2i.push_back(i);
+        }
+        const std::vector<unsigned short> dist = distances(csr, D.to->GetDescriptors());
+        for (int q = 0; q < csr.rows(); q++) {
+            int bestDist = INT_MAX, bestIdx = -1;
+            for (int c = csr.row_ptr[q]; c < csr.row_ptr[q + 1]; c++)
+                if (dist[c] < bestDist) { bestDist = dist[c]; bestIdx = csr.cols[c]; }
+            if (bestDist <= TH_HIGH) (*D.match)[q2i[q]] = bestIdx;
+        }
+    }
+    int nFound = 0;  // :1486-1502: keep mutual agreements
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vp2[idx2]; nFound++; }
+    }
+    return nFound;
 }
 
 }  // namespace ORB_SLAM

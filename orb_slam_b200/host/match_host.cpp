@@ -730,3 +730,33 @@ extern "C" int orbfe_search_for_triangulation(OrbfeMatcher *m, int n1, const Orb
     *nmatches_out = nmatches;
     return ORBFE_OK;
 }
+
+// Guided search without slot bookkeeping (Fuse :1090-1107 / :1222-1239, SearchBySim3 :1356-1378 / :1436-1458):
+// best candidate per query, kept iff best <= th_dist.  One distance launch for all queries.
+extern "C" int orbfe_guided_best(OrbfeMatcher *m, const OrbfeFrameView *f, int nq, const float *qu, const float *qv, const float *qr,
+                                 const int32_t *qlo, const int32_t *qhi, const uint8_t *qdesc, int th_dist, int32_t *best_idx_out) {
+    if (!m || !f || nq < 0 || !best_idx_out) return ORBFE_ERR_ARG;
+    if (nq > 0 && (!qu || !qv || !qr || !qlo || !qhi || !qdesc)) return ORBFE_ERR_ARG;
+    Grid grid;
+    build_grid(*f, grid);
+    std::vector<int32_t> row_ptr(1, 0), cols;
+    std::vector<int> tmp;
+    for (int q = 0; q < nq; q++) {
+        tmp.clear();
+        features_in_area(*f, grid, qu[q], qv[q], qr[q], qlo[q], qhi[q], tmp);
+        cols.insert(cols.end(), tmp.begin(), tmp.end());
+        row_ptr.push_back((int32_t)cols.size());
+        best_idx_out[q] = -1;
+    }
+    if (cols.empty()) return ORBFE_OK;
+    std::vector<uint16_t> dist(cols.size());
+    const int rc = orbfe_hamming_csr(m, qdesc, nq, f->desc, f->n, row_ptr.data(), cols.data(), dist.data());
+    if (rc) return rc;
+    for (int q = 0; q < nq; q++) {
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int c = row_ptr[q]; c < row_ptr[q + 1]; c++)
+            if (dist[c] < bestDist) { bestDist = dist[c]; bestIdx = cols[c]; }
+        if (bestDist <= th_dist) best_idx_out[q] = bestIdx;
+    }
+    return ORBFE_OK;
+}

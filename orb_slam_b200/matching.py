@@ -47,6 +47,7 @@ def _bind():
     L.orbfe_guided_search.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp]
     L.orbfe_search_for_triangulation.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
                                                  vp, vp, C.c_int, vp, vp]
+    L.orbfe_guided_best.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp]
     L.orbfe_window_search.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp]
     _bound = True
@@ -230,3 +231,12 @@ def search_for_triangulation(matcher: ORBmatcher, keys1, desc1, has_mp1, fv1, ke
                                             len(keys2), _p(keys2), _p(desc2), _p(has_mp2), len(i2), _p(i2), _p(p2), _p(t2),
                                             _p(F12), _p(sigma2), int(matcher.mbCheckOrientation), _p(out), C.byref(nm)))
     return nm.value, out[:len(keys1)]
+
+
+def guided_best(matcher: ORBmatcher, f, qu, qv, qr, qlo, qhi, qdesc, th_dist):
+    L = _bind()
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    qu, qv, qr, qlo, qhi, qdesc = a(qu, np.float32), a(qv, np.float32), a(qr, np.float32), a(qlo, np.int32), a(qhi, np.int32), a(qdesc, np.uint8)
+    out = np.full(max(len(qu), 1), -1, np.int32)
+    _check(L.orbfe_guided_best(matcher.handle, C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), th_dist, _p(out)))
+    return out[:len(qu)]

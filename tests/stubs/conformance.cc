@@ -42,6 +42,29 @@ std::vector<size_t> Frame::GetFeaturesInArea(const float &x, const float &y, con
     return out;
 }
 
+// link-only definitions of the KeyFrame stub (the real KeyFrame.cc is linked in a real integration)
+namespace ORB_SLAM {
+cv::Mat KeyFrame::GetRotation() { return cv::Mat(); }
+cv::Mat KeyFrame::GetTranslation() { return cv::Mat(); }
+cv::Mat KeyFrame::GetCameraCenter() { return cv::Mat(); }
+DBoW2::FeatureVector KeyFrame::GetFeatureVector() { return DBoW2::FeatureVector(); }
+std::set<MapPoint *> KeyFrame::GetMapPoints() { return std::set<MapPoint *>(); }
+std::vector<MapPoint *> KeyFrame::GetMapPointMatches() { return std::vector<MapPoint *>(); }
+MapPoint *KeyFrame::GetMapPoint(const size_t &) { return NULL; }
+void KeyFrame::AddMapPoint(MapPoint *, const size_t &) {}
+cv::KeyPoint KeyFrame::GetKeyPointUn(const size_t &) const { return cv::KeyPoint(); }
+cv::Mat KeyFrame::GetDescriptor(const size_t &) { return cv::Mat(); }
+int KeyFrame::GetKeyPointScaleLevel(const size_t &) const { return 0; }
+std::vector<cv::KeyPoint> KeyFrame::GetKeyPointsUn() const { return std::vector<cv::KeyPoint>(); }
+cv::Mat KeyFrame::GetDescriptors() { return cv::Mat(); }
+std::vector<size_t> KeyFrame::GetFeaturesInArea(const float &, const float &, const float &) const { return std::vector<size_t>(); }
+bool KeyFrame::IsInImage(const float &, const float &) const { return false; }
+float KeyFrame::GetScaleFactor(int) const { return 1.f; }
+std::vector<float> KeyFrame::GetScaleFactors() const { return std::vector<float>(1, 1.f); }
+float KeyFrame::GetSigma2(int) const { return 1.f; }
+int KeyFrame::GetScaleLevels() const { return 1; }
+}
+
 static void fill_frame(Frame &F, ORBextractor *ex, cv::Mat &im) {
     (*ex)(im, cv::Mat(), F.mvKeys, F.mDescriptors);  // Frame.cc:60
     F.N = (int)F.mvKeys.size();

@@ -5,6 +5,7 @@
 #include <opencv2/core/core.hpp>
 #include "ORBextractor.h"
 #include "MapPoint.h"
+#include "KeyFrame.h"
 namespace ORB_SLAM {
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
@@ -23,6 +24,7 @@ public:
     int mnScaleLevels;
     float mfScaleFactor;
     std::vector<float> mvScaleFactors;
+    DBoW2::FeatureVector mFeatVec;
     // reference Frame.cc:200-265 (a restatement lives in the conformance TU; the real Frame.cc is linked unchanged)
     std::vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const int minLevel = -1, const int maxLevel = -1) const;
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];

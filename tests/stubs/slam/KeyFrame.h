@@ -1,3 +1,37 @@
-// TEST STUB: ORB_SLAM::KeyFrame is only named (pointer parameters) by the facade header.
+// TEST STUB of the slice of ORB_SLAM::KeyFrame (reference include/KeyFrame.h:44-140) that ORBmatcher calls.
+// Exists only so that the facade's KeyFrame-level methods can be compile-checked without the SLAM sources.
 #pragma once
-namespace ORB_SLAM { class KeyFrame; }
+#include <cstddef>
+#include <map>
+#include <set>
+#include <vector>
+#include <opencv2/core/core.hpp>
+#include "MapPoint.h"
+namespace DBoW2 {
+class FeatureVector : public std::map<unsigned int, std::vector<unsigned int> > {};  // Thirdparty/DBoW2/DBoW2/FeatureVector.h
+}
+namespace ORB_SLAM {
+class KeyFrame {
+public:
+    float fx, fy, cx, cy;
+    cv::Mat GetRotation();
+    cv::Mat GetTranslation();
+    cv::Mat GetCameraCenter();
+    DBoW2::FeatureVector GetFeatureVector();
+    std::set<MapPoint *> GetMapPoints();
+    std::vector<MapPoint *> GetMapPointMatches();
+    MapPoint *GetMapPoint(const size_t &idx);
+    void AddMapPoint(MapPoint *pMP, const size_t &idx);
+    cv::KeyPoint GetKeyPointUn(const size_t &idx) const;
+    cv::Mat GetDescriptor(const size_t &idx);
+    int GetKeyPointScaleLevel(const size_t &idx) const;
+    std::vector<cv::KeyPoint> GetKeyPointsUn() const;
+    cv::Mat GetDescriptors();
+    std::vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r) const;
+    bool IsInImage(const float &x, const float &y) const;
+    float GetScaleFactor(int nLevel = 1) const;
+    std::vector<float> GetScaleFactors() const;
+    float GetSigma2(int nLevel = 1) const;
+    int GetScaleLevels() const;
+};
+}

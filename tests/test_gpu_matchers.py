@@ -272,6 +272,12 @@ def test_guided_search_all_rules(gpu_required):
         n_o, so_o = O.guided_search(o2, qu, qv, qr, lo, hi, d1, k1["angle"], rule, 0.8, th, hist, slot_owner=occ)
         assert n == n_o and np.array_equal(so, so_o), (rule, th, hist, filt)
         assert n > 100
+        # the slot-free variant used by Fuse / SearchBySim3
+        lo2 = (k1["octave"] - 1).astype(np.int32)
+        hi2 = k1["octave"].astype(np.int32)
+        bi = M.guided_best(m, f2v, qu, qv, qr, lo2, hi2, d1, 50 if rule == 0 else 100)
+        bi_o = O.guided_best(o2, qu, qv, qr, lo2, hi2, d1, 50 if rule == 0 else 100)
+        assert np.array_equal(bi, bi_o) and (bi >= 0).sum() > 100
         m.close()
 
 
