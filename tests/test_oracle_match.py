@@ -168,3 +168,104 @@ def test_knn2_first_minimum_and_second():
     for i in range(20):
         ds = sorted((_ham(q[i], db[j]), j) for j in range(300))
         assert bd[i] == ds[0][0] and bi[i] == ds[0][1] and sd[i] == ds[1][0]
+
+
+def test_search_by_bow_against_python_loop():
+    """Oracle M9 (both overloads) vs a direct Python restatement of ORBmatcher.cc:155-284 / :715-850."""
+    rng = np.random.default_rng(3)
+    n1, n2 = 300, 280
+    d1 = random_descriptors(n1, 5)
+    perm = rng.permutation(n1)[:n2]
+    d2 = noisy_copies(d1[perm], 0.05, 6)
+    a1 = rng.uniform(0, 360, n1).astype(np.float32)
+    a2 = ((a1[perm] + rng.normal(5, 3, n2)) % 360).astype(np.float32)
+    node1 = (d1[:, 0].astype(np.int32) >> 4) * 5 + 1
+    node2 = (d2[:, 0].astype(np.int32) >> 4) * 5 + 1
+    node2[rng.random(n2) < 0.05] = 777
+
+    def fv(nodes):
+        order = np.argsort(nodes, kind="stable")
+        ids, cnt = np.unique(nodes, return_counts=True)
+        return ids.astype(np.int32), np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32), order.astype(np.int32)
+
+    fv1, fv2 = fv(node1), fv(node2)
+    v1 = (rng.random(n1) < 0.8).astype(np.uint8)
+    v2 = (rng.random(n2) < 0.9).astype(np.uint8)
+    nnr = np.float32(0.75)
+    for variant in (0, 1):
+        n, out = O.search_by_bow(variant, d1, v1, a1, fv1, d2, v2, a2, fv2, nnratio=0.75, check_orientation=True)
+        exp = np.full(n2 if variant == 0 else n1, -1, np.int64)
+        matched2 = np.zeros(n2, bool)
+        hist = [[] for _ in range(30)]
+        m1 = {int(i): fv1[2][fv1[1][k]:fv1[1][k + 1]] for k, i in enumerate(fv1[0])}
+        m2 = {int(i): fv2[2][fv2[1][k]:fv2[1][k + 1]] for k, i in enumerate(fv2[0])}
+        for node in sorted(set(m1) & set(m2)):
+            for i1 in m1[node]:
+                if not v1[i1]:
+                    continue
+                b1 = b2 = 2 ** 31 - 1
+                bi = -1
+                for i2 in m2[node]:
+                    if variant == 0:
+                        if exp[i2] >= 0:
+                            continue
+                    elif matched2[i2] or not v2[i2]:
+                        continue
+                    dd = _ham(d1[i1], d2[i2])
+                    if dd < b1:
+                        b2, b1, bi = b1, dd, i2
+                    elif dd < b2:
+                        b2 = dd
+                ok = (b1 <= 50) if variant == 0 else (b1 < 50)
+                if ok and np.float32(b1) < nnr * np.float32(b2):
+                    if variant == 0:
+                        exp[bi] = i1
+                        hist[_bin(a1[i1], a2[bi])].append(bi)
+                    else:
+                        exp[i1] = bi
+                        matched2[bi] = True
+                        hist[_bin(a1[i1], a2[bi])].append(i1)
+        keep = _three_max_py([len(h) for h in hist])
+        for b in range(30):
+            if b not in keep:
+                for i in hist[b]:
+                    exp[i] = -1
+        assert np.array_equal(out, exp) and n == int((exp >= 0).sum()) and n > 60
+
+
+def test_guided_search_rule0_against_python_loop():
+    """Oracle guided search (rule 0, histogram filter) vs Python: the skeleton of ORBmatcher.cc:1547-1617."""
+    k1, d1 = _rand_frame(300, 11)
+    k2 = k1.copy()
+    rng = np.random.default_rng(12)
+    k2["x"] = (k1["x"] + rng.uniform(-3, 3, 300)).astype(np.float32)
+    k2["y"] = (k1["y"] + rng.uniform(-3, 3, 300)).astype(np.float32)
+    k2["angle"] = ((k1["angle"] + rng.normal(4, 3, 300)) % 360).astype(np.float32)
+    d2 = noisy_copies(d1, 0.07, 13)
+    f2 = O.OracleFrame(k2, d2, W, H)
+    qr = np.full(300, 12.0, np.float32)
+    lo, hi = (k1["octave"] - 1).astype(np.int32), (k1["octave"] + 1).astype(np.int32)
+    occ = np.full(300, -1, np.int32)
+    occ[::17] = 4
+    n, so = O.guided_search(f2, k1["x"], k1["y"], qr, lo, hi, d1, k1["angle"], 0, 0.9, 100, 1, slot_owner=occ)
+    cells, gx, gy = _grid_py(k2)
+    exp = occ.astype(np.int64).copy()
+    hist = [[] for _ in range(30)]
+    for q in range(300):
+        cand = _area_py(k2, cells, gx, gy, k1["x"][q], k1["y"][q], 12.0, lo[q], hi[q])
+        b1, bi = 2 ** 31 - 1, -1
+        for i2 in cand:
+            if exp[i2] >= 0:
+                continue
+            dd = _ham(d1[q], d2[i2])
+            if dd < b1:
+                b1, bi = dd, i2
+        if b1 <= 100:
+            exp[bi] = q
+            hist[_bin(k1["angle"][q], k2["angle"][bi])].append(bi)
+    keep = _three_max_py([len(h) for h in hist])
+    for b in range(30):
+        if b not in keep:
+            for i in hist[b]:
+                exp[i] = -1
+    assert np.array_equal(so, exp) and n > 150
