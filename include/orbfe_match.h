@@ -66,6 +66,21 @@ int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, const OrbfeKe
                                       float fx, float fy, float cx, float cy, float th, int check_orientation,
                                       int *d_cur_mp, int *d_nmatches, void *stream);
 
+/* Guided search (the skeleton shared by ORBmatcher.cc:49-125, :519-594, :1622-1746 and WindowSearch-style loops) with
+ * EVERYTHING device-resident: job j searches frame d_frame_idx[j] (layout as above) with the explicit query windows
+ * [d_q_base[j], d_q_base[j] + d_q_cnt[j]) of the concatenated arrays: centre (qu, qv), half-size qr, octave filter
+ * [qlo, qhi] ((-1,-1) = none), 32-byte descriptor, angle (only read when check_orientation).  qcap >= every d_q_cnt[j].
+ * rule 0: best <= th_dist; rule 1: best <= second*nnratio && best <= TH_HIGH (:469, :586); rule 2: best <= TH_HIGH &&
+ * !(bestLevel == secondLevel && best > nnratio*second) (:113-121).  d_slot_owner (njobs x cap, in/out): >= 0 on entry =
+ * occupied slot (never reassigned); free slots matched in this call receive the job-local query index.
+ * d_nmatches[j] = number of matches kept (-1: candidate scratch overflow -> ORBFE_ERR_CAPACITY at sync). */
+int orbfe_guided_search_device(OrbfeMatcher *m, int njobs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                               const int *d_counts, int cap, const int *d_frame_idx, const float *d_qu, const float *d_qv,
+                               const float *d_qr, const int *d_qlo, const int *d_qhi, const uint8_t *d_qdesc,
+                               const float *d_qangle, const int *d_q_base, const int *d_q_cnt, int qcap, float min_x,
+                               float min_y, float max_x, float max_y, int rule, float nnratio, int th_dist,
+                               int check_orientation, int *d_slot_owner, int *d_nmatches, void *stream);
+
 /* int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, float th) (ORBmatcher.cc:49-125), local-map
  * tracking.  Per map point: in_view = mbTrackInView && !isBad(); proj_xy = (mTrackProjX, mTrackProjY); level =
  * mnTrackScaleLevel; view_cos = mTrackViewCos; desc = GetDescriptor().  f_mp_inout[i2] >= 0 <=> F.mvpMapPoints[i2] set

@@ -4,6 +4,8 @@
 // of two 32-byte descriptors.  On the device that is 8 x (XOR + POPC) on 32-bit words.  These kernels are
 // bound by the integer/POPC issue rate (all-pairs sweep) or by launch latency (windowed CSR lists), never
 // by HBM; no tensor cores (the north star forbids reshaping Hamming into a GEMM).
+#include <cstring>
+
 #include "orbfe_internal.h"
 
 namespace orbfe {
@@ -155,9 +157,28 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp /*[SBP_WARPS]*
 
 struct SbpQuery {
     float u, v, r;
-    int oct, x0, x1, y0, y1;
+    int lo, hi;  // octave filter [lo, hi]; (-1, -1) = none (KeyFrame::GetFeaturesInArea has none)
+    int x0, x1, y0, y1;
     bool ok;
 };
+
+// cell range of Frame::GetFeaturesInArea (Frame.cc:205-223); false if the window misses the grid
+__device__ __forceinline__ bool sbp_cell_range(const SbpParams &P, SbpQuery &q) {
+    int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.u, P.min_x), q.r), P.gw));
+    x0 = max(0, x0);
+    if (x0 >= SBP_GCOLS) return false;
+    int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.u, P.min_x), q.r), P.gw));
+    x1 = min(SBP_GCOLS - 1, x1);
+    if (x1 < 0) return false;
+    int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.v, P.min_y), q.r), P.gh));
+    y0 = max(0, y0);
+    if (y0 >= SBP_GROWS) return false;
+    int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.v, P.min_y), q.r), P.gh));
+    y1 = min(SBP_GROWS - 1, y1);
+    if (y1 < 0) return false;
+    q.x0 = x0; q.x1 = x1; q.y0 = y0; q.y1 = y1;
+    return true;
+}
 
 __device__ __forceinline__ SbpQuery sbp_project(const SbpParams &P, const OrbfeKeyPoint &kl, const float *X, const float *T) {
     SbpQuery q;
@@ -174,38 +195,39 @@ __device__ __forceinline__ SbpQuery sbp_project(const SbpParams &P, const OrbfeK
     q.v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, xc3[1]), invzc), P.cy);
     if (q.u < P.min_x || q.u > P.max_x) return q;
     if (q.v < P.min_y || q.v > P.max_y) return q;
-    q.oct = kl.octave;
-    q.r = __fmul_rn(P.th, P.scale[q.oct]);
-    int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.u, P.min_x), q.r), P.gw));
-    x0 = max(0, x0);
-    if (x0 >= SBP_GCOLS) return q;
-    int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.u, P.min_x), q.r), P.gw));
-    x1 = min(SBP_GCOLS - 1, x1);
-    if (x1 < 0) return q;
-    int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.v, P.min_y), q.r), P.gh));
-    y0 = max(0, y0);
-    if (y0 >= SBP_GROWS) return q;
-    int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.v, P.min_y), q.r), P.gh));
-    y1 = min(SBP_GROWS - 1, y1);
-    if (y1 < 0) return q;
-    q.x0 = x0; q.x1 = x1; q.y0 = y0; q.y1 = y1;
-    q.ok = true;
+    q.lo = kl.octave - 1;
+    q.hi = kl.octave + 1;
+    q.r = __fmul_rn(P.th, P.scale[kl.octave]);
+    q.ok = sbp_cell_range(P, q);
     return q;
 }
 
+// explicit queries (guided search): one job = `q_cnt` queries starting at `q_base` of the concatenated arrays
+struct GuidedQueries {
+    const float *qu, *qv, *qr, *qangle;
+    const int *qlo, *qhi;
+    const uint8_t *qdesc;
+    const int *q_base, *q_cnt;
+};
+
+__device__ __forceinline__ bool octave_ok(int o, int lo, int hi) {
+    return (lo == -1 && hi == -1) || (o >= lo && o <= hi);
+}
+
+template <bool EXPLICIT>
 __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, const OrbfeKeyPoint *__restrict__ kps,
                                                                  const uint8_t *__restrict__ desc, const int *__restrict__ counts,
                                                                  const int *__restrict__ cur_idx, const int *__restrict__ last_idx,
                                                                  const float *__restrict__ world, const uint8_t *__restrict__ flags,
-                                                                 const float *__restrict__ Tcw, uint32_t *__restrict__ scratch,
-                                                                 int *__restrict__ cur_mp, int *__restrict__ nmatches,
-                                                                 int *__restrict__ err) {
+                                                                 const float *__restrict__ Tcw, GuidedQueries GQ,
+                                                                 uint32_t *__restrict__ scratch, int *__restrict__ cur_mp,
+                                                                 int *__restrict__ nmatches, int *__restrict__ err) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int cap = P.cap;
     int *cell_start = reinterpret_cast<int *>(smem);                 // [NCELL + 1]
     int *cell_cur = cell_start + SBP_NCELL + 1;                      // [NCELL]
-    int *q_off = cell_cur + SBP_NCELL;                               // [cap + 1]
-    float *kx = reinterpret_cast<float *>(q_off + cap + 1);          // [cap] Current keypoint x
+    int *q_off = cell_cur + SBP_NCELL;                               // [qcap + 1]
+    float *kx = reinterpret_cast<float *>(q_off + P.qcap + 1);       // [cap] Current keypoint x
     float *ky = kx + cap;                                            // [cap]
     uint32_t *taken = reinterpret_cast<uint32_t *>(ky + cap);        // [(cap + 31) / 32]
     uint16_t *items = reinterpret_cast<uint16_t *>(taken + (cap + 31) / 32);  // [cap]
@@ -215,17 +237,32 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem + P.smem_fixed);  // entry staging area
 
     const int pair = blockIdx.x;
-    const int fc = cur_idx[pair], fl = last_idx[pair];
-    const int nc = min(counts[fc], cap), nl = min(counts[fl], cap);
+    const int fc = cur_idx[pair], fl = EXPLICIT ? 0 : last_idx[pair];
+    const int nc = min(counts[fc], cap);
+    const int qb = EXPLICIT ? GQ.q_base[pair] : 0;
+    const int nl = EXPLICIT ? min(GQ.q_cnt[pair], P.qcap) : min(counts[fl], cap);
     const OrbfeKeyPoint *__restrict__ kc = kps + (size_t)fc * cap;
     const OrbfeKeyPoint *__restrict__ kl = kps + (size_t)fl * cap;
     const uint4 *__restrict__ dc = reinterpret_cast<const uint4 *>(desc + (size_t)fc * cap * 32);
-    const uint4 *__restrict__ dl = reinterpret_cast<const uint4 *>(desc + (size_t)fl * cap * 32);
-    const float *__restrict__ wl = world + (size_t)fl * cap * 3;
-    const uint8_t *__restrict__ fll = flags + (size_t)fl * cap;
-    const float *__restrict__ T = Tcw + (size_t)pair * 12;
+    const uint4 *__restrict__ dl = EXPLICIT ? reinterpret_cast<const uint4 *>(GQ.qdesc + (size_t)qb * 32)
+                                            : reinterpret_cast<const uint4 *>(desc + (size_t)fl * cap * 32);
+    const float *__restrict__ wl = EXPLICIT ? nullptr : world + (size_t)fl * cap * 3;
+    const uint8_t *__restrict__ fll = EXPLICIT ? nullptr : flags + (size_t)fl * cap;
+    const float *__restrict__ T = EXPLICIT ? nullptr : Tcw + (size_t)pair * 12;
     int *__restrict__ mp = cur_mp + (size_t)pair * cap;
     const int tid = threadIdx.x;
+    // query q of this job (projection of a Last feature, or an explicit (u, v, r, lo, hi) window)
+    auto get_query = [&](int q) -> SbpQuery {
+        if (EXPLICIT) {
+            SbpQuery Q;
+            Q.u = GQ.qu[qb + q]; Q.v = GQ.qv[qb + q]; Q.r = GQ.qr[qb + q];
+            Q.lo = GQ.qlo[qb + q]; Q.hi = GQ.qhi[qb + q];
+            Q.ok = sbp_cell_range(P, Q);
+            return Q;
+        }
+        return sbp_project(P, kl[q], wl + 3 * q, T);
+    };
+    auto query_angle = [&](int q) -> float { return EXPLICIT ? GQ.qangle[qb + q] : kl[q].angle; };
 
     // ---- A: grid of the Current frame ----
     for (int i = tid; i < SBP_NCELL; i += SBP_THREADS) cell_cur[i] = 0;
@@ -282,16 +319,15 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     for (int it = 0; it < nq_iter; it++) {
         const int q = it * SBP_THREADS + tid;
         int cnt = 0;
-        if (q < nl && fll[q]) {
-            const SbpQuery Q = sbp_project(P, kl[q], wl + 3 * q, T);
+        if (q < nl && (EXPLICIT || fll[q])) {
+            const SbpQuery Q = get_query(q);
             if (Q.ok) {
                 for (int ix = Q.x0; ix <= Q.x1; ix++) {
                     // cells (ix, y0..y1) are contiguous in the cell-major layout: one item range per column
                     const int kb = cell_start[ix * SBP_GROWS + Q.y0], ke = cell_start[ix * SBP_GROWS + Q.y1 + 1];
                     for (int k = kb; k < ke; k++) {
                         const int i2 = items[k];
-                        const int o = koct[i2];
-                        if (o < Q.oct - 1 || o > Q.oct + 1) continue;
+                        if (!octave_ok(koct[i2], Q.lo, Q.hi)) continue;
                         if (fabsf(__fsub_rn(kx[i2], Q.u)) > Q.r || fabsf(__fsub_rn(ky[i2], Q.v)) > Q.r) continue;
                         cnt++;
                     }
@@ -316,14 +352,13 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     for (int q = tid; q < nl; q += SBP_THREADS) {
         int o = q_off[q];
         if (q_off[q + 1] == o) continue;
-        const SbpQuery Q = sbp_project(P, kl[q], wl + 3 * q, T);
+        const SbpQuery Q = get_query(q);
         const uint4 a0 = __ldg(&dl[2 * q]), a1 = __ldg(&dl[2 * q + 1]);
         for (int ix = Q.x0; ix <= Q.x1; ix++) {
             const int kb = cell_start[ix * SBP_GROWS + Q.y0], ke = cell_start[ix * SBP_GROWS + Q.y1 + 1];
             for (int k = kb; k < ke; k++) {
                 const int i2 = items[k];
-                const int oc = koct[i2];
-                if (oc < Q.oct - 1 || oc > Q.oct + 1) continue;
+                if (!octave_ok(koct[i2], Q.lo, Q.hi)) continue;
                 if (fabsf(__fsub_rn(kx[i2], Q.u)) > Q.r || fabsf(__fsub_rn(ky[i2], Q.v)) > Q.r) continue;
                 const int d = ham256(a0, a1, __ldg(&dc[2 * i2]), __ldg(&dc[2 * i2 + 1]));
                 ent[o++] = (uint32_t)i2 | ((uint32_t)d << 16);
@@ -357,7 +392,33 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
                     }
                     best = min(best, __reduce_min_sync(0xffffffffu, key));
                 }
-                if (best != 0xFFFFFFFFu && (int)(best >> 16) <= 100 /* TH_HIGH */) {
+                bool accept = best != 0xFFFFFFFFu && (int)(best >> 16) <= P.th_dist;  // rule 0 (th_dist = TH_HIGH for :1576)
+                if (EXPLICIT && P.rule != 0 && best != 0xFFFFFFFFu) {
+                    // second best among the remaining free candidates (strict-< order does not matter for the value)
+                    const int bpos = (int)(best & 0xFFFF);
+                    uint32_t second = 0xFFFFFFFFu;
+                    for (int p0 = b; p0 < e; p0 += 32) {
+                        const int p = p0 + lane;
+                        uint32_t key = 0xFFFFFFFFu;
+                        if (p < e && p - b != bpos) {
+                            const uint32_t c2 = ent[p];
+                            const int j2 = (int)(c2 & 0xFFFF);
+                            if (!((taken[j2 >> 5] >> (j2 & 31)) & 1u)) key = (c2 & 0xFFFF0000u) | (uint32_t)(p - b);
+                        }
+                        second = min(second, __reduce_min_sync(0xffffffffu, key));
+                    }
+                    const int bd = (int)(best >> 16);
+                    // INT_MAX stands for "no second candidate": (float)INT_MAX in the reference's comparisons
+                    const float sd = second == 0xFFFFFFFFu ? 2147483648.0f : (float)(int)(second >> 16);
+                    if (P.rule == 1) {
+                        accept = (float)bd <= __fmul_rn(sd, P.nnratio) && bd <= 100;
+                    } else {
+                        const int lb = koct[ent[b + bpos] & 0xFFFF];
+                        const int ls = second == 0xFFFFFFFFu ? -1 : (int)koct[ent[b + (int)(second & 0xFFFF)] & 0xFFFF];
+                        accept = bd <= 100 && !(lb == ls && (float)bd > __fmul_rn(P.nnratio, sd));
+                    }
+                }
+                if (accept) {
                     const int i2 = (int)(ent[b + (int)(best & 0xFFFF)] & 0xFFFF);
                     if (lane == 0) {
                         taken[i2 >> 5] |= 1u << (i2 & 31);
@@ -379,7 +440,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
         // rotation histogram of the new matches (:1583-1590), in parallel: bin = round((aLast - aCur [+360]) / 30)
         for (int i = tid; i < nc; i += SBP_THREADS) {
             if (newbin[i] != 0xFE) continue;
-            float rot = __fsub_rn(kl[mp[i]].angle, kc[i].angle);
+            float rot = __fsub_rn(query_angle(mp[i]), kc[i].angle);
             if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
             int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
             if (bin == 30) bin = 0;
@@ -411,8 +472,8 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     if (tid == 0) nmatches[pair] = s_nm - s_removed;
 }
 
-size_t sbp_smem_fixed_bytes(int cap) {
-    size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)cap + 1) +
+size_t sbp_smem_fixed_bytes(int cap, int qcap) {
+    size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)qcap + 1) +
                2 * sizeof(float) * (size_t)cap + sizeof(uint32_t) * (((size_t)cap + 31) / 32) + sizeof(uint16_t) * (size_t)cap +
                2 * (size_t)cap;
     return (b + 15) / 16 * 16;
@@ -421,14 +482,29 @@ size_t sbp_smem_fixed_bytes(int cap) {
 int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const OrbfeKeyPoint *kps, const uint8_t *desc,
                       const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
                       const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s) {
-    static size_t configured = 0;
-    if (smem_bytes > 48 * 1024 && smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (smem_bytes > 48 * 1024) {  // per device/context attribute: set on every call (cheap), never cached process-wide
+        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return (int)e;
-        configured = smem_bytes;
     }
-    sbp_device_kernel<<<npairs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, cur_idx, last_idx, world, flags, Tcw, scratch,
-                                                      cur_mp, nmatches, err);
+    GuidedQueries none;
+    memset(&none, 0, sizeof(none));
+    sbp_device_kernel<false><<<npairs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, cur_idx, last_idx, world, flags, Tcw, none,
+                                                             scratch, cur_mp, nmatches, err);
+    return 0;
+}
+
+int launch_guided_device(const SbpParams &P, size_t smem_bytes, int njobs, const OrbfeKeyPoint *kps, const uint8_t *desc,
+                         const int *counts, const int *frame_idx, const float *qu, const float *qv, const float *qr,
+                         const int *qlo, const int *qhi, const uint8_t *qdesc, const float *qangle, const int *q_base,
+                         const int *q_cnt, uint32_t *scratch, int *slot_owner, int *nmatches, int *err, cudaStream_t s) {
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    GuidedQueries G;
+    G.qu = qu; G.qv = qv; G.qr = qr; G.qangle = qangle; G.qlo = qlo; G.qhi = qhi; G.qdesc = qdesc; G.q_base = q_base; G.q_cnt = q_cnt;
+    sbp_device_kernel<true><<<njobs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, frame_idx, nullptr, nullptr, nullptr, nullptr, G,
+                                                            scratch, slot_owner, nmatches, err);
     return 0;
 }
 

@@ -599,7 +599,11 @@ extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int 
     for (int k = 0; k < nchunks; k++) {
         const int f0 = (int)((long long)batch * k / nchunks), f1 = (int)((long long)batch * (k + 1) / nchunks);
         if (f1 <= f0) continue;
-        if (frame_stride == stride * (size_t)height) {
+        if (frame_stride == stride * (size_t)height && stride == (size_t)width && L0.pitch == width) {
+            // fully contiguous on both sides: one linear DMA
+            CU_TRY(cudaMemcpyAsync(L0.pyr + (size_t)f0 * L0.plane, imgs + (size_t)f0 * frame_stride, (size_t)width * height * (f1 - f0),
+                                   cudaMemcpyHostToDevice, ex->copy_stream));
+        } else if (frame_stride == stride * (size_t)height) {
             CU_TRY(cudaMemcpy2DAsync(L0.pyr + (size_t)f0 * L0.plane, L0.pitch, imgs + (size_t)f0 * frame_stride, stride, width,
                                      (size_t)height * (f1 - f0), cudaMemcpyHostToDevice, ex->copy_stream));
         } else {
@@ -803,8 +807,9 @@ extern "C" int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, co
     P.scale[0] = 1.0f;                           // Frame.cc:95-103
     for (int i = 1; i < nlevels; i++) P.scale[i] = P.scale[i - 1] * scale_factor;
     P.nlevels = nlevels; P.cap = cap; P.check_ori = check_orientation ? 1 : 0;
+    P.qcap = cap; P.rule = 0; P.th_dist = 100 /* TH_HIGH, ORBmatcher.cc:1576 */; P.nnratio = 0.f;
     P.scratch_per_pair = 64 * cap;
-    const size_t fixed = sbp_smem_fixed_bytes(cap);
+    const size_t fixed = sbp_smem_fixed_bytes(cap, cap);
     const size_t total = std::max<size_t>(fixed + 16 * 1024, 100 * 1024);
     if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large for the device matcher", cap);
     P.smem_fixed = (int)fixed;
@@ -819,6 +824,52 @@ extern "C" int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, co
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
     int rc = launch_sbp_device(P, total, npairs, d_kps, d_desc, d_counts, d_cur_idx, d_last_idx, d_world, d_flags, d_Tcw,
                                m->scratch, d_cur_mp, d_nmatches, m->d_err, s);
+    if (rc) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)rc));
+    CU_TRY(cudaGetLastError());
+    m->launches += 1;
+    return ORBFE_OK;
+}
+
+// Guided search with explicit query windows, device-resident (same kernel, EXPLICIT query source).
+extern "C" int orbfe_guided_search_device(OrbfeMatcher *m, int njobs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                          const int *d_counts, int cap, const int *d_frame_idx, const float *d_qu,
+                                          const float *d_qv, const float *d_qr, const int *d_qlo, const int *d_qhi,
+                                          const uint8_t *d_qdesc, const float *d_qangle, const int *d_q_base,
+                                          const int *d_q_cnt, int qcap, float min_x, float min_y, float max_x, float max_y,
+                                          int rule, float nnratio, int th_dist, int check_orientation, int *d_slot_owner,
+                                          int *d_nmatches, void *stream) {
+    if (!m || njobs < 0 || cap < 1 || cap > 65535 || qcap < 1 || rule < 0 || rule > 2) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (njobs == 0) return ORBFE_OK;
+    if (!d_kps || !d_desc || !d_counts || !d_frame_idx || !d_qu || !d_qv || !d_qr || !d_qlo || !d_qhi || !d_qdesc || !d_q_base ||
+        !d_q_cnt || !d_slot_owner || !d_nmatches || (check_orientation && !d_qangle))
+        return fail(ORBFE_ERR_ARG, "NULL argument");
+    if (!(max_x > min_x) || !(max_y > min_y)) return fail(ORBFE_ERR_ARG, "bad image bounds");
+    CU_TRY(cudaSetDevice(m->device));
+    SbpParams P;
+    memset(&P, 0, sizeof(P));
+    P.min_x = min_x; P.min_y = min_y; P.max_x = max_x; P.max_y = max_y;
+    P.gw = (float)64 / (float)(max_x - min_x);   // Frame.cc:77
+    P.gh = (float)48 / (float)(max_y - min_y);   // Frame.cc:78
+    P.nlevels = 1; P.cap = cap; P.check_ori = check_orientation ? 1 : 0;
+    P.qcap = qcap; P.rule = rule; P.th_dist = th_dist; P.nnratio = nnratio;
+    const size_t per_job = (size_t)64 * std::max(cap, qcap);
+    if (per_job > (size_t)INT_MAX) return fail(ORBFE_ERR_UNSUPPORTED, "too many queries per job");
+    P.scratch_per_pair = (int)per_job;
+    const size_t fixed = sbp_smem_fixed_bytes(cap, qcap);
+    const size_t total = std::max<size_t>(fixed + 16 * 1024, 100 * 1024);
+    if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d / qcap %d too large for the device matcher", cap, qcap);
+    P.smem_fixed = (int)fixed;
+    P.smem_entries = (int)((total - fixed) / sizeof(uint32_t));
+    const size_t need = (size_t)njobs * P.scratch_per_pair;
+    if (m->scratch_entries < need) {
+        if (m->scratch) cudaFree(m->scratch);
+        m->scratch = nullptr; m->scratch_entries = 0;
+        CU_TRY(cudaMalloc((void **)&m->scratch, need * sizeof(uint32_t)));
+        m->scratch_entries = need;
+    }
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    int rc = launch_guided_device(P, total, njobs, d_kps, d_desc, d_counts, d_frame_idx, d_qu, d_qv, d_qr, d_qlo, d_qhi, d_qdesc,
+                                  d_qangle, d_q_base, d_q_cnt, m->scratch, d_slot_owner, d_nmatches, m->d_err, s);
     if (rc) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)rc));
     CU_TRY(cudaGetLastError());
     m->launches += 1;
@@ -1017,5 +1068,67 @@ extern "C" int orbfe_sbp_frames_via_device(OrbfeMatcher *m, int npairs, const Or
         if (cur[j].n) memcpy(cur_mp_inout[j], H + o_mp + (size_t)j * cap * sizeof(int), (size_t)cur[j].n * sizeof(int));
         nmatches_out[j] = h_nm[j];
     }
+    return ORBFE_OK;
+}
+
+// Guided search on host arrays through the device kernel: pack -> H2D -> kernel -> D2H.  Returns 1 when the inputs
+// do not fit the kernel (the caller then takes the CSR + host-replay path).  slot_new receives, per feature of `f`,
+// the query index newly matched to it or -1.
+extern "C" int orbfe_guided_via_device(OrbfeMatcher *m, const OrbfeFrameView *f, int nq, const float *qu, const float *qv,
+                                       const float *qr, const int *qlo, const int *qhi, const uint8_t *const *qdesc,
+                                       const float *qangle, int rule, float nnratio, int th_dist, int check_orientation,
+                                       const int *slot_owner, int *slot_new, int *nmatches_out) {
+    if (f->n < 1 || f->n > 65535 || nq < 1) return 1;
+    if (f->grid_inv_w != (float)64 / (float)(f->max_x - f->min_x) || f->grid_inv_h != (float)48 / (float)(f->max_y - f->min_y)) return 1;
+    const int cap = f->n, qcap = nq;
+    if (std::max<size_t>(sbp_smem_fixed_bytes(cap, qcap) + 16 * 1024, 100 * 1024) > 220 * 1024) return 1;
+    CU_TRY(cudaSetDevice(m->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_kps = take((size_t)cap * sizeof(OrbfeKeyPoint)), o_desc = take((size_t)cap * 32), o_cnt = take(sizeof(int));
+    const size_t o_fi = take(sizeof(int)), o_qb = take(sizeof(int)), o_qc = take(sizeof(int));
+    const size_t o_qu = take((size_t)nq * 4), o_qv = take((size_t)nq * 4), o_qr = take((size_t)nq * 4), o_qa = take((size_t)nq * 4);
+    const size_t o_lo = take((size_t)nq * 4), o_hi = take((size_t)nq * 4), o_qd = take((size_t)nq * 32);
+    const size_t o_mp = take((size_t)cap * sizeof(int));
+    const size_t in_bytes = off;
+    const size_t o_nm = take(sizeof(int));
+    const size_t total = off;
+    if (m->stage_cap < total) {
+        if (m->h_stage) cudaFreeHost(m->h_stage);
+        if (m->d_stage) cudaFree(m->d_stage);
+        m->h_stage = nullptr; m->d_stage = nullptr; m->stage_cap = 0;
+        const size_t want = total + total / 4;
+        CU_TRY(cudaHostAlloc((void **)&m->h_stage, want, cudaHostAllocDefault));
+        CU_TRY(cudaMalloc((void **)&m->d_stage, want));
+        m->stage_cap = want;
+    }
+    unsigned char *H = m->h_stage, *D = m->d_stage;
+    memcpy(H + o_kps, f->keys_un, (size_t)cap * sizeof(OrbfeKeyPoint));
+    memcpy(H + o_desc, f->desc, (size_t)cap * 32);
+    *(int *)(H + o_cnt) = cap; *(int *)(H + o_fi) = 0; *(int *)(H + o_qb) = 0; *(int *)(H + o_qc) = nq;
+    memcpy(H + o_qu, qu, (size_t)nq * 4); memcpy(H + o_qv, qv, (size_t)nq * 4); memcpy(H + o_qr, qr, (size_t)nq * 4);
+    if (qangle) memcpy(H + o_qa, qangle, (size_t)nq * 4); else memset(H + o_qa, 0, (size_t)nq * 4);
+    memcpy(H + o_lo, qlo, (size_t)nq * 4); memcpy(H + o_hi, qhi, (size_t)nq * 4);
+    for (int q = 0; q < nq; q++) memcpy(H + o_qd + (size_t)q * 32, qdesc[q], 32);
+    memcpy(H + o_mp, slot_owner, (size_t)cap * sizeof(int));
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(D, H, in_bytes, cudaMemcpyHostToDevice, s));
+    int rc = orbfe_guided_search_device(m, 1, (const OrbfeKeyPoint *)(D + o_kps), D + o_desc, (const int *)(D + o_cnt), cap,
+                                        (const int *)(D + o_fi), (const float *)(D + o_qu), (const float *)(D + o_qv),
+                                        (const float *)(D + o_qr), (const int *)(D + o_lo), (const int *)(D + o_hi), D + o_qd,
+                                        (const float *)(D + o_qa), (const int *)(D + o_qb), (const int *)(D + o_qc), qcap, f->min_x,
+                                        f->min_y, f->max_x, f->max_y, rule, nnratio, th_dist, check_orientation, (int *)(D + o_mp),
+                                        (int *)(D + o_nm), s);
+    if (rc == ORBFE_ERR_UNSUPPORTED) return 1;
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(H + o_mp, D + o_mp, total - o_mp, cudaMemcpyDeviceToHost, s));
+    rc = orbfe_matcher_sync(m);
+    if (rc == ORBFE_ERR_CAPACITY) return 1;
+    if (rc) return rc;
+    m->h2d_bytes += in_bytes;
+    m->d2h_bytes += total - o_mp;
+    const int *mp = (const int *)(H + o_mp);
+    for (int i = 0; i < cap; i++) slot_new[i] = slot_owner[i] >= 0 ? -1 : mp[i];
+    *nmatches_out = *(const int *)(H + o_nm);
     return ORBFE_OK;
 }

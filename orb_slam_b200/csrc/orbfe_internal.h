@@ -106,11 +106,18 @@ struct SbpParams {
     float fx, fy, cx, cy, th;
     float scale[ORBFE_MAX_LEVELS];             // Frame::mvScaleFactors
     int nlevels, cap, check_ori;
+    int qcap;                                  // queries per job the shared-memory offset table is sized for
+    int rule, th_dist;                         // accept rule 0/1/2 and distance threshold (guided search); projection mode: 0, TH_HIGH
+    float nnratio;
     int scratch_per_pair;                      // global scratch entries per pair
     int smem_entries;                          // entries that fit in the dynamic shared-memory staging area
     int smem_fixed;                            // bytes of the fixed shared-memory part
 };
-size_t sbp_smem_fixed_bytes(int cap);
+size_t sbp_smem_fixed_bytes(int cap, int qcap);
+int launch_guided_device(const SbpParams &P, size_t smem_bytes, int njobs, const OrbfeKeyPoint *kps, const uint8_t *desc,
+                         const int *counts, const int *frame_idx, const float *qu, const float *qv, const float *qr,
+                         const int *qlo, const int *qhi, const uint8_t *qdesc, const float *qangle, const int *q_base,
+                         const int *q_cnt, uint32_t *scratch, int *slot_owner, int *nmatches, int *err, cudaStream_t s);
 int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const OrbfeKeyPoint *kps, const uint8_t *desc,
                       const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
                       const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s);

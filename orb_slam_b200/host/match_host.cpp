@@ -28,6 +28,10 @@ extern "C" int orbfe_sbp_frames_via_device(OrbfeMatcher *m, int npairs, const Or
                                            const float *const *last_world, const float *const *Tcw, float fx, float fy,
                                            float cx, float cy, float th, int check_orientation, int *const *cur_mp_inout,
                                            int *nmatches_out);
+extern "C" int orbfe_guided_via_device(OrbfeMatcher *m, const OrbfeFrameView *f, int nq, const float *qu, const float *qv,
+                                       const float *qr, const int *qlo, const int *qhi, const uint8_t *const *qdesc,
+                                       const float *qangle, int rule, float nnratio, int th_dist, int check_orientation,
+                                       const int *slot_owner, int *slot_new, int *nmatches_out);
 static bool g_force_host_replay = false;
 // test hook: 1 = always use host candidate lists + device distances + host greedy replay
 extern "C" void orbfe_matcher_force_host_replay(int on) { g_force_host_replay = on != 0; }
@@ -399,6 +403,26 @@ struct GuidedQuery { float u, v, r; int lo, hi; const uint8_t *desc; float angle
 
 int guided_search(OrbfeMatcher *m, const OrbfeFrameView &f, const std::vector<GuidedQuery> &Q, int rule, float nnratio,
                   int th_dist, int hist_mode, int *slot_owner, const std::vector<int> &owner_id, int *nmatches_out) {
+    if (!g_force_host_replay && !Q.empty() && f.n > 0) {
+        // fused device kernel (grid, candidates, distances, greedy accept loop, rotation histogram in one launch)
+        const size_t nq = Q.size();
+        std::vector<float> qu(nq), qv(nq), qr(nq), qa(nq);
+        std::vector<int> qlo(nq), qhi(nq), slot_new(f.n);
+        std::vector<const uint8_t *> qd(nq);
+        for (size_t q = 0; q < nq; q++) {
+            qu[q] = Q[q].u; qv[q] = Q[q].v; qr[q] = Q[q].r; qa[q] = Q[q].angle;
+            qlo[q] = Q[q].lo; qhi[q] = Q[q].hi; qd[q] = Q[q].desc;
+        }
+        const int rc = orbfe_guided_via_device(m, &f, (int)nq, qu.data(), qv.data(), qr.data(), qlo.data(), qhi.data(), qd.data(),
+                                               qa.data(), rule, nnratio, th_dist, hist_mode == 1, slot_owner, slot_new.data(),
+                                               nmatches_out);
+        if (rc == ORBFE_OK) {
+            for (int i = 0; i < f.n; i++)
+                if (slot_new[i] >= 0) slot_owner[i] = owner_id[slot_new[i]];
+            return ORBFE_OK;
+        }
+        if (rc != 1) return rc;  // 1 = does not fit the kernel: CSR distances + host replay below
+    }
     std::vector<Job> jobs(1);
     Job &J = jobs[0];
     build_grid(f, J.grid);

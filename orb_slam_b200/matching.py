@@ -37,6 +37,9 @@ def _bind():
     L.orbfe_search_by_projection_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp,
                                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp]
+    L.orbfe_guided_search_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int,
+                                             C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
+                                             vp, vp, vp]
     L.orbfe_search_local_points.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]
     L.orbfe_search_by_projection_kf.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float,
                                                 C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
@@ -138,6 +141,19 @@ def search_by_projection_device(matcher: ORBmatcher, npairs, d_kps, d_desc, d_co
                                                0.0, 0.0, float(width), float(height), scale_factor, nlevels,
                                                fx, fy, cx, cy, th, int(matcher.mbCheckOrientation), vp(d_cur_mp),
                                                vp(d_nmatches), vp(stream)))
+
+
+def guided_search_device(matcher: ORBmatcher, njobs, d_kps, d_desc, d_counts, cap, d_frame_idx, d_qu, d_qv, d_qr, d_qlo, d_qhi,
+                         d_qdesc, d_qangle, d_q_base, d_q_cnt, qcap, width, height, rule, th_dist, d_slot_owner, d_nmatches,
+                         stream=0):
+    """Device-pointer form of the guided-search skeleton (explicit query windows); see include/orbfe_match.h."""
+    L = _bind()
+    vp = C.c_void_p
+    _check(L.orbfe_guided_search_device(matcher.handle, njobs, vp(d_kps), vp(d_desc), vp(d_counts), cap, vp(d_frame_idx),
+                                        vp(d_qu), vp(d_qv), vp(d_qr), vp(d_qlo), vp(d_qhi), vp(d_qdesc), vp(d_qangle),
+                                        vp(d_q_base), vp(d_q_cnt), qcap, 0.0, 0.0, float(width), float(height), rule,
+                                        float(matcher.mfNNratio), th_dist, int(matcher.mbCheckOrientation), vp(d_slot_owner),
+                                        vp(d_nmatches), vp(stream)))
 
 
 def search_local_points(matcher: ORBmatcher, f, in_view, proj_xy, level, view_cos, desc, th, f_mp=None):

@@ -171,9 +171,18 @@ def test_device_resident_search_by_projection(gpu_required):
     m2.close()
 
 
-def test_local_points_reloc_and_f1f2_projection(gpu_required):
+@pytest.fixture(params=[0, 1], ids=["fused-kernel", "host-replay"])
+def guided_path(request):
+    """Both implementations behind the guided matchers: the fused device kernel (default) and the CSR-distance +
+    host-replay path it falls back to when a problem does not fit the kernel."""
+    fe.lib().orbfe_matcher_force_host_replay(request.param)
+    yield request.param
+    fe.lib().orbfe_matcher_force_host_replay(0)
+
+
+def test_local_points_reloc_and_f1f2_projection(gpu_required, guided_path):
     """M3 (local-map points), M4 (Frame vs KeyFrame, relocalisation) and M6 (F1->F2 projection window): array-level
-    C-ABI (host candidates + device distances + host replay) against the oracle's restatement."""
+    C-ABI against the oracle's restatement, through the fused kernel and through the host-replay path."""
     feats, shifts = _features(2)
     (k1, d1), (k2, d2) = feats
     n1 = len(k1)
@@ -250,7 +259,7 @@ def test_search_by_bow_both_overloads(gpu_required):
             m.close()
 
 
-def test_guided_search_all_rules(gpu_required):
+def test_guided_search_all_rules(gpu_required, guided_path):
     """The exported guided-search skeleton (used by the KeyFrame-level facade methods) against the oracle, for every
     accept rule / histogram mode, with and without octave filters (KeyFrame::GetFeaturesInArea has none)."""
     feats, shifts = _features(2)
@@ -279,6 +288,74 @@ def test_guided_search_all_rules(gpu_required):
         bi_o = O.guided_best(o2, qu, qv, qr, lo2, hi2, d1, 50 if rule == 0 else 100)
         assert np.array_equal(bi, bi_o) and (bi >= 0).sum() > 100
         m.close()
+
+
+def test_device_resident_guided_search(gpu_required):
+    """orbfe_guided_search_device: several jobs with different frames / query counts / occupied slots in one launch,
+    every accept rule, against the oracle."""
+    import torch
+    feats, shifts = _features(4)
+    cap = 1000
+    nfr = len(feats)
+    kps_all = np.zeros((nfr, cap), fe.KP_DTYPE)
+    desc_all = np.zeros((nfr, cap, 32), np.uint8)
+    counts = np.zeros(nfr, np.int32)
+    for f, (k, d) in enumerate(feats):
+        n = len(k) - 23 * f
+        counts[f] = n
+        kps_all[f, :n], desc_all[f, :n] = k[:n], d[:n]
+    rng = np.random.default_rng(17)
+    jobs = [(1, 0), (2, 1), (3, 2), (0, 3), (2, 2)]  # (searched frame, frame the queries come from)
+    qu, qv, qr, qlo, qhi, qd, qa, qbase, qcnt = [], [], [], [], [], [], [], [], []
+    for tgt, src in jobs:
+        k, d = feats[src]
+        keep = rng.random(len(k)) < 0.8
+        k, d = k[keep], d[keep]
+        dx = sum(s[0] for s in shifts[src + 1:tgt + 1]) if tgt > src else -sum(s[0] for s in shifts[tgt + 1:src + 1])
+        dy = sum(s[1] for s in shifts[src + 1:tgt + 1]) if tgt > src else -sum(s[1] for s in shifts[tgt + 1:src + 1])
+        qbase.append(sum(qcnt))
+        qcnt.append(len(k))
+        qu.append(k["x"] + np.float32(dx) + rng.normal(0, 1.0, len(k)).astype(np.float32))
+        qv.append(k["y"] + np.float32(dy) + rng.normal(0, 1.0, len(k)).astype(np.float32))
+        qr.append((np.float32(7.0) * np.float32(1.2) ** k["octave"]).astype(np.float32))
+        nofilt = rng.random(len(k)) < 0.2
+        qlo.append(np.where(nofilt, -1, k["octave"] - 1).astype(np.int32))
+        qhi.append(np.where(nofilt, -1, k["octave"] + (rng.random(len(k)) < 0.5)).astype(np.int32))
+        qd.append(d)
+        qa.append(k["angle"])
+    cat = lambda xs, t: np.ascontiguousarray(np.concatenate(xs).astype(t))
+    QU, QV, QR, QA = cat(qu, np.float32), cat(qv, np.float32), cat(qr, np.float32), cat(qa, np.float32)
+    QLO, QHI, QD = cat(qlo, np.int32), cat(qhi, np.int32), np.ascontiguousarray(np.concatenate(qd))
+    njobs, qcap = len(jobs), max(qcnt)
+    pre = np.full((njobs, cap), -1, np.int32)
+    pre[rng.random((njobs, cap)) < 0.03] = 4
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_kps, d_desc, d_cnt = t(kps_all.view(np.uint8).reshape(nfr, cap, 28)), t(desc_all), t(counts)
+    d_fi = t(np.array([j[0] for j in jobs], np.int32))
+    d_q = [t(x) for x in (QU, QV, QR, QLO, QHI, QD, QA)]
+    d_qb, d_qc = t(np.array(qbase, np.int32)), t(np.array(qcnt, np.int32))
+    total = 0
+    for rule, th, ori in ((0, 60, True), (0, 100, False), (1, 0, False), (2, 0, False), (1, 0, True)):
+        m = fe.ORBmatcher(0.8, ori)
+        d_so, d_nm = t(pre), torch.zeros(njobs, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        M.guided_search_device(m, njobs, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, d_fi.data_ptr(),
+                               *[x.data_ptr() for x in d_q], d_qb.data_ptr(), d_qc.data_ptr(), qcap, W, H, rule, th,
+                               d_so.data_ptr(), d_nm.data_ptr())
+        m.sync()
+        so, nm = d_so.cpu().numpy(), d_nm.cpu().numpy()
+        for j, (tgt, src) in enumerate(jobs):
+            nc = counts[tgt]
+            fr = O.OracleFrame(kps_all[tgt, :nc], desc_all[tgt, :nc], W, H)
+            sl = slice(qbase[j], qbase[j] + qcnt[j])
+            n_o, so_o = O.guided_search(fr, QU[sl], QV[sl], QR[sl], QLO[sl], QHI[sl], QD[sl], QA[sl], rule, 0.8, th,
+                                        1 if ori else 0, slot_owner=pre[j, :nc])
+            assert nm[j] == n_o, (rule, j, nm[j], n_o)
+            assert np.array_equal(so[j, :nc], so_o), (rule, j)
+            total += n_o
+        m.close()
+    assert total > 3000
 
 
 def test_search_for_triangulation(gpu_required):

@@ -24,9 +24,10 @@ hc = torch.empty((B,), dtype=torch.int32).pin_memory()
 def call():
     ex.extract_batch_ptr(h.data_ptr(), W, H, W, W * H, B, hk.data_ptr(), hd.data_ptr(), NF, hc.data_ptr())
 for _ in range(3): call()
-t = time.perf_counter()
-for _ in range(10): call()
-print("orbfe_extract_batch (host buffers): %.3f ms / step" % ((time.perf_counter() - t) / 10 * 1e3))
+for rep in range(3):
+    t = time.perf_counter()
+    for _ in range(30): call()
+    print("orbfe_extract_batch (host buffers): %.3f ms / step" % ((time.perf_counter() - t) / 30 * 1e3))
 kps = hk.numpy().view(fe.KP_DTYPE).reshape(B, NF); desc = hd.numpy(); cnt = hc.numpy()
 Tc = [bench.tcw_for_shift(*shifts[i]) for i in range(B)]
 def match():
