@@ -382,30 +382,53 @@ def main():
         host_t["extract_call"] += time.perf_counter() - t0
         return nm
 
-    # ---- e2e: host buffers in, host results out.  A stream of frames is processed as a two-stage pipeline:
-    # while step t is being matched (worker thread: orbfe_search_by_projection_frames), step t+1 is already being
-    # uploaded and extracted (orbfe_extract_batch; ctypes releases the GIL).  Outputs are double-buffered.
+    # ---- e2e: host buffers in, host results out.  A stream of frames is processed as a software pipeline over the
+    # public C-ABI calls only: two extractor handles (each with its own device buffers and streams) alternate steps on
+    # two host threads, so the upload of step t+1 overlaps the kernels of step t and there is no bubble at a call
+    # boundary; a third thread matches finished steps in order (orbfe_search_by_projection_frames on host views).
+    # ctypes releases the GIL inside the calls.  Outputs rotate through four pinned buffer sets.
     from concurrent.futures import ThreadPoolExecutor
+    NBUF = 4
     e2e_bufs = []
-    for _ in range(2):
+    for _ in range(NBUF):
         hk = torch.empty((B, NFEAT, 28), dtype=torch.uint8).pin_memory()
         hd = torch.empty((B, NFEAT, 32), dtype=torch.uint8).pin_memory()
         hc = torch.empty((B,), dtype=torch.int32).pin_memory()
         e2e_bufs.append((hk, hd, hc, hk.numpy().view(fe.KP_DTYPE).reshape(B, NFEAT), hd.numpy(), hc.numpy()))
+    ex_b = fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank)
+    e2e_ex = (ex, ex_b)
+    e2e_ex_pool = (ThreadPoolExecutor(max_workers=1), ThreadPoolExecutor(max_workers=1))
     e2e_pool = ThreadPoolExecutor(max_workers=1)
 
+    def extract_step(st):
+        t0 = time.perf_counter()
+        x = e2e_ex[st & 1]
+        hk, hd, hc, _, _, c_np = e2e_bufs[st % NBUF]
+        x.extract_batch_ptr(h_frames.data_ptr(), W, H, W, W * H, B, hk.data_ptr(), hd.data_ptr(), NFEAT, hc.data_ptr())
+        host_t["extract_call"] += time.perf_counter() - t0
+        return x.last_launches(), int(c_np.sum())
+
     def run_e2e(steps):
-        nm, fut = 0, None
+        nm = 0
+        ex_futs, m_futs = {}, {}
+
+        def finish_extract(st):
+            nl, nk = ex_futs.pop(st).result()
+            launches[0] += nl
+            kp_total[0] += nk
+            _, _, _, k_np, d_np, c_np = e2e_bufs[st % NBUF]
+            m_futs[st] = e2e_pool.submit(match_step, k_np, d_np, c_np)
+
         for st in range(steps):
-            hk, hd, hc, k_np, d_np, c_np = e2e_bufs[st & 1]
-            ex.extract_batch_ptr(h_frames.data_ptr(), W, H, W, W * H, B, hk.data_ptr(), hd.data_ptr(), NFEAT, hc.data_ptr())
-            launches[0] += ex.last_launches()
-            kp_total[0] += int(c_np.sum())
-            if fut is not None:
-                nm += fut.result()
-            fut = e2e_pool.submit(match_step, k_np, d_np, c_np)
-        if fut is not None:
-            nm += fut.result()
+            if st - (NBUF - 1) in m_futs:             # buffer set st % NBUF was last used by step st - NBUF
+                nm += m_futs.pop(st - (NBUF - 1)).result()
+            ex_futs[st] = e2e_ex_pool[st & 1].submit(extract_step, st)
+            if st >= 1:
+                finish_extract(st - 1)
+        if steps:
+            finish_extract(steps - 1)
+        for st in sorted(m_futs):
+            nm += m_futs[st].result()
         return nm
 
     def timed(run_fn, steps):
@@ -509,6 +532,7 @@ def main():
                                     "sample": "%d of the step's frames (about %.0f CPU-seconds), CPU oracle port on %d threads, %.1f s wall" % (nfr, 0.25 * nfr, cores, dt)}
         print(json.dumps(line))
     ex.close()
+    ex_b.close()
     mt.close()
     if world > 1:
         dist.destroy_process_group()

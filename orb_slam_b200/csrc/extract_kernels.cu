@@ -79,16 +79,29 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
         }
         return;
     }
+    // all table loads, then all 24 pixel-word loads, then the arithmetic: the loads of the four rows are independent
+    // and in flight together (rows past the bottom edge are clamped for the loads and skipped at the store)
+    int2 rr[RZ_ROWS];
+    short2 bb[RZ_ROWS];
+#pragma unroll
+    for (int ry = 0; ry < RZ_ROWS; ry++) {
+        const int y = min(ybase + ry, dh - 1);
+        rr[ry] = __ldg(&D.yrows[y]);
+        bb[ry] = __ldg(&D.yab[y]);
+    }
+    uint32_t u[RZ_ROWS][3], v[RZ_ROWS][3];
+#pragma unroll
+    for (int ry = 0; ry < RZ_ROWS; ry++) {
+        const uint32_t *p0 = reinterpret_cast<const uint32_t *>(src + (size_t)rr[ry].x * spitch);
+        const uint32_t *p1 = reinterpret_cast<const uint32_t *>(src + (size_t)rr[ry].y * spitch);
+        u[ry][0] = __ldg(p0); u[ry][1] = __ldg(p0 + 1); u[ry][2] = __ldg(p0 + 2);
+        v[ry][0] = __ldg(p1); v[ry][1] = __ldg(p1 + 1); v[ry][2] = __ldg(p1 + 2);
+    }
 #pragma unroll
     for (int ry = 0; ry < RZ_ROWS; ry++) {
         const int y = ybase + ry;
-        if (y >= dh) break;
-        const int2 rr = __ldg(&D.yrows[y]);
-        const short2 bb = __ldg(&D.yab[y]);
-        const uint32_t *p0 = reinterpret_cast<const uint32_t *>(src + (size_t)rr.x * spitch);
-        const uint32_t *p1 = reinterpret_cast<const uint32_t *>(src + (size_t)rr.y * spitch);
-        const uint32_t u0 = __ldg(p0), u1 = __ldg(p0 + 1), u2 = __ldg(p0 + 2);
-        const uint32_t v0 = __ldg(p1), v1 = __ldg(p1 + 1), v2 = __ldg(p1 + 2);
+        const uint32_t u0 = u[ry][0], u1 = u[ry][1], u2 = u[ry][2], v0 = v[ry][0], v1 = v[ry][1], v2 = v[ry][2];
+        const int b0 = bb[ry].x, b1 = bb[ry].y;
         uint32_t out = 0;
 #define RZ_PIX(i, o, abv)                                                                                   \
         {                                                                                                   \
@@ -98,9 +111,9 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
             const uint32_t pv = __funnelshift_r(hiw ? v1 : v0, hiw ? v2 : v1, sh);                          \
             const int r0 = (int)__dp2a_lo((abv), pu, 0u);  /* S[s]*a0 + S[s+1]*a1 */                        \
             const int r1 = (int)__dp2a_lo((abv), pv, 0u);                                                   \
-            int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;           \
-            v = min(max(v, 0), 255);                                                                        \
-            out |= (uint32_t)v << (8 * (i));                                                                \
+            int q = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;                         \
+            q = min(max(q, 0), 255);                                                                        \
+            out |= (uint32_t)q << (8 * (i));                                                                \
         }
         RZ_PIX(0, o0, ab.x)
         RZ_PIX(1, o1, ab.y)
@@ -108,7 +121,7 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
         RZ_PIX(3, o3, ab.w)
 #undef RZ_PIX
         // pitch is a multiple of 128 and x4 a multiple of 4: aligned 32-bit store (bytes beyond w land in row padding)
-        *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch) = out;
+        if (y < dh) *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch) = out;
     }
 }
 
@@ -932,7 +945,8 @@ __device__ __forceinline__ uint32_t blur_round_u8(int s) {
     return (uint32_t)min(q, 255);
 }
 
-__global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ plan, const BTileInfo *__restrict__ btiles, int f0) {
+__global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ plan, const BTileInfo *__restrict__ btiles, int f0,
+                                                    int dst_f0) {
     __shared__ __align__(16) uint8_t pix[B2_PH * B2_PS];
 
     const int f = blockIdx.y + f0;
@@ -968,7 +982,7 @@ __global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ 
         A[r] = __byte_perm(wv, 0, 0x4240);
         B[r] = __byte_perm(wv, 0, 0x4341);
     }
-    uint8_t *__restrict__ dst = L.blur + (size_t)f * L.plane;
+    uint8_t *__restrict__ dst = L.blur + (size_t)(blockIdx.y + dst_f0) * L.plane;
     const int gx = x0 - 4 + 4 * g;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -998,9 +1012,10 @@ __global__ void __launch_bounds__(256) blur7_kernel(const PlanDev *__restrict__ 
     }
 }
 
-void launch_blur(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+// smoothed planes of frames [f0, f0+nf) are written to plane slots [dst_f0, dst_f0+nf) of lv[].blur
+void launch_blur(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, int dst_f0, cudaStream_t s) {
     dim3 grid(hp.nbtiles_total, nf);
-    blur7_kernel<<<grid, 256, 0, s>>>(d_plan, w.btile_info, f0);
+    blur7_kernel<<<grid, 256, 0, s>>>(d_plan, w.btile_info, f0, dst_f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1123,6 +1138,170 @@ __global__ void __launch_bounds__(256) describe_kernel(const PlanDev *__restrict
         r.class_id = -1;
         out_kps[o] = r;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused variant (the one the pipeline runs): the 7x7 Gaussian is evaluated only where a descriptor reads it.
+// A rotated BRIEF offset has |dx|,|dy| <= 18 (pattern radius 18.38), so every smoothed value a keypoint needs
+// comes from the raw 43x43 patch around it.  Per warp: stage the patch in shared memory (reflect-101 at the image
+// border, exactly the frame blur7_kernel stages), IC_Angle from the staged patch, horizontal 7-tap of all 43 rows
+// (two IDP.4A per output, u16 results: 255*257 = 65535), then the vertical 7-tap + round-half-even only at the
+// 512 sampled positions.  Integer arithmetic throughout: bit-identical to blur7_kernel + describe_kernel, without
+// writing and re-reading a blurred copy of the pyramid (2 x P bytes per frame) and ~6x fewer filter taps.
+// ------------------------------------------------------------------------------------------------
+#define DF_R 21                 // patch radius: 18 (largest rotated offset) + 3 (filter taps)
+#define DF_ROWS (2 * DF_R + 1)  // 43
+#define DF_RW 13                // raw row stride in words (52 bytes >= 3 + 43 + 6)
+#define DF_HW 20                // filtered row stride in words (40 u16 >= 37)
+#define DF_WARP_WORDS (DF_ROWS * DF_RW + 1 + DF_ROWS * DF_HW)  // 559 + 1 (pad to even) + 860
+
+__global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
+                                                             const int8_t *__restrict__ g_pattern,
+                                                             OrbfeKeyPoint *__restrict__ out_kps,
+                                                             uint8_t *__restrict__ out_desc, int *__restrict__ out_counts, int f0) {
+    __shared__ __align__(16) int8_t pat[1024];
+    __shared__ __align__(16) uint32_t patch[8 * DF_WARP_WORDS];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(pat)[i] = __ldg(reinterpret_cast<const uint32_t *>(g_pattern) + i);
+    __syncthreads();
+
+    const int f = blockIdx.y + f0;
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nlev = plan->nlevels;
+    const int *__restrict__ lcnt = wk.level_cnt + (size_t)f * nlev;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < nlev; k++) tot += lcnt[k];
+        out_counts[f] = tot;
+    }
+    if (slot >= plan->nfeatures) return;
+    const int l = find_level_by(plan, slot, 3);
+    const LevelDev &L = plan->lv[l];
+    const int idx = slot - L.kp_base;
+    if (idx >= lcnt[l]) return;
+    int out_idx = idx;
+    for (int k = 0; k < l; k++) out_idx += lcnt[k];
+
+    const int2 kp = wk.kp_xy_score[(size_t)f * plan->nfeatures + slot];
+    const int x = kp.x & 0xFFFF, y = kp.x >> 16;
+    const int w = L.w, h = L.h, pitch = L.pitch;
+    const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
+
+    uint32_t *rawW = patch + (threadIdx.x >> 5) * DF_WARP_WORDS;   // [43][13] words
+    uint32_t *hpW = rawW + DF_ROWS * DF_RW + 1;                    // [43][20] words = [43][40] u16 (8-byte aligned)
+    uint8_t *rawB = reinterpret_cast<uint8_t *>(rawW);
+    const uint16_t *hpH = reinterpret_cast<const uint16_t *>(hpW);
+
+    // ---- stage the raw patch: patch column j (image column x-21+j) sits at byte off + j of its row ----
+    const int xa = (x - DF_R) & ~3;
+    const bool fast = (x >= DF_R) && (x + DF_R < w) && (xa + 4 * DF_RW <= pitch);
+    const int off = fast ? ((x - DF_R) & 3) : 0;
+    if (fast) {
+        for (int i = lane; i < DF_ROWS * DF_RW; i += 32) {
+            const int r = i / DF_RW, c = i - r * DF_RW;
+            const int gy = reflect101(y - DF_R + r, h);
+            rawW[i] = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gy * pitch + xa) + c);
+        }
+    } else {
+        for (int i = lane; i < DF_ROWS * 4 * DF_RW; i += 32) {
+            const int r = i / (4 * DF_RW), j = i - r * (4 * DF_RW);
+            const int gy = reflect101(y - DF_R + r, h);
+            const int gx = reflect101(x - DF_R + j, w);
+            rawB[i] = __ldg(img + (size_t)gy * pitch + gx);
+        }
+    }
+    __syncwarp();
+    const uint8_t *ctr = rawB + DF_R * (4 * DF_RW) + off + DF_R;   // the keypoint's own pixel
+
+    // ---- IC_Angle: lane <-> column u = lane-15, loop over rows v ----
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - 15;
+        const int au = abs(u);
+        if (lane < 31) {
+            int colsum = 0;
+#pragma unroll
+            for (int v = -15; v <= 15; v++) {
+                const int val = (au <= c_umax[v < 0 ? -v : v]) ? (int)ctr[v * (4 * DF_RW) + u] : 0;
+                colsum += val;
+                m01 += v * val;
+            }
+            m10 = u * colsum;
+        }
+        m10 = warp_sum(m10);
+        m01 = warp_sum(m01);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- horizontal 7-tap of every staged row: task = (row, 4 output columns) ----
+    {
+        const uint32_t T0 = 18u | (34u << 8) | (49u << 16) | (55u << 24), T1 = 49u | (34u << 8) | (18u << 16);
+        const int sh = 8 * off;
+        for (int t = lane; t < DF_ROWS * 10; t += 32) {
+            const int r = t / 10, q = t - r * 10;
+            const uint32_t *rw = rawW + r * DF_RW + q;
+            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2], w3 = rw[3];
+            const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+            const uint32_t h0 = __dp4a(a0, T0, __dp4a(a1, T1, 0u));
+            const uint32_t h1 = __dp4a(__funnelshift_r(a0, a1, 8), T0, __dp4a(__funnelshift_r(a1, a2, 8), T1, 0u));
+            const uint32_t h2 = __dp4a(__funnelshift_r(a0, a1, 16), T0, __dp4a(__funnelshift_r(a1, a2, 16), T1, 0u));
+            const uint32_t h3 = __dp4a(__funnelshift_r(a0, a1, 24), T0, __dp4a(__funnelshift_r(a1, a2, 24), T1, 0u));
+            *reinterpret_cast<uint2 *>(hpW + r * DF_HW + 2 * q) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+        }
+    }
+    __syncwarp();
+
+    // ---- rotated BRIEF: lane <-> descriptor byte; smoothed value = vertical 7-tap of the row sums at the sample ----
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);  // (float)(CV_PI/180.f)
+    const float th = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)th), b = (float)sin((double)th);
+    int val = 0;
+    const int8_t *pp = pat + lane * 32;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int t[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float px = (float)pp[4 * k + 2 * e], py = (float)pp[4 * k + 2 * e + 1];
+            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const int sx = x + rx, sy = y + ry;
+            if (sx >= 0 && sx < w && sy >= 0 && sy < h) {
+                const uint16_t *hc = hpH + (ry + DF_R - 3) * (2 * DF_HW) + (rx + 18);
+                const int s = 55 * (int)hc[3 * 2 * DF_HW] + 49 * ((int)hc[2 * 2 * DF_HW] + (int)hc[4 * 2 * DF_HW]) +
+                              34 * ((int)hc[1 * 2 * DF_HW] + (int)hc[5 * 2 * DF_HW]) + 18 * ((int)hc[0] + (int)hc[6 * 2 * DF_HW]);
+                t[e] = (int)blur_round_u8(s);
+            } else {
+                t[e] = ctr[ry * (4 * DF_RW) + rx];  // outside the image: the reflected, unblurred frame
+            }
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    uint32_t word = (uint32_t)val;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 1) << 8;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 2) << 16;
+    word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 3) << 24;
+    const size_t o = (size_t)f * plan->nfeatures + out_idx;
+    if ((lane & 3) == 0) reinterpret_cast<uint32_t *>(out_desc + o * 32)[lane >> 2] = word;
+    if (lane == 0) {
+        OrbfeKeyPoint r;
+        r.x = l ? __fmul_rn((float)x, L.scale) : (float)x;  // :768-775
+        r.y = l ? __fmul_rn((float)y, L.scale) : (float)y;
+        r.size = L.patch_size;
+        r.angle = angle;
+        r.response = wk.cand_keys64 ? __int_as_float(kp.y) : (float)kp.y;  // Harris response or FAST score
+        r.octave = l;
+        r.class_id = -1;
+        out_kps[o] = r;
+    }
+}
+
+void launch_describe_fused(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, const int8_t *d_pattern,
+                           OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s) {
+    dim3 grid((hp.nfeatures + 7) / 8, nf);
+    if (grid.x == 0) grid.x = 1;
+    describe_fused_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, d_kps, d_desc, d_counts, f0);
 }
 
 void launch_describe(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, const int8_t *d_pattern,

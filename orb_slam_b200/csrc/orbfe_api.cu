@@ -68,6 +68,7 @@ struct StageTimer {
 
 struct OrbfeExtractor {
     int nfeatures = 0, nlevels = 0, score_type = 1, fast_th = 20, device = 0;
+    bool blur_planes = false;   // ORBFE_BLUR_PLANES=1: unfused blur7 + describe (smoothed copies of every level kept in HBM)
     double scale_factor = 1.2;  // double member initialised from a float (ORBextractor.h:62, .cc:459)
     float scale[ORBFE_MAX_LEVELS], inv_scale[ORBFE_MAX_LEVELS];
     int quota[ORBFE_MAX_LEVELS];
@@ -238,7 +239,7 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     for (int l = 0; l < ex->nlevels; l++) {
         LevelDev &L = P.lv[l];
         CU_TRY(dmalloc(ex, &L.pyr, L.plane * B + 256));
-        CU_TRY(dmalloc(ex, &L.blur, L.plane * B + 256));
+        CU_TRY(dmalloc(ex, &L.blur, L.plane * (ex->blur_planes ? B : 1) + 256));  // fused describe: one debug plane only
         CU_TRY(cudaMemsetAsync(L.pyr, 0, L.plane * B + 256, ex->stream));
         if (l > 0) {
             const LevelDev &S = P.lv[l - 1];
@@ -414,6 +415,7 @@ extern "C" int orbfe_extractor_create(int nfeatures, float scale_factor, int nle
     ex->score_type = score_type;
     ex->fast_th = fast_th;
     ex->device = device;
+    ex->blur_planes = getenv("ORBFE_BLUR_PLANES") != nullptr;
     ex->scale_factor = (double)scale_factor;
     const double sf = ex->scale_factor;
     // mvScaleFactor / mvInvScaleFactor, :461-471
@@ -509,9 +511,14 @@ static int enqueue_pipeline(OrbfeExtractor *ex, int f0, int nf, OrbfeKeyPoint *d
     stage_mark(ex, s, "cell_select");
     launch_level_select(ex->dplan, hp, ex->work, ex->ls_smem, f0, nf, s); launches++;
     stage_mark(ex, s, "level_select");
-    launch_blur(ex->dplan, hp, ex->work, f0, nf, s); launches++;
-    stage_mark(ex, s, "blur7");
-    launch_describe(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, f0, nf, s); launches++;
+    if (ex->blur_planes) {
+        // unfused variant (ORBFE_BLUR_PLANES=1): smooth whole levels, then describe from the smoothed planes
+        launch_blur(ex->dplan, hp, ex->work, f0, nf, f0, s); launches++;
+        stage_mark(ex, s, "blur7");
+        launch_describe(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, f0, nf, s); launches++;
+    } else {
+        launch_describe_fused(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, f0, nf, s); launches++;
+    }
     stage_mark(ex, s, "describe");
     CU_TRY(cudaGetLastError());
     ex->last_launches += launches;
@@ -690,7 +697,12 @@ extern "C" int orbfe_debug_read_level(OrbfeExtractor *ex, int frame, int level, 
         return fail(ORBFE_ERR_ARG, "bad arguments");
     CU_TRY(cudaSetDevice(ex->device));
     const LevelDev &L = ex->hplan.lv[level];
-    const uint8_t *src = (which ? L.blur : L.pyr) + (size_t)frame * L.plane;
+    const uint8_t *src = which ? L.blur + (ex->blur_planes ? (size_t)frame * L.plane : 0) : L.pyr + (size_t)frame * L.plane;
+    if (which && !ex->blur_planes) {
+        // the pipeline smooths only descriptor patches; materialise the smoothed level of this frame on demand
+        launch_blur(ex->dplan, ex->hplan, ex->work, frame, 1, 0, ex->stream);
+        CU_TRY(cudaGetLastError());
+    }
     CU_TRY(cudaStreamSynchronize(ex->stream));
     CU_TRY(cudaMemcpy2D(out, out_stride, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
     return ORBFE_OK;

@@ -259,62 +259,6 @@ extern "C" int orbfe_search_by_projection_frames(OrbfeMatcher *m, int npairs, co
 // ------------------------------------------------------------------------------------------------
 // WindowSearch, ORBmatcher.cc:409-516
 // ------------------------------------------------------------------------------------------------
-extern "C" int orbfe_window_search(OrbfeMatcher *m, const OrbfeFrameView *f1, const OrbfeFrameView *f2,
-                                   const uint8_t *f1_has_mp, int window, int min_level, int max_level, float nnratio,
-                                   int check_orientation, int *match21_out, int *nmatches_out) {
-    if (!m || !f1 || !f2 || !f1_has_mp || !match21_out || !nmatches_out) return ORBFE_ERR_ARG;
-    std::vector<Job> jobs(1);
-    Job &J = jobs[0];
-    build_grid(*f2, J.grid);
-    J.row_ptr.push_back(0);
-    const bool bMin = min_level > 0, bMax = max_level < INT_MAX;
-    for (int i1 = 0; i1 < f1->n; i1++) {
-        if (!f1_has_mp[i1]) continue;
-        const OrbfeKeyPoint &kp1 = f1->keys_un[i1];
-        const int level1 = kp1.octave;
-        if (bMin && level1 < min_level) continue;
-        if (bMax && level1 > max_level) continue;
-        const size_t before = J.cols.size();
-        features_in_area(*f2, J.grid, kp1.x, kp1.y, (float)window, level1, level1, J.cols);
-        if (J.cols.size() == before) continue;
-        J.qidx.push_back(i1);
-        J.row_ptr.push_back((int)J.cols.size());
-    }
-    std::vector<uint16_t> dist;
-    std::vector<const OrbfeFrameView *> qf{f1}, tf{f2};
-    int rc = run_distances(m, jobs, qf, tf, dist);
-    if (rc) return rc;
-    for (int i = 0; i < f2->n; i++) match21_out[i] = -1;
-    int nmatches = 0;
-    std::vector<int> rotHist[kHisto];
-    for (size_t k = 0; k < J.qidx.size(); k++) {
-        const int i1 = J.qidx[k];
-        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
-        for (int c = J.row_ptr[k]; c < J.row_ptr[k + 1]; c++) {
-            const int i2 = J.cols[c];
-            if (match21_out[i2] >= 0) continue;  // :451
-            const int d = dist[c];
-            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
-            else if (d < bestDist2) bestDist2 = d;
-        }
-        if ((float)bestDist <= (float)bestDist2 * nnratio && bestDist <= kThHigh) {  // :469
-            match21_out[bestIdx2] = i1;
-            nmatches++;
-            rotHist[rot_bin(f1->keys_un[i1].angle, f2->keys_un[bestIdx2].angle)].push_back(bestIdx2);
-        }
-    }
-    if (check_orientation) {
-        int i1 = -1, i2 = -1, i3 = -1;
-        three_maxima(rotHist, kHisto, i1, i2, i3);
-        for (int b = 0; b < kHisto; b++) {
-            if (b == i1 || b == i2 || b == i3) continue;
-            for (int idx : rotHist[b]) { match21_out[idx] = -1; nmatches--; }
-        }
-    }
-    *nmatches_out = nmatches;
-    return ORBFE_OK;
-}
-
 // ------------------------------------------------------------------------------------------------
 // SearchForInitialization, ORBmatcher.cc:598-713
 // ------------------------------------------------------------------------------------------------
@@ -483,6 +427,30 @@ inline void Rx_plus_t(const float *T, const float *X, float out[3]) {
 }
 
 }  // namespace
+
+// WindowSearch(F1, F2, windowSize, matches, minLevel, maxLevel), ORBmatcher.cc:393-517: the guided skeleton with the
+// F1 keypoint as window centre, same-octave filter, accept rule 1 (:469) and the rotation histogram of :472-489.
+extern "C" int orbfe_window_search(OrbfeMatcher *m, const OrbfeFrameView *f1, const OrbfeFrameView *f2,
+                                   const uint8_t *f1_has_mp, int window, int min_level, int max_level, float nnratio,
+                                   int check_orientation, int *match21_out, int *nmatches_out) {
+    if (!m || !f1 || !f2 || !f1_has_mp || !match21_out || !nmatches_out) return ORBFE_ERR_ARG;
+    const bool bMin = min_level > 0, bMax = max_level < INT_MAX;
+    std::vector<GuidedQuery> Q;
+    std::vector<int> id;
+    for (int i1 = 0; i1 < f1->n; i1++) {
+        if (!f1_has_mp[i1]) continue;
+        const OrbfeKeyPoint &kp1 = f1->keys_un[i1];
+        const int level1 = kp1.octave;
+        if (bMin && level1 < min_level) continue;
+        if (bMax && level1 > max_level) continue;
+        Q.push_back({kp1.x, kp1.y, (float)window, level1, level1, f1->desc + (size_t)i1 * 32, kp1.angle});
+        id.push_back(i1);
+    }
+    for (int i = 0; i < f2->n; i++) match21_out[i] = -1;
+    *nmatches_out = 0;
+    if (Q.empty() || f2->n == 0) return ORBFE_OK;
+    return guided_search(m, *f2, Q, 1, nnratio, kThHigh, check_orientation ? 1 : 2, match21_out, id, nmatches_out);
+}
 
 // SearchByProjection(Frame &F, const vector<MapPoint*>&, th), ORBmatcher.cc:49-125
 extern "C" int orbfe_search_local_points(OrbfeMatcher *m, const OrbfeFrameView *f, int npts, const uint8_t *in_view,

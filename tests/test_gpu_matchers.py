@@ -44,6 +44,15 @@ def _world(k):
     return w
 
 
+@pytest.fixture(params=[0, 1], ids=["fused-kernel", "host-replay"])
+def guided_path(request):
+    """Both implementations behind the guided matchers: the fused device kernel (default) and the CSR-distance +
+    host-replay path it falls back to when a problem does not fit the kernel."""
+    fe.lib().orbfe_matcher_force_host_replay(request.param)
+    yield request.param
+    fe.lib().orbfe_matcher_force_host_replay(0)
+
+
 def test_search_by_projection_pairs(gpu_required):
     feats, shifts = _features(4)
     m = fe.ORBmatcher(0.9, True)
@@ -79,7 +88,7 @@ def test_search_by_projection_pairs(gpu_required):
     m.close()
 
 
-def test_window_search_and_initialization(gpu_required):
+def test_window_search_and_initialization(gpu_required, guided_path):
     feats, shifts = _features(2)
     (k1, d1), (k2, d2) = feats
     f1, f2 = M.FrameView(k1, d1, W, H), M.FrameView(k2, d2, W, H)
@@ -169,15 +178,6 @@ def test_device_resident_search_by_projection(gpu_required):
         assert nm2[j] == n_o and np.array_equal(mp2[j, :nc], mp_o)
     m.close()
     m2.close()
-
-
-@pytest.fixture(params=[0, 1], ids=["fused-kernel", "host-replay"])
-def guided_path(request):
-    """Both implementations behind the guided matchers: the fused device kernel (default) and the CSR-distance +
-    host-replay path it falls back to when a problem does not fit the kernel."""
-    fe.lib().orbfe_matcher_force_host_replay(request.param)
-    yield request.param
-    fe.lib().orbfe_matcher_force_host_replay(0)
 
 
 def test_local_points_reloc_and_f1f2_projection(gpu_required, guided_path):
