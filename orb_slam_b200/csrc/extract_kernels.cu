@@ -12,6 +12,8 @@
 // All pixel arithmetic is integer; floats appear only in IC_Angle's atan2 polynomial, the BRIEF
 // rotation and the coordinate rescale, each written with explicit round-to-nearest intrinsics
 // (no FMA contraction).  No tensor cores: there is no dense contraction on this path.
+#include <cuda_fp16.h>
+
 #include "orbfe_internal.h"
 
 namespace orbfe {
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
         }
         return;
     }
+    const bool lo3 = D.rz_fast == 2;
+    const uint32_t sel0 = (uint32_t)(o0 | ((o0 + 1) << 4)), sel1 = (uint32_t)(o1 | ((o1 + 1) << 4)), sel2 = (uint32_t)(o2 | ((o2 + 1) << 4));
     // all table loads, then all 24 pixel-word loads, then the arithmetic: the loads of the four rows are independent
     // and in flight together (rows past the bottom edge are clamped for the loads and skipped at the store)
     int2 rr[RZ_ROWS];
@@ -103,23 +107,36 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
         const uint32_t u0 = u[ry][0], u1 = u[ry][1], u2 = u[ry][2], v0 = v[ry][0], v1 = v[ry][1], v2 = v[ry][2];
         const int b0 = bb[ry].x, b1 = bb[ry].y;
         uint32_t out = 0;
-#define RZ_PIX(i, o, abv)                                                                                   \
+        // bytes S[s], S[s+1] of a column that starts o bytes into (u0 u1 u2).  With rz_fast == 2 the first three
+        // columns of every quad start within 6 bytes: one PRMT on (u0,u1) with a per-thread selector; otherwise a
+        // word select + funnel shift.  The weighted sum is <= 255 by construction (weights sum to 2048): no clamp.
+#define RZ_MIX(i, pu, pv, abv)                                                                              \
+        {                                                                                                   \
+            const int r0 = (int)__dp2a_lo((abv), (pu), 0u);  /* S[s]*a0 + S[s+1]*a1 */                      \
+            const int r1 = (int)__dp2a_lo((abv), (pv), 0u);                                                 \
+            const int q = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;                   \
+            out |= (uint32_t)q << (8 * (i));                                                                \
+        }
+#define RZ_PIX_SEL(i, o, abv)                                                                               \
         {                                                                                                   \
             const int sh = 8 * ((o) & 3);                                                                   \
             const bool hiw = (o) >= 4;                                                                      \
-            const uint32_t pu = __funnelshift_r(hiw ? u1 : u0, hiw ? u2 : u1, sh);  /* bytes S[s], S[s+1] */ \
-            const uint32_t pv = __funnelshift_r(hiw ? v1 : v0, hiw ? v2 : v1, sh);                          \
-            const int r0 = (int)__dp2a_lo((abv), pu, 0u);  /* S[s]*a0 + S[s+1]*a1 */                        \
-            const int r1 = (int)__dp2a_lo((abv), pv, 0u);                                                   \
-            int q = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;                         \
-            q = min(max(q, 0), 255);                                                                        \
-            out |= (uint32_t)q << (8 * (i));                                                                \
+            RZ_MIX(i, __funnelshift_r(hiw ? u1 : u0, hiw ? u2 : u1, sh), __funnelshift_r(hiw ? v1 : v0, hiw ? v2 : v1, sh), abv) \
         }
-        RZ_PIX(0, o0, ab.x)
-        RZ_PIX(1, o1, ab.y)
-        RZ_PIX(2, o2, ab.z)
-        RZ_PIX(3, o3, ab.w)
-#undef RZ_PIX
+#define RZ_PIX_LO(i, sel, abv) RZ_MIX(i, __byte_perm(u0, u1, (sel)), __byte_perm(v0, v1, (sel)), abv)
+        if (lo3) {
+            RZ_PIX_LO(0, sel0, ab.x)
+            RZ_PIX_LO(1, sel1, ab.y)
+            RZ_PIX_LO(2, sel2, ab.z)
+        } else {
+            RZ_PIX_SEL(0, o0, ab.x)
+            RZ_PIX_SEL(1, o1, ab.y)
+            RZ_PIX_SEL(2, o2, ab.z)
+        }
+        RZ_PIX_SEL(3, o3, ab.w)
+#undef RZ_PIX_LO
+#undef RZ_PIX_SEL
+#undef RZ_MIX
         // pitch is a multiple of 128 and x4 a multiple of 4: aligned 32-bit store (bytes beyond w land in row padding)
         if (y < dh) *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch) = out;
     }
@@ -260,8 +277,9 @@ __device__ __forceinline__ void fast_push(uint32_t *q, int *q_n, int xl, int yl,
 // cell of (x, y) and its detect window [xa, xb] x [ya, yb]  (ORBextractor.cc:560-599)
 __device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int ymax, int x, int y, int &ci, int &cj, int &xa,
                                             int &xb, int &ya, int &yb) {
-    cj = min((x - ORBFE_EDGE) / L.cw, L.cols - 1);
-    ci = min((y - ORBFE_EDGE) / L.ch, L.rows - 1);
+    // x, y >= 16 here; division by the cell size as a multiply-high with the host-computed reciprocal (exact below 2^16)
+    cj = min((int)__umulhi((uint32_t)(x - ORBFE_EDGE), L.cw_rcp), L.cols - 1);
+    ci = min((int)__umulhi((uint32_t)(y - ORBFE_EDGE), L.ch_rcp), L.rows - 1);
     xa = ORBFE_EDGE + cj * L.cw;
     ya = ORBFE_EDGE + ci * L.ch;
     xb = (cj == L.cols - 1) ? xmax - 1 : xa + L.cw - 1;
@@ -1159,10 +1177,13 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
                                                              const int8_t *__restrict__ g_pattern,
                                                              OrbfeKeyPoint *__restrict__ out_kps,
                                                              uint8_t *__restrict__ out_desc, int *__restrict__ out_counts, int f0) {
-    __shared__ __align__(16) int8_t pat[1024];
+    // the pattern as fp16 (x, y) pairs: small integers are exact, and fp16 -> fp32 is a full-rate conversion
+    __shared__ __align__(16) __half2 pat[512];
     __shared__ __align__(16) uint32_t patch[8 * DF_WARP_WORDS];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
-        reinterpret_cast<uint32_t *>(pat)[i] = __ldg(reinterpret_cast<const uint32_t *>(g_pattern) + i);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        const char2 p = *reinterpret_cast<const char2 *>(g_pattern + 2 * i);
+        pat[i] = __floats2half2_rn((float)p.x, (float)p.y);
+    }
     __syncthreads();
 
     const int f = blockIdx.y + f0;
@@ -1195,13 +1216,25 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
 
     // ---- stage the raw patch: patch column j (image column x-21+j) sits at byte off + j of its row ----
     const int xa = (x - DF_R) & ~3;
-    const bool fast = (x >= DF_R) && (x + DF_R < w) && (xa + 4 * DF_RW <= pitch);
+    const bool fast = (x >= DF_R) && (x + DF_R < w) && (xa + 4 * DF_RW <= pitch) && (h > 2 * DF_R);
     const int off = fast ? ((x - DF_R) & 3) : 0;
     if (fast) {
-        for (int i = lane; i < DF_ROWS * DF_RW; i += 32) {
+        // 559 aligned words, 18 per lane: every load is issued before the first store waits on one
+        constexpr int NW = (DF_ROWS * DF_RW + 31) / 32;
+        uint32_t v[NW];
+        const uint8_t *base = img + xa;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const int i = lane + 32 * k;
             const int r = i / DF_RW, c = i - r * DF_RW;
-            const int gy = reflect101(y - DF_R + r, h);
-            rawW[i] = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gy * pitch + xa) + c);
+            int gy = y - DF_R + r;
+            gy = gy < 0 ? -gy : (gy >= h ? 2 * (h - 1) - gy : gy);  // one reflection suffices: h > 2*21
+            v[k] = (i < DF_ROWS * DF_RW) ? __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)gy * pitch) + c) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const int i = lane + 32 * k;
+            if (i < DF_ROWS * DF_RW) rawW[i] = v[k];
         }
     } else {
         for (int i = lane; i < DF_ROWS * 4 * DF_RW; i += 32) {
@@ -1238,16 +1271,29 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
     {
         const uint32_t T0 = 18u | (34u << 8) | (49u << 16) | (55u << 24), T1 = 49u | (34u << 8) | (18u << 16);
         const int sh = 8 * off;
-        for (int t = lane; t < DF_ROWS * 10; t += 32) {
-            const int r = t / 10, q = t - r * 10;
-            const uint32_t *rw = rawW + r * DF_RW + q;
-            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2], w3 = rw[3];
-            const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
-            const uint32_t h0 = __dp4a(a0, T0, __dp4a(a1, T1, 0u));
-            const uint32_t h1 = __dp4a(__funnelshift_r(a0, a1, 8), T0, __dp4a(__funnelshift_r(a1, a2, 8), T1, 0u));
-            const uint32_t h2 = __dp4a(__funnelshift_r(a0, a1, 16), T0, __dp4a(__funnelshift_r(a1, a2, 16), T1, 0u));
-            const uint32_t h3 = __dp4a(__funnelshift_r(a0, a1, 24), T0, __dp4a(__funnelshift_r(a1, a2, 24), T1, 0u));
-            *reinterpret_cast<uint2 *>(hpW + r * DF_HW + 2 * q) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+        // two tasks per iteration: the 8 shared-memory loads are issued before either result is needed
+        for (int t0 = lane; t0 < DF_ROWS * 10; t0 += 64) {
+            uint32_t wv[2][4];
+            int ro[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int t = min(t0 + 32 * e, DF_ROWS * 10 - 1);
+                const int r = t / 10, q = t - r * 10;
+                const uint32_t *rw = rawW + r * DF_RW + q;
+                wv[e][0] = rw[0]; wv[e][1] = rw[1]; wv[e][2] = rw[2]; wv[e][3] = rw[3];
+                ro[e] = r * DF_HW + 2 * q;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const uint32_t a0 = __funnelshift_r(wv[e][0], wv[e][1], sh), a1 = __funnelshift_r(wv[e][1], wv[e][2], sh),
+                               a2 = __funnelshift_r(wv[e][2], wv[e][3], sh);
+                const uint32_t h0 = __dp4a(a0, T0, __dp4a(a1, T1, 0u));
+                const uint32_t h1 = __dp4a(__funnelshift_r(a0, a1, 8), T0, __dp4a(__funnelshift_r(a1, a2, 8), T1, 0u));
+                const uint32_t h2 = __dp4a(__funnelshift_r(a0, a1, 16), T0, __dp4a(__funnelshift_r(a1, a2, 16), T1, 0u));
+                const uint32_t h3 = __dp4a(__funnelshift_r(a0, a1, 24), T0, __dp4a(__funnelshift_r(a1, a2, 24), T1, 0u));
+                // (a clamped duplicate of the last task rewrites the same values)
+                *reinterpret_cast<uint2 *>(hpW + ro[e]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+            }
         }
     }
     __syncwarp();
@@ -1255,17 +1301,22 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
     // ---- rotated BRIEF: lane <-> descriptor byte; smoothed value = vertical 7-tap of the row sums at the sample ----
     const float factorPI = (float)(3.14159265358979323846 / 180.f);  // (float)(CV_PI/180.f)
     const float th = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)th), b = (float)sin((double)th);
+    double sd, cd;
+    sincos((double)th, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
     int val = 0;
-    const int8_t *pp = pat + lane * 32;
+    const __half2 *pp = pat + lane * 16;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int t[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const float px = (float)pp[4 * k + 2 * e], py = (float)pp[4 * k + 2 * e + 1];
-            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            const float2 pf = __half22float2(pp[2 * k + e]);
+            const float px = pf.x, py = pf.y;
+            // cvRound (round half to even) of |v| < 2^22 as one FADD: v + 1.5 * 2^23 has ulp 1
+            const float fy = __fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.0f);
+            const float fx = __fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.0f);
+            const int ry = __float_as_int(fy) - 0x4B400000, rx = __float_as_int(fx) - 0x4B400000;
             const int sx = x + rx, sy = y + ry;
             if (sx >= 0 && sx < w && sy >= 0 && sy < h) {
                 const uint16_t *hc = hpH + (ry + DF_R - 3) * (2 * DF_HW) + (rx + 18);

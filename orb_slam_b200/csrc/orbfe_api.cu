@@ -182,6 +182,10 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
                         L.quota, L.cols, L.rows);
         L.cw = (int)std::ceil((float)Wd / (float)L.cols);
         L.ch = (int)std::ceil((float)Hd / (float)L.rows);
+        if (L.cw < 2 || L.ch < 2)
+            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %dx%d-pixel cells (image too small for %d features)", l, L.cw, L.ch, L.quota);
+        L.cw_rcp = (uint32_t)((0x100000000ull + (unsigned)L.cw - 1) / (unsigned)L.cw);
+        L.ch_rcp = (uint32_t)((0x100000000ull + (unsigned)L.ch - 1) / (unsigned)L.ch);
         L.ncells = L.rows * L.cols;
         L.nfc = (int)std::ceil((float)L.quota / (float)L.ncells);
         if ((L.cols - 1) * L.cw > Wd || (L.rows - 1) * L.ch > Hd)
@@ -257,6 +261,11 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
             L.rz_fast = 1;
             for (size_t x4 = 0; x4 + 3 < xo.size(); x4 += 4)
                 if (xo[x4 + 3] - (xo[x4] & ~3) > 7) L.rz_fast = 0;
+            if (L.rz_fast) {  // 2: the first three columns of every quad start within 6 bytes (single-PRMT extraction)
+                L.rz_fast = 2;
+                for (size_t x4 = 0; x4 + 3 < xo.size(); x4 += 4)
+                    if (xo[x4 + 2] - (xo[x4] & ~3) > 6) L.rz_fast = 1;
+            }
             int *dxo; short2 *dxab; int2 *dyr; short2 *dyab;
             CU_TRY(dmalloc(ex, &dxo, xo.size()));
             CU_TRY(dmalloc(ex, &dxab, xab.size()));

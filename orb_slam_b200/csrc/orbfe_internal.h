@@ -28,6 +28,7 @@ struct LevelDev {
     int w, h, pitch;
     // cell grid (reference ORBextractor.cc:527-547); detect windows tile [16, w-16) x [16, h-16)
     int cols, rows, cw, ch, ncells, nfc, quota;
+    uint32_t cw_rcp, ch_rcp;    // ceil(2^32 / cw), ceil(2^32 / ch): n / cw == __umulhi(n, cw_rcp) exactly for 0 <= n < 2^16
     int cell_base;              // global id of this level's cell 0
     int kp_base;                // sum of quotas of lower levels = first keypoint slot of this level
     int kept_base, kept_cap;    // region of the per-frame "kept" list
@@ -40,7 +41,7 @@ struct LevelDev {
     const short2 *xab;    // [w]  11-bit weights (a0, a1)
     const int2 *yrows;    // [h]  source rows (r0, r1), each clipped to [0, h_src-1]
     const short2 *yab;    // [h]  (b0, b1)
-    int rz_fast;          // the 4 source columns of every aligned destination quad fit three aligned words
+    int rz_fast;          // >= 1: the 4 source columns of every aligned destination quad fit three aligned words; 2: see build_plan
 };
 
 struct PlanDev {

@@ -3,6 +3,19 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #define ITERS 4096
+__device__ __forceinline__ unsigned hmax2u(unsigned a, unsigned b) { unsigned d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned hmin2u(unsigned a, unsigned b) { unsigned d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+__global__ void denorm_check(unsigned *o) {
+    // u16 values 0..255 are fp16 subnormals: max/min must order them like integers and return them unflushed
+    unsigned bad = 0;
+    for (unsigned x = threadIdx.x; x < 65536; x += blockDim.x) {
+        const unsigned a = (x & 0xFF) | ((x >> 8) << 16), b = ((x * 7 + 3) & 0xFF) | (((x * 13 + 5) & 0xFF) << 16);
+        const unsigned mx = hmax2u(a, b), mn = hmin2u(a, b);
+        if (mx != __vmaxu2(a, b) || mn != __vminu2(a, b)) bad++;
+    }
+    atomicAdd(o, bad);
+}
 template <int OP>
 __global__ void k(unsigned *out, unsigned seed) {
     unsigned a[8];
@@ -24,6 +37,12 @@ __global__ void k(unsigned *out, unsigned seed) {
             if (OP == 8) a[i] = __vmaxs2(a[i], b);                    // 2-input
             if (OP == 9) a[i] = __popc(a[i]) + b;                          // POPC
             if (OP == 10) a[i] = __funnelshift_r(a[i], b, 8);              // SHF
+            if (OP == 11) a[i] = hmax2u(a[i], b);                          // HMNMX2 on u16x2 bit patterns (< 0x7C00: ordered like fp16)
+            if (OP == 12) a[i] = (i & 1) ? hmax2u(a[i], b) : __vimax3_u16x2(a[i], b, c);   // 4 + 4: different pipes?
+            if (OP == 13) a[i] = (i & 1) ? a[i] * b + c : __vimax3_u16x2(a[i], b, c);     // VIMNMX3 + IMAD (ALU + FMA pipe)
+            if (OP == 14) a[i] = __float_as_uint(fmax3(__uint_as_float(a[i]), __uint_as_float(b), __uint_as_float(c)));
+            if (OP == 15) a[i] = (i % 3 == 2) ? hmax2u(a[i], b) : __vimax3_u16x2(a[i], b, c);  // 5-6 VIMNMX3 + 2-3 HMNMX2
+            if (OP == 16) a[i] = (i & 1) ? hmin2u(hmax2u(a[i], b), c) : __vimax3_u16x2(a[i], b, c);   // 4 VIMNMX3 + 8 HMNMX2
         }
         b += 0x00010001u;
     }
@@ -51,6 +70,15 @@ void run(const char *name) {
 }
 int main() {
     run<0>("vimin3_s16x2+iadd"); run<1>("vimin3_s16x2"); run<2>("vimin3_s32"); run<3>("vabsdiffu4"); run<4>("prmt");
+    {
+        unsigned *d, hbad = 123;
+        cudaMalloc(&d, 4); cudaMemset(d, 0, 4);
+        denorm_check<<<1, 256>>>(d);
+        cudaMemcpy(&hbad, d, 4, cudaMemcpyDeviceToHost);
+        printf("HMNMX2 on u16x2 subnormal bit patterns: %u mismatches vs vmaxu2/vminu2\n", hbad);
+    }
+    run<11>("hmnmx2"); run<12>("4 vimnmx3 + 4 hmnmx2"); run<13>("4 vimnmx3 + 4 imad"); run<14>("fmnmx3"); run<15>("vimnmx3:hmnmx2 ~2:1");
+    run<16>("4 vimnmx3 + 8 hmnmx2");
     run<5>("lop3"); run<6>("iadd3"); run<7>("imad"); run<8>("vimax_s16x2"); run<9>("popc+iadd"); run<10>("shf");
     return 0;
 }
