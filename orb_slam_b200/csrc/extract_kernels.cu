@@ -345,6 +345,8 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
     //      interior cell boundary are masked to 0 -- per-lane u16x2 masks for vertical boundaries (they kill
     //      the left/right/diagonal terms), per-row flags for horizontal ones (they kill the row above/below).
     //      Rows 1..62 and groups 1..30 are the detect tile.
+    uint32_t fbits = 0;  // candidate flags of the lane's 4 pixels x 8 rows: bit 8k + r
+    const int r0 = seg * 8;
     if (g >= 1 && g <= 30) {
         // relation (gx+d-1 <-> gx+d), d = 0..4, crosses a boundary at X = 16 + cj*cw  <=>  X == gx + d
         uint32_t mLA = 0xFFFFFFFFu, mRA = 0xFFFFFFFFu, mLB = 0xFFFFFFFFu, mRB = 0xFFFFFFFFu;
@@ -359,8 +361,6 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
         // ti.hmask bit r: tile row r (image y0-1+r) is the top row of a cell (interior horizontal boundary above it)
         const unsigned long long hmask = ti.hmask;
         uint32_t A[3], B[3], lrA[3], lrB[3], fullA[3], fullB[3];
-        uint32_t fbits = 0;  // 4 flag bits per row x 8 rows
-        const int r0 = seg * 8;
 #pragma unroll
         for (int j = 0; j < 10; j++) {
             // load tile row r0 - 1 + j into slot j % 3
@@ -386,21 +386,37 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
                 // neighbour maximum, floored at t_lo: m must exceed both to be a candidate
                 const uint32_t nbA = __vmaxu2(__vimax3_u16x2(upA, dnA, lrA[c]), tlo2);
                 const uint32_t nbB = __vmaxu2(__vimax3_u16x2(upB, dnB, lrB[c]), tlo2);
-                const uint32_t tA = __vmaxu2(A[c], nbA) ^ nbA;  // half != 0  <=>  m > t_lo and m > every window neighbour
-                const uint32_t tB = __vmaxu2(B[c], nbB) ^ nbB;
-                // one flag bit per pixel; the (rare) candidates are pushed after the loop, outside the unrolled code
-                if (cr >= 1 && cr <= F2_H) {
-                    const uint32_t f4 = ((tA & 0x0000FFFFu) ? 1u : 0u) | ((tB & 0x0000FFFFu) ? 2u : 0u) |
-                                        ((tA & 0xFFFF0000u) ? 4u : 0u) | ((tB & 0xFFFF0000u) ? 8u : 0u);
-                    fbits |= f4 << (4 * (j - 2));
-                }
+                // m - nb + 0x7FFF per half (both < 0x8000: no borrow between halves): bit 15 set  <=>  m > nb
+                const uint32_t tA = A[c] + 0x7FFF7FFFu - nbA;
+                const uint32_t tB = B[c] + 0x7FFF7FFFu - nbB;
+                // flag bytes of pixels k = 0..3 -> byte k, bit (row inside the segment); the (rare) candidates are
+                // pushed after the loop, outside the unrolled code
+                if (cr >= 1 && cr <= F2_H) fbits |= (__byte_perm(tA, tB, 0x7351) & 0x80808080u) >> (7 - (j - 2));
             }
         }
-        while (fbits) {
-            const int b = __ffs(fbits) - 1;
-            fbits &= fbits - 1;
-            const int cr = r0 + (b >> 2), k = b & 3;
-            fast_push(s_cand, &s_n, gx + k - x0, cr - 1, m_at(mt, cr, 4 * g + k));
+    }
+    // warp-aggregated queue reservation (all 32 lanes; the halo lanes have no flags): one shared-memory atomic per
+    // warp, then every lane writes its own candidates
+    {
+        {
+            const int mine = __popc(fbits);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (g >= o) incl += v;
+            }
+            int wbase = 0;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (g == 31 && total) wbase = atomicAdd(&s_n, total);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            int n = wbase + incl - mine;
+            while (fbits) {
+                const int b = __ffs(fbits) - 1;
+                fbits &= fbits - 1;
+                const int cr = r0 + (b & 7), k = b >> 3;
+                s_cand[n++] = (uint32_t)(gx + k - x0) | ((uint32_t)(cr - 1) << 7) | ((uint32_t)m_at(mt, cr, 4 * g + k) << 13);
+            }
         }
     }
     __syncthreads();
@@ -1162,16 +1178,53 @@ __global__ void __launch_bounds__(256) describe_kernel(const PlanDev *__restrict
 // Fused variant (the one the pipeline runs): the 7x7 Gaussian is evaluated only where a descriptor reads it.
 // A rotated BRIEF offset has |dx|,|dy| <= 18 (pattern radius 18.38), so every smoothed value a keypoint needs
 // comes from the raw 43x43 patch around it.  Per warp: stage the patch in shared memory (reflect-101 at the image
-// border, exactly the frame blur7_kernel stages), IC_Angle from the staged patch, horizontal 7-tap of all 43 rows
-// (two IDP.4A per output, u16 results: 255*257 = 65535), then the vertical 7-tap + round-half-even only at the
-// 512 sampled positions.  Integer arithmetic throughout: bit-identical to blur7_kernel + describe_kernel, without
+// border, exactly the frame blur7_kernel stages), IC_Angle from the staged patch, vertical 7-tap of the 37 rows a
+// sample can fall on (4x4 byte transposes, then two IDP.4A per output; u16 results: 255*257 = 65535), then the
+// horizontal 7-tap (four IDP.2A on contiguous u16) + round-half-even only at the 512 sampled positions.  Integer arithmetic throughout: bit-identical to blur7_kernel + describe_kernel, without
 // writing and re-reading a blurred copy of the pyramid (2 x P bytes per frame) and ~6x fewer filter taps.
 // ------------------------------------------------------------------------------------------------
 #define DF_R 21                 // patch radius: 18 (largest rotated offset) + 3 (filter taps)
 #define DF_ROWS (2 * DF_R + 1)  // 43
 #define DF_RW 13                // raw row stride in words (52 bytes >= 3 + 43 + 6)
-#define DF_HW 20                // filtered row stride in words (40 u16 >= 37)
-#define DF_WARP_WORDS (DF_ROWS * DF_RW + 1 + DF_ROWS * DF_HW)  // 559 + 1 (pad to even) + 860
+#define DF_VR 37                // column-filtered rows: sample rows -18 .. 18
+#define DF_VW 24                // their stride in words (48 u16 >= 3 + 43)
+#define DF_WARP_WORDS (DF_ROWS * DF_RW + 1 + DF_VR * DF_VW)  // 559 + 1 (pad to even) + 888
+
+// one descriptor byte (8 comparisons) of the fused kernel: vpW = column sums of the staged patch (row ry+18, u16
+// index xoff + rx - 3 + tap), ctr = the patch's centre pixel
+template <bool CHECK>
+__device__ __forceinline__ int brief_byte_fused(const __half2 *pp, float a, float b, int x, int y, int w, int h,
+                                                const uint32_t *vpW, int xoff, const uint8_t *ctr) {
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int t[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float2 pf = __half22float2(pp[2 * k + e]);
+            const float px = pf.x, py = pf.y;
+            // cvRound (round half to even) of |v| < 2^22 as one FADD: v + 1.5 * 2^23 has ulp 1
+            const float fy = __fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.0f);
+            const float fx = __fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.0f);
+            const int ry = __float_as_int(fy) - 0x4B400000, rx = __float_as_int(fx) - 0x4B400000;
+            const int sx = x + rx, sy = y + ry;
+            if (!CHECK || (sx >= 0 && sx < w && sy >= 0 && sy < h)) {
+                // 7 contiguous column sums starting at u16 index c0 of row ry + 18: four words from the even index
+                // below c0; the taps sit on even or odd positions of those words
+                const int c0 = xoff + rx;
+                const uint32_t *vw = vpW + (ry + 18) * DF_VW + (c0 >> 1);
+                const bool odd = c0 & 1;
+                const uint32_t TX = odd ? 0x31221200u : 0x37312212u, TY = odd ? 0x12223137u : 0x00122231u;
+                const int s = (int)__dp2a_lo(vw[0], TX, __dp2a_hi(vw[1], TX, __dp2a_lo(vw[2], TY, __dp2a_hi(vw[3], TY, 0u))));
+                t[e] = (int)blur_round_u8(s);
+            } else {
+                t[e] = ctr[ry * (4 * DF_RW) + rx];  // outside the image: the reflected, unblurred frame
+            }
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    return val;
+}
 
 __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
                                                              const int8_t *__restrict__ g_pattern,
@@ -1197,12 +1250,15 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
         out_counts[f] = tot;
     }
     if (slot >= plan->nfeatures) return;
-    const int l = find_level_by(plan, slot, 3);
+    // level of this slot and its position in the frame's output, warp-cooperatively: lane k holds level k's slot
+    // base and kept count (bases are non-decreasing: the last level whose base <= slot owns it)
+    const int base_k = lane < nlev ? plan->lv[lane].kp_base : 0x7FFFFFFF;
+    const int cnt_k = lane < nlev ? lcnt[lane] : 0;
+    const int l = 31 - __clz(__ballot_sync(0xffffffffu, slot >= base_k));
     const LevelDev &L = plan->lv[l];
-    const int idx = slot - L.kp_base;
-    if (idx >= lcnt[l]) return;
-    int out_idx = idx;
-    for (int k = 0; k < l; k++) out_idx += lcnt[k];
+    const int idx = slot - __shfl_sync(0xffffffffu, base_k, l);
+    if (idx >= __shfl_sync(0xffffffffu, cnt_k, l)) return;
+    const int out_idx = idx + warp_sum(lane < l ? cnt_k : 0);
 
     const int2 kp = wk.kp_xy_score[(size_t)f * plan->nfeatures + slot];
     const int x = kp.x & 0xFFFF, y = kp.x >> 16;
@@ -1210,31 +1266,28 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
     const uint8_t *__restrict__ img = L.pyr + (size_t)f * L.plane;
 
     uint32_t *rawW = patch + (threadIdx.x >> 5) * DF_WARP_WORDS;   // [43][13] words
-    uint32_t *hpW = rawW + DF_ROWS * DF_RW + 1;                    // [43][20] words = [43][40] u16 (8-byte aligned)
+    uint32_t *vpW = rawW + DF_ROWS * DF_RW + 1;                    // [37][24] words = [37][48] u16 (8-byte aligned)
     uint8_t *rawB = reinterpret_cast<uint8_t *>(rawW);
-    const uint16_t *hpH = reinterpret_cast<const uint16_t *>(hpW);
 
     // ---- stage the raw patch: patch column j (image column x-21+j) sits at byte off + j of its row ----
     const int xa = (x - DF_R) & ~3;
-    const bool fast = (x >= DF_R) && (x + DF_R < w) && (xa + 4 * DF_RW <= pitch) && (h > 2 * DF_R);
+    // interior keypoints (all but a thin border band): 43 rows x 13 aligned words, two rows per step on lanes 0..25;
+    // every load is issued before the first store waits on one
+    const bool fast = (x >= DF_R) && (x + DF_R < w) && (y >= DF_R) && (y + DF_R < h) && (xa + 4 * DF_RW <= pitch);
     const int off = fast ? ((x - DF_R) & 3) : 0;
     if (fast) {
-        // 559 aligned words, 18 per lane: every load is issued before the first store waits on one
-        constexpr int NW = (DF_ROWS * DF_RW + 31) / 32;
-        uint32_t v[NW];
-        const uint8_t *base = img + xa;
+        const int sub = lane >= DF_RW ? 1 : 0, c = lane - sub * DF_RW;
+        constexpr int NS = (DF_ROWS + 1) / 2;  // 22 steps
+        uint32_t v[NS];
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)(y - DF_R + sub) * pitch + xa) + c;
+        const size_t step = (size_t)pitch >> 1;  // two rows, in words
+        if (lane < 2 * DF_RW) {
 #pragma unroll
-        for (int k = 0; k < NW; k++) {
-            const int i = lane + 32 * k;
-            const int r = i / DF_RW, c = i - r * DF_RW;
-            int gy = y - DF_R + r;
-            gy = gy < 0 ? -gy : (gy >= h ? 2 * (h - 1) - gy : gy);  // one reflection suffices: h > 2*21
-            v[k] = (i < DF_ROWS * DF_RW) ? __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)gy * pitch) + c) : 0u;
-        }
+            for (int q = 0; q < NS; q++)
+                if (2 * q + sub < DF_ROWS) v[q] = __ldg(src + q * step);
 #pragma unroll
-        for (int k = 0; k < NW; k++) {
-            const int i = lane + 32 * k;
-            if (i < DF_ROWS * DF_RW) rawW[i] = v[k];
+            for (int q = 0; q < NS; q++)
+                if (2 * q + sub < DF_ROWS) rawW[(2 * q) * DF_RW + lane] = v[q];  // (2q + sub) * 13 + c == 2q * 13 + lane
         }
     } else {
         for (int i = lane; i < DF_ROWS * 4 * DF_RW; i += 32) {
@@ -1267,34 +1320,47 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
     }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- horizontal 7-tap of every staged row: task = (row, 4 output columns) ----
-    {
+    // ---- vertical 7-tap: V[o][c] = sum_k T[k] * raw[o + k][c], o = 0..36 (sample rows -18..18), all 48 staged columns.
+    //      lane = (word column cw, half): 12 x 2 lanes; a lane walks down its 4 byte columns in groups of 4 rows,
+    //      transposing each 4x4 byte block so that 4 vertically adjacent pixels share a register ----
+    if (lane < 24) {
         const uint32_t T0 = 18u | (34u << 8) | (49u << 16) | (55u << 24), T1 = 49u | (34u << 8) | (18u << 16);
-        const int sh = 8 * off;
-        // two tasks per iteration: the 8 shared-memory loads are issued before either result is needed
-        for (int t0 = lane; t0 < DF_ROWS * 10; t0 += 64) {
-            uint32_t wv[2][4];
-            int ro[2];
+        const int half = lane >= 12 ? 1 : 0, cw = lane - 12 * half;
+        // half 0: output rows 0..19 (input rows 0..27), half 1: output rows 20..36 (input rows 20..42, clamped loads)
+        const int obase = 20 * half;
+        const uint32_t *rw = rawW + obase * DF_RW + cw;
+        uint32_t *vw = vpW + obase * DF_VW + 2 * cw;
+        uint32_t col[3][4];  // transposed blocks g, g+1, g+2: col[b][j] = 4 consecutive rows of byte column j
+#define DF_LOAD_BLOCK(dst, g)                                                                               \
+        {                                                                                                   \
+            const int rmax = DF_ROWS - 1 - obase;                                                           \
+            const uint32_t q0 = rw[min(4 * (g), rmax) * DF_RW], q1 = rw[min(4 * (g) + 1, rmax) * DF_RW];     \
+            const uint32_t q2 = rw[min(4 * (g) + 2, rmax) * DF_RW], q3 = rw[min(4 * (g) + 3, rmax) * DF_RW]; \
+            const uint32_t t0 = __byte_perm(q0, q1, 0x5140), t1 = __byte_perm(q0, q1, 0x7362);               \
+            const uint32_t t2 = __byte_perm(q2, q3, 0x5140), t3 = __byte_perm(q2, q3, 0x7362);               \
+            dst[0] = __byte_perm(t0, t2, 0x5410); dst[1] = __byte_perm(t0, t2, 0x7632);                       \
+            dst[2] = __byte_perm(t1, t3, 0x5410); dst[3] = __byte_perm(t1, t3, 0x7632);                       \
+        }
+        DF_LOAD_BLOCK(col[0], 0)
+        DF_LOAD_BLOCK(col[1], 1)
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int t = min(t0 + 32 * e, DF_ROWS * 10 - 1);
-                const int r = t / 10, q = t - r * 10;
-                const uint32_t *rw = rawW + r * DF_RW + q;
-                wv[e][0] = rw[0]; wv[e][1] = rw[1]; wv[e][2] = rw[2]; wv[e][3] = rw[3];
-                ro[e] = r * DF_HW + 2 * q;
-            }
+        for (int g = 0; g < 5; g++) {
+            DF_LOAD_BLOCK(col[(g + 2) % 3], g + 2)
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const uint32_t a0 = __funnelshift_r(wv[e][0], wv[e][1], sh), a1 = __funnelshift_r(wv[e][1], wv[e][2], sh),
-                               a2 = __funnelshift_r(wv[e][2], wv[e][3], sh);
-                const uint32_t h0 = __dp4a(a0, T0, __dp4a(a1, T1, 0u));
-                const uint32_t h1 = __dp4a(__funnelshift_r(a0, a1, 8), T0, __dp4a(__funnelshift_r(a1, a2, 8), T1, 0u));
-                const uint32_t h2 = __dp4a(__funnelshift_r(a0, a1, 16), T0, __dp4a(__funnelshift_r(a1, a2, 16), T1, 0u));
-                const uint32_t h3 = __dp4a(__funnelshift_r(a0, a1, 24), T0, __dp4a(__funnelshift_r(a1, a2, 24), T1, 0u));
-                // (a clamped duplicate of the last task rewrites the same values)
-                *reinterpret_cast<uint2 *>(hpW + ro[e]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+            for (int sft = 0; sft < 4; sft++) {
+                const int o = 4 * g + sft;  // output row inside this half
+                uint32_t hv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t lo = __funnelshift_r(col[g % 3][j], col[(g + 1) % 3][j], 8 * sft);        // rows o .. o+3
+                    const uint32_t hi = __funnelshift_r(col[(g + 1) % 3][j], col[(g + 2) % 3][j], 8 * sft);  // rows o+4 .. o+7
+                    hv[j] = __dp4a(lo, T0, __dp4a(hi, T1, 0u));
+                }
+                if (obase + o < DF_VR)
+                    *reinterpret_cast<uint2 *>(vw + o * DF_VW) = make_uint2(__byte_perm(hv[0], hv[1], 0x5410), __byte_perm(hv[2], hv[3], 0x5410));
             }
         }
+#undef DF_LOAD_BLOCK
     }
     __syncwarp();
 
@@ -1304,31 +1370,12 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
     double sd, cd;
     sincos((double)th, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
-    int val = 0;
-    const __half2 *pp = pat + lane * 16;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int t[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const float2 pf = __half22float2(pp[2 * k + e]);
-            const float px = pf.x, py = pf.y;
-            // cvRound (round half to even) of |v| < 2^22 as one FADD: v + 1.5 * 2^23 has ulp 1
-            const float fy = __fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.0f);
-            const float fx = __fadd_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)), 12582912.0f);
-            const int ry = __float_as_int(fy) - 0x4B400000, rx = __float_as_int(fx) - 0x4B400000;
-            const int sx = x + rx, sy = y + ry;
-            if (sx >= 0 && sx < w && sy >= 0 && sy < h) {
-                const uint16_t *hc = hpH + (ry + DF_R - 3) * (2 * DF_HW) + (rx + 18);
-                const int s = 55 * (int)hc[3 * 2 * DF_HW] + 49 * ((int)hc[2 * 2 * DF_HW] + (int)hc[4 * 2 * DF_HW]) +
-                              34 * ((int)hc[1 * 2 * DF_HW] + (int)hc[5 * 2 * DF_HW]) + 18 * ((int)hc[0] + (int)hc[6 * 2 * DF_HW]);
-                t[e] = (int)blur_round_u8(s);
-            } else {
-                t[e] = ctr[ry * (4 * DF_RW) + rx];  // outside the image: the reflected, unblurred frame
-            }
-        }
-        val |= (t[0] < t[1]) << k;
-    }
+    // keypoints at least 18 px inside the image (all but a 2-px band behind the 16-px detection border) cannot sample
+    // outside it: no per-sample bounds test
+    const bool inner = (x >= 18) && (x + 18 < w) && (y >= 18) && (y + 18 < h);
+    const int xoff = off + DF_R - 3;  // u16 index of the leftmost tap of a sample at rx = 0
+    const int val = inner ? brief_byte_fused<false>(pat + lane * 16, a, b, x, y, w, h, vpW, xoff, ctr)
+                          : brief_byte_fused<true>(pat + lane * 16, a, b, x, y, w, h, vpW, xoff, ctr);
     uint32_t word = (uint32_t)val;
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 1) << 8;
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 2) << 16;
