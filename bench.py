@@ -274,27 +274,34 @@ def main():
     stage_acc, stage_n = {}, [0]
     kp_total = [0]
     launches = [0]
-    host_t = {"extract_call": 0.0, "match_call": 0.0, "views": 0.0, "n": 0}
+    host_t = {"extract_call": 0.0, "e2e_extract_call": 0.0, "match_call": 0.0, "views": 0.0, "n": 0}
 
-    def match_step(kps_a=None, desc_a=None, cnt_a=None):
-        kps_a = kps_np if kps_a is None else kps_a
-        desc_a = desc_np if desc_a is None else desc_a
-        cnt_a = cnt_np if cnt_a is None else cnt_a
+    ones_u8, zeros_u8 = np.ones(NFEAT, np.uint8), np.zeros(NFEAT, np.uint8)
+
+    def prepare_views(kps_a, desc_a, cnt_a):
+        """Frame views + synthetic map points of one step's host results (runs on the thread that extracted them)."""
         t0 = time.perf_counter()
         views = [M.FrameView(kps_a[i, :cnt_a[i]], desc_a[i, :cnt_a[i]], W, H, SCALE, NLEVELS) for i in range(B)]
-        lasts = [prev["view"] if prev["view"] is not None else views[B - 1]] + views[:-1]
-        has = [np.ones(f.n, np.uint8) for f in lasts]
-        outl = [np.zeros(f.n, np.uint8) for f in lasts]
-        world = [backproject(f.kps) for f in lasts]
+        world = [backproject(f.kps) for f in views]
+        host_t["views"] += time.perf_counter() - t0
+        return views, world
+
+    def match_step(prepared):
+        views, world_cur = prepared
         t1 = time.perf_counter()
+        if prev["view"] is None:
+            prev["view"], prev["world"] = views[B - 1], world_cur[B - 1]
+        lasts = [prev["view"]] + views[:-1]
+        world = [prev["world"]] + world_cur[:-1]
+        has = [ones_u8[:f.n] for f in lasts]
+        outl = [zeros_u8[:f.n] for f in lasts]
         nm, _ = M.search_by_projection_frames(mt, views, lasts, has, outl, world, Tcws, FX, FY, CX, CY, MATCH_TH)
-        t2 = time.perf_counter()
-        host_t["views"] += t1 - t0
-        host_t["match_call"] += t2 - t1
+        host_t["match_call"] += time.perf_counter() - t1
         host_t["n"] += 1
-        # keep a private copy of the last frame's features for the next step
-        lk, ld = kps_a[B - 1, :cnt_a[B - 1]].copy(), desc_a[B - 1, :cnt_a[B - 1]].copy()
+        # keep a private copy of the last frame's features for the next step (the pinned buffers are reused)
+        lk, ld = views[B - 1].kps.copy(), views[B - 1].desc.copy()
         prev["view"] = M.FrameView(lk, ld, W, H, SCALE, NLEVELS)
+        prev["world"] = world_cur[B - 1].copy()
         return int(nm.sum())
 
     def collect_stages():
@@ -388,45 +395,45 @@ def main():
     # boundary; a third thread matches finished steps in order (orbfe_search_by_projection_frames on host views).
     # ctypes releases the GIL inside the calls.  Outputs rotate through four pinned buffer sets.
     from concurrent.futures import ThreadPoolExecutor
-    NBUF = 4
+    NEX = max(1, int(os.environ.get("ORBFE_E2E_EXTRACTORS", "2")))   # extractor handles in flight
+    NBUF = NEX + 2
     e2e_bufs = []
     for _ in range(NBUF):
         hk = torch.empty((B, NFEAT, 28), dtype=torch.uint8).pin_memory()
         hd = torch.empty((B, NFEAT, 32), dtype=torch.uint8).pin_memory()
         hc = torch.empty((B,), dtype=torch.int32).pin_memory()
         e2e_bufs.append((hk, hd, hc, hk.numpy().view(fe.KP_DTYPE).reshape(B, NFEAT), hd.numpy(), hc.numpy()))
-    ex_b = fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank)
-    e2e_ex = (ex, ex_b)
-    e2e_ex_pool = (ThreadPoolExecutor(max_workers=1), ThreadPoolExecutor(max_workers=1))
+    e2e_ex = [ex] + [fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank) for _ in range(NEX - 1)]
+    e2e_ex_pool = [ThreadPoolExecutor(max_workers=1) for _ in range(NEX)]
     e2e_pool = ThreadPoolExecutor(max_workers=1)
 
     def extract_step(st):
         t0 = time.perf_counter()
-        x = e2e_ex[st & 1]
+        x = e2e_ex[st % NEX]
         hk, hd, hc, _, _, c_np = e2e_bufs[st % NBUF]
         x.extract_batch_ptr(h_frames.data_ptr(), W, H, W, W * H, B, hk.data_ptr(), hd.data_ptr(), NFEAT, hc.data_ptr())
-        host_t["extract_call"] += time.perf_counter() - t0
-        return x.last_launches(), int(c_np.sum())
+        host_t["e2e_extract_call"] += time.perf_counter() - t0
+        _, _, _, k_np, d_np, _ = e2e_bufs[st % NBUF]
+        return x.last_launches(), int(c_np.sum()), prepare_views(k_np, d_np, c_np)
 
     def run_e2e(steps):
         nm = 0
         ex_futs, m_futs = {}, {}
 
         def finish_extract(st):
-            nl, nk = ex_futs.pop(st).result()
+            nl, nk, prepared = ex_futs.pop(st).result()
             launches[0] += nl
             kp_total[0] += nk
-            _, _, _, k_np, d_np, c_np = e2e_bufs[st % NBUF]
-            m_futs[st] = e2e_pool.submit(match_step, k_np, d_np, c_np)
+            m_futs[st] = e2e_pool.submit(match_step, prepared)
 
         for st in range(steps):
             if st - (NBUF - 1) in m_futs:             # buffer set st % NBUF was last used by step st - NBUF
                 nm += m_futs.pop(st - (NBUF - 1)).result()
-            ex_futs[st] = e2e_ex_pool[st & 1].submit(extract_step, st)
-            if st >= 1:
-                finish_extract(st - 1)
-        if steps:
-            finish_extract(steps - 1)
+            ex_futs[st] = e2e_ex_pool[st % NEX].submit(extract_step, st)
+            if st >= NEX - 1:
+                finish_extract(st - (NEX - 1))
+        for st in sorted(ex_futs):
+            finish_extract(st)
         for st in sorted(m_futs):
             nm += m_futs[st].result()
         return nm
@@ -545,8 +552,8 @@ def main():
             line["cpu_baseline"] = {"value": kp / dt / 1e6, "unit": "Mkeypoints/s", "cores": cores, "kind": "port",
                                     "sample": "%d of the step's frames (about %.0f CPU-seconds), CPU oracle port on %d threads, %.1f s wall" % (nfr, 0.25 * nfr, cores, dt)}
         print(json.dumps(line))
-    ex.close()
-    ex_b.close()
+    for x in e2e_ex:
+        x.close()
     mt.close()
     if world > 1:
         dist.destroy_process_group()

@@ -52,7 +52,7 @@ class Frame(C.Structure):
 
 def build(force=False):
     """Compile the oracle with oracle/Makefile (gcc/g++). Building the checker is not using it."""
-    srcs = ["orb_oracle.c", "orb_oracle_match.c", "orb_oracle_nth.cpp", "orb_oracle.h",
+    srcs = ["orb_oracle.c", "orb_oracle_match.c", "orb_oracle_bow.c", "orb_oracle_nth.cpp", "orb_oracle.h",
             os.path.join("..", "include", "orbfe_brief_pattern.inc")]
     stale = force or not os.path.exists(_SO) or any(
         os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_SO) for s in srcs)
@@ -393,3 +393,41 @@ def guided_best(f, qu, qv, qr, qlo, qhi, qdesc, th_dist):
     out = np.full(max(len(qu), 1), -1, np.int32)
     lib().orb_oracle_guided_best(C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), th_dist, _p(out))
     return out[:len(qu)]
+
+
+# ---- SURVEY section 8(f) rows N2 / N4 (orb_oracle_bow.c) ----
+def bow_descend(voc, desc, levelsup=4):
+    """voc: dict(node_desc, child_ptr, children, word_id, weight, L).  Returns (leaf, node) per descriptor."""
+    desc = _a(desc, np.uint8)
+    n = len(desc)
+    leaf, node = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+    f = lib().orb_oracle_bow_descend
+    f.restype = None
+    f(_p(voc["node_desc"]), _p(voc["child_ptr"]), _p(voc["children"]), C.c_int(voc["L"]), _p(desc), C.c_int(n), C.c_int(levelsup),
+      _p(leaf), _p(node))
+    return leaf[:n], node[:n]
+
+
+def bow_transform(voc, desc, levelsup=4, weighting=0, norm=1):
+    desc = _a(desc, np.uint8)
+    n = len(desc)
+    cap = max(n, 1)
+    bow_ids, bow_vals = np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+    fv_ids, fv_ptr, fv_feats = np.zeros(cap, np.int32), np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32)
+    nw, nn = C.c_int(0), C.c_int(0)
+    f = lib().orb_oracle_bow_transform
+    f.restype = None
+    f(_p(voc["node_desc"]), _p(voc["child_ptr"]), _p(voc["children"]), _p(voc["word_id"]), _p(voc["weight"]), C.c_int(voc["L"]),
+      C.c_int(weighting), C.c_int(norm), _p(desc), C.c_int(n), C.c_int(levelsup), C.byref(nw), _p(bow_ids), _p(bow_vals),
+      C.byref(nn), _p(fv_ids), _p(fv_ptr), _p(fv_feats))
+    return (bow_ids[:nw.value], bow_vals[:nw.value]), (fv_ids[:nn.value], fv_ptr[:nn.value + 1], fv_feats[:fv_ptr[nn.value]])
+
+
+def distinctive_descriptors(desc, group_ptr):
+    desc, group_ptr = _a(desc, np.uint8), _a(group_ptr, np.int32)
+    ng = len(group_ptr) - 1
+    best = np.zeros(max(ng, 1), np.int32)
+    f = lib().orb_oracle_distinctive
+    f.restype = None
+    f(_p(desc), _p(group_ptr), C.c_int(ng), _p(best))
+    return best[:ng]

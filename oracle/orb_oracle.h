@@ -206,6 +206,15 @@ int orb_oracle_search_for_triangulation(int n1, const OrbOracleKeyPoint *keys1, 
 void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,
                      int *best_dist, int *best_idx, int *second_dist);
 
+/* ---- SURVEY section 8(f) rows N2 / N4 (orb_oracle_bow.c) ---- */
+void orb_oracle_bow_descend(const uint8_t *node_desc, const int32_t *child_ptr, const int32_t *children, int depth_L,
+                            const uint8_t *desc, int n, int levelsup, int32_t *leaf_out, int32_t *node_out);
+void orb_oracle_bow_transform(const uint8_t *node_desc, const int32_t *child_ptr, const int32_t *children, const int32_t *word_id,
+                              const double *weight, int depth_L, int weighting, int norm, const uint8_t *desc, int n,
+                              int levelsup, int *nwords_out, int32_t *bow_ids, double *bow_vals, int *nnodes_out,
+                              int32_t *fv_ids, int32_t *fv_ptr, int32_t *fv_feats);
+void orb_oracle_distinctive(const uint8_t *desc, const int32_t *group_ptr, int ngroups, int32_t *best_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <atomic>
+#include <thread>
+#include <unordered_map>
 
 #include "orbfe_internal.h"
 
@@ -27,6 +30,15 @@ using namespace orbfe;
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// the same for the other translation units of the library (bow_kernels.cu, host/*.cpp)
+int orbfe::set_error(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -602,7 +614,8 @@ extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int 
     rc = zero_counters(ex, s);
     if (rc) return rc;
     // H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream)
-    const int nchunks = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
+    int nchunks = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
+    if (const char *e = getenv("ORBFE_CHUNKS")) nchunks = std::max(1, std::min(batch, atoi(e)));  // tuning knob
     if (!ex->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&ex->copy_stream, cudaStreamNonBlocking));
     while ((int)ex->chunk_ev.size() < nchunks + 1) {
         cudaEvent_t e;
@@ -957,6 +970,33 @@ extern "C" int orbfe_hamming_dense(OrbfeMatcher *m, const uint8_t *q, int nq, co
     return ORBFE_OK;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors for many map points in one launch (include/orbfe_bow.h)
+#include "../../include/orbfe_bow.h"
+namespace orbfe { void launch_distinctive(const uint8_t *d_desc, const int *d_group_ptr, int ngroups, int *d_best, cudaStream_t s); }
+extern "C" int orbfe_distinctive_descriptors(OrbfeMatcher *m, const uint8_t *desc, const int32_t *group_ptr, int ngroups,
+                                             int32_t *best_out) {
+    if (!m || ngroups < 0) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (ngroups == 0) return ORBFE_OK;
+    if (!group_ptr || !best_out) return fail(ORBFE_ERR_ARG, "NULL argument");
+    const int total = group_ptr[ngroups];
+    if (group_ptr[0] != 0 || total < 0 || (total > 0 && !desc)) return fail(ORBFE_ERR_ARG, "bad group_ptr");
+    for (int g = 0; g < ngroups; g++)
+        if (group_ptr[g + 1] < group_ptr[g]) return fail(ORBFE_ERR_ARG, "group_ptr must be non-decreasing");
+    CU_TRY(cudaSetDevice(m->device));
+    CU_TRY(mreserve(m, 0, (size_t)std::max(total, 1) * 32));
+    CU_TRY(mreserve(m, 2, sizeof(int) * ((size_t)ngroups + 1)));
+    CU_TRY(mreserve(m, 3, sizeof(int) * (size_t)ngroups));
+    cudaStream_t s = m->stream;
+    if (total > 0) CU_TRY(cudaMemcpyAsync(m->buf[0], desc, (size_t)total * 32, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(m->buf[2], group_ptr, sizeof(int) * ((size_t)ngroups + 1), cudaMemcpyHostToDevice, s));
+    launch_distinctive((const uint8_t *)m->buf[0], (const int *)m->buf[2], ngroups, (int *)m->buf[3], s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(best_out, m->buf[3], sizeof(int) * (size_t)ngroups, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    m->launches += 1;
+    return ORBFE_OK;
+}
+
 extern "C" int orbfe_knn2_groups_device(OrbfeMatcher *m, const uint8_t *d_q, int nq, const uint8_t *d_db, int ngroups,
                                         int group_size, uint16_t *d_best, int32_t *d_best_idx, uint16_t *d_second,
                                         void *stream) {
@@ -1030,7 +1070,36 @@ extern "C" int orbfe_sbp_frames_via_device(OrbfeMatcher *m, int npairs, const Or
         for (int l = 1; l < R.nlevels; l++) { s = s * sf; if (s != R.scale_factors[l]) return 1; }
     }
     CU_TRY(cudaSetDevice(m->device));
-    const size_t nf = (size_t)2 * npairs;  // frame slot 2j = Current of pair j, 2j+1 = Last of pair j
+    // frame slots: a frame that appears several times (in a video stream the Last frame of pair j is the Current
+    // frame of pair j-1) is staged and uploaded once.  Identity = same keypoint and descriptor arrays.
+    // A frame used as Last carries that pair's world/flags arrays; two pairs that share a Last frame but pass
+    // different world/flags arrays get separate slots.
+    struct Slot { const OrbfeFrameView *v; const float *world; const uint8_t *has, *outl; };
+    std::vector<Slot> slots;
+    std::vector<int> ci(npairs), li(npairs);
+    {
+        std::unordered_map<const void *, std::vector<int>> by_keys;
+        auto find_slot = [&](const OrbfeFrameView &v, const float *world, const uint8_t *has, const uint8_t *outl, bool as_last) {
+            auto &cand = by_keys[(const void *)v.keys_un];
+            for (int sidx : cand) {
+                Slot &S = slots[sidx];
+                if (S.v->desc != v.desc || S.v->n != v.n) continue;
+                if (as_last) {
+                    if (S.world && (S.world != world || S.has != has || S.outl != outl)) continue;
+                    S.world = world; S.has = has; S.outl = outl;
+                }
+                return sidx;
+            }
+            slots.push_back({&v, as_last ? world : nullptr, as_last ? has : nullptr, as_last ? outl : nullptr});
+            cand.push_back((int)slots.size() - 1);
+            return (int)slots.size() - 1;
+        };
+        for (int j = 0; j < npairs; j++) {
+            ci[j] = find_slot(cur[j], nullptr, nullptr, nullptr, false);
+            li[j] = find_slot(last[j], last_world[j], last_has_mp[j], last_outlier[j], true);
+        }
+    }
+    const size_t nf = slots.size();
     // layout of the staging block
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -1051,22 +1120,34 @@ extern "C" int orbfe_sbp_frames_via_device(OrbfeMatcher *m, int npairs, const Or
     }
     unsigned char *H = m->h_stage, *D = m->d_stage;
     int *h_cnt = (int *)(H + o_cnt), *h_ci = (int *)(H + o_ci), *h_li = (int *)(H + o_li);
+    auto pack_slot = [&](int sidx) {
+        const Slot &S = slots[sidx];
+        const OrbfeFrameView &V = *S.v;
+        h_cnt[sidx] = V.n;
+        if (!V.n) return;
+        memcpy(H + o_kps + (size_t)sidx * cap * sizeof(OrbfeKeyPoint), V.keys_un, (size_t)V.n * sizeof(OrbfeKeyPoint));
+        memcpy(H + o_desc + (size_t)sidx * cap * 32, V.desc, (size_t)V.n * 32);
+        if (S.world) {
+            memcpy(H + o_world + (size_t)sidx * cap * 3 * sizeof(float), S.world, (size_t)V.n * 3 * sizeof(float));
+            unsigned char *fl = H + o_flags + (size_t)sidx * cap;
+            for (int i = 0; i < V.n; i++) fl[i] = (S.has[i] && !S.outl[i]) ? 1 : 0;
+        }
+    };
+    {   // staging is a plain memory copy of ~150 KB per frame: spread it over a few host threads
+        const int nt = (int)std::min<size_t>(8, nf);
+        if (nt <= 1) {
+            for (size_t k = 0; k < nf; k++) pack_slot((int)k);
+        } else {
+            std::atomic<int> next(0);
+            std::vector<std::thread> th;
+            for (int w = 0; w < nt; w++)
+                th.emplace_back([&]() { for (int k = next++; k < (int)nf; k = next++) pack_slot(k); });
+            for (auto &w : th) w.join();
+        }
+    }
     for (int j = 0; j < npairs; j++) {
-        const OrbfeFrameView &C = cur[j], &L = last[j];
-        h_cnt[2 * j] = C.n; h_cnt[2 * j + 1] = L.n;
-        h_ci[j] = 2 * j; h_li[j] = 2 * j + 1;
-        if (C.n) {
-            memcpy(H + o_kps + (size_t)(2 * j) * cap * sizeof(OrbfeKeyPoint), C.keys_un, (size_t)C.n * sizeof(OrbfeKeyPoint));
-            memcpy(H + o_desc + (size_t)(2 * j) * cap * 32, C.desc, (size_t)C.n * 32);
-            memcpy(H + o_mp + (size_t)j * cap * sizeof(int), cur_mp_inout[j], (size_t)C.n * sizeof(int));
-        }
-        if (L.n) {
-            memcpy(H + o_kps + (size_t)(2 * j + 1) * cap * sizeof(OrbfeKeyPoint), L.keys_un, (size_t)L.n * sizeof(OrbfeKeyPoint));
-            memcpy(H + o_desc + (size_t)(2 * j + 1) * cap * 32, L.desc, (size_t)L.n * 32);
-            memcpy(H + o_world + (size_t)(2 * j + 1) * cap * 3 * sizeof(float), last_world[j], (size_t)L.n * 3 * sizeof(float));
-            unsigned char *fl = H + o_flags + (size_t)(2 * j + 1) * cap;
-            for (int i = 0; i < L.n; i++) fl[i] = (last_has_mp[j][i] && !last_outlier[j][i]) ? 1 : 0;
-        }
+        h_ci[j] = ci[j]; h_li[j] = li[j];
+        if (cur[j].n) memcpy(H + o_mp + (size_t)j * cap * sizeof(int), cur_mp_inout[j], (size_t)cur[j].n * sizeof(int));
         memcpy(H + o_T + (size_t)j * 12 * sizeof(float), Tcw[j], 12 * sizeof(float));
     }
     cudaStream_t s = m->stream;

@@ -125,6 +125,9 @@ int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const O
                       const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
                       const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s);
 
+// records the thread's last-error string (orbfe_last_error) and returns `code`
+int set_error(int code, const char *fmt, ...);
+
 // ---- launchers (match_kernels.cu) ----
 void launch_hamming_csr(const uint8_t *q, const uint8_t *t, const int32_t *row_ptr, const int32_t *cols, int nq,
                         int npairs, uint16_t *out, cudaStream_t s);

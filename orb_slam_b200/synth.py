@@ -59,3 +59,46 @@ def noisy_copies(desc, flip_prob, seed=0):
     bits = np.unpackbits(desc, axis=1)
     flips = rng.random(bits.shape) < flip_prob
     return np.packbits(bits ^ flips, axis=1)
+
+
+def random_vocabulary(k=10, L=3, seed=0, flip=0.12, stop_fraction=0.02, ragged=False):
+    """A synthetic DBoW2-style vocabulary tree as flat arrays (see include/orbfe_bow.h): complete k-ary tree of depth L
+    whose node descriptors are noisy copies of their parent's (so that descents are decided by small margins and ties
+    occur), word ids in leaf order, positive idf-like weights with a few stopped (zero-weight) words.  ragged=True
+    prunes some subtrees so that leaves sit at different depths."""
+    rng = np.random.default_rng(seed)
+    desc = [np.zeros(32, np.uint8)]
+    children_of = [[]]
+    level_of = [0]
+    frontier = [0]
+    for lev in range(1, L + 1):
+        nxt = []
+        for parent in frontier:
+            if ragged and lev > 1 and rng.random() < 0.15:
+                continue  # this node stays a leaf
+            base = rng.integers(0, 256, 32, dtype=np.uint8) if parent == 0 else desc[parent]
+            for _ in range(k):
+                bits = np.unpackbits(base)
+                bits ^= (rng.random(256) < flip).astype(np.uint8)
+                desc.append(np.packbits(bits))
+                children_of.append([])
+                level_of.append(lev)
+                children_of[parent].append(len(desc) - 1)
+                nxt.append(len(desc) - 1)
+        frontier = nxt
+    n = len(desc)
+    child_ptr = np.zeros(n + 1, np.int32)
+    children = []
+    for i in range(n):
+        children += children_of[i]
+        child_ptr[i + 1] = len(children)
+    word_id = np.full(n, -1, np.int32)
+    weight = np.zeros(n, np.float64)
+    w = 0
+    for i in range(n):
+        if not children_of[i] and i != 0:
+            word_id[i] = w
+            w += 1
+            weight[i] = 0.0 if rng.random() < stop_fraction else float(rng.uniform(0.5, 9.0))
+    return {"node_desc": np.stack(desc).astype(np.uint8), "child_ptr": child_ptr, "children": np.array(children, np.int32),
+            "word_id": word_id, "weight": weight, "L": L, "k": k}

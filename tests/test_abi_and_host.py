@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("orbfe.h", "orbfe_match.h"):
+    for h in ("orbfe.h", "orbfe_match.h", "orbfe_bow.h"):
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         names |= set(re.findall(r"\b(orbfe_[a-z0-9_]+)\s*\(", txt))
