@@ -711,15 +711,31 @@ __global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restr
                 if (k >= min_key && (k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xFF], 1);
             }
             __syncthreads();
-            if (tid == 0) {
-                int k = s_k, cum = 0, b = 255;
-                for (; b >= 0; b--) {
-                    if (cum + hist[b] >= k) break;
-                    cum += hist[b];
+            if (tid < 32) {
+                // bin of the k-th largest: warp 0 walks the 256 bins from the top, 8 bins per lane (lane 0 = bins 255..248)
+                const int k = s_k;
+                int hb[8], sum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) { hb[t] = hist[255 - 8 * tid - t]; sum += hb[t]; }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += v;
                 }
-                s_k = k - cum;  // rank inside bin b
-                s_prefix = prefix | ((uint32_t)b << shift);
-                s_mask = mask | (0xFFu << shift);
+                const int fl = __ffs(__ballot_sync(0xffffffffu, incl >= k)) - 1;  // the bins are known to hold >= k keys
+                if (tid == fl) {
+                    int cum = incl - sum, b = 255 - 8 * tid;
+#pragma unroll
+                    for (int t = 0; t < 8; t++) {
+                        if (cum + hb[t] >= k) break;
+                        cum += hb[t];
+                        b--;
+                    }
+                    s_k = k - cum;  // rank inside bin b
+                    s_prefix = prefix | ((uint32_t)b << shift);
+                    s_mask = mask | (0xFFu << shift);
+                }
             }
             __syncthreads();
         }
