@@ -279,29 +279,26 @@ def main():
     ones_u8, zeros_u8 = np.ones(NFEAT, np.uint8), np.zeros(NFEAT, np.uint8)
 
     def prepare_views(kps_a, desc_a, cnt_a):
-        """Frame views + synthetic map points of one step's host results (runs on the thread that extracted them)."""
+        """Frame views + synthetic map points of one step's host results, plus a private copy of the step's last frame
+        (it is the Last frame of the next step's first pair, and the pinned result buffers are reused)."""
         t0 = time.perf_counter()
         views = [M.FrameView(kps_a[i, :cnt_a[i]], desc_a[i, :cnt_a[i]], W, H, SCALE, NLEVELS) for i in range(B)]
         world = [backproject(f.kps) for f in views]
+        tail = (M.FrameView(views[B - 1].kps.copy(), views[B - 1].desc.copy(), W, H, SCALE, NLEVELS), world[B - 1].copy())
         host_t["views"] += time.perf_counter() - t0
-        return views, world
+        return views, world, tail
 
-    def match_step(prepared):
-        views, world_cur = prepared
+    def match_step(prepared, prev_prepared, matcher):
+        views, world_cur, tail = prepared
         t1 = time.perf_counter()
-        if prev["view"] is None:
-            prev["view"], prev["world"] = views[B - 1], world_cur[B - 1]
-        lasts = [prev["view"]] + views[:-1]
-        world = [prev["world"]] + world_cur[:-1]
+        pv, pw = prev_prepared[2] if prev_prepared is not None else tail
+        lasts = [pv] + views[:-1]
+        world = [pw] + world_cur[:-1]
         has = [ones_u8[:f.n] for f in lasts]
         outl = [zeros_u8[:f.n] for f in lasts]
-        nm, _ = M.search_by_projection_frames(mt, views, lasts, has, outl, world, Tcws, FX, FY, CX, CY, MATCH_TH)
+        nm, _ = M.search_by_projection_frames(matcher, views, lasts, has, outl, world, Tcws, FX, FY, CX, CY, MATCH_TH)
         host_t["match_call"] += time.perf_counter() - t1
         host_t["n"] += 1
-        # keep a private copy of the last frame's features for the next step (the pinned buffers are reused)
-        lk, ld = views[B - 1].kps.copy(), views[B - 1].desc.copy()
-        prev["view"] = M.FrameView(lk, ld, W, H, SCALE, NLEVELS)
-        prev["world"] = world_cur[B - 1].copy()
         return int(nm.sum())
 
     def collect_stages():
@@ -334,7 +331,7 @@ def main():
     d_T = torch.from_numpy(np.stack(Tcws).reshape(B, 12)).to(dev)
     d_cur = torch.arange(0, B, dtype=torch.int32, device=dev)
     d_last = torch.tensor([B] + list(range(0, B - 1)), dtype=torch.int32, device=dev)
-    stream_m = torch.cuda.Stream(device=dev)
+    stream_m = torch.cuda.Stream(device=dev, priority=-1)   # the short matcher kernel goes first when SMs free up
     stream_b = stream_m
     dev_state = {"step": 0}
 
@@ -392,7 +389,8 @@ def main():
     # ---- e2e: host buffers in, host results out.  A stream of frames is processed as a software pipeline over the
     # public C-ABI calls only: two extractor handles (each with its own device buffers and streams) alternate steps on
     # two host threads, so the upload of step t+1 overlaps the kernels of step t and there is no bubble at a call
-    # boundary; a third thread matches finished steps in order (orbfe_search_by_projection_frames on host views).
+    # boundary; frame views (the host-side Frame objects of the reference) are built on their own worker threads and
+    # a last thread matches finished steps in order (orbfe_search_by_projection_frames on host views).
     # ctypes releases the GIL inside the calls.  Outputs rotate through four pinned buffer sets.
     from concurrent.futures import ThreadPoolExecutor
     NEX = max(1, int(os.environ.get("ORBFE_E2E_EXTRACTORS", "2")))   # extractor handles in flight
@@ -405,7 +403,9 @@ def main():
         e2e_bufs.append((hk, hd, hc, hk.numpy().view(fe.KP_DTYPE).reshape(B, NFEAT), hd.numpy(), hc.numpy()))
     e2e_ex = [ex] + [fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank) for _ in range(NEX - 1)]
     e2e_ex_pool = [ThreadPoolExecutor(max_workers=1) for _ in range(NEX)]
-    e2e_pool = ThreadPoolExecutor(max_workers=1)
+    e2e_mt = (mt, fe.ORBmatcher(0.9, True, device=local_rank))
+    e2e_match_pool = (ThreadPoolExecutor(max_workers=1), ThreadPoolExecutor(max_workers=1))
+    e2e_views_pool = ThreadPoolExecutor(max_workers=2)
 
     def extract_step(st):
         t0 = time.perf_counter()
@@ -413,18 +413,24 @@ def main():
         hk, hd, hc, _, _, c_np = e2e_bufs[st % NBUF]
         x.extract_batch_ptr(h_frames.data_ptr(), W, H, W, W * H, B, hk.data_ptr(), hd.data_ptr(), NFEAT, hc.data_ptr())
         host_t["e2e_extract_call"] += time.perf_counter() - t0
-        _, _, _, k_np, d_np, _ = e2e_bufs[st % NBUF]
-        return x.last_launches(), int(c_np.sum()), prepare_views(k_np, d_np, c_np)
+        return x.last_launches(), int(c_np.sum())
 
     def run_e2e(steps):
         nm = 0
-        ex_futs, m_futs = {}, {}
+        ex_futs, m_futs, v_futs = {}, {}, {}
 
         def finish_extract(st):
-            nl, nk, prepared = ex_futs.pop(st).result()
+            nl, nk = ex_futs.pop(st).result()
             launches[0] += nl
             kp_total[0] += nk
-            m_futs[st] = e2e_pool.submit(match_step, prepared)
+            _, _, _, k_np, d_np, c_np = e2e_bufs[st % NBUF]
+            vf = e2e_views_pool.submit(prepare_views, k_np, d_np, c_np)   # frame views: a stage of its own
+            pf = v_futs.get(st - 1)
+            v_futs[st] = vf
+            v_futs.pop(st - 2, None)
+            # two matcher handles alternate so that the queueing latency of one call hides behind the other
+            m_futs[st] = e2e_match_pool[st & 1].submit(
+                lambda f=vf, p=pf, mm=e2e_mt[st & 1]: match_step(f.result(), p.result() if p is not None else None, mm))
 
         for st in range(steps):
             if st - (NBUF - 1) in m_futs:             # buffer set st % NBUF was last used by step st - NBUF
@@ -441,7 +447,7 @@ def main():
     def timed(run_fn, steps):
         kp_total[0] = 0
         launches[0] = 0
-        c0 = mt.counters()
+        c0 = [sum(x) for x in zip(*(m_.counters() for m_ in e2e_mt))]
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -454,7 +460,7 @@ def main():
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = max(e0.elapsed_time(e1), 0.0)
-        c1 = mt.counters()
+        c1 = [sum(x) for x in zip(*(m_.counters() for m_ in e2e_mt))]
         t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
         k = torch.tensor([kp_total[0], nm], dtype=torch.float64, device=dev)
         if world > 1:
@@ -554,7 +560,8 @@ def main():
         print(json.dumps(line))
     for x in e2e_ex:
         x.close()
-    mt.close()
+    for m_ in e2e_mt:
+        m_.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

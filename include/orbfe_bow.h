@@ -3,6 +3,8 @@
  *   N2  DBoW2 vocabulary-tree transform: descriptors -> BowVector + FeatureVector
  *       (reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1126-1262, FORB.cpp:79-99 (distance),
  *        BowVector.cpp:34-84, FeatureVector.cpp:32-48; callers Frame.cc:280-287, KeyFrame.cc:56-65)
+ *   N3  KeyFrameDatabase::DetectLoopCandidates / DetectRelocalisationCandidates on arrays
+ *       (reference src/KeyFrameDatabase.cc:73-308, L1Scoring::score Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-67)
  *   N4  MapPoint::ComputeDistinctiveDescriptors, batched over map points (reference src/MapPoint.cc:185-250)
  *
  * Plain pointers and sizes; host arrays unless a parameter is named d_*.  Return values: OrbfeStatus (orbfe.h).
@@ -57,6 +59,23 @@ int orbfe_bow_transform(OrbfeVocabulary *v, const uint8_t *desc, int n, int leve
  * (median = sorted[(int)(0.5*(N-1))], first minimum wins, MapPoint.cc:228-243), -1 for an empty group.
  * All N x N distances and the medians are computed on the device (one warp per map point). */
 int orbfe_distinctive_descriptors(OrbfeMatcher *m, const uint8_t *desc, const int32_t *group_ptr, int ngroups, int32_t *best_out);
+
+/* KeyFrameDatabase::DetectLoopCandidates (mode 0, KeyFrameDatabase.cc:73-195) / DetectRelocalisationCandidates (mode 1,
+ * :197-308) with the database as arrays.  Keyframe k (k = 0..nkf-1, in the order the keyframes were add()ed: that is
+ * the order inside every inverted-file list) owns the BowVector db_ids/db_vals[kf_ptr[k] .. kf_ptr[k+1]) (word ids
+ * ascending); the query BowVector is q_ids/q_vals (ascending).  connected[k] != 0 marks the query keyframe's
+ * GetConnectedKeyFrames() (mode 0 only, may be NULL); covis/covis_ptr hold GetBestCovisibilityKeyFrames(10) of every
+ * keyframe in the order that call returns them.  min_score: the minScore argument (mode 0 only).
+ * One device thread per keyframe walks the two sorted word lists (shared-word count, first shared word, and the L1
+ * score accumulated in ascending word order exactly as L1Scoring::score does); thresholds, the covisibility
+ * accumulation and the candidate list are replayed on the host in the reference's list order.
+ * cand_out (capacity nkf) receives *ncand_out keyframe indices in the order of the returned vector.  common_out /
+ * score_out (capacity nkf each, may be NULL) receive mnLoopWords / the float score of every keyframe that shares a word
+ * (score = -1 where the reference does not compute one). */
+int orbfe_bow_db_detect(OrbfeMatcher *m, int mode, int nq, const int32_t *q_ids, const double *q_vals, int nkf,
+                        const int32_t *kf_ptr, const int32_t *db_ids, const double *db_vals, const uint8_t *connected,
+                        const int32_t *covis_ptr, const int32_t *covis, float min_score, int *ncand_out, int32_t *cand_out,
+                        int32_t *common_out, float *score_out);
 
 #ifdef __cplusplus
 }

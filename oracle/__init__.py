@@ -431,3 +431,16 @@ def distinctive_descriptors(desc, group_ptr):
     f.restype = None
     f(_p(desc), _p(group_ptr), C.c_int(ng), _p(best))
     return best[:ng]
+
+
+def bow_db_detect(mode, q_ids, q_vals, kf_ptr, db_ids, db_vals, connected, covis_ptr, covis, min_score):
+    q_ids, q_vals, kf_ptr = _a(q_ids, np.int32), _a(q_vals, np.float64), _a(kf_ptr, np.int32)
+    db_ids, db_vals, covis_ptr, covis = _a(db_ids, np.int32), _a(db_vals, np.float64), _a(covis_ptr, np.int32), _a(covis, np.int32)
+    connected = _a(connected, np.uint8)
+    nkf = len(kf_ptr) - 1
+    cand, common, score = np.zeros(max(nkf, 1), np.int32), np.zeros(max(nkf, 1), np.int32), np.zeros(max(nkf, 1), np.float32)
+    f = lib().orb_oracle_bow_db_detect
+    f.restype = C.c_int
+    n = f(C.c_int(mode), C.c_int(len(q_ids)), _p(q_ids), _p(q_vals), C.c_int(nkf), _p(kf_ptr), _p(db_ids), _p(db_vals), _p(connected),
+          _p(covis_ptr), _p(covis), C.c_float(min_score), _p(cand), _p(common), _p(score))
+    return cand[:n], common[:nkf], score[:nkf]

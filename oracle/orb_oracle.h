@@ -214,6 +214,9 @@ void orb_oracle_bow_transform(const uint8_t *node_desc, const int32_t *child_ptr
                               int levelsup, int *nwords_out, int32_t *bow_ids, double *bow_vals, int *nnodes_out,
                               int32_t *fv_ids, int32_t *fv_ptr, int32_t *fv_feats);
 void orb_oracle_distinctive(const uint8_t *desc, const int32_t *group_ptr, int ngroups, int32_t *best_out);
+int orb_oracle_bow_db_detect(int mode, int nq, const int32_t *q_ids, const double *q_vals, int nkf, const int32_t *kf_ptr,
+                             const int32_t *db_ids, const double *db_vals, const uint8_t *connected, const int32_t *covis_ptr,
+                             const int32_t *covis, float minScore, int32_t *cand_out, int32_t *common_out, float *score_out);
 
 #ifdef __cplusplus
 }

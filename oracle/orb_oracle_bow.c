@@ -149,3 +149,122 @@ void orb_oracle_distinctive(const uint8_t *desc, const int32_t *group_ptr, int n
         free(v); free(D);
     }
 }
+
+/* L1Scoring::score, ScoringObject.cpp:23-67 (with the lower_bound jumps restated as linear advances to the first
+ * element >= the other side's id: the same element) */
+static double l1_score(const int32_t *i1, const double *v1, int n1, const int32_t *i2, const double *v2, int n2) {
+    int a = 0, b = 0;
+    double score = 0;
+    while (a != n1 && b != n2) {
+        const double vi = v1[a], wi = v2[b];
+        if (i1[a] == i2[b]) {
+            score += fabs(vi - wi) - fabs(vi) - fabs(wi);
+            ++a; ++b;
+        } else if (i1[a] < i2[b]) {
+            while (a != n1 && i1[a] < i2[b]) ++a; /* v1.lower_bound(v2_it->first) */
+        } else {
+            while (b != n2 && i2[b] < i1[a]) ++b;
+        }
+    }
+    score = -score / 2.0;
+    return score;
+}
+
+/* KeyFrameDatabase::DetectLoopCandidates (mode 0, KeyFrameDatabase.cc:73-195) and DetectRelocalisationCandidates
+ * (mode 1, :197-308) on arrays, written with a real inverted file (one list per word, keyframes appended in index
+ * order = add() order, :40-46) and the reference's per-keyframe bookkeeping fields.  A keyframe's mRelocScore that
+ * the reference would read without having written it in this query counts as 0.  Returns the number of candidates. */
+int orb_oracle_bow_db_detect(int mode, int nq, const int32_t *q_ids, const double *q_vals, int nkf, const int32_t *kf_ptr,
+                             const int32_t *db_ids, const double *db_vals, const uint8_t *connected, const int32_t *covis_ptr,
+                             const int32_t *covis, float minScore, int32_t *cand_out, int32_t *common_out, float *score_out) {
+    int nwords = 0;
+    for (int k = 0; k < kf_ptr[nkf]; k++) if (db_ids[k] + 1 > nwords) nwords = db_ids[k] + 1;
+    for (int k = 0; k < nq; k++) if (q_ids[k] + 1 > nwords) nwords = q_ids[k] + 1;
+    /* mvInvertedFile: CSR built by add()ing keyframes 0..nkf-1 in order */
+    int *inv_ptr = (int *)calloc((size_t)nwords + 2, sizeof(int));
+    for (int k = 0; k < kf_ptr[nkf]; k++) inv_ptr[db_ids[k] + 1]++;
+    for (int w = 0; w < nwords; w++) inv_ptr[w + 1] += inv_ptr[w];
+    int *inv = (int *)malloc(sizeof(int) * (size_t)(kf_ptr[nkf] > 0 ? kf_ptr[nkf] : 1));
+    int *fill = (int *)calloc((size_t)nwords + 1, sizeof(int));
+    for (int kf = 0; kf < nkf; kf++)
+        for (int k = kf_ptr[kf]; k < kf_ptr[kf + 1]; k++) inv[inv_ptr[db_ids[k]] + fill[db_ids[k]]++] = kf;
+    free(fill);
+
+    int *query = (int *)calloc((size_t)nkf, sizeof(int));   /* mnLoopQuery == this query */
+    int *words = (int *)calloc((size_t)nkf, sizeof(int));   /* mnLoopWords / mnRelocWords */
+    float *sc = (float *)calloc((size_t)nkf, sizeof(float)); /* mLoopScore / mRelocScore */
+    int *sharing = (int *)malloc(sizeof(int) * (size_t)(nkf > 0 ? nkf : 1));
+    int nsharing = 0;
+    for (int qi = 0; qi < nq; qi++) {
+        const int w = q_ids[qi];
+        for (int p = inv_ptr[w]; p < inv_ptr[w + 1]; p++) {
+            const int kfi = inv[p];
+            if (!query[kfi]) {
+                words[kfi] = 0;
+                if (mode == 1 || !(connected && connected[kfi])) {
+                    query[kfi] = 1;
+                    sharing[nsharing++] = kfi;
+                }
+            }
+            words[kfi]++;
+        }
+    }
+    if (common_out) memcpy(common_out, words, sizeof(int) * (size_t)nkf);
+    if (score_out) for (int k = 0; k < nkf; k++) score_out[k] = -1.0f;
+    int ncand = 0;
+    if (nsharing > 0) {
+        int maxCommonWords = 0;
+        for (int s = 0; s < nsharing; s++) if (words[sharing[s]] > maxCommonWords) maxCommonWords = words[sharing[s]];
+        const int minCommonWords = maxCommonWords * 0.8f;
+        float *lsc = (float *)malloc(sizeof(float) * (size_t)nsharing);
+        int *lkf = (int *)malloc(sizeof(int) * (size_t)nsharing);
+        int nl = 0;
+        for (int s = 0; s < nsharing; s++) {
+            const int kfi = sharing[s];
+            if (words[kfi] > minCommonWords) {
+                const float si = (float)l1_score(q_ids, q_vals, nq, db_ids + kf_ptr[kfi], db_vals + kf_ptr[kfi], kf_ptr[kfi + 1] - kf_ptr[kfi]);
+                sc[kfi] = si;
+                if (score_out) score_out[kfi] = si;
+                if (mode == 1 || si >= minScore) { lsc[nl] = si; lkf[nl] = kfi; nl++; }
+            }
+        }
+        if (nl > 0) {
+            float *acc = (float *)malloc(sizeof(float) * (size_t)nl);
+            int *bestkf = (int *)malloc(sizeof(int) * (size_t)nl);
+            float bestAccScore = mode == 0 ? minScore : 0;
+            for (int e = 0; e < nl; e++) {
+                const int kfi = lkf[e];
+                float bestScore = lsc[e], accScore = lsc[e];
+                int pBest = kfi;
+                for (int c = covis_ptr[kfi]; c < covis_ptr[kfi + 1]; c++) {
+                    const int kf2 = covis[c];
+                    if (mode == 0) {
+                        if (query[kf2] && words[kf2] > minCommonWords) {
+                            accScore += sc[kf2];
+                            if (sc[kf2] > bestScore) { pBest = kf2; bestScore = sc[kf2]; }
+                        }
+                    } else {
+                        if (!query[kf2]) continue;
+                        accScore += sc[kf2];
+                        if (sc[kf2] > bestScore) { pBest = kf2; bestScore = sc[kf2]; }
+                    }
+                }
+                acc[e] = accScore;
+                bestkf[e] = pBest;
+                if (accScore > bestAccScore) bestAccScore = accScore;
+            }
+            const float minScoreToRetain = 0.75f * bestAccScore;
+            uint8_t *added = (uint8_t *)calloc((size_t)nkf, 1);
+            for (int e = 0; e < nl; e++) {
+                if (acc[e] > minScoreToRetain && !added[bestkf[e]]) {
+                    cand_out[ncand++] = bestkf[e];
+                    added[bestkf[e]] = 1;
+                }
+            }
+            free(added); free(acc); free(bestkf);
+        }
+        free(lsc); free(lkf);
+    }
+    free(inv_ptr); free(inv); free(query); free(words); free(sc); free(sharing);
+    return ncand;
+}

@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "orbfe_search_for_initialization",
     # include/orbfe_bow.h
     "orbfe_vocabulary_create", "orbfe_vocabulary_destroy", "orbfe_bow_descend_device", "orbfe_bow_descend", "orbfe_bow_transform",
-    "orbfe_distinctive_descriptors",
+    "orbfe_distinctive_descriptors", "orbfe_bow_db_detect",
 ]
 
 

@@ -28,6 +28,7 @@ def _bind():
     L.orbfe_bow_descend.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.orbfe_bow_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.orbfe_distinctive_descriptors.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.orbfe_bow_db_detect.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp]
     _bound = True
     return L
 
@@ -105,3 +106,18 @@ def distinctive_descriptors(matcher: ORBmatcher, desc, group_ptr):
     best = np.zeros(max(ng, 1), np.int32)
     _check(_bind().orbfe_distinctive_descriptors(matcher.handle, _p(desc), _p(group_ptr), ng, _p(best)))
     return best[:ng]
+
+
+def db_detect(matcher: ORBmatcher, mode, q_ids, q_vals, kf_ptr, db_ids, db_vals, connected, covis_ptr, covis, min_score=0.0):
+    """KeyFrameDatabase::DetectLoopCandidates (mode 0) / DetectRelocalisationCandidates (mode 1) on arrays
+    (reference src/KeyFrameDatabase.cc:73-308).  Returns (candidate keyframe indices, shared-word counts, scores)."""
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    q_ids, q_vals, kf_ptr = a(q_ids, np.int32), a(q_vals, np.float64), a(kf_ptr, np.int32)
+    db_ids, db_vals, covis_ptr, covis = a(db_ids, np.int32), a(db_vals, np.float64), a(covis_ptr, np.int32), a(covis, np.int32)
+    connected = a(connected, np.uint8)
+    nkf = len(kf_ptr) - 1
+    cand, common, score = np.zeros(max(nkf, 1), np.int32), np.zeros(max(nkf, 1), np.int32), np.zeros(max(nkf, 1), np.float32)
+    nc = C.c_int(0)
+    _check(_bind().orbfe_bow_db_detect(matcher.handle, mode, len(q_ids), _p(q_ids), _p(q_vals), nkf, _p(kf_ptr), _p(db_ids), _p(db_vals),
+                                       _p(connected), _p(covis_ptr), _p(covis), min_score, C.byref(nc), _p(cand), _p(common), _p(score)))
+    return cand[:nc.value], common[:nkf], score[:nkf]

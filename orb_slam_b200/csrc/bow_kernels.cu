@@ -105,6 +105,44 @@ __global__ void __launch_bounds__(128) distinctive_kernel(const uint4 *__restric
     if (lane == 0) best_out[g] = bestIdx;
 }
 
+// KeyFrameDatabase scoring: one thread per keyframe, two-pointer walk over the (ascending) word lists of the query and
+// of the keyframe.  score accumulates |vi - wi| - |vi| - |wi| over the shared words in ascending word order, as
+// L1Scoring::score does (ScoringObject.cpp:33-56; its lower_bound jumps visit the same shared words in the same order).
+__global__ void __launch_bounds__(128) bow_db_score_kernel(int nq, const int *__restrict__ q_ids, const double *__restrict__ q_vals,
+                                                           int nkf, const int *__restrict__ kf_ptr, const int *__restrict__ db_ids,
+                                                           const double *__restrict__ db_vals, int *__restrict__ common_out,
+                                                           int *__restrict__ first_out, double *__restrict__ score_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkf) return;
+    int a = 0, b = __ldg(&kf_ptr[k]);
+    const int be = __ldg(&kf_ptr[k + 1]);
+    int common = 0, first = -1;
+    double score = 0.0;
+    while (a < nq && b < be) {
+        const int ia = __ldg(&q_ids[a]), ib = __ldg(&db_ids[b]);
+        if (ia == ib) {
+            const double vi = __ldg(&q_vals[a]), wi = __ldg(&db_vals[b]);
+            score = __dadd_rn(score, __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi)));
+            if (common == 0) first = ia;
+            common++;
+            a++; b++;
+        } else if (ia < ib) {
+            a++;
+        } else {
+            b++;
+        }
+    }
+    common_out[k] = common;
+    first_out[k] = first;
+    score_out[k] = -score / 2.0;
+}
+
+void launch_bow_db_score(int nq, const int *q_ids, const double *q_vals, int nkf, const int *kf_ptr, const int *db_ids,
+                         const double *db_vals, int *common, int *first, double *score, cudaStream_t s) {
+    if (nkf <= 0) return;
+    bow_db_score_kernel<<<(nkf + 127) / 128, 128, 0, s>>>(nq, q_ids, q_vals, nkf, kf_ptr, db_ids, db_vals, common, first, score);
+}
+
 }  // namespace orbfe
 
 using namespace orbfe;

@@ -773,7 +773,13 @@ extern "C" int orbfe_matcher_create(int device, OrbfeMatcher **out) {
     OrbfeMatcher *m = new OrbfeMatcher();
     m->device = device;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // matching is a short, latency-critical job that usually shares the GPU with an extractor's long kernels: its
+        // thread blocks go first whenever an SM frees up
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(m->d_err, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_err, sizeof(int), cudaHostAllocDefault);
@@ -996,6 +1002,44 @@ extern "C" int orbfe_distinctive_descriptors(OrbfeMatcher *m, const uint8_t *des
     m->launches += 1;
     return ORBFE_OK;
 }
+
+// Device half of orbfe_bow_db_detect (host/bow_host.cpp): per-keyframe shared-word count, first shared word, L1 score.
+namespace orbfe {
+void launch_bow_db_score(int nq, const int *q_ids, const double *q_vals, int nkf, const int *kf_ptr, const int *db_ids,
+                         const double *db_vals, int *common, int *first, double *score, cudaStream_t s);
+int bow_db_score(OrbfeMatcher *m, int nq, const int32_t *q_ids, const double *q_vals, int nkf, const int32_t *kf_ptr,
+                 const int32_t *db_ids, const double *db_vals, int32_t *common, int32_t *first, double *score) {
+    const size_t nw = (size_t)kf_ptr[nkf];
+    CU_TRY(cudaSetDevice(m->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_qi = take(sizeof(int) * (size_t)std::max(nq, 1)), o_qv = take(sizeof(double) * (size_t)std::max(nq, 1));
+    const size_t o_kp = take(sizeof(int) * ((size_t)nkf + 1)), o_di = take(sizeof(int) * std::max<size_t>(nw, 1));
+    const size_t o_dv = take(sizeof(double) * std::max<size_t>(nw, 1));
+    const size_t o_c = take(sizeof(int) * (size_t)nkf), o_f = take(sizeof(int) * (size_t)nkf), o_s = take(sizeof(double) * (size_t)nkf);
+    CU_TRY(mreserve(m, 5, off));
+    unsigned char *D = (unsigned char *)m->buf[5];
+    cudaStream_t s = m->stream;
+    if (nq > 0) {
+        CU_TRY(cudaMemcpyAsync(D + o_qi, q_ids, sizeof(int) * (size_t)nq, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(D + o_qv, q_vals, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, s));
+    }
+    CU_TRY(cudaMemcpyAsync(D + o_kp, kf_ptr, sizeof(int) * ((size_t)nkf + 1), cudaMemcpyHostToDevice, s));
+    if (nw > 0) {
+        CU_TRY(cudaMemcpyAsync(D + o_di, db_ids, sizeof(int) * nw, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(D + o_dv, db_vals, sizeof(double) * nw, cudaMemcpyHostToDevice, s));
+    }
+    launch_bow_db_score(nq, (const int *)(D + o_qi), (const double *)(D + o_qv), nkf, (const int *)(D + o_kp), (const int *)(D + o_di),
+                        (const double *)(D + o_dv), (int *)(D + o_c), (int *)(D + o_f), (double *)(D + o_s), s);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(common, D + o_c, sizeof(int) * (size_t)nkf, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(first, D + o_f, sizeof(int) * (size_t)nkf, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(score, D + o_s, sizeof(double) * (size_t)nkf, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    m->launches += 1;
+    return ORBFE_OK;
+}
+}  // namespace orbfe
 
 extern "C" int orbfe_knn2_groups_device(OrbfeMatcher *m, const uint8_t *d_q, int nq, const uint8_t *d_db, int ngroups,
                                         int group_size, uint16_t *d_best, int32_t *d_best_idx, uint16_t *d_second,

@@ -102,3 +102,38 @@ def random_vocabulary(k=10, L=3, seed=0, flip=0.12, stop_fraction=0.02, ragged=F
             weight[i] = 0.0 if rng.random() < stop_fraction else float(rng.uniform(0.5, 9.0))
     return {"node_desc": np.stack(desc).astype(np.uint8), "child_ptr": child_ptr, "children": np.array(children, np.int32),
             "word_id": word_id, "weight": weight, "L": L, "k": k}
+
+
+def random_keyframe_db(nkf=300, nwords=6000, words_per_kf=300, seed=0, loop_at=40):
+    """A synthetic keyframe database for the KeyFrameDatabase rows: keyframes along a trajectory see a sliding window of a
+    long random word sequence (neighbours share most words), a stretch near `loop_at` is revisited by the query.
+    Returns dict(kf_ptr, db_ids, db_vals, covis_ptr, covis, connected, q_ids, q_vals)."""
+    rng = np.random.default_rng(seed)
+    track = rng.integers(0, nwords, nkf * 40 + words_per_kf * 2)
+
+    def bow_at(pos, noise_seed):
+        r = np.random.default_rng(noise_seed)
+        w = track[pos:pos + words_per_kf].copy()
+        flip = r.random(len(w)) < 0.25
+        w[flip] = r.integers(0, nwords, int(flip.sum()))
+        ids, cnt = np.unique(w, return_counts=True)
+        vals = cnt.astype(np.float64) * r.uniform(0.5, 3.0, len(ids))
+        return ids.astype(np.int32), vals / vals.sum()
+
+    kf_ptr, ids_all, vals_all = [0], [], []
+    for k in range(nkf):
+        ids, vals = bow_at(40 * k, 1000 + k)
+        ids_all.append(ids); vals_all.append(vals)
+        kf_ptr.append(kf_ptr[-1] + len(ids))
+    covis_ptr, covis = [0], []
+    for k in range(nkf):
+        nb = [k + d for d in (1, -1, 2, -2, 3, -3, 4, -4, 5, -5) if 0 <= k + d < nkf]
+        rng.shuffle(nb)
+        covis += nb[:int(rng.integers(0, 11))]
+        covis_ptr.append(len(covis))
+    connected = np.zeros(nkf, np.uint8)
+    connected[max(0, nkf - 6):] = 1                      # the query keyframe follows the last ones
+    q_ids, q_vals = bow_at(40 * loop_at + 7, 99)          # ... and revisits the place of keyframe loop_at
+    return {"kf_ptr": np.array(kf_ptr, np.int32), "db_ids": np.concatenate(ids_all), "db_vals": np.concatenate(vals_all),
+            "covis_ptr": np.array(covis_ptr, np.int32), "covis": np.array(covis, np.int32), "connected": connected,
+            "q_ids": q_ids, "q_vals": q_vals}

@@ -7,7 +7,7 @@ import pytest
 import oracle as O
 import orb_slam_b200 as fe
 from orb_slam_b200 import bow as B
-from orb_slam_b200.synth import random_descriptors, noisy_copies, random_vocabulary
+from orb_slam_b200.synth import random_descriptors, noisy_copies, random_vocabulary, random_keyframe_db
 
 pytestmark = pytest.mark.gpu
 
@@ -87,4 +87,26 @@ def test_distinctive_descriptors_matches_oracle(gpu_required):
     assert (best >= 0).sum() > 600
     # empty batch
     assert len(B.distinctive_descriptors(m, np.zeros((0, 32), np.uint8), np.zeros(1, np.int32))) == 0
+    m.close()
+
+
+def test_keyframe_db_detect_matches_oracle(gpu_required):
+    """N3: DetectLoopCandidates / DetectRelocalisationCandidates on arrays, CUDA scoring + host list logic vs the oracle's
+    literal inverted-file walk: candidates in the same order, identical shared-word counts and float scores."""
+    m = fe.ORBmatcher(0.75, True)
+    for seed, nkf in ((0, 400), (1, 1500), (2, 60)):
+        db = random_keyframe_db(nkf=nkf, nwords=8000, words_per_kf=300, seed=seed, loop_at=nkf // 5)
+        for mode, ms in ((0, 0.0), (0, 0.03), (1, 0.0)):
+            args = (db["q_ids"], db["q_vals"], db["kf_ptr"], db["db_ids"], db["db_vals"], db["connected"], db["covis_ptr"], db["covis"], ms)
+            cand, common, score = B.db_detect(m, mode, *args)
+            cand_o, common_o, score_o = O.bow_db_detect(mode, *args)
+            assert np.array_equal(cand, cand_o), (seed, mode, ms)
+            assert np.array_equal(common, common_o)
+            assert np.array_equal(score.view(np.uint32), score_o.view(np.uint32))
+            assert len(cand) > 0 and (nkf // 5 in cand or nkf // 5 + 1 in cand or nkf // 5 - 1 in cand)
+    # a query that shares nothing
+    db = random_keyframe_db(nkf=50, nwords=2000, words_per_kf=100, seed=5)
+    cand, common, score = B.db_detect(m, 1, np.array([2001, 2002], np.int32), np.array([0.5, 0.5]), db["kf_ptr"], db["db_ids"], db["db_vals"],
+                                      db["connected"], db["covis_ptr"], db["covis"], 0.0)
+    assert len(cand) == 0 and common.sum() == 0
     m.close()

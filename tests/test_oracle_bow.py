@@ -5,7 +5,7 @@ import math
 import numpy as np
 
 import oracle as O
-from orb_slam_b200.synth import random_descriptors, noisy_copies, random_vocabulary
+from orb_slam_b200.synth import random_descriptors, noisy_copies, random_vocabulary, random_keyframe_db
 
 
 def _ham(a, b):
@@ -102,3 +102,74 @@ def test_distinctive_oracle_vs_python():
             if med < bm:
                 bm, bi = med, i
         assert best[g] == bi
+
+
+def _py_db_detect(mode, db, min_score):
+    """KeyFrameDatabase.cc:73-308 with Python lists/dicts standing in for the inverted file and the keyframe fields."""
+    f32 = np.float32
+    kf_ptr, ids, vals = db["kf_ptr"], db["db_ids"], db["db_vals"]
+    nkf = len(kf_ptr) - 1
+    inv = {}
+    for k in range(nkf):
+        for w in ids[kf_ptr[k]:kf_ptr[k + 1]]:
+            inv.setdefault(int(w), []).append(k)
+    query, words, score, sharing = set(), {}, {}, []
+    for w in db["q_ids"]:
+        for k in inv.get(int(w), []):
+            if k not in query:
+                words[k] = 0
+                if mode == 1 or not db["connected"][k]:
+                    query.add(k)
+                    sharing.append(k)
+            words[k] += 1
+    if not sharing:
+        return []
+    max_common = max(words[k] for k in sharing)
+    min_common = int(f32(max_common) * f32(0.8))
+    qd = dict(zip(db["q_ids"].tolist(), db["q_vals"].tolist()))
+    lsm = []
+    for k in sharing:
+        if words[k] > min_common:
+            s = 0.0
+            for w, v in zip(ids[kf_ptr[k]:kf_ptr[k + 1]].tolist(), vals[kf_ptr[k]:kf_ptr[k + 1]].tolist()):
+                if w in qd:
+                    s += abs(qd[w] - v) - abs(qd[w]) - abs(v)
+            si = f32(-s / 2.0)
+            score[k] = si
+            if mode == 1 or si >= f32(min_score):
+                lsm.append((si, k))
+    if not lsm:
+        return []
+    acc = []
+    best_acc = f32(min_score) if mode == 0 else f32(0)
+    for si, k in lsm:
+        best_s, acc_s, best_k = si, si, k
+        for k2 in db["covis"][db["covis_ptr"][k]:db["covis_ptr"][k + 1]]:
+            k2 = int(k2)
+            if k2 not in query:
+                continue
+            if mode == 0 and not words[k2] > min_common:
+                continue
+            s2 = score.get(k2, f32(0))
+            acc_s = f32(acc_s + s2)
+            if s2 > best_s:
+                best_k, best_s = k2, s2
+        acc.append((acc_s, best_k))
+        if acc_s > best_acc:
+            best_acc = acc_s
+    keep = f32(0.75) * best_acc
+    out = []
+    for a, k in acc:
+        if a > keep and k not in out:
+            out.append(k)
+    return out
+
+
+def test_db_detect_oracle_vs_python():
+    for seed in range(4):
+        db = random_keyframe_db(nkf=120 + 30 * seed, nwords=3000, words_per_kf=200, seed=seed, loop_at=20 + seed)
+        for mode, ms in ((0, 0.0), (0, 0.05), (1, 0.0)):
+            cand, common, score = O.bow_db_detect(mode, db["q_ids"], db["q_vals"], db["kf_ptr"], db["db_ids"], db["db_vals"],
+                                                  db["connected"], db["covis_ptr"], db["covis"], ms)
+            assert list(cand) == _py_db_detect(mode, db, ms), (seed, mode, ms)
+            assert len(cand) > 0
