@@ -157,6 +157,22 @@ int orbfe_search_for_initialization(OrbfeMatcher *m, const OrbfeFrameView *f1, c
                                     float *prev_matched, int window, float nnratio, int check_orientation,
                                     int *match12_out, int *nmatches_out);
 
+/* ---- Frame feature post-processing ---- */
+
+/* Frame::UndistortKeyPoints (reference src/Frame.cc:289-319): cv::undistortPoints(pts, mK, mDistCoef, cv::Mat(), mK) on
+ * the (x, y) of n keypoints, every other field copied.  dist5 = (k1, k2, p1, p2, k3) on the HOST (the reference's
+ * mDistCoef has the first four; pass k3 = 0).  k1 == 0 copies the keypoints (:291-295).  Double-precision arithmetic
+ * in OpenCV's evaluation order: bit-exact against OpenCV.  In-place (d_in == d_out) is allowed.
+ * Device form: enqueued on `stream` (NULL = the matcher's stream), not synchronised; it chains after
+ * orbfe_extract_batch_device on all batch * capacity keypoint slots at once. */
+int orbfe_undistort_keypoints_device(OrbfeMatcher *m, const OrbfeKeyPoint *d_in, OrbfeKeyPoint *d_out, int n, float fx, float fy,
+                                     float cx, float cy, const float *dist5, void *stream);
+int orbfe_undistort_keypoints(OrbfeMatcher *m, const OrbfeKeyPoint *in, OrbfeKeyPoint *out, int n, float fx, float fy, float cx,
+                              float cy, const float *dist5);
+/* Frame::ComputeImageBounds (Frame.cc:321-350): bounds4 = (mnMinX, mnMinY, mnMaxX, mnMaxY). */
+int orbfe_image_bounds(OrbfeMatcher *m, int cols, int rows, float fx, float fy, float cx, float cy, const float *dist5,
+                       float *bounds4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -444,3 +444,31 @@ def bow_db_detect(mode, q_ids, q_vals, kf_ptr, db_ids, db_vals, connected, covis
     n = f(C.c_int(mode), C.c_int(len(q_ids)), _p(q_ids), _p(q_vals), C.c_int(nkf), _p(kf_ptr), _p(db_ids), _p(db_vals), _p(connected),
           _p(covis_ptr), _p(covis), C.c_float(min_score), _p(cand), _p(common), _p(score))
     return cand[:n], common[:nkf], score[:nkf]
+
+
+# ---- Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:289-350) ----
+def undistort_points(pts, fx, fy, cx, cy, dist):
+    pts, dist = _a(pts, np.float32).reshape(-1, 2), _a(dist, np.float32)
+    out = np.zeros_like(pts)
+    f = lib().orb_oracle_undistort_points
+    f.restype = None
+    f(_p(pts), C.c_int(len(pts)), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(dist), _p(out))
+    return out
+
+
+def undistort_keypoints(kps, fx, fy, cx, cy, dist):
+    kps, dist = _a(kps, KP_DTYPE), _a(dist, np.float32)
+    out = np.zeros_like(kps)
+    f = lib().orb_oracle_undistort_keypoints
+    f.restype = None
+    f(_p(kps), C.c_int(len(kps)), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(dist), _p(out))
+    return out
+
+
+def image_bounds(cols, rows, fx, fy, cx, cy, dist):
+    dist = _a(dist, np.float32)
+    b = np.zeros(4, np.float32)
+    f = lib().orb_oracle_image_bounds
+    f.restype = None
+    f(C.c_int(cols), C.c_int(rows), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(dist), _p(b))
+    return b

@@ -206,6 +206,12 @@ int orb_oracle_search_for_triangulation(int n1, const OrbOracleKeyPoint *keys1, 
 void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,
                      int *best_dist, int *best_idx, int *second_dist);
 
+/* ---- Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:289-350), SURVEY section 8(f) row N1 ---- */
+void orb_oracle_undistort_points(const float *pts, int n, float fx, float fy, float cx, float cy, const float *dist, float *out);
+void orb_oracle_undistort_keypoints(const OrbOracleKeyPoint *in, int n, float fx, float fy, float cx, float cy, const float *dist,
+                                    OrbOracleKeyPoint *out);
+void orb_oracle_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float *dist, float *bounds);
+
 /* ---- SURVEY section 8(f) rows N2 / N4 (orb_oracle_bow.c) ---- */
 void orb_oracle_bow_descend(const uint8_t *node_desc, const int32_t *child_ptr, const int32_t *children, int depth_L,
                             const uint8_t *desc, int n, int levelsup, int32_t *leaf_out, int32_t *node_out);

@@ -705,3 +705,62 @@ void orb_oracle_guided_best(const OrbOracleFrame *f, int nq, const float *qu, co
     }
     free(cand);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame::UndistortKeyPoints / ComputeImageBounds (reference src/Frame.cc:289-350): cv::undistortPoints(mat, mat, mK,
+ * mDistCoef, cv::Mat(), mK) = OpenCV's cvUndistortPoints with R = I, P = K: 5 fixed-point iterations of the inverse
+ * distortion model in double, then the re-projection with P.  Pinned bit-exactly against python-cv2
+ * (tests/golden/opencv_undistort.npz).  dist = (k1, k2, p1, p2, k3); k4..k6 = 0 as in the reference's settings.
+ * ------------------------------------------------------------------------------------------------ */
+void orb_oracle_undistort_points(const float *pts, int n, float fx, float fy, float cx, float cy, const float *dist, float *out) {
+    const double k0 = dist[0], k1 = dist[1], k2 = dist[2], k3 = dist[3], k4 = dist[4];
+    const double fxd = fx, fyd = fy, cxd = cx, cyd = cy;
+    const double ifx = 1. / fxd, ify = 1. / fyd;
+    for (int i = 0; i < n; i++) {
+        double x = pts[2 * i], y = pts[2 * i + 1];
+        double x0 = x = (x - cxd) * ifx;
+        double y0 = y = (y - cyd) * ify;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0.0 * r2 + 0.0) * r2 + 0.0) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+            const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x);
+            const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fxd * x + 0.0 * y + cxd;
+        const double yy = 0.0 * x + fyd * y + cyd;
+        const double ww = 1. / (0.0 * x + 0.0 * y + 1.0);
+        out[2 * i] = (float)(xx * ww);
+        out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+/* UndistortKeyPoints on the 28-byte keypoints: mvKeysUn = mvKeys when k1 == 0 (:291-295) */
+void orb_oracle_undistort_keypoints(const OrbOracleKeyPoint *in, int n, float fx, float fy, float cx, float cy, const float *dist,
+                                    OrbOracleKeyPoint *out) {
+    for (int i = 0; i < n; i++) out[i] = in[i];
+    if (dist[0] == 0.0f) return;
+    for (int i = 0; i < n; i++) {
+        const float p[2] = {in[i].x, in[i].y};
+        float q[2];
+        orb_oracle_undistort_points(p, 1, fx, fy, cx, cy, dist, q);
+        out[i].x = q[0];
+        out[i].y = q[1];
+    }
+}
+
+/* ComputeImageBounds, Frame.cc:321-350: bounds = (mnMinX, mnMinY, mnMaxX, mnMaxY) */
+void orb_oracle_image_bounds(int cols, int rows, float fx, float fy, float cx, float cy, const float *dist, float *bounds) {
+    if (dist[0] != 0.0f) {
+        const float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+        float u[8];
+        orb_oracle_undistort_points(c, 4, fx, fy, cx, cy, dist, u);
+        bounds[0] = fminf(floorf(u[0]), floorf(u[4]));
+        bounds[2] = fmaxf(ceilf(u[2]), ceilf(u[6]));
+        bounds[1] = fminf(floorf(u[1]), floorf(u[3]));
+        bounds[3] = fmaxf(ceilf(u[5]), ceilf(u[7]));
+    } else {
+        bounds[0] = 0; bounds[2] = (float)cols; bounds[1] = 0; bounds[3] = (float)rows;
+    }
+}

@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "orbfe_search_by_projection_f1f2", "orbfe_search_by_bow", "orbfe_guided_search", "orbfe_guided_best", "orbfe_search_for_triangulation",
     "orbfe_window_search",
     "orbfe_search_for_initialization",
+    "orbfe_undistort_keypoints_device", "orbfe_undistort_keypoints", "orbfe_image_bounds",
     # include/orbfe_bow.h
     "orbfe_vocabulary_create", "orbfe_vocabulary_destroy", "orbfe_bow_descend_device", "orbfe_bow_descend", "orbfe_bow_transform",
     "orbfe_distinctive_descriptors", "orbfe_bow_db_detect",

@@ -508,4 +508,55 @@ int launch_guided_device(const SbpParams &P, size_t smem_bytes, int njobs, const
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Frame::UndistortKeyPoints (reference src/Frame.cc:289-319) = cv::undistortPoints(pts, K, D, R = I, P = K): five
+// fixed-point iterations of the inverse distortion model in double, then the re-projection; every operation
+// individually rounded (no FMA), in the order OpenCV evaluates them -- bit-exact against python-cv2
+// (tests/golden/opencv_undistort.npz).  One thread per keypoint; the other keypoint fields are copied.
+// ------------------------------------------------------------------------------------------------
+struct UndistortParams { double fx, fy, cx, cy, ifx, ify, k0, k1, k2, k3, k4; };
+
+__device__ __forceinline__ void undistort_point(const UndistortParams &U, float px, float py, float &ox, float &oy) {
+    double x = __dmul_rn(__dsub_rn((double)px, U.cx), U.ifx), y = __dmul_rn(__dsub_rn((double)py, U.cy), U.ify);
+    const double x0 = x, y0 = y;
+#pragma unroll 1
+    for (int j = 0; j < 5; j++) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        // (1 + ((k7*r2 + k6)*r2 + k5)*r2) / (1 + ((k4*r2 + k1)*r2 + k0)*r2) with k5..k7 = 0: the numerator is exactly 1
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(U.k4, r2), U.k1), r2), U.k0), r2));
+        const double icdist = __ddiv_rn(1.0, den);
+        const double twoxy_k2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, U.k2), x), y);                          // 2*k2*x*y
+        const double dX = __dadd_rn(twoxy_k2, __dmul_rn(U.k3, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));  // + k3*(r2 + 2*x*x)
+        const double dY = __dadd_rn(__dmul_rn(U.k2, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                    __dmul_rn(__dmul_rn(__dmul_rn(2.0, U.k3), x), y));                      // k2*(r2 + 2*y*y) + 2*k3*x*y
+        x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+        y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+    }
+    // xx = fx*x + 0*y + cx, yy = 0*x + fy*y + cy, ww = 1/(0*x + 0*y + 1) = 1 (the zero products add exactly)
+    ox = (float)__dadd_rn(__dmul_rn(U.fx, x), U.cx);
+    oy = (float)__dadd_rn(__dmul_rn(U.fy, y), U.cy);
+}
+
+__global__ void __launch_bounds__(256) undistort_kernel(UndistortParams U, const OrbfeKeyPoint *__restrict__ in,
+                                                        OrbfeKeyPoint *__restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OrbfeKeyPoint k = in[i];
+    float ox, oy;
+    undistort_point(U, k.x, k.y, ox, oy);
+    k.x = ox;
+    k.y = oy;
+    out[i] = k;
+}
+
+void launch_undistort(float fx, float fy, float cx, float cy, const float *dist5, const OrbfeKeyPoint *d_in, OrbfeKeyPoint *d_out,
+                      int n, cudaStream_t s) {
+    if (n <= 0) return;
+    UndistortParams U;
+    U.fx = fx; U.fy = fy; U.cx = cx; U.cy = cy;
+    U.ifx = 1. / U.fx; U.ify = 1. / U.fy;
+    U.k0 = dist5[0]; U.k1 = dist5[1]; U.k2 = dist5[2]; U.k3 = dist5[3]; U.k4 = dist5[4];
+    undistort_kernel<<<(n + 255) / 256, 256, 0, s>>>(U, d_in, d_out, n);
+}
+
 }  // namespace orbfe

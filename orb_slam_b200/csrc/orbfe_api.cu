@@ -976,6 +976,64 @@ extern "C" int orbfe_hamming_dense(OrbfeMatcher *m, const uint8_t *q, int nq, co
     return ORBFE_OK;
 }
 
+// Frame::UndistortKeyPoints / ComputeImageBounds (include/orbfe_match.h)
+extern "C" int orbfe_undistort_keypoints_device(OrbfeMatcher *m, const OrbfeKeyPoint *d_in, OrbfeKeyPoint *d_out, int n, float fx,
+                                                float fy, float cx, float cy, const float *dist5, void *stream) {
+    if (!m || n < 0 || !dist5 || !(fx != 0.f) || !(fy != 0.f)) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (n == 0) return ORBFE_OK;
+    if (!d_in || !d_out) return fail(ORBFE_ERR_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(m->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    if (dist5[0] == 0.0f) {  // mvKeysUn = mvKeys (Frame.cc:291-295)
+        if (d_in != d_out) CU_TRY(cudaMemcpyAsync(d_out, d_in, sizeof(OrbfeKeyPoint) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+        return ORBFE_OK;
+    }
+    launch_undistort(fx, fy, cx, cy, dist5, d_in, d_out, n, s);
+    CU_TRY(cudaGetLastError());
+    m->launches += 1;
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_undistort_keypoints(OrbfeMatcher *m, const OrbfeKeyPoint *in, OrbfeKeyPoint *out, int n, float fx, float fy,
+                                         float cx, float cy, const float *dist5) {
+    if (!m || n < 0 || !dist5) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (n == 0) return ORBFE_OK;
+    if (!in || !out) return fail(ORBFE_ERR_ARG, "NULL argument");
+    if (dist5[0] == 0.0f) {
+        if (in != out) memcpy(out, in, sizeof(OrbfeKeyPoint) * (size_t)n);
+        return ORBFE_OK;
+    }
+    CU_TRY(cudaSetDevice(m->device));
+    CU_TRY(mreserve(m, 0, sizeof(OrbfeKeyPoint) * (size_t)n));
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemcpyAsync(m->buf[0], in, sizeof(OrbfeKeyPoint) * (size_t)n, cudaMemcpyHostToDevice, s));
+    const int rc = orbfe_undistort_keypoints_device(m, (const OrbfeKeyPoint *)m->buf[0], (OrbfeKeyPoint *)m->buf[0], n, fx, fy, cx, cy,
+                                                    dist5, s);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(out, m->buf[0], sizeof(OrbfeKeyPoint) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_image_bounds(OrbfeMatcher *m, int cols, int rows, float fx, float fy, float cx, float cy, const float *dist5,
+                                  float *bounds4) {
+    if (!m || !dist5 || !bounds4 || cols < 1 || rows < 1) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (dist5[0] == 0.0f) {  // Frame.cc:343-348
+        bounds4[0] = 0.f; bounds4[1] = 0.f; bounds4[2] = (float)cols; bounds4[3] = (float)rows;
+        return ORBFE_OK;
+    }
+    OrbfeKeyPoint c[4];
+    memset(c, 0, sizeof(c));
+    c[1].x = (float)cols; c[2].y = (float)rows; c[3].x = (float)cols; c[3].y = (float)rows;   // Frame.cc:325-329
+    const int rc = orbfe_undistort_keypoints(m, c, c, 4, fx, fy, cx, cy, dist5);
+    if (rc) return rc;
+    bounds4[0] = std::min(std::floor(c[0].x), std::floor(c[2].x));   // :336-339
+    bounds4[2] = std::max(std::ceil(c[1].x), std::ceil(c[3].x));
+    bounds4[1] = std::min(std::floor(c[0].y), std::floor(c[1].y));
+    bounds4[3] = std::max(std::ceil(c[2].y), std::ceil(c[3].y));
+    return ORBFE_OK;
+}
+
 // MapPoint::ComputeDistinctiveDescriptors for many map points in one launch (include/orbfe_bow.h)
 #include "../../include/orbfe_bow.h"
 namespace orbfe { void launch_distinctive(const uint8_t *d_desc, const int *d_group_ptr, int ngroups, int *d_best, cudaStream_t s); }

@@ -125,6 +125,9 @@ int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const O
                       const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
                       const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s);
 
+void launch_undistort(float fx, float fy, float cx, float cy, const float *dist5, const OrbfeKeyPoint *d_in, OrbfeKeyPoint *d_out,
+                      int n, cudaStream_t s);
+
 // records the thread's last-error string (orbfe_last_error) and returns `code`
 int set_error(int code, const char *fmt, ...);
 

@@ -40,6 +40,9 @@ def _bind():
     L.orbfe_guided_search_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int,
                                              C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
                                              vp, vp, vp]
+    L.orbfe_undistort_keypoints_device.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
+    L.orbfe_undistort_keypoints.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    L.orbfe_image_bounds.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     L.orbfe_search_local_points.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]
     L.orbfe_search_by_projection_kf.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float,
                                                 C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
@@ -256,3 +259,32 @@ def guided_best(matcher: ORBmatcher, f, qu, qv, qr, qlo, qhi, qdesc, th_dist):
     out = np.full(max(len(qu), 1), -1, np.int32)
     _check(L.orbfe_guided_best(matcher.handle, C.byref(f.c), len(qu), _p(qu), _p(qv), _p(qr), _p(qlo), _p(qhi), _p(qdesc), th_dist, _p(out)))
     return out[:len(qu)]
+
+
+def undistort_keypoints(matcher: ORBmatcher, kps, fx, fy, cx, cy, dist):
+    """Frame::UndistortKeyPoints (reference src/Frame.cc:289-319) on a keypoint array; dist = (k1, k2, p1, p2[, k3])."""
+    L = _bind()
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    d = np.zeros(5, np.float32)
+    d[:len(dist)] = dist
+    out = np.zeros_like(kps)
+    _check(L.orbfe_undistort_keypoints(matcher.handle, _p(kps), _p(out), len(kps), fx, fy, cx, cy, _p(d)))
+    return out
+
+
+def undistort_keypoints_device(matcher: ORBmatcher, d_in, d_out, n, fx, fy, cx, cy, dist, stream=0):
+    L = _bind()
+    d = np.zeros(5, np.float32)
+    d[:len(dist)] = dist
+    vp = C.c_void_p
+    _check(L.orbfe_undistort_keypoints_device(matcher.handle, vp(d_in), vp(d_out), n, fx, fy, cx, cy, _p(d), vp(stream)))
+
+
+def image_bounds(matcher: ORBmatcher, cols, rows, fx, fy, cx, cy, dist):
+    """Frame::ComputeImageBounds (Frame.cc:321-350): (mnMinX, mnMinY, mnMaxX, mnMaxY)."""
+    L = _bind()
+    d = np.zeros(5, np.float32)
+    d[:len(dist)] = dist
+    b = np.zeros(4, np.float32)
+    _check(L.orbfe_image_bounds(matcher.handle, cols, rows, fx, fy, cx, cy, _p(d), _p(b)))
+    return b

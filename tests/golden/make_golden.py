@@ -58,6 +58,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "opencv_primitives.npz"), **g)
     print("wrote", os.path.join(OUT, "opencv_primitives.npz"), "cv2", cv2.__version__)
 
+    # cv::undistortPoints(pts, K, D, R = I, P = K) as Frame::UndistortKeyPoints calls it (reference src/Frame.cc:289-319):
+    # a separate small file so that the older fixture stays byte-identical
+    u = {}
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)
+    u["K"] = K
+    pts = np.stack([rng.uniform(0, 640, 3000), rng.uniform(0, 480, 3000)], axis=1).astype(np.float32)
+    pts[:4] = [[0, 0], [640, 0], [0, 480], [640, 480]]  # the corners ComputeImageBounds undistorts
+    u["pts"] = pts
+    coeffs = np.array([[0.2624, -0.9531, -0.0054, 0.0026, 1.1633],     # TUM fr1 (strong)
+                       [-0.28, 0.07, 0.0002, 0.00002, 0.0],            # 4-coefficient model (ORB-SLAM settings files)
+                       [0.1, 0.0, 0.0, 0.0, 0.0]], np.float32)
+    u["coeffs"] = coeffs
+    for i, D in enumerate(coeffs):
+        u["out_%d" % i] = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "opencv_undistort.npz"), **u)
+    print("wrote", os.path.join(OUT, "opencv_undistort.npz"))
+
 
 if __name__ == "__main__":
     main()

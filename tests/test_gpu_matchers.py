@@ -379,3 +379,34 @@ def test_search_for_triangulation(gpu_required):
         assert n == n_o and np.array_equal(m12, m12_o)
         assert n > 20
         m.close()
+
+
+def test_undistort_keypoints_and_image_bounds(gpu_required):
+    """N1: Frame::UndistortKeyPoints / ComputeImageBounds on the device vs python-cv2 golden vectors and the oracle,
+    bit-exact; host-array form, device in-place form, and the k1 == 0 shortcut."""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "opencv_undistort.npz"))
+    K = g["K"]
+    fx, fy, cx, cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    n = len(g["pts"])
+    kps = np.zeros(n, fe.KP_DTYPE)
+    kps["x"], kps["y"] = g["pts"][:, 0], g["pts"][:, 1]
+    kps["size"], kps["angle"], kps["response"], kps["octave"], kps["class_id"] = 31.0, 12.5, 40.0, np.arange(n) % 8, -1
+    m = fe.ORBmatcher(0.9, True)
+    for i, D in enumerate(g["coeffs"]):
+        out = M.undistort_keypoints(m, kps, fx, fy, cx, cy, D)
+        assert np.array_equal(out["x"].view(np.uint32), g["out_%d" % i][:, 0].view(np.uint32))
+        assert np.array_equal(out["y"].view(np.uint32), g["out_%d" % i][:, 1].view(np.uint32))
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(out[f], kps[f])
+        assert np.array_equal(out, O.undistort_keypoints(kps, fx, fy, cx, cy, D))
+        assert np.array_equal(M.image_bounds(m, 640, 480, fx, fy, cx, cy, D), O.image_bounds(640, 480, fx, fy, cx, cy, D))
+        # device form, in place
+        d = torch.from_numpy(kps.view(np.uint8).reshape(n, 28).copy()).to("cuda:0")
+        M.undistort_keypoints_device(m, d.data_ptr(), d.data_ptr(), n, fx, fy, cx, cy, D)
+        m.sync()
+        assert np.array_equal(d.cpu().numpy().reshape(-1).view(fe.KP_DTYPE), out)
+    assert np.array_equal(M.undistort_keypoints(m, kps, fx, fy, cx, cy, [0, 0.2, 0.1, 0.1]), kps)
+    assert list(M.image_bounds(m, 640, 480, fx, fy, cx, cy, [0, 0, 0, 0])) == [0, 0, 640, 480]
+    m.close()

@@ -185,3 +185,23 @@ def test_fallback_cells_and_flat_image():
     assert rc == 0 and len(k) == 0
     rc, k, d, _ = O.extract(p, np.zeros((40, 40), np.uint8))
     assert rc == -2  # degenerate grid: outside the supported domain
+
+
+def test_undistort_points_vs_cv2_golden():
+    """Frame::UndistortKeyPoints' cv::undistortPoints(pts, K, D, I, K): the oracle against python-cv2 vectors, bit-exact."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "opencv_undistort.npz"))
+    K = g["K"]
+    for i, D in enumerate(g["coeffs"]):
+        out = O.undistort_points(g["pts"], K[0, 0], K[1, 1], K[0, 2], K[1, 2], D)
+        assert np.array_equal(out.view(np.uint32), g["out_%d" % i].view(np.uint32))
+        # ComputeImageBounds from the four corners (the first four fixture points), Frame.cc:336-339
+        c = g["out_%d" % i][:4]
+        b = O.image_bounds(640, 480, K[0, 0], K[1, 1], K[0, 2], K[1, 2], D)
+        exp = [min(np.floor(c[0, 0]), np.floor(c[2, 0])), min(np.floor(c[0, 1]), np.floor(c[1, 1])),
+               max(np.ceil(c[1, 0]), np.ceil(c[3, 0])), max(np.ceil(c[2, 1]), np.ceil(c[3, 1]))]
+        assert list(b) == exp
+    # k1 == 0: keypoints are copied and the bounds are the image (Frame.cc:291-295, :343-348)
+    kps = np.zeros(3, O.KP_DTYPE)
+    kps["x"], kps["y"], kps["octave"] = [1.5, 2.5, 3.5], [4, 5, 6], [0, 1, 2]
+    assert np.array_equal(O.undistort_keypoints(kps, 500, 500, 320, 240, [0, 0.3, 0.1, 0.1, 0]), kps)
+    assert list(O.image_bounds(640, 480, 500, 500, 320, 240, [0, 0, 0, 0, 0])) == [0, 0, 640, 480]
