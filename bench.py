@@ -503,6 +503,17 @@ def main():
         iso_acc[name] = iso_acc.get(name, 0.0) + ms / iso_n
     ex.set_profiling(False)
 
+    # latency of the reference's own usage pattern: one frame per call, host image in, host keypoints/descriptors out
+    # (ORBextractor::operator(), src/ORBextractor.cc:718-779), nothing else on the GPU
+    lat = []
+    hk1, hd1, hc1 = e2e_bufs[0][0], e2e_bufs[0][1], e2e_bufs[0][2]
+    for i in range(25):
+        t0 = time.perf_counter()
+        ex.extract_batch_ptr(h_frames.data_ptr() + (i % B) * W * H, W, H, W, W * H, 1, hk1.data_ptr(), hd1.data_ptr(), NFEAT,
+                             hc1.data_ptr())
+        lat.append((time.perf_counter() - t0) * 1e3)
+    single_ms = float(np.median(lat[5:]))
+
     if rank == 0:
         ab = algorithmic_bytes()
         peaks = {}
@@ -550,6 +561,7 @@ def main():
                 "keypoints_per_step": r_dev["kp"] / args.steps,
                 "wall_ms_per_step": r_dev["wall_ms"] / args.steps,
                 "host_ms_per_step": {k: 1e3 * v / max(host_t["n"], 1) for k, v in host_t.items() if k != "n"},
+                "single_frame_latency_ms": single_ms,
                 "roofline": roof, "clocks": clocks}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

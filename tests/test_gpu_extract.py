@@ -94,3 +94,13 @@ def test_strided_input_and_empty(gpu_required):
     k0, d0 = ex(np.zeros((0, 0), np.uint8))
     assert len(k0) == 0 and d0.shape == (0, 32)
     ex.close()
+
+
+@pytest.mark.parametrize("env", [{"ORBFE_BLUR_PLANES": "1"}, {"ORBFE_FAST_NO_TMA": "1"}, {"ORBFE_BLUR_PLANES": "1", "ORBFE_FAST_NO_TMA": "1"}])
+def test_alternate_kernel_paths(gpu_required, env, monkeypatch):
+    """The variants behind environment switches (whole-level blur7 + describe instead of the fused descriptor kernel;
+    plain staged FAST tiles instead of the TMA pipeline) produce the same bits as the default path and the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _compare(textured_frame(752, 480, seed=3), 1000, 8)
+    _compare(textured_frame(641, 479, seed=6), 700, 6, fast_th=12)
