@@ -403,6 +403,7 @@ def main():
         e2e_bufs.append((hk, hd, hc, hk.numpy().view(fe.KP_DTYPE).reshape(B, NFEAT), hd.numpy(), hc.numpy()))
     e2e_ex = [ex] + [fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank) for _ in range(NEX - 1)]
     e2e_ex_pool = [ThreadPoolExecutor(max_workers=1) for _ in range(NEX)]
+    E2E_MODE = int(os.environ.get("ORBFE_E2E_BATCH_MODE", "0"))   # measured: chunked 28.7 vs phased 26.8 Mkp/s with two handles
     e2e_mt = (mt, fe.ORBmatcher(0.9, True, device=local_rank))
     e2e_match_pool = (ThreadPoolExecutor(max_workers=1), ThreadPoolExecutor(max_workers=1))
     e2e_views_pool = ThreadPoolExecutor(max_workers=2)
@@ -410,6 +411,7 @@ def main():
     def extract_step(st):
         t0 = time.perf_counter()
         x = e2e_ex[st % NEX]
+        x.set_batch_mode(E2E_MODE)
         hk, hd, hc, _, _, c_np = e2e_bufs[st % NBUF]
         x.extract_batch_ptr(h_frames.data_ptr(), W, H, W, W * H, B, hk.data_ptr(), hd.data_ptr(), NFEAT, hc.data_ptr())
         host_t["e2e_extract_call"] += time.perf_counter() - t0

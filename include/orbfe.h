@@ -90,6 +90,14 @@ int orbfe_extract_batch_device(OrbfeExtractor *ex, const uint8_t *d_imgs, int wi
 int orbfe_extractor_sync(OrbfeExtractor *ex);
 /* number of kernels the last extract call launched (for bench.py's gpu_launches) */
 int orbfe_extractor_last_launches(const OrbfeExtractor *ex);
+
+/* How orbfe_extract_batch schedules a batch (default 0).
+ *   0 "chunked": the upload of chunk k+1 overlaps ALL kernels of chunk k -- best for a caller with one handle;
+ *   1 "phased":  only the pyramids follow the upload chunk by chunk, detection and description then run once over the
+ *                whole batch in full-size launches -- best for a caller that alternates two handles on two threads, where
+ *                one handle's upload overlaps the other handle's kernels.
+ * Results are identical in both modes. */
+int orbfe_extractor_set_batch_mode(OrbfeExtractor *ex, int mode);
 /* With profiling on, every extract call records CUDA events around its stages on the launching stream.
  * orbfe_extractor_stage_times returns (name, ms) of every stage interval recorded since the previous read --
  * possibly from several calls -- and clears the list; the caller must have synchronised any external stream it

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "orbfe_last_error", "orbfe_version", "orbfe_device_count",
     "orbfe_extractor_create", "orbfe_extractor_destroy", "orbfe_extractor_levels", "orbfe_extractor_scale_factor",
     "orbfe_extractor_tables", "orbfe_extract", "orbfe_extract_batch", "orbfe_extract_batch_device",
-    "orbfe_extractor_sync", "orbfe_extractor_last_launches", "orbfe_extractor_set_profiling",
+    "orbfe_extractor_sync", "orbfe_extractor_last_launches", "orbfe_extractor_set_profiling", "orbfe_extractor_set_batch_mode",
     "orbfe_extractor_stage_times", "orbfe_debug_level_size", "orbfe_debug_read_level",
     "orbfe_matcher_create", "orbfe_matcher_destroy", "orbfe_hamming_csr", "orbfe_hamming_dense",
     "orbfe_knn2_groups", "orbfe_knn2_groups_device", "orbfe_hamming_csr_device", "orbfe_matcher_sync",
@@ -76,6 +76,7 @@ def lib():
     L.orbfe_last_error.restype = C.c_char_p
     L.orbfe_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.orbfe_extractor_destroy.argtypes = [vp]
+    L.orbfe_extractor_set_batch_mode.argtypes = [vp, C.c_int]
     L.orbfe_extractor_levels.argtypes = [vp]
     L.orbfe_extractor_scale_factor.argtypes = [vp]
     L.orbfe_extractor_scale_factor.restype = C.c_float
@@ -191,6 +192,10 @@ class ORBextractor:
         _check(lib().orbfe_extract_batch_device(self._h, C.c_void_p(d_imgs), W, H, stride, frame_stride, B,
                                                 C.c_void_p(d_kps), C.c_void_p(d_desc), C.c_void_p(d_counts),
                                                 C.c_void_p(stream)))
+
+    def set_batch_mode(self, mode):
+        """0 = chunked (one handle), 1 = phased (two alternating handles); see include/orbfe.h."""
+        _check(lib().orbfe_extractor_set_batch_mode(self._h, int(mode)))
 
     def sync(self):
         _check(lib().orbfe_extractor_sync(self._h))

@@ -80,6 +80,7 @@ struct StageTimer {
 
 struct OrbfeExtractor {
     int nfeatures = 0, nlevels = 0, score_type = 1, fast_th = 20, device = 0;
+    int batch_mode = 0;         // orbfe_extractor_set_batch_mode
     bool blur_planes = false;   // ORBFE_BLUR_PLANES=1: unfused blur7 + describe (smoothed copies of every level kept in HBM)
     double scale_factor = 1.2;  // double member initialised from a float (ORBextractor.h:62, .cc:459)
     float scale[ORBFE_MAX_LEVELS], inv_scale[ORBFE_MAX_LEVELS];
@@ -518,12 +519,18 @@ static int zero_counters(OrbfeExtractor *ex, cudaStream_t s) {
     return ORBFE_OK;
 }
 
+static void enqueue_pyramid(OrbfeExtractor *ex, int f0, int nf, cudaStream_t s) {
+    const PlanDev &hp = ex->hplan;
+    for (int l = 1; l < hp.nlevels; l++) launch_resize_level(ex->dplan, hp, l, f0, nf, s);
+    ex->last_launches += hp.nlevels - 1;
+    stage_mark(ex, s, "pyramid");
+}
+
 static int enqueue_pipeline(OrbfeExtractor *ex, int f0, int nf, OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool with_pyramid = true) {
     const PlanDev &hp = ex->hplan;
     int launches = 0;
-    for (int l = 1; l < hp.nlevels; l++) { launch_resize_level(ex->dplan, hp, l, f0, nf, s); launches++; }
-    stage_mark(ex, s, "pyramid");
+    if (with_pyramid) enqueue_pyramid(ex, f0, nf, s);
     launch_fast_nms(ex->dplan, hp, ex->work, f0, nf, s); launches++;
     stage_mark(ex, s, "fast_nms");
     launch_cell_quota(ex->dplan, hp, ex->work, f0, nf, s); launches++;
@@ -642,7 +649,15 @@ extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int 
         }
         CU_TRY(cudaEventRecord(ex->chunk_ev[k], ex->copy_stream));
         CU_TRY(cudaStreamWaitEvent(s, ex->chunk_ev[k], 0));
-        rc = enqueue_pipeline(ex, f0, f1 - f0, ex->d_kps, ex->d_desc, ex->d_counts, s);
+        if (ex->batch_mode == 1) {
+            enqueue_pyramid(ex, f0, f1 - f0, s);   // phased: only the pyramids follow the upload chunk by chunk
+        } else {
+            rc = enqueue_pipeline(ex, f0, f1 - f0, ex->d_kps, ex->d_desc, ex->d_counts, s);
+            if (rc) return rc;
+        }
+    }
+    if (ex->batch_mode == 1) {   // ... detection and description run once over the whole batch (full-size launches)
+        rc = enqueue_pipeline(ex, 0, batch, ex->d_kps, ex->d_desc, ex->d_counts, s, false);
         if (rc) return rc;
     }
     const int ncopy = std::min(cap, P.nfeatures);
@@ -685,6 +700,12 @@ extern "C" int orbfe_extractor_sync(OrbfeExtractor *ex) {
 }
 
 extern "C" int orbfe_extractor_last_launches(const OrbfeExtractor *ex) { return ex ? ex->last_launches : 0; }
+
+extern "C" int orbfe_extractor_set_batch_mode(OrbfeExtractor *ex, int mode) {
+    if (!ex || mode < 0 || mode > 1) return fail(ORBFE_ERR_ARG, "bad arguments");
+    ex->batch_mode = mode;
+    return ORBFE_OK;
+}
 
 extern "C" int orbfe_extractor_set_profiling(OrbfeExtractor *ex, int on) {
     if (!ex) return fail(ORBFE_ERR_ARG, "ex is NULL");

@@ -104,3 +104,18 @@ def test_alternate_kernel_paths(gpu_required, env, monkeypatch):
         monkeypatch.setenv(k, v)
     _compare(textured_frame(752, 480, seed=3), 1000, 8)
     _compare(textured_frame(641, 479, seed=6), 700, 6, fast_th=12)
+
+
+def test_phased_batch_mode_matches_chunked(gpu_required):
+    """orbfe_extractor_set_batch_mode: the two schedules of a batch give identical results."""
+    frames = np.stack([textured_frame(640, 480, seed=40 + i) for i in range(12)])
+    ex = fe.ORBextractor(800, 1.2, 8)
+    k0, d0, c0 = ex.extract_batch(frames)
+    ex.set_batch_mode(1)
+    k1, d1, c1 = ex.extract_batch(frames)
+    assert np.array_equal(c0, c1) and c0.min() > 300
+    for f in range(len(frames)):
+        assert np.array_equal(k0[f, :c0[f]], k1[f, :c1[f]]) and np.array_equal(d0[f, :c0[f]], d1[f, :c1[f]])
+    with pytest.raises(fe.OrbfeError):
+        ex.set_batch_mode(7)
+    ex.close()
