@@ -556,8 +556,9 @@ def main():
                            "frames_per_step_per_gpu": B, "parallelism": "frames sharded one stream per GPU, no data-path collective",
                            "l2": "inputs+pyramids per step (%.0f MB) larger than L2 (126 MB)" % (B * (W * H + 2 * ab["P"]) / 1e6)},
                 "e2e": {"value": e2e_val, "unit": "Mkeypoints/s", "ms_per_step": r_e2e["ms"] / args.steps,
-                        "h2d_bytes_per_step": B * W * H + r_e2e["mh2d"] // args.steps,
-                        "d2h_bytes_per_step": B * (NFEAT * 60 + 4) + r_e2e["md2h"] // args.steps},
+                        # whole job: every rank moves the same amount
+                        "h2d_bytes_per_step": world * (B * W * H + r_e2e["mh2d"] // args.steps),
+                        "d2h_bytes_per_step": world * (B * (NFEAT * 60 + 4) + r_e2e["md2h"] // args.steps)},
                 "gpu_launches": int(r_dev["launches"]),
                 "matches_per_step": r_dev["matches"] / args.steps / world,
                 "keypoints_per_step": r_dev["kp"] / args.steps,
