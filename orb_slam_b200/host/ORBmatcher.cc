@@ -445,6 +445,8 @@ int ORBmatcher::Fuse(KeyFrame *pKF, std::vector<MapPoint *> &vpMapPoints, float 
             if (dist[c] < bestDist) { bestDist = dist[c]; bestIdx = csr.cols[c]; }
         if (bestDist <= TH_LOW) {
             MapPoint *pMP = vpMapPoints[q2mp[q]];
+            // the reference evaluates this gate at the point's turn (:1040): a pointer listed twice is fused once
+            if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
             MapPoint *pMPinKF = pKF->GetMapPoint(bestIdx);
             if (pMPinKF) { if (!pMPinKF->isBad()) pMP->Replace(pMPinKF); }
             else { pMP->AddObservation(pKF, bestIdx); pKF->AddMapPoint(pMP, bestIdx); }

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
+#include <set>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -42,27 +44,292 @@ std::vector<size_t> Frame::GetFeaturesInArea(const float &x, const float &y, con
     return out;
 }
 
-// link-only definitions of the KeyFrame stub (the real KeyFrame.cc is linked in a real integration)
+// functional stand-ins for the KeyFrame methods ORBmatcher calls (reference src/KeyFrame.cc; the real KeyFrame.cc is
+// linked in a real integration).  GetFeaturesInArea / IsInImage follow KeyFrame.cc:612-657.
 namespace ORB_SLAM {
-cv::Mat KeyFrame::GetRotation() { return cv::Mat(); }
-cv::Mat KeyFrame::GetTranslation() { return cv::Mat(); }
-cv::Mat KeyFrame::GetCameraCenter() { return cv::Mat(); }
-DBoW2::FeatureVector KeyFrame::GetFeatureVector() { return DBoW2::FeatureVector(); }
-std::set<MapPoint *> KeyFrame::GetMapPoints() { return std::set<MapPoint *>(); }
-std::vector<MapPoint *> KeyFrame::GetMapPointMatches() { return std::vector<MapPoint *>(); }
-MapPoint *KeyFrame::GetMapPoint(const size_t &) { return NULL; }
-void KeyFrame::AddMapPoint(MapPoint *, const size_t &) {}
-cv::KeyPoint KeyFrame::GetKeyPointUn(const size_t &) const { return cv::KeyPoint(); }
-cv::Mat KeyFrame::GetDescriptor(const size_t &) { return cv::Mat(); }
-int KeyFrame::GetKeyPointScaleLevel(const size_t &) const { return 0; }
-std::vector<cv::KeyPoint> KeyFrame::GetKeyPointsUn() const { return std::vector<cv::KeyPoint>(); }
-cv::Mat KeyFrame::GetDescriptors() { return cv::Mat(); }
-std::vector<size_t> KeyFrame::GetFeaturesInArea(const float &, const float &, const float &) const { return std::vector<size_t>(); }
-bool KeyFrame::IsInImage(const float &, const float &) const { return false; }
-float KeyFrame::GetScaleFactor(int) const { return 1.f; }
-std::vector<float> KeyFrame::GetScaleFactors() const { return std::vector<float>(1, 1.f); }
-float KeyFrame::GetSigma2(int) const { return 1.f; }
-int KeyFrame::GetScaleLevels() const { return 1; }
+cv::Mat KeyFrame::GetRotation() { return t_Rcw.clone(); }
+cv::Mat KeyFrame::GetTranslation() { return t_tcw.clone(); }
+cv::Mat KeyFrame::GetCameraCenter() { return t_Ow.clone(); }
+DBoW2::FeatureVector KeyFrame::GetFeatureVector() { return t_fv; }
+std::set<MapPoint *> KeyFrame::GetMapPoints() {
+    std::set<MapPoint *> s;
+    for (size_t i = 0; i < t_mps.size(); i++)
+        if (t_mps[i] && !t_mps[i]->isBad()) s.insert(t_mps[i]);   // KeyFrame.cc:244-257
+    return s;
+}
+std::vector<MapPoint *> KeyFrame::GetMapPointMatches() { return t_mps; }
+MapPoint *KeyFrame::GetMapPoint(const size_t &idx) { return t_mps[idx]; }
+void KeyFrame::AddMapPoint(MapPoint *pMP, const size_t &idx) { t_mps[idx] = pMP; }
+cv::KeyPoint KeyFrame::GetKeyPointUn(const size_t &idx) const { return t_keys[idx]; }
+cv::Mat KeyFrame::GetDescriptor(const size_t &idx) { return t_desc.row((int)idx).clone(); }
+int KeyFrame::GetKeyPointScaleLevel(const size_t &idx) const { return t_keys[idx].octave; }
+std::vector<cv::KeyPoint> KeyFrame::GetKeyPointsUn() const { return t_keys; }
+cv::Mat KeyFrame::GetDescriptors() { return t_desc.clone(); }
+std::vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const {
+    std::vector<size_t> out;
+    int x0 = (int)std::floor((x - t_minx - r) * t_ginvw); x0 = x0 < 0 ? 0 : x0;
+    if (x0 >= 64) return out;
+    int x1 = (int)std::ceil((x - t_minx + r) * t_ginvw); x1 = x1 > 63 ? 63 : x1;
+    if (x1 < 0) return out;
+    int y0 = (int)std::floor((y - t_miny - r) * t_ginvh); y0 = y0 < 0 ? 0 : y0;
+    if (y0 >= 48) return out;
+    int y1 = (int)std::ceil((y - t_miny + r) * t_ginvh); y1 = y1 > 47 ? 47 : y1;
+    if (y1 < 0) return out;
+    for (int ix = x0; ix <= x1; ix++)
+        for (int iy = y0; iy <= y1; iy++)
+            for (size_t j = 0; j < t_grid[ix][iy].size(); j++) {
+                const cv::KeyPoint &kp = t_keys[t_grid[ix][iy][j]];
+                if (std::fabs(kp.pt.x - x) <= r && std::fabs(kp.pt.y - y) <= r) out.push_back(t_grid[ix][iy][j]);
+            }
+    return out;
+}
+bool KeyFrame::IsInImage(const float &x, const float &y) const { return x >= t_minx && x < t_maxx && y >= t_miny && y < t_maxy; }
+float KeyFrame::GetScaleFactor(int nLevel) const { return t_sf[nLevel]; }
+std::vector<float> KeyFrame::GetScaleFactors() const { return t_sf; }
+float KeyFrame::GetSigma2(int nLevel) const { return t_sf[nLevel] * t_sf[nLevel]; }
+int KeyFrame::GetScaleLevels() const { return (int)t_sf.size(); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plain-loop restatements (host popcount, no GPU, no candidate lists shared with the facade) of the KeyFrame-level
+// routines, used to check the facade end to end: ORBmatcher.cc:286-405 (SearchByProjection with Scw), :1034-1130 (Fuse)
+// and :1132-1234 (Fuse with Scw).  They read the reference line by line; the cv::Mat algebra is spelled out with
+// OpenCV 2.4's semantics (gemm / dot / norm accumulate in double, Mat / scalar multiplies by the reciprocal).
+// ------------------------------------------------------------------------------------------------
+namespace ref {
+static int ham(const cv::Mat &a, const cv::Mat &b) {
+    int d = 0;
+    for (int i = 0; i < 32; i++) d += __builtin_popcount((unsigned)(a.ptr(0)[i] ^ b.ptr(0)[i]));
+    return d;
+}
+struct Cam { float R[9], t[3], Ow[3]; };
+static Cam cam_from_Scw(const cv::Mat &Scw) {   // :297-301
+    Cam c;
+    double dd = 0;
+    for (int k = 0; k < 3; k++) dd += (double)Scw.at<float>(0, k) * (double)Scw.at<float>(0, k);
+    const float scw = (float)std::sqrt(dd);
+    const float inv = (float)(1.0 / (double)scw);
+    for (int r = 0; r < 3; r++) {
+        for (int k = 0; k < 3; k++) c.R[3 * r + k] = Scw.at<float>(r, k) * inv;
+        c.t[r] = Scw.at<float>(r, 3) * inv;
+    }
+    for (int k = 0; k < 3; k++)
+        c.Ow[k] = (float)(((double)c.R[k] * c.t[0] + (double)c.R[3 + k] * c.t[1] + (double)c.R[6 + k] * c.t[2]) * -1.0);
+    return c;
+}
+static Cam cam_from_kf(KeyFrame *kf) {
+    Cam c;
+    const cv::Mat R = kf->GetRotation(), t = kf->GetTranslation(), O = kf->GetCameraCenter();
+    for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) c.R[3 * r + k] = R.at<float>(r, k); c.t[r] = t.at<float>(r, 0); c.Ow[r] = O.at<float>(r, 0); }
+    return c;
+}
+// the projection gates shared by the three routines; returns the best keypoint (or -1) and its distance
+static int best_for_point(KeyFrame *pKF, MapPoint *pMP, const Cam &c, float th, bool invz_double, const std::vector<MapPoint *> *skipMatched,
+                          int &bestDist) {
+    bestDist = INT_MAX;
+    const cv::Mat Xw = pMP->GetWorldPos();
+    const float X[3] = {Xw.at<float>(0, 0), Xw.at<float>(1, 0), Xw.at<float>(2, 0)};
+    float Xc[3];
+    for (int k = 0; k < 3; k++)
+        Xc[k] = (float)(((double)c.R[3 * k] * X[0] + (double)c.R[3 * k + 1] * X[1] + (double)c.R[3 * k + 2] * X[2]) + (double)c.t[k]);
+    if (Xc[2] < 0.0f) return -1;
+    const float invz = invz_double ? (float)(1.0 / (double)Xc[2]) : 1.0f / Xc[2];
+    const float x = Xc[0] * invz, y = Xc[1] * invz;
+    const float u = pKF->fx * x + pKF->cx, v = pKF->fy * y + pKF->cy;
+    if (!pKF->IsInImage(u, v)) return -1;
+    const float maxD = pMP->GetMaxDistanceInvariance(), minD = pMP->GetMinDistanceInvariance();
+    const float PO[3] = {X[0] - c.Ow[0], X[1] - c.Ow[1], X[2] - c.Ow[2]};
+    const float dist = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+    if (dist < minD || dist > maxD) return -1;
+    const cv::Mat Pn = pMP->GetNormal();
+    const double dot = (double)PO[0] * Pn.at<float>(0, 0) + (double)PO[1] * Pn.at<float>(1, 0) + (double)PO[2] * Pn.at<float>(2, 0);
+    if (dot < 0.5 * dist) return -1;
+    const float ratio = dist / minD;
+    const std::vector<float> sf = pKF->GetScaleFactors();
+    int lvl = 0;
+    while (lvl < (int)sf.size() && sf[lvl] < ratio) lvl++;   // lower_bound
+    const int nPredictedLevel = std::min(lvl, pKF->GetScaleLevels() - 1);
+    const float radius = th * sf[nPredictedLevel];
+    const std::vector<size_t> vIndices = pKF->GetFeaturesInArea(u, v, radius);
+    int bestIdx = -1;
+    const cv::Mat dMP = pMP->GetDescriptor();
+    for (size_t k = 0; k < vIndices.size(); k++) {
+        const size_t idx = vIndices[k];
+        if (skipMatched && (*skipMatched)[idx]) continue;
+        const int kpLevel = pKF->GetKeyPointScaleLevel(idx);
+        if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+        const int d = ham(dMP, pKF->GetDescriptor(idx));
+        if (d < bestDist) { bestDist = d; bestIdx = (int)idx; }
+    }
+    return bestIdx;
+}
+static int SearchByProjection(KeyFrame *pKF, const cv::Mat &Scw, const std::vector<MapPoint *> &vpPoints, std::vector<MapPoint *> &vpMatched, int th) {
+    const Cam c = cam_from_Scw(Scw);
+    std::set<MapPoint *> found(vpMatched.begin(), vpMatched.end());
+    found.erase(static_cast<MapPoint *>(NULL));
+    int nmatches = 0;
+    for (size_t i = 0; i < vpPoints.size(); i++) {
+        MapPoint *pMP = vpPoints[i];
+        if (pMP->isBad() || found.count(pMP)) continue;
+        int bd;
+        const int bi = best_for_point(pKF, pMP, c, (float)th, false, &vpMatched, bd);
+        if (bd <= ORBmatcher::TH_LOW) { vpMatched[bi] = pMP; nmatches++; }
+    }
+    return nmatches;
+}
+static int Fuse(KeyFrame *pKF, std::vector<MapPoint *> &vpMapPoints, float th) {
+    const Cam c = cam_from_kf(pKF);
+    int nFused = 0;
+    for (size_t i = 0; i < vpMapPoints.size(); i++) {
+        MapPoint *pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        int bd;
+        const int bi = best_for_point(pKF, pMP, c, th, false, NULL, bd);
+        if (bd <= ORBmatcher::TH_LOW) {
+            MapPoint *in = pKF->GetMapPoint(bi);
+            if (in) { if (!in->isBad()) pMP->Replace(in); }
+            else { pMP->AddObservation(pKF, bi); pKF->AddMapPoint(pMP, bi); }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+static int FuseScw(KeyFrame *pKF, const cv::Mat &Scw, const std::vector<MapPoint *> &vpPoints, float th) {
+    const Cam c = cam_from_Scw(Scw);
+    const std::set<MapPoint *> found = pKF->GetMapPoints();
+    int nFused = 0;
+    for (size_t i = 0; i < vpPoints.size(); i++) {
+        MapPoint *pMP = vpPoints[i];
+        if (pMP->isBad() || found.count(pMP)) continue;
+        int bd;
+        const int bi = best_for_point(pKF, pMP, c, th, true, NULL, bd);
+        if (bd <= ORBmatcher::TH_LOW) {
+            MapPoint *in = pKF->GetMapPoint(bi);
+            if (in) { if (!in->isBad()) in->Replace(pMP); }
+            else { pMP->AddObservation(pKF, bi); pKF->AddMapPoint(pMP, bi); }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+}  // namespace ref
+
+// a keyframe from a frame's features, observed from pose [R|t] = [I | (tx,0,0)]; `occupied`: every n-th slot already
+// holds a (foreign) map point
+static void make_keyframe(KeyFrame &kf, const Frame &F, float tx, std::vector<MapPoint> &foreign, int every) {
+    kf.fx = Frame::fx; kf.fy = Frame::fy; kf.cx = Frame::cx; kf.cy = Frame::cy;
+    kf.t_keys = F.mvKeysUn;
+    kf.t_desc = F.mDescriptors.clone();
+    kf.t_sf = F.mvScaleFactors;
+    kf.t_minx = (float)Frame::mnMinX; kf.t_miny = (float)Frame::mnMinY; kf.t_maxx = (float)Frame::mnMaxX; kf.t_maxy = (float)Frame::mnMaxY;
+    kf.t_ginvw = Frame::mfGridElementWidthInv; kf.t_ginvh = Frame::mfGridElementHeightInv;
+    for (int ix = 0; ix < 64; ix++) for (int iy = 0; iy < 48; iy++) kf.t_grid[ix][iy] = F.mGrid[ix][iy];
+    kf.t_Rcw.create(3, 3, CV_32F); kf.t_tcw.create(3, 1, CV_32F); kf.t_Ow.create(3, 1, CV_32F);
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) kf.t_Rcw.at<float>(r, c) = r == c ? 1.f : 0.f; kf.t_tcw.at<float>(r, 0) = 0.f; kf.t_Ow.at<float>(r, 0) = 0.f; }
+    kf.t_tcw.at<float>(0, 0) = tx; kf.t_Ow.at<float>(0, 0) = -tx;
+    kf.t_mps.assign(F.N, static_cast<MapPoint *>(NULL));
+    foreign.assign(F.N / every + 1, MapPoint());
+    for (int i = 0, k = 0; i < F.N; i += every, k++) kf.t_mps[i] = &foreign[k];
+}
+
+// KeyFrame-level facade methods against the plain-loop restatements above, on identical copies of the scene
+static int check_keyframe_routines(const Frame &F1, const Frame &F2) {
+    const float tx = 3.f * 4.f / Frame::fx;  // F2 sees the scene shifted by +3 px
+    // map points from F1's features at depth 4 (camera 1 = world), ORB-SLAM's UpdateNormalAndDepth conventions
+    struct Scene {
+        std::vector<MapPoint> pts, foreign;
+        KeyFrame kf;
+        std::vector<MapPoint *> vp;
+    };
+    Scene A, B;  // A: facade, B: restatement
+    Scene *S[2] = {&A, &B};
+    for (int s = 0; s < 2; s++) {
+        Scene &sc = *S[s];
+        make_keyframe(sc.kf, F2, tx, sc.foreign, 9);
+        sc.pts.assign(F1.N, MapPoint());
+        for (int i = 0; i < F1.N; i++) {
+            MapPoint &p = sc.pts[i];
+            p.mWorldPos.create(3, 1, CV_32F);
+            const float X = (F1.mvKeysUn[i].pt.x - Frame::cx) / Frame::fx * 4.f, Y = (F1.mvKeysUn[i].pt.y - Frame::cy) / Frame::fy * 4.f, Z = 4.f;
+            p.mWorldPos.at<float>(0, 0) = X; p.mWorldPos.at<float>(1, 0) = Y; p.mWorldPos.at<float>(2, 0) = Z;
+            const float d = std::sqrt(X * X + Y * Y + Z * Z);
+            p.mNormal.create(3, 1, CV_32F);
+            p.mNormal.at<float>(0, 0) = X / d; p.mNormal.at<float>(1, 0) = Y / d; p.mNormal.at<float>(2, 0) = Z / d;
+            const int lv = F1.mvKeysUn[i].octave;
+            // scale-invariance range in the spirit of MapPoint.cc:300-310, chosen so that the level predicted from
+            // dist / minDistance is lv + 1 (accepting key points of level lv and lv + 1) for most points, lv + 2 for some
+            p.mfMinDistance = d / (F1.mvScaleFactors[lv] * (i % 7 == 0 ? 1.25f : 1.05f));
+            p.mfMaxDistance = (i % 11 == 0 ? 0.999f : 1.2f) * d * F1.mvScaleFactors[F1.mnScaleLevels - 1 - lv];
+            p.mDescriptor = F1.mDescriptors.row(i).clone();
+            p.mbBad = (i % 53 == 0);
+            sc.vp.push_back(&p);
+        }
+    }
+    ORBmatcher matcher(0.75, true);
+    int rc = 0;
+    // ---- SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), ORBmatcher.cc:286-405 ----
+    {
+        cv::Mat Scw(4, 4, CV_32F);
+        const float s = 1.07f;   // a similarity with scale: sR = s*I, st = s*t
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) Scw.at<float>(r, c) = r == c ? (r < 3 ? s : 1.f) : 0.f;
+        Scw.at<float>(0, 3) = s * tx;
+        std::vector<MapPoint *> mA(A.kf.t_mps), mB(B.kf.t_mps);
+        const int nA = matcher.SearchByProjection(&A.kf, Scw, A.vp, mA, 10);
+        const int nB = ref::SearchByProjection(&B.kf, Scw, B.vp, mB, 10);
+        int diff = 0, newm = 0;
+        for (size_t i = 0; i < mA.size(); i++) {
+            const long ia = mA[i] && mA[i] >= &A.pts[0] && mA[i] < &A.pts[0] + A.pts.size() ? (long)(mA[i] - &A.pts[0]) : (mA[i] ? -2 : -1);
+            const long ib = mB[i] && mB[i] >= &B.pts[0] && mB[i] < &B.pts[0] + B.pts.size() ? (long)(mB[i] - &B.pts[0]) : (mB[i] ? -2 : -1);
+            if (ia != ib) diff++;
+            if (ia >= 0) newm++;
+        }
+        std::printf("SearchByProjection(KF,Scw): facade %d, restatement %d, %d new, %d slots differ\n", nA, nB, newm, diff);
+        if (nA != nB || diff || nA < 200) rc = 10;
+    }
+    // ---- Fuse(KeyFrame*, vpMapPoints, th), ORBmatcher.cc:1034-1130 ----
+    {
+        const int nA = matcher.Fuse(&A.kf, A.vp, 3.0f);
+        const int nB = ref::Fuse(&B.kf, B.vp, 3.0f);
+        int diff = 0, repl = 0, added = 0;
+        for (size_t i = 0; i < A.pts.size(); i++) {
+            const bool ra = A.pts[i].t_replaced_by != NULL, rb = B.pts[i].t_replaced_by != NULL;
+            if (ra != rb) diff++;
+            else if (ra && (A.pts[i].t_replaced_by - &A.foreign[0]) != (B.pts[i].t_replaced_by - &B.foreign[0])) diff++;
+            if (A.pts[i].GetIndexInKeyFrame(&A.kf) != B.pts[i].GetIndexInKeyFrame(&B.kf)) diff++;
+            repl += ra; added += A.pts[i].IsInKeyFrame(&A.kf);
+        }
+        std::printf("Fuse(KF,points): facade %d, restatement %d (%d replaced, %d added), %d differences\n", nA, nB, repl, added, diff);
+        if (nA != nB || diff || nA < 200 || repl == 0 || added == 0) rc = rc ? rc : 11;
+    }
+    // ---- Fuse(KeyFrame*, Scw, vpPoints, th), ORBmatcher.cc:1132-1234, on fresh copies ----
+    {
+        Scene C, D;
+        Scene *T[2] = {&C, &D};
+        for (int s = 0; s < 2; s++) {
+            make_keyframe(T[s]->kf, F2, tx, T[s]->foreign, 5);
+            T[s]->pts = A.pts;   // same geometry; reset the bookkeeping
+            for (size_t i = 0; i < T[s]->pts.size(); i++) { T[s]->pts[i].t_obs.clear(); T[s]->pts[i].t_replaced_by = NULL; T[s]->pts[i].mbBad = (i % 41 == 0); T[s]->vp.push_back(&T[s]->pts[i]); }
+        }
+        cv::Mat Scw(4, 4, CV_32F);
+        const float s = 0.93f;
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) Scw.at<float>(r, c) = r == c ? (r < 3 ? s : 1.f) : 0.f;
+        Scw.at<float>(0, 3) = s * tx;
+        const int nC = matcher.Fuse(&C.kf, Scw, C.vp, 4.0f);
+        const int nD = ref::FuseScw(&D.kf, Scw, D.vp, 4.0f);
+        int diff = 0, repl = 0;
+        for (size_t i = 0; i < C.foreign.size(); i++) {
+            const bool rc_ = C.foreign[i].t_replaced_by != NULL, rd = D.foreign[i].t_replaced_by != NULL;
+            if (rc_ != rd) diff++;
+            else if (rc_ && (C.foreign[i].t_replaced_by - &C.pts[0]) != (D.foreign[i].t_replaced_by - &D.pts[0])) diff++;
+            repl += rc_;
+        }
+        for (size_t i = 0; i < C.pts.size(); i++)
+            if (C.pts[i].GetIndexInKeyFrame(&C.kf) != D.pts[i].GetIndexInKeyFrame(&D.kf)) diff++;
+        std::printf("Fuse(KF,Scw,points): facade %d, restatement %d (%d replaced), %d differences\n", nC, nD, repl, diff);
+        if (nC != nD || diff || nC < 200 || repl == 0) rc = rc ? rc : 12;
+    }
+    return rc;
 }
 
 static void fill_frame(Frame &F, ORBextractor *ex, cv::Mat &im) {
@@ -175,6 +442,14 @@ int main() {
     int n4 = m3.SearchByProjection(F4, mvpLocalMapPoints, th);                             // Tracking.cc:724
     std::printf("SearchByProjection(F,LocalMapPoints,3): %d matches\n", n4);
     if (n4 < 300) return 5;
+    // KeyFrame-level routines (loop closing / local mapping): facade vs plain-loop restatement on functional stubs
+    {
+        Frame K1, K2;
+        fill_frame(K1, mpORBextractor, im1);
+        fill_frame(K2, mpORBextractor, im2);
+        const int krc = check_keyframe_routines(K1, K2);
+        if (krc) return krc;
+    }
     delete mpORBextractor;
     delete mpIniORBextractor;
     std::puts("conformance: run ok");

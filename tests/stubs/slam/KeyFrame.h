@@ -33,5 +33,14 @@ public:
     std::vector<float> GetScaleFactors() const;
     float GetSigma2(int nLevel = 1) const;
     int GetScaleLevels() const;
+    // ---- test-only state behind the getters above (the real class keeps the same data protected, KeyFrame.h:150-190) ----
+    std::vector<cv::KeyPoint> t_keys;           // mvKeysUn
+    cv::Mat t_desc;                             // mDescriptors
+    std::vector<MapPoint *> t_mps;              // mvpMapPoints
+    std::vector<float> t_sf;                    // mvScaleFactors
+    cv::Mat t_Rcw, t_tcw, t_Ow;
+    float t_minx, t_miny, t_maxx, t_maxy, t_ginvw, t_ginvh;   // mnMinX.., mfGridElementWidthInv..
+    std::vector<size_t> t_grid[64][48];         // mGrid
+    DBoW2::FeatureVector t_fv;
 };
 }
