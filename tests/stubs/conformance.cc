@@ -213,6 +213,86 @@ static int FuseScw(KeyFrame *pKF, const cv::Mat &Scw, const std::vector<MapPoint
     }
     return nFused;
 }
+// SearchBySim3, ORBmatcher.cc:1264-1451: both projection directions, then the mutual-agreement filter
+static void sim3_direction(KeyFrame *from, KeyFrame *to, const float Rw[9], const float tw[3], const float sR[9], const float t[3],
+                           const std::vector<MapPoint *> &vp, const std::vector<bool> &done, float fx, float fy, float cx, float cy,
+                           float th, std::vector<int> &match) {
+    (void)from;
+    const std::vector<float> sf = to->GetScaleFactors();
+    const int nMaxLevel = to->GetScaleLevels() - 1;
+    for (size_t i = 0; i < vp.size(); i++) {
+        MapPoint *pMP = vp[i];
+        if (!pMP || done[i]) continue;
+        if (pMP->isBad()) continue;
+        const cv::Mat Xw = pMP->GetWorldPos();
+        float a[3], b[3];
+        for (int k = 0; k < 3; k++)
+            a[k] = (float)(((double)Rw[3 * k] * Xw.at<float>(0, 0) + (double)Rw[3 * k + 1] * Xw.at<float>(1, 0) + (double)Rw[3 * k + 2] * Xw.at<float>(2, 0)) + (double)tw[k]);
+        for (int k = 0; k < 3; k++)
+            b[k] = (float)(((double)sR[3 * k] * a[0] + (double)sR[3 * k + 1] * a[1] + (double)sR[3 * k + 2] * a[2]) + (double)t[k]);
+        if (b[2] < 0.0) continue;
+        const float invz = (float)(1.0 / b[2]);
+        const float x = b[0] * invz, y = b[1] * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!to->IsInImage(u, v)) continue;
+        const float maxD = pMP->GetMaxDistanceInvariance(), minD = pMP->GetMinDistanceInvariance();
+        const float dist3D = (float)std::sqrt((double)b[0] * b[0] + (double)b[1] * b[1] + (double)b[2] * b[2]);
+        if (dist3D < minD || dist3D > maxD) continue;
+        const float ratio = dist3D / minD;
+        int lvl = 0;
+        while (lvl < (int)sf.size() && sf[lvl] < ratio) lvl++;
+        const int nPredictedLevel = std::min(lvl, nMaxLevel);
+        const float radius = th * sf[nPredictedLevel];
+        const std::vector<size_t> vIndices = to->GetFeaturesInArea(u, v, radius);
+        if (vIndices.empty()) continue;
+        const cv::Mat dMP = pMP->GetDescriptor();
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (size_t k = 0; k < vIndices.size(); k++) {
+            const cv::KeyPoint kp = to->GetKeyPointUn(vIndices[k]);
+            if (kp.octave < nPredictedLevel - 1 || kp.octave > nPredictedLevel) continue;
+            const int d = ham(dMP, to->GetDescriptor(vIndices[k]));
+            if (d < bestDist) { bestDist = d; bestIdx = (int)vIndices[k]; }
+        }
+        if (bestDist <= ORBmatcher::TH_HIGH) match[i] = bestIdx;
+    }
+}
+static int SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12, float s12, const cv::Mat &R12,
+                        const cv::Mat &t12, float th) {
+    const Cam c1 = cam_from_kf(pKF1), c2 = cam_from_kf(pKF2);
+    float sR12[9], sR21[9], t21[3], t12f[3];
+    const float inv_s = (float)(1.0 / (double)s12);   // (1.0/s12) * Mat: the double scalar multiplies in double, one rounding
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) {
+            sR12[3 * r + k] = (float)((double)R12.at<float>(r, k) * (double)s12);
+            sR21[3 * r + k] = R12.at<float>(k, r) * inv_s;
+        }
+    for (int k = 0; k < 3; k++) t12f[k] = t12.at<float>(k, 0);
+    for (int k = 0; k < 3; k++)
+        t21[k] = (float)(((double)sR21[3 * k] * t12f[0] + (double)sR21[3 * k + 1] * t12f[1] + (double)sR21[3 * k + 2] * t12f[2]) * -1.0);
+    const std::vector<MapPoint *> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vp1.size(), N2 = (int)vp2.size();
+    std::vector<bool> done1(N1, false), done2(N2, false);
+    for (int i = 0; i < N1; i++) {
+        MapPoint *pMP = vpMatches12[i];
+        if (pMP) {
+            done1[i] = true;
+            const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) done2[idx2] = true;
+        }
+    }
+    std::vector<int> m1(N1, -1), m2(N2, -1);
+    sim3_direction(pKF1, pKF2, c1.R, c1.t, sR21, t21, vp1, done1, pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy, th, m1);
+    sim3_direction(pKF2, pKF1, c2.R, c2.t, sR12, t12f, vp2, done2, pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy, th, m2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int idx2 = m1[i1];
+        if (idx2 >= 0) {
+            const int idx1 = m2[idx2];
+            if (idx1 == i1) { vpMatches12[i1] = vp2[idx2]; nFound++; }
+        }
+    }
+    return nFound;
+}
 }  // namespace ref
 
 // a keyframe from a frame's features, observed from pose [R|t] = [I | (tx,0,0)]; `occupied`: every n-th slot already
@@ -328,6 +408,48 @@ static int check_keyframe_routines(const Frame &F1, const Frame &F2) {
             if (C.pts[i].GetIndexInKeyFrame(&C.kf) != D.pts[i].GetIndexInKeyFrame(&D.kf)) diff++;
         std::printf("Fuse(KF,Scw,points): facade %d, restatement %d (%d replaced), %d differences\n", nC, nD, repl, diff);
         if (nC != nD || diff || nC < 200 || repl == 0) rc = rc ? rc : 12;
+    }
+    // ---- SearchBySim3(KF1, KF2, vpMatches12, s12, R12, t12, th), ORBmatcher.cc:1264-1451 (no mutations: one scene) ----
+    {
+        KeyFrame kf1, kf2;
+        std::vector<MapPoint> unused1, unused2;
+        make_keyframe(kf1, F1, 0.f, unused1, 1 << 30);
+        make_keyframe(kf2, F2, tx, unused2, 1 << 30);
+        const Frame *Fs[2] = {&F1, &F2};
+        KeyFrame *kfs[2] = {&kf1, &kf2};
+        const float txs[2] = {0.f, tx};
+        std::vector<MapPoint> pts[2];
+        for (int s = 0; s < 2; s++) {
+            const Frame &F = *Fs[s];
+            pts[s].assign(F.N, MapPoint());
+            for (int i = 0; i < F.N; i++) {
+                MapPoint &p = pts[s][i];
+                const float Xc = (F.mvKeysUn[i].pt.x - Frame::cx) / Frame::fx * 4.f, Yc = (F.mvKeysUn[i].pt.y - Frame::cy) / Frame::fy * 4.f;
+                p.mWorldPos.create(3, 1, CV_32F);
+                p.mWorldPos.at<float>(0, 0) = Xc - txs[s]; p.mWorldPos.at<float>(1, 0) = Yc; p.mWorldPos.at<float>(2, 0) = 4.f;
+                const float d = std::sqrt(Xc * Xc + Yc * Yc + 16.f);
+                const int lv = F.mvKeysUn[i].octave;
+                p.mfMinDistance = d / (F.mvScaleFactors[lv] * (i % 5 == 0 ? 1.3f : 1.05f));
+                p.mfMaxDistance = (i % 13 == 0 ? 0.999f : 1.2f) * d * F.mvScaleFactors[F.mnScaleLevels - 1 - lv];
+                p.mDescriptor = F.mDescriptors.row(i).clone();
+                p.mbBad = (i % 37 == 0);
+                p.t_obs[kfs[s]] = (size_t)i;
+                if (i % 4 != 3) kfs[s]->t_mps[i] = &p;   // a quarter of the features have no map point
+            }
+        }
+        cv::Mat R12(3, 3, CV_32F), t12(3, 1, CV_32F);
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R12.at<float>(r, c) = r == c ? 1.f : 0.f;
+        const float s12 = 1.01f;
+        t12.at<float>(0, 0) = -tx; t12.at<float>(1, 0) = 0.f; t12.at<float>(2, 0) = 0.02f;
+        std::vector<MapPoint *> mA(F1.N, static_cast<MapPoint *>(NULL));
+        for (int i = 0; i < F1.N && i < F2.N; i += 17) mA[i] = &pts[1][(i * 7) % F2.N];   // already matched pairs
+        std::vector<MapPoint *> mB(mA);
+        const int nA = matcher.SearchBySim3(&kf1, &kf2, mA, s12, R12, t12, 7.5f);
+        const int nB = ref::SearchBySim3(&kf1, &kf2, mB, s12, R12, t12, 7.5f);
+        int diff = 0;
+        for (size_t i = 0; i < mA.size(); i++) diff += mA[i] != mB[i];
+        std::printf("SearchBySim3: facade %d, restatement %d, %d slots differ\n", nA, nB, diff);
+        if (nA != nB || diff || nA < 150) rc = rc ? rc : 13;
     }
     return rc;
 }
