@@ -43,7 +43,8 @@ def is_stale():
 def build_native(force=False, verbose=False):
     if not force and not is_stale():
         return SO
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("ORBFE_NVCC_EXTRA", "").split()   # experiments, e.g. -DORBFE_FAST_MINBLOCKS=3
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

@@ -29,7 +29,9 @@ __global__ void __launch_bounds__(256) bow_descend_kernel(const uint4 *__restric
     const uint4 a0 = __ldg(&desc[2 * i]), a1 = __ldg(&desc[2 * i + 1]);
     int cur = 0, level = 0, nid = 0;
     int cb = __ldg(&child_ptr[0]), ce = __ldg(&child_ptr[1]);
-    while (ce > cb) {  // do { ... } while (!isLeaf): the root of a non-empty vocabulary has children
+    // do { ... } while (!isLeaf): the root of a non-empty vocabulary has children.  The level cap only guards against a
+    // malformed table with a cycle (a DBoW2 tree is a handful of levels deep): the kernel must terminate.
+    while (ce > cb && level < 64) {
         level++;
         uint32_t best = 0xFFFFFFFFu;
         for (int c0 = cb; c0 < ce; c0 += 32) {

@@ -544,7 +544,10 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, ui
 #define F2_TMA_SMEM (2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4 + 128)
 static_assert(F2_MAXC * 4 <= F2_PIXSLOT, "the candidate queue lives in the pixel slot that was just consumed");
 
-__global__ void __launch_bounds__(256, 4) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
+#ifndef ORBFE_FAST_MINBLOCKS
+#define ORBFE_FAST_MINBLOCKS 4   // resident CTAs per SM the register budget is sized for (64 registers)
+#endif
+__global__ void __launch_bounds__(256, ORBFE_FAST_MINBLOCKS) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint8_t *pixbuf0 = dsm, *pixbuf1 = dsm + F2_PIXSLOT;
     uint32_t *mt = reinterpret_cast<uint32_t *>(dsm + 2 * F2_PIXSLOT);
