@@ -269,3 +269,163 @@ def test_guided_search_rule0_against_python_loop():
             for i in hist[b]:
                 exp[i] = -1
     assert np.array_equal(so, exp) and n > 150
+
+
+def _pair(n, seed, jitter=4.0, dang=6.0, flip=0.06, levels=4):
+    """Two small random frames: the second is a jittered, re-ordered, noisy copy of the first."""
+    k1, d1 = _rand_frame(n, seed)
+    k1["octave"] = np.random.default_rng(seed + 100).integers(0, levels, n)
+    rng = np.random.default_rng(seed + 1)
+    k2 = k1.copy()
+    k2["x"] = (k1["x"] + rng.uniform(-jitter, jitter, n)).astype(np.float32)
+    k2["y"] = (k1["y"] + rng.uniform(-jitter, jitter, n)).astype(np.float32)
+    k2["angle"] = ((k1["angle"] + rng.normal(dang, 3, n)) % 360).astype(np.float32)
+    d2 = noisy_copies(d1, flip, seed + 2)
+    perm = rng.permutation(n)
+    return k1, d1, k2[perm], d2[perm], rng
+
+
+def test_search_for_initialization_against_python_loop():
+    """ORBmatcher.cc:598-713: level-0 features only, candidates around the previously matched position, a better match
+    steals an already matched F2 feature (vMatchedDistance), rotation filter, prev-matched update."""
+    k1, d1, k2, d2, rng = _pair(500, 21, levels=2)
+    f1, f2 = O.OracleFrame(k1, d1, W, H), O.OracleFrame(k2, d2, W, H)
+    prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+    nnr = np.float32(0.9)
+    for rounds in range(2):
+        n, m12, prev_out = O.search_for_initialization(f1, f2, prev, 40, nnratio=0.9, check_orientation=True)
+        cells, gx, gy = _grid_py(k2)
+        e12 = np.full(len(k1), -1, np.int64)
+        e21 = np.full(len(k2), -1, np.int64)
+        mdist = np.full(len(k2), 2 ** 31 - 1, np.int64)
+        hist = [[] for _ in range(30)]
+        nm = 0
+        for i1 in range(len(k1)):
+            if k1["octave"][i1] > 0:
+                continue
+            cand = _area_py(k2, cells, gx, gy, prev[i1, 0], prev[i1, 1], 40, 0, 0)
+            b1 = b2 = 2 ** 31 - 1
+            bi = -1
+            for i2 in cand:
+                dd = _ham(d1[i1], d2[i2])
+                if mdist[i2] <= dd:
+                    continue
+                if dd < b1:
+                    b2, b1, bi = b1, dd, i2
+                elif dd < b2:
+                    b2 = dd
+            if b1 <= 50 and np.float32(b1) < np.float32(b2) * nnr:
+                if e21[bi] >= 0:
+                    e12[e21[bi]] = -1
+                    nm -= 1
+                e12[i1], e21[bi], mdist[bi] = bi, i1, b1
+                nm += 1
+                hist[_bin(k1["angle"][i1], k2["angle"][bi])].append(i1)
+        keep = _three_max_py([len(h) for h in hist])
+        for b in range(30):
+            if b not in keep:
+                for i1 in hist[b]:
+                    if e12[i1] >= 0:
+                        e12[i1] = -1
+                        nm -= 1
+        exp_prev = prev.copy()
+        for i1 in range(len(k1)):
+            if e12[i1] >= 0:
+                exp_prev[i1] = (k2["x"][e12[i1]], k2["y"][e12[i1]])
+        assert np.array_equal(m12, e12) and n == nm and n > 60
+        assert np.array_equal(prev_out, exp_prev)
+        prev = prev_out  # Tracking::Initialize feeds the updated positions back in
+
+
+def test_guided_search_rules_1_2_against_python_loop():
+    """The ratio rules of the guided skeleton: rule 1 (ORBmatcher.cc:469, :586) and rule 2 (:113-121, with the
+    best/second-best LEVELS of the Frame-vs-map-points search)."""
+    k1, d1, k2, d2, rng = _pair(350, 31, jitter=5.0)
+    f2 = O.OracleFrame(k2, d2, W, H)
+    qr = np.full(len(k1), 14.0, np.float32)
+    lo, hi = (k1["octave"] - 1).astype(np.int32), k1["octave"].astype(np.int32)
+    occ = np.full(len(k2), -1, np.int32)
+    occ[::23] = 9
+    cells, gx, gy = _grid_py(k2)
+    for rule, nnr in ((1, 0.8), (2, 0.8), (1, 0.6), (2, 0.95)):
+        n, so = O.guided_search(f2, k1["x"], k1["y"], qr, lo, hi, d1, k1["angle"], rule, nnr, 0, 0, slot_owner=occ)
+        exp = occ.astype(np.int64).copy()
+        r = np.float32(nnr)
+        for q in range(len(k1)):
+            b1 = b2 = 2 ** 31 - 1
+            bi, l1, l2 = -1, -1, -1
+            for i2 in _area_py(k2, cells, gx, gy, k1["x"][q], k1["y"][q], 14.0, lo[q], hi[q]):
+                if exp[i2] >= 0:
+                    continue
+                dd = _ham(d1[q], d2[i2])
+                if dd < b1:
+                    b2, b1, l2, l1, bi = b1, dd, l1, int(k2["octave"][i2]), i2
+                elif dd < b2:
+                    l2, b2 = int(k2["octave"][i2]), dd
+            if rule == 1:
+                ok = np.float32(b1) <= np.float32(b2) * r and b1 <= 100
+            else:
+                ok = b1 <= 100 and not (l1 == l2 and np.float32(b1) > r * np.float32(b2))
+            if ok:
+                exp[bi] = q
+        assert np.array_equal(so, exp), (rule, nnr)
+        assert n == int((exp >= 0).sum() - (occ >= 0).sum()) and n > 100
+
+
+def test_search_by_projection_frames_against_python_loop():
+    """ORBmatcher.cc:1507-1620 (Current vs Last with a pose): projection in cv::gemm's arithmetic (double accumulation,
+    one rounding), octave window, free-slot best match <= TH_HIGH, rotation filter."""
+    k1, d1, k2, d2, rng = _pair(400, 41, jitter=2.0)
+    FX = FY = np.float32(500.0)
+    CX, CY, Z = np.float32(W / 2), np.float32(H / 2), np.float32(4.0)
+    world = np.empty((len(k1), 3), np.float32)
+    world[:, 0] = (k1["x"] - CX) / FX * Z
+    world[:, 1] = (k1["y"] - CY) / FY * Z
+    world[:, 2] = Z
+    T = np.zeros((3, 4), np.float32)
+    T[0, 0] = T[1, 1] = T[2, 2] = 1
+    T[0, 3], T[1, 3], T[2, 3] = 0.011, -0.007, 0.05
+    has = (rng.random(len(k1)) < 0.9).astype(np.uint8)
+    outl = (rng.random(len(k1)) < 0.05).astype(np.uint8)
+    pre = np.full(len(k2), -1, np.int32)
+    pre[::19] = 3
+    fc, fl = O.OracleFrame(k2, d2, W, H), O.OracleFrame(k1, d1, W, H)
+    for ori in (True, False):
+        n, mp = O.search_by_projection_ff(fc, fl, has, outl, world, T, float(FX), float(FY), float(CX), float(CY), 7.0, ori, cur_mp=pre)
+        cells, gx, gy = _grid_py(k2)
+        exp = pre.astype(np.int64).copy()
+        hist = [[] for _ in range(30)]
+        nm = 0
+        sf = fc.sf
+        for i in range(len(k1)):
+            if not has[i] or outl[i]:
+                continue
+            xc = [np.float32(np.float64(T[k, 0]) * np.float64(world[i, 0]) + np.float64(T[k, 1]) * np.float64(world[i, 1]) +
+                             np.float64(T[k, 2]) * np.float64(world[i, 2]) + np.float64(T[k, 3])) for k in range(3)]
+            invz = np.float32(1.0 / np.float64(xc[2]))
+            u = FX * xc[0] * invz + CX
+            v = FY * xc[1] * invz + CY
+            if u < 0 or u > W or v < 0 or v > H:
+                continue
+            oc = int(k1["octave"][i])
+            radius = np.float32(7.0) * sf[oc]
+            b1, bi = 2 ** 31 - 1, -1
+            for i2 in _area_py(k2, cells, gx, gy, u, v, radius, oc - 1, oc + 1):
+                if exp[i2] >= 0:
+                    continue
+                dd = _ham(d1[i], d2[i2])
+                if dd < b1:
+                    b1, bi = dd, i2
+            if b1 <= 100:
+                exp[bi] = i
+                nm += 1
+                hist[_bin(k1["angle"][i], k2["angle"][bi])].append(bi)
+        if ori:
+            keep = _three_max_py([len(h) for h in hist])
+            for b in range(30):
+                if b not in keep:
+                    for i2 in hist[b]:
+                        exp[i2] = -1
+                        nm -= 1
+        assert np.array_equal(mp, exp), ori
+        assert n == nm and n > 150
