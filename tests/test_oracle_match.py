@@ -429,3 +429,150 @@ def test_search_by_projection_frames_against_python_loop():
                         nm -= 1
         assert np.array_equal(mp, exp), ori
         assert n == nm and n > 150
+
+
+def _project_py(T, X, fx, fy, cx, cy):
+    """x3Dc = Rcw*x3Dw + tcw (gemm: double accumulation, one rounding); invz = 1.0/z in double; u, v in float."""
+    xc = [np.float32(np.float64(T[k, 0]) * np.float64(X[0]) + np.float64(T[k, 1]) * np.float64(X[1]) +
+                     np.float64(T[k, 2]) * np.float64(X[2]) + np.float64(T[k, 3])) for k in range(3)]
+    invz = np.float32(1.0 / np.float64(xc[2]))
+    return np.float32(fx) * xc[0] * invz + np.float32(cx), np.float32(fy) * xc[1] * invz + np.float32(cy)
+
+
+def test_search_local_points_against_python_loop():
+    """ORBmatcher.cc:49-125 (Frame vs local-map points with cached projections)."""
+    k1, d1, k2, d2, rng = _pair(400, 51, jitter=2.5)
+    n1 = len(k1)
+    f2 = O.OracleFrame(k2, d2, W, H)
+    in_view = (rng.random(n1) < 0.9).astype(np.uint8)
+    proj = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+    level = k1["octave"].astype(np.int32)
+    vcos = np.where(rng.random(n1) < 0.5, 0.9995, 0.9).astype(np.float32)
+    occ = np.full(len(k2), -1, np.int32)
+    occ[::29] = 5
+    cells, gx, gy = _grid_py(k2)
+    for th, nnr in ((1.0, 0.8), (3.0, 0.7)):
+        n, mp = O.search_local_points(f2, in_view, proj, level, vcos, d1, th, nnratio=nnr, f_mp=occ)
+        exp = occ.astype(np.int64).copy()
+        nm = 0
+        for i in range(n1):
+            if not in_view[i]:
+                continue
+            r = np.float32(2.5) if vcos[i] > 0.998 else np.float32(4.0)
+            if th != 1.0:
+                r = np.float32(r * np.float32(th))
+            lv = int(level[i])
+            b1 = b2 = 2 ** 31 - 1
+            bi, l1, l2 = -1, -1, -1
+            for i2 in _area_py(k2, cells, gx, gy, proj[i, 0], proj[i, 1], np.float32(r * f2.sf[lv]), lv - 1, lv):
+                if exp[i2] >= 0:
+                    continue
+                dd = _ham(d1[i], d2[i2])
+                if dd < b1:
+                    b2, b1, l2, l1, bi = b1, dd, l1, int(k2["octave"][i2]), i2
+                elif dd < b2:
+                    l2, b2 = int(k2["octave"][i2]), dd
+            if b1 <= 100:
+                if l1 == l2 and np.float32(b1) > np.float32(nnr) * np.float32(b2):
+                    continue
+                exp[bi] = i
+                nm += 1
+        assert np.array_equal(mp, exp) and n == nm and n > 100, (th, nnr)
+
+
+def test_search_by_projection_kf_against_python_loop():
+    """ORBmatcher.cc:1622-1746 (relocalisation refinement): level predicted from dist3D / minDistance with lower_bound."""
+    k1, d1, k2, d2, rng = _pair(400, 61, jitter=2.0)
+    n1 = len(k1)
+    FX, FY, CX, CY, Z = 500.0, 500.0, W / 2, H / 2, np.float32(4.0)
+    world = np.empty((n1, 3), np.float32)
+    world[:, 0] = (k1["x"] - np.float32(CX)) / np.float32(FX) * Z
+    world[:, 1] = (k1["y"] - np.float32(CY)) / np.float32(FY) * Z
+    world[:, 2] = Z
+    T = np.zeros((3, 4), np.float32)
+    T[0, 0] = T[1, 1] = T[2, 2] = 1
+    T[0, 3], T[1, 3], T[2, 3] = -0.012, 0.004, 0.2
+    min_dist = (Z / np.float32(1.2) ** k1["octave"].astype(np.float32) * rng.uniform(0.8, 1.1, n1)).astype(np.float32)
+    valid = (rng.random(n1) < 0.85).astype(np.uint8)
+    f2 = O.OracleFrame(k2, d2, W, H)
+    cells, gx, gy = _grid_py(k2)
+    # Ow = -Rcw.t()*tcw (gemm with alpha = -1: double accumulation, scaled, one rounding)
+    Ow = [np.float32((np.float64(T[0, k]) * np.float64(T[0, 3]) + np.float64(T[1, k]) * np.float64(T[1, 3]) +
+                      np.float64(T[2, k]) * np.float64(T[2, 3])) * -1.0) for k in range(3)]
+    for th, od, ori in ((10.0, 100, True), (4.0, 64, False)):
+        n, mp = O.search_by_projection_kf(f2, valid, world, min_dist, d1, k1["angle"], T, FX, FY, CX, CY, th, od, ori)
+        exp = np.full(len(k2), -1, np.int64)
+        hist = [[] for _ in range(30)]
+        nm = 0
+        for i in range(n1):
+            if not valid[i]:
+                continue
+            u, v = _project_py(T, world[i], FX, FY, CX, CY)
+            if u < 0 or u > W or v < 0 or v > H:
+                continue
+            PO = [np.float32(world[i, k] - Ow[k]) for k in range(3)]
+            d3 = np.float32(np.sqrt(np.float64(PO[0]) * np.float64(PO[0]) + np.float64(PO[1]) * np.float64(PO[1]) + np.float64(PO[2]) * np.float64(PO[2])))
+            ratio = np.float32(d3 / min_dist[i])
+            lv = min(int(np.searchsorted(f2.sf, ratio, side="left")), len(f2.sf) - 1)
+            radius = np.float32(np.float32(th) * f2.sf[lv])
+            b1, bi = 2 ** 31 - 1, -1
+            for i2 in _area_py(k2, cells, gx, gy, u, v, radius, lv - 1, lv + 1):
+                if exp[i2] >= 0:
+                    continue
+                dd = _ham(d1[i], d2[i2])
+                if dd < b1:
+                    b1, bi = dd, i2
+            if b1 <= od:
+                exp[bi] = i
+                nm += 1
+                hist[_bin(k1["angle"][i], k2["angle"][bi])].append(bi)
+        if ori:
+            keep = _three_max_py([len(h) for h in hist])
+            for b in range(30):
+                if b not in keep:
+                    for i2 in hist[b]:
+                        exp[i2] = -1
+                        nm -= 1
+        assert np.array_equal(mp, exp) and n == nm and n > 40, (th, od, ori)
+
+
+def test_search_by_projection_f1f2_against_python_loop():
+    """ORBmatcher.cc:519-594 (F1 map points projected into F2, same-octave window, ratio test)."""
+    k1, d1, k2, d2, rng = _pair(400, 71, jitter=3.0)
+    n1 = len(k1)
+    FX, FY, CX, CY, Z = 500.0, 500.0, W / 2, H / 2, np.float32(4.0)
+    world = np.empty((n1, 3), np.float32)
+    world[:, 0] = (k1["x"] - np.float32(CX)) / np.float32(FX) * Z
+    world[:, 1] = (k1["y"] - np.float32(CY)) / np.float32(FY) * Z
+    world[:, 2] = Z
+    T = np.zeros((3, 4), np.float32)
+    T[0, 0] = T[1, 1] = T[2, 2] = 1
+    T[0, 3] = 0.01
+    valid = (rng.random(n1) < 0.8).astype(np.uint8)
+    occ = np.full(len(k2), -1, np.int32)
+    occ[::31] = 2 ** 31 - 1
+    f1, f2 = O.OracleFrame(k1, d1, W, H), O.OracleFrame(k2, d2, W, H)
+    cells, gx, gy = _grid_py(k2)
+    for win, nnr in ((15, 0.9), (40, 0.7)):
+        n, mp = O.search_by_projection_f1f2(f1, f2, valid, world, T, FX, FY, CX, CY, win, nnratio=nnr, f2_mp=occ)
+        exp = occ.astype(np.int64).copy()
+        nm = 0
+        for i in range(n1):
+            if not valid[i]:
+                continue
+            u, v = _project_py(T, world[i], FX, FY, CX, CY)
+            lv = int(k1["octave"][i])
+            b1 = b2 = 2 ** 31 - 1
+            bi = -1
+            for i2 in _area_py(k2, cells, gx, gy, u, v, win, lv, lv):
+                if exp[i2] >= 0:
+                    continue
+                dd = _ham(d1[i], d2[i2])
+                if dd < b1:
+                    b2, b1, bi = b1, dd, i2
+                elif dd < b2:
+                    b2 = dd
+            if np.float32(b1) <= np.float32(b2) * np.float32(nnr) and b1 <= 100:
+                exp[bi] = i
+                nm += 1
+        assert np.array_equal(mp, exp) and n == nm and n > 80, (win, nnr)
