@@ -205,3 +205,112 @@ def test_undistort_points_vs_cv2_golden():
     kps["x"], kps["y"], kps["octave"] = [1.5, 2.5, 3.5], [4, 5, 6], [0, 1, 2]
     assert np.array_equal(O.undistort_keypoints(kps, 500, 500, 320, 240, [0, 0.3, 0.1, 0.1, 0]), kps)
     assert list(O.image_bounds(640, 480, 500, 500, 320, 240, [0, 0, 0, 0, 0])) == [0, 0, 640, 480]
+
+
+def test_extract_composition_against_live_cv2():
+    """ComputeKeyPoints (reference src/ORBextractor.cc:522-708) composed in Python from REAL OpenCV calls -- cv2.resize
+    for the pyramid, cv2.FastFeatureDetector on every cell window (threshold fallback to 7), the quota redistribution
+    loops, retainBest with the canonical tie rule -- against the oracle's extract(): same keypoints, same responses,
+    same order.  Orientation and descriptors are cross-checked separately (test_ic_angle_and_brief_against_numpy)."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    import math
+    f32 = np.float32
+
+    def compose(img, nfeatures, nlevels, fast_th):
+        p = O.make_params(nfeatures, 1.2, nlevels, 1, fast_th)
+        H0, W0 = img.shape
+        ratio = f32(W0) / f32(H0)                                     # (float)cols/rows
+        out = []
+        level_img = img
+        for level in range(nlevels):
+            if level > 0:
+                w, h = int(np.rint(f32(W0) * f32(p.inv_scale[level]))), int(np.rint(f32(H0) * f32(p.inv_scale[level])))   # cvRound
+                level_img = cv2.resize(level_img, (w, h), interpolation=cv2.INTER_LINEAR)
+            h, w = level_img.shape
+            nDesired = int(p.quota[level])
+            cols = int(math.sqrt(f32(nDesired) / (f32(5) * ratio)))
+            rows = int(ratio * f32(cols))
+            minB, maxBX, maxBY = 16, w - 16, h - 16
+            Wd, Hd = maxBX - minB, maxBY - minB
+            cellW, cellH = int(math.ceil(f32(Wd) / f32(cols))), int(math.ceil(f32(Hd) / f32(rows)))
+            nCells = rows * cols
+            nfCell = int(math.ceil(f32(nDesired) / f32(nCells)))
+            cells = [[[] for _ in range(cols)] for _ in range(rows)]
+            nToRetain = [[0] * cols for _ in range(rows)]
+            nTotal = [[0] * cols for _ in range(rows)]
+            noMore = [[False] * cols for _ in range(rows)]
+            iniX, iniY = [0] * cols, [0] * rows
+            nNoMore = nToDistribute = 0
+            hY = cellH + 6
+            for i in range(rows):
+                y0 = minB + i * cellH - 3
+                iniY[i] = y0
+                if i == rows - 1:
+                    hY = maxBY + 3 - y0
+                    if hY <= 0:
+                        continue
+                hX = cellW + 6
+                for j in range(cols):
+                    x0 = minB + j * cellW - 3
+                    iniX[j] = x0
+                    if j == cols - 1:
+                        hX = maxBX + 3 - x0
+                        if hX <= 0:
+                            continue
+                    roi = np.ascontiguousarray(level_img[y0:y0 + hY, x0:x0 + hX])
+                    det = cv2.FastFeatureDetector_create(threshold=fast_th, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+                    kps = det.detect(roi)
+                    if len(kps) <= 3:
+                        det = cv2.FastFeatureDetector_create(threshold=7, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+                        kps = det.detect(roi)
+                    cells[i][j] = [(int(k.pt[0]), int(k.pt[1]), float(k.response)) for k in kps]
+                    n = len(kps)
+                    nTotal[i][j] = n
+                    if n > nfCell:
+                        nToRetain[i][j] = nfCell
+                    else:
+                        nToRetain[i][j] = n
+                        nToDistribute += nfCell - n
+                        noMore[i][j] = True
+                        nNoMore += 1
+            while nToDistribute > 0 and nNoMore < nCells:
+                nNew = nfCell + int(math.ceil(f32(nToDistribute) / f32(nCells - nNoMore)))
+                nToDistribute = 0
+                for i in range(rows):
+                    for j in range(cols):
+                        if not noMore[i][j]:
+                            if nTotal[i][j] > nNew:
+                                nToRetain[i][j] = nNew
+                            else:
+                                nToRetain[i][j] = nTotal[i][j]
+                                nToDistribute += nNew - nTotal[i][j]
+                                noMore[i][j] = True
+                                nNoMore += 1
+            level_kps = []
+            for i in range(rows):
+                for j in range(cols):
+                    # retainBest + resize(n): the n largest responses, ties at the cut by earlier raster position (canonical);
+                    # survivors in raster order inside the cell (canonical output order)
+                    c = sorted(cells[i][j], key=lambda t: (-t[2], t[1], t[0]))[:nToRetain[i][j]]
+                    c.sort(key=lambda t: (t[1], t[0]))
+                    level_kps += [(x + iniX[j], y + iniY[i], r, (i, j)) for x, y, r in c]
+            if len(level_kps) > nDesired:
+                # level-wide retainBest: ties at the cut by cell row-major order, then raster; order of the survivors kept
+                order = sorted(range(len(level_kps)), key=lambda q: (-level_kps[q][2], q))[:nDesired]
+                level_kps = [level_kps[q] for q in sorted(order)]
+            out += [(x, y, level, r) for x, y, r, _ in level_kps]
+        return p, out
+
+    from orb_slam_b200.synth import textured_frame as tf
+    for (W_, H_, nf, nl, th, seed) in ((640, 480, 1000, 8, 20, 1), (752, 480, 600, 6, 12, 4), (320, 240, 300, 4, 20, 9)):
+        img = tf(W_, H_, seed=seed)
+        p, exp = compose(img, nf, nl, th)
+        rc, ok, od, _ = O.extract(p, img)
+        assert rc == 0 and len(ok) == len(exp), (len(ok), len(exp))
+        sc = [f32(p.scale[l]) for l in range(nl)]
+        ex = np.array([f32(x) * sc[l] if l else f32(x) for x, y, l, r in exp], np.float32)
+        ey = np.array([f32(y) * sc[l] if l else f32(y) for x, y, l, r in exp], np.float32)
+        assert np.array_equal(ok["x"], ex) and np.array_equal(ok["y"], ey)
+        assert np.array_equal(ok["octave"], np.array([l for _, _, l, _ in exp]))
+        assert np.array_equal(ok["response"], np.array([r for _, _, _, r in exp], np.float32))
