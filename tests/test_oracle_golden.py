@@ -221,7 +221,7 @@ def test_extract_composition_against_live_cv2():
         p = O.make_params(nfeatures, 1.2, nlevels, 1, fast_th)
         H0, W0 = img.shape
         ratio = f32(W0) / f32(H0)                                     # (float)cols/rows
-        out = []
+        out, levels = [], []
         level_img = img
         for level in range(nlevels):
             if level > 0:
@@ -300,12 +300,13 @@ def test_extract_composition_against_live_cv2():
                 order = sorted(range(len(level_kps)), key=lambda q: (-level_kps[q][2], q))[:nDesired]
                 level_kps = [level_kps[q] for q in sorted(order)]
             out += [(x, y, level, r) for x, y, r, _ in level_kps]
-        return p, out
+            levels.append(level_img)
+        return p, out, levels
 
     from orb_slam_b200.synth import textured_frame as tf
     for (W_, H_, nf, nl, th, seed) in ((640, 480, 1000, 8, 20, 1), (752, 480, 600, 6, 12, 4), (320, 240, 300, 4, 20, 9)):
         img = tf(W_, H_, seed=seed)
-        p, exp = compose(img, nf, nl, th)
+        p, exp, levels = compose(img, nf, nl, th)
         rc, ok, od, _ = O.extract(p, img)
         assert rc == 0 and len(ok) == len(exp), (len(ok), len(exp))
         sc = [f32(p.scale[l]) for l in range(nl)]
@@ -314,3 +315,35 @@ def test_extract_composition_against_live_cv2():
         assert np.array_equal(ok["x"], ex) and np.array_equal(ok["y"], ey)
         assert np.array_equal(ok["octave"], np.array([l for _, _, l, _ in exp]))
         assert np.array_equal(ok["response"], np.array([r for _, _, _, r in exp], np.float32))
+        # orientation and descriptor of every keypoint, again from real OpenCV pieces: copyMakeBorder (the 16-px reflect-101
+        # frame), sepFilter2D with the 2.4 integer taps (the smoothed interior), cv2.fastAtan2, and the rotated pattern
+        # sampled in numpy with the reference's float32 expressions
+        pat = np.array([int(x) for x in open(os.path.join(os.path.dirname(__file__), "..", "include", "orbfe_brief_pattern.inc"))
+                        .read().split("*/")[1].replace("\n", " ").split(",") if x.strip()], np.int32).reshape(512, 2)
+        taps = np.array([18, 34, 49, 55, 49, 34, 18], np.float64) / 256.0
+        umax = O.UMAX
+        frames = []
+        for lv in levels:
+            raw = cv2.copyMakeBorder(lv, 16, 16, 16, 16, cv2.BORDER_REFLECT_101)
+            work = raw.copy()
+            work[16:-16, 16:-16] = cv2.sepFilter2D(lv, cv2.CV_8U, taps, taps, borderType=cv2.BORDER_REFLECT_101)
+            frames.append((raw.astype(np.int64), work.astype(np.int64)))
+        px, py = pat[:, 0].astype(np.float32), pat[:, 1].astype(np.float32)
+        us = [np.arange(-umax[abs(v)], umax[abs(v)] + 1) for v in range(-15, 16)]
+        for q, (x, y, l, r) in enumerate(exp):
+            raw, work = frames[l]
+            m10 = m01 = 0
+            for v, u in zip(range(-15, 16), us):
+                row = raw[y + 16 + v, x + 16 + u]
+                m10 += int((u * row).sum())
+                m01 += v * int(row.sum())
+            ang = f32(cv2.fastAtan2(float(m01), float(m10)))
+            assert ang == ok["angle"][q], (q, ang, ok["angle"][q])
+            th_ = f32(ang) * f32(np.pi / f32(180.0))
+            a, b = f32(np.cos(np.float64(th_))), f32(np.sin(np.float64(th_)))
+            ry = np.rint((px * b + py * a).astype(np.float64)).astype(np.int64)    # float32 products and sum, cvRound
+            rx = np.rint((px * a - py * b).astype(np.float64)).astype(np.int64)
+            vals = work[y + 16 + ry, x + 16 + rx].reshape(256, 2)
+            bits = (vals[:, 0] < vals[:, 1]).astype(np.uint8)
+            ref = np.packbits(bits.reshape(32, 8)[:, ::-1], axis=1).ravel()
+            assert np.array_equal(od[q], ref), q
