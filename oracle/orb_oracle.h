@@ -9,10 +9,14 @@
  *
  * PARITY PIN STATUS: the reference has no tests / golden vectors for this path and cannot be compiled
  * here (needs OpenCV 2.4 + ROS + Boost).  The OpenCV primitives restated here (resize, FAST, integer
- * GaussianBlur engine, fastAtan2, copyMakeBorder) are pinned bit-for-bit against python cv2 4.13 by
- * tests/golden/ (generator: tests/golden/make_golden.py) and live in tests/test_oracle_vs_cv2.py.
- * The pipeline glue (cell grid, quota, retention, descriptor) has no executable reference:
- * that part is "parity unpinned" and is stated as such in DESIGN.md.
+ * GaussianBlur engine, fastAtan2, copyMakeBorder, undistortPoints) are pinned bit-for-bit against python cv2 4.13 by
+ * tests/golden/ (generator: tests/golden/make_golden.py; tests/test_oracle_golden.py).
+ * The extractor's pipeline glue (cell grid, quota, retention, orientation, descriptor) is pinned end to end against a
+ * Python composition of LIVE cv2 calls that follows ComputeKeyPoints / operator() line by line
+ * (test_extract_composition_against_live_cv2): identical keypoints, responses, order, angles and descriptors.
+ * The matcher / BoW / keyframe-database routines have no executable reference and no golden vectors ("parity
+ * unpinned", stated as such in DESIGN.md); each is cross-checked against an independent pure-Python loop written
+ * from the reference source (tests/test_oracle_match.py, tests/test_oracle_bow.py).
  *
  * Canonical choices where the reference itself is toolchain-dependent (see DESIGN.md "Canonical semantics"):
  *   - GaussianBlur: OpenCV-2.4 integer engine, taps [18,34,49,55,49,34,18]/256 per pass, /65536 half-even.
