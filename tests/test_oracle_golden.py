@@ -217,8 +217,23 @@ def test_extract_composition_against_live_cv2():
     import math
     f32 = np.float32
 
-    def compose(img, nfeatures, nlevels, fast_th):
-        p = O.make_params(nfeatures, 1.2, nlevels, 1, fast_th)
+    def harris(lv, x, y):
+        # HarrisResponses, ORBextractor.cc:79-120 (blockSize 7, k = 0.04): integer gradient sums, float32 finish
+        a = b = c = 0
+        L = lv.astype(np.int64)
+        for i in range(-3, 4):
+            for j in range(-3, 4):
+                yy, xx = y + i, x + j
+                Ix = (L[yy, xx + 1] - L[yy, xx - 1]) * 2 + (L[yy - 1, xx + 1] - L[yy - 1, xx - 1]) + (L[yy + 1, xx + 1] - L[yy + 1, xx - 1])
+                Iy = (L[yy + 1, xx] - L[yy - 1, xx]) * 2 + (L[yy + 1, xx - 1] - L[yy - 1, xx - 1]) + (L[yy + 1, xx + 1] - L[yy - 1, xx + 1])
+                a += Ix * Ix; b += Iy * Iy; c += Ix * Iy
+        fa, fb, fc = f32(a), f32(b), f32(c)
+        scale = f32(1.0) / f32(f32(28) * f32(255.0))
+        s4 = f32(f32(f32(scale * scale) * scale) * scale)
+        return float(f32(f32(f32(fa * fb) - f32(fc * fc)) - f32(f32(f32(0.04) * f32(fa + fb)) * f32(fa + fb))) * s4)
+
+    def compose(img, nfeatures, nlevels, fast_th, score_type=1):
+        p = O.make_params(nfeatures, 1.2, nlevels, score_type, fast_th)
         H0, W0 = img.shape
         ratio = f32(W0) / f32(H0)                                     # (float)cols/rows
         out, levels = [], []
@@ -264,7 +279,8 @@ def test_extract_composition_against_live_cv2():
                     if len(kps) <= 3:
                         det = cv2.FastFeatureDetector_create(threshold=7, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
                         kps = det.detect(roi)
-                    cells[i][j] = [(int(k.pt[0]), int(k.pt[1]), float(k.response)) for k in kps]
+                    cells[i][j] = [(int(k.pt[0]), int(k.pt[1]),
+                                    float(k.response) if score_type == 1 else harris(level_img, x0 + int(k.pt[0]), y0 + int(k.pt[1]))) for k in kps]
                     n = len(kps)
                     nTotal[i][j] = n
                     if n > nfCell:
@@ -304,9 +320,10 @@ def test_extract_composition_against_live_cv2():
         return p, out, levels
 
     from orb_slam_b200.synth import textured_frame as tf
-    for (W_, H_, nf, nl, th, seed) in ((640, 480, 1000, 8, 20, 1), (752, 480, 600, 6, 12, 4), (320, 240, 300, 4, 20, 9)):
+    for (W_, H_, nf, nl, th, seed, st) in ((640, 480, 1000, 8, 20, 1, 1), (752, 480, 600, 6, 12, 4, 1), (320, 240, 300, 4, 20, 9, 1),
+                                           (400, 300, 400, 5, 20, 12, 0)):   # the last one: HARRIS_SCORE
         img = tf(W_, H_, seed=seed)
-        p, exp, levels = compose(img, nf, nl, th)
+        p, exp, levels = compose(img, nf, nl, th, st)
         rc, ok, od, _ = O.extract(p, img)
         assert rc == 0 and len(ok) == len(exp), (len(ok), len(exp))
         sc = [f32(p.scale[l]) for l in range(nl)]
