@@ -576,3 +576,103 @@ def test_search_by_projection_f1f2_against_python_loop():
                 exp[bi] = i
                 nm += 1
         assert np.array_equal(mp, exp) and n == nm and n > 80, (win, nnr)
+
+
+def _fv(nodes):
+    """FeatureVector as CSR (ids ascending, feature indices ascending inside a node)."""
+    ids = np.unique(nodes)
+    ptr, items = [0], []
+    for n in ids:
+        items += list(np.nonzero(nodes == n)[0])
+        ptr.append(len(items))
+    return ids.astype(np.int32), np.array(ptr, np.int32), np.array(items, np.int32)
+
+
+def test_search_for_triangulation_against_python_loop():
+    """ORBmatcher.cc:852-1032 + CheckDistEpipolarLine :136-153: per shared vocabulary node, candidates <= TH_LOW sorted by
+    (distance, index), the first one within round(2*best) that satisfies the epipolar constraint wins."""
+    k1, d1, k2, d2, rng = _pair(500, 81, jitter=3.0, flip=0.04)
+    k2["y"] = (k2["y"] - np.float32(1.0)).astype(np.float32)
+    has1 = (rng.random(len(k1)) < 0.4).astype(np.uint8)
+    has2 = (rng.random(len(k2)) < 0.4).astype(np.uint8)
+    node1 = (d1[:, 3].astype(np.int32) >> 5) * 7 + 2
+    node2 = (d2[:, 3].astype(np.int32) >> 5) * 7 + 2
+    node2[rng.random(len(k2)) < 0.05] = 999
+    fv1, fv2 = _fv(node1), _fv(node2)
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 1.0]], np.float32)   # epipolar lines y2 = y1 - 1
+    sigma2 = (np.float32(1.2) ** np.arange(8, dtype=np.float32)) ** 2
+    f32 = np.float32
+    for ori in (True, False):
+        n, m12 = O.search_for_triangulation(k1, d1, has1, fv1, k2, d2, has2, fv2, F12, sigma2, check_orientation=ori)
+        exp = np.full(len(k1), -1, np.int64)
+        matched2 = np.zeros(len(k2), bool)
+        hist = [[] for _ in range(30)]
+        nm = 0
+        n2 = {int(i): fv2[2][fv2[1][q]:fv2[1][q + 1]] for q, i in enumerate(fv2[0])}
+        for q, nid in enumerate(fv1[0]):
+            if int(nid) not in n2:
+                continue
+            for idx1 in fv1[2][fv1[1][q]:fv1[1][q + 1]]:
+                if has1[idx1]:
+                    continue
+                cand = []
+                for idx2 in n2[int(nid)]:
+                    if matched2[idx2] or has2[idx2]:
+                        continue
+                    dd = _ham(d1[idx1], d2[idx2])
+                    if dd > 50:
+                        continue
+                    cand.append((dd, int(idx2)))
+                if not cand:
+                    continue
+                cand.sort()
+                dist_th = 2 * cand[0][0]
+                for dd, idx2 in cand:
+                    if dd > dist_th:
+                        break
+                    x1, y1, x2, y2 = f32(k1["x"][idx1]), f32(k1["y"][idx1]), f32(k2["x"][idx2]), f32(k2["y"][idx2])
+                    a = f32(f32(x1 * F12[0, 0]) + f32(y1 * F12[1, 0])) + F12[2, 0]
+                    b = f32(f32(x1 * F12[0, 1]) + f32(y1 * F12[1, 1])) + F12[2, 1]
+                    c = f32(f32(x1 * F12[0, 2]) + f32(y1 * F12[1, 2])) + F12[2, 2]
+                    num = f32(f32(f32(a * x2) + f32(b * y2)) + c)
+                    den = f32(f32(a * a) + f32(b * b))
+                    if den == 0:
+                        continue
+                    dsqr = f32(f32(num * num) / den)
+                    if np.float64(dsqr) < 3.84 * np.float64(sigma2[int(k2["octave"][idx2])]):
+                        matched2[idx2] = True
+                        exp[idx1] = idx2
+                        nm += 1
+                        hist[_bin(k1["angle"][idx1], k2["angle"][idx2])].append(idx1)
+                        break
+        if ori:
+            keep = _three_max_py([len(h) for h in hist])
+            for bb in range(30):
+                if bb not in keep:
+                    for i1 in hist[bb]:
+                        exp[i1] = -1
+                        nm -= 1
+        assert np.array_equal(m12, exp) and n == nm and n > 40, ori
+
+
+def test_guided_best_against_python_loop():
+    """The slot-free best-candidate search shared by Fuse / SearchBySim3 (level filter [lo, hi], best distance <= th)."""
+    k1, d1, k2, d2, rng = _pair(350, 91, jitter=4.0)
+    f2 = O.OracleFrame(k2, d2, W, H)
+    qr = (np.float32(9.0) * np.float32(1.2) ** k1["octave"]).astype(np.float32)
+    lo, hi = (k1["octave"] - 1).astype(np.int32), k1["octave"].astype(np.int32)
+    cells, gx, gy = _grid_py(k2)
+    for th in (50, 100):
+        best = O.guided_best(f2, k1["x"], k1["y"], qr, lo, hi, d1, th)
+        exp = np.full(len(k1), -1, np.int64)
+        for q in range(len(k1)):
+            b1, bi = 2 ** 31 - 1, -1
+            for i2 in _area_py(k2, cells, gx, gy, k1["x"][q], k1["y"][q], qr[q], -1, -1):   # KeyFrame::GetFeaturesInArea: no filter
+                if k2["octave"][i2] < lo[q] or k2["octave"][i2] > hi[q]:
+                    continue
+                dd = _ham(d1[q], d2[i2])
+                if dd < b1:
+                    b1, bi = dd, i2
+            if b1 <= th:
+                exp[q] = bi
+        assert np.array_equal(best, exp) and (exp >= 0).sum() > 100, th
