@@ -211,12 +211,14 @@ def run_reference(args):
         tot_kp += kp
         tot_t += dt
     val = tot_kp / tot_t / 1e6
+    kp1, dt1 = cpu_reference_pass(frames[:2], shifts[:2], 1)   # the reference's own mode: one Tracking thread
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mkeypoints/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "configs[1]: 1920x1080 u8 stream, 2000 kp, 8 levels, scale 1.2, SearchByProjection th=15",
                        "frames_per_step": nframes},
             "cpu_baseline": {"value": val, "unit": "Mkeypoints/s", "cores": cores, "kind": "port",
+                             "single_thread_value": kp1 / dt1 / 1e6,
                              "sample": "%d distinct frames, repeated to %d extract+match tasks per step, x %d steps, CPU oracle port on "
                                        "%d threads (reference cannot be compiled: needs OpenCV 2.4/ROS/Boost)"
                                        % (nframes, nframes * max(1, -(-2 * cores // nframes)), args.steps, cores)},
@@ -579,7 +581,9 @@ def main():
             nfr = max(2, min(B, 64))
             kp, dt = cpu_reference_pass(frames_np[:nfr], shifts[:nfr], cores)
             ntasks = nfr * max(1, -(-2 * cores // nfr))
+            kp1, dt1 = cpu_reference_pass(frames_np[:2], shifts[:2], 1)   # the reference's own mode: one Tracking thread
             line["cpu_baseline"] = {"value": kp / dt / 1e6, "unit": "Mkeypoints/s", "cores": cores, "kind": "port",
+                                    "single_thread_value": kp1 / dt1 / 1e6,
                                     "sample": "%d of the step's frames repeated to %d extract+match tasks (about %.0f CPU-seconds), "
                                               "CPU oracle port on %d threads, %.1f s wall" % (nfr, ntasks, 0.25 * ntasks, cores, dt)}
         print(json.dumps(line))
