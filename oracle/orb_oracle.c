@@ -208,15 +208,24 @@ static const int kRingX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2
 static const int kRingY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 
 static inline int m_from_diffs(const int *d /*16 signed v-ring*/) {
-    /* max over the 16 circular 9-arcs of min(d) and of min(-d); clamp at 0 */
+    /* max over the 16 circular 9-arcs of min(d) and of min(-d); clamp at 0.
+     * A 9-arc is three consecutive 3-arcs: with the ring unrolled to 24 entries, t[k] = min/max(e[k..k+2]) and
+     * arc(k) = min/max(t[k], t[k+3], t[k+6]).  Fixed-size loops without index masking: the compiler vectorises them. */
+    int e[24], tmn[22], tmx[22];
+    for (int k = 0; k < 16; k++) e[k] = d[k];
+    for (int k = 0; k < 8; k++) e[16 + k] = d[k];
+    for (int k = 0; k < 22; k++) {
+        const int a = e[k], b = e[k + 1], c = e[k + 2];
+        const int lo = a < b ? a : b, hi = a > b ? a : b;
+        tmn[k] = lo < c ? lo : c;
+        tmx[k] = hi > c ? hi : c;
+    }
     int best = 0;
     for (int k = 0; k < 16; k++) {
-        int mn = d[k], mx = d[k];
-        for (int j = 1; j < 9; j++) {
-            int v = d[(k + j) & 15];
-            if (v < mn) mn = v;
-            if (v > mx) mx = v;
-        }
+        int mn = tmn[k] < tmn[k + 3] ? tmn[k] : tmn[k + 3];
+        mn = mn < tmn[k + 6] ? mn : tmn[k + 6];
+        int mx = tmx[k] > tmx[k + 3] ? tmx[k] : tmx[k + 3];
+        mx = mx > tmx[k + 6] ? mx : tmx[k + 6];
         if (mn > best) best = mn;   /* all 9 darker than centre by >= mn */
         if (-mx > best) best = -mx; /* all 9 brighter */
     }
@@ -230,27 +239,42 @@ int orb_oracle_fast_m(const uint8_t *p, size_t stride) {
     return m_from_diffs(d);
 }
 
-/* corner test at threshold t (strict), with the usual opposite-pair early rejects; returns m (>t) or 0 */
-static inline int fast_corner_m(const uint8_t *p, const ptrdiff_t *ofs, int t) {
-    const int v = p[0];
-    const int lo = v - t, hi = v + t;
-#define CLS(k) (((int)p[ofs[k]] < lo ? 1 : 0) | ((int)p[ofs[k]] > hi ? 2 : 0))
-    int c = CLS(0) | CLS(8);
-    if (!c) return 0;
-    c &= CLS(2) | CLS(10);
-    c &= CLS(4) | CLS(12);
-    c &= CLS(6) | CLS(14);
-    if (!c) return 0;
-    c &= CLS(1) | CLS(9);
-    c &= CLS(3) | CLS(11);
-    c &= CLS(5) | CLS(13);
-    c &= CLS(7) | CLS(15);
-    if (!c) return 0;
-#undef CLS
-    int d[16];
-    for (int k = 0; k < 16; k++) d[k] = v - (int)p[ofs[k]];
-    int m = m_from_diffs(d);
-    return m > t ? m : 0;
+/* m for the pixels [j0, j0 + n) of one row, n <= FAST_CHUNK: the same definition as m_from_diffs, laid out as
+ * arrays over the columns so that every loop is a plain element-wise loop the compiler vectorises (int16 lanes).
+ * Used by orb_oracle_fast_detect; m_from_diffs (behind orb_oracle_fast_m) stays as the per-pixel statement of the same
+ * quantity.  Both are pinned against cv2 (tests/test_oracle_golden.py: FAST lists of whole images and ROIs; the m
+ * definition against cv2's keypoint responses). */
+#define FAST_CHUNK 256
+static void fast_m_columns(const uint8_t *row, const ptrdiff_t *ofs, int n, uint8_t *m_out) {
+    int16_t e[16][FAST_CHUNK], tmn[22][FAST_CHUNK], tmx[22][FAST_CHUNK], best[FAST_CHUNK];
+    for (int k = 0; k < 16; k++) {
+        const uint8_t *r = row + ofs[k];
+        for (int x = 0; x < n; x++) e[k][x] = (int16_t)((int)row[x] - (int)r[x]);
+    }
+    for (int k = 0; k < 22; k++) {
+        const int16_t *a = e[k & 15], *b = e[(k + 1) & 15], *c = e[(k + 2) & 15];
+        for (int x = 0; x < n; x++) {
+            const int16_t lo = a[x] < b[x] ? a[x] : b[x], hi = a[x] > b[x] ? a[x] : b[x];
+            tmn[k][x] = lo < c[x] ? lo : c[x];
+            tmx[k][x] = hi > c[x] ? hi : c[x];
+        }
+    }
+    for (int x = 0; x < n; x++) best[x] = 0;
+    for (int k = 0; k < 16; k++) {
+        const int16_t *a = tmn[k], *b = tmn[k + 3], *c = tmn[k + 6], *A = tmx[k], *B = tmx[k + 3], *C = tmx[k + 6];
+        for (int x = 0; x < n; x++) {
+            int16_t mn = a[x] < b[x] ? a[x] : b[x];
+            mn = mn < c[x] ? mn : c[x];
+            int16_t mx = A[x] > B[x] ? A[x] : B[x];
+            mx = mx > C[x] ? mx : C[x];
+            const int16_t nmx = (int16_t)-mx;
+            int16_t bb = best[x];
+            bb = mn > bb ? mn : bb;
+            bb = nmx > bb ? nmx : bb;
+            best[x] = bb;
+        }
+    }
+    for (int x = 0; x < n; x++) m_out[x] = (uint8_t)best[x];
 }
 
 int orb_oracle_fast_detect(const uint8_t *img, int w, int h, size_t stride, int th,
@@ -266,9 +290,12 @@ int orb_oracle_fast_detect(const uint8_t *img, int w, int h, size_t stride, int 
         memset(curr, 0, (size_t)w);
         if (i < h - 3) {
             const uint8_t *row = img + (size_t)i * stride;
-            for (int j = 3; j < w - 3; j++) {
-                int m = fast_corner_m(row + j, ofs, th);
-                if (m) curr[j] = (uint8_t)(m - 1);
+            for (int j0 = 3; j0 < w - 3; j0 += FAST_CHUNK) {
+                const int n_ = (w - 3 - j0) < FAST_CHUNK ? (w - 3 - j0) : FAST_CHUNK;
+                uint8_t mrow[FAST_CHUNK];
+                fast_m_columns(row + j0, ofs, n_, mrow);
+                for (int x = 0; x < n_; x++)
+                    if (mrow[x] > th) curr[j0 + x] = (uint8_t)(mrow[x] - 1);   /* corner at th <=> m > th; score = m - 1 */
             }
         }
         if (i == 3) continue;
