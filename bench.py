@@ -585,7 +585,7 @@ def main():
             line["cpu_baseline"] = {"value": kp / dt / 1e6, "unit": "Mkeypoints/s", "cores": cores, "kind": "port",
                                     "single_thread_value": kp1 / dt1 / 1e6,
                                     "sample": "%d of the step's frames repeated to %d extract+match tasks (about %.0f CPU-seconds), "
-                                              "CPU oracle port on %d threads, %.1f s wall" % (nfr, ntasks, 0.12 * ntasks, cores, dt)}
+                                              "CPU oracle port on %d threads, %.1f s wall" % (nfr, ntasks, 0.11 * ntasks, cores, dt)}
         print(json.dumps(line))
     for x in e2e_ex:
         x.close()

@@ -246,35 +246,41 @@ int orb_oracle_fast_m(const uint8_t *p, size_t stride) {
  * definition against cv2's keypoint responses). */
 #define FAST_CHUNK 256
 static void fast_m_columns(const uint8_t *row, const ptrdiff_t *ofs, int n, uint8_t *m_out) {
-    int16_t e[16][FAST_CHUNK], tmn[22][FAST_CHUNK], tmx[22][FAST_CHUNK], best[FAST_CHUNK];
+    /* two unsigned passes: dk[k] = max(v - ring_k, 0) ("darker than the centre by"), br[k] = max(ring_k - v, 0).
+     * min over an arc of the clamped values = max(min over the arc of the signed values, 0), and m is clamped at 0
+     * anyway, so m = max over arcs and polarities of the arc minimum of the clamped values (uint8 lanes). */
+    uint8_t dk[16][FAST_CHUNK], br[16][FAST_CHUNK], t0[22][FAST_CHUNK], t1[22][FAST_CHUNK];
     for (int k = 0; k < 16; k++) {
         const uint8_t *r = row + ofs[k];
-        for (int x = 0; x < n; x++) e[k][x] = (int16_t)((int)row[x] - (int)r[x]);
+        for (int x = 0; x < n; x++) {
+            const uint8_t v = row[x], q = r[x];
+            dk[k][x] = (uint8_t)((v > q ? v : q) - q);
+            br[k][x] = (uint8_t)((v > q ? v : q) - v);
+        }
     }
     for (int k = 0; k < 22; k++) {
-        const int16_t *a = e[k & 15], *b = e[(k + 1) & 15], *c = e[(k + 2) & 15];
+        const uint8_t *a = dk[k & 15], *b = dk[(k + 1) & 15], *c = dk[(k + 2) & 15];
+        const uint8_t *A = br[k & 15], *B = br[(k + 1) & 15], *C = br[(k + 2) & 15];
         for (int x = 0; x < n; x++) {
-            const int16_t lo = a[x] < b[x] ? a[x] : b[x], hi = a[x] > b[x] ? a[x] : b[x];
-            tmn[k][x] = lo < c[x] ? lo : c[x];
-            tmx[k][x] = hi > c[x] ? hi : c[x];
+            const uint8_t lo = a[x] < b[x] ? a[x] : b[x], LO = A[x] < B[x] ? A[x] : B[x];
+            t0[k][x] = lo < c[x] ? lo : c[x];
+            t1[k][x] = LO < C[x] ? LO : C[x];
         }
     }
-    for (int x = 0; x < n; x++) best[x] = 0;
+    for (int x = 0; x < n; x++) m_out[x] = 0;
     for (int k = 0; k < 16; k++) {
-        const int16_t *a = tmn[k], *b = tmn[k + 3], *c = tmn[k + 6], *A = tmx[k], *B = tmx[k + 3], *C = tmx[k + 6];
+        const uint8_t *a = t0[k], *b = t0[k + 3], *c = t0[k + 6], *A = t1[k], *B = t1[k + 3], *C = t1[k + 6];
         for (int x = 0; x < n; x++) {
-            int16_t mn = a[x] < b[x] ? a[x] : b[x];
+            uint8_t mn = a[x] < b[x] ? a[x] : b[x];
             mn = mn < c[x] ? mn : c[x];
-            int16_t mx = A[x] > B[x] ? A[x] : B[x];
-            mx = mx > C[x] ? mx : C[x];
-            const int16_t nmx = (int16_t)-mx;
-            int16_t bb = best[x];
+            uint8_t MN = A[x] < B[x] ? A[x] : B[x];
+            MN = MN < C[x] ? MN : C[x];
+            uint8_t bb = m_out[x];
             bb = mn > bb ? mn : bb;
-            bb = nmx > bb ? nmx : bb;
-            best[x] = bb;
+            bb = MN > bb ? MN : bb;
+            m_out[x] = bb;
         }
     }
-    for (int x = 0; x < n; x++) m_out[x] = (uint8_t)best[x];
 }
 
 int orb_oracle_fast_detect(const uint8_t *img, int w, int h, size_t stride, int th,
