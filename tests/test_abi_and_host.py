@@ -85,3 +85,18 @@ def test_synth_is_deterministic():
     from orb_slam_b200.synth import textured_frame
     a, b = textured_frame(160, 120, seed=3), textured_frame(160, 120, seed=3)
     assert np.array_equal(a, b) and a.dtype == np.uint8 and a.std() > 20
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: the three headers compile as C99 (-pedantic) and a C program links against liborbfe.so."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "orbfe.h"\n#include "orbfe_match.h"\n#include "orbfe_bow.h"\n'
+                   'int main(void) { return (sizeof(OrbfeKeyPoint) == 28 && orbfe_version() == ORBFE_VERSION) ? 0 : 1; }\n')
+    exe = tmp_path / "abi.bin"
+    so_dir = os.path.dirname(fe.library_path())
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-L", so_dir, "-lorbfe", "-Wl,-rpath," + so_dir, "-o", str(exe)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert subprocess.run([str(exe)]).returncode == 0
