@@ -32,6 +32,11 @@ public:
 
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
 
+    // Addition (not in the reference, whose matchers cannot fail): what happens when a liborbfe call fails.  The
+    // default handler logs and the method returns 0 matches, map untouched; ORBFE_ABORT_ON_ERROR=1 makes it abort.
+    typedef void (*ErrorHandler)(int code, const char *message);
+    static void SetErrorHandler(ErrorHandler handler);  // NULL restores the default
+
     // popcount(a XOR b) over two 32-byte descriptor rows (reference ORBmatcher.cc:1794-1810)
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
 

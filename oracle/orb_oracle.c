@@ -88,9 +88,16 @@ int orb_oracle_cell_grid(const OrbOracleParams *p, int level, int W0, int H0, in
     const int nd = p->quota[level];
     const int cols = (int)sqrtf((float)nd / (5.0f * ratio)); /* :533 */
     const int rows = (int)(ratio * (float)cols);             /* :534 */
-    if (cols < 1 || rows < 1) return -2;
     const int Wd = (w - ORB_ORACLE_EDGE) - ORB_ORACLE_EDGE; /* :536-542 */
     const int Hd = (h - ORB_ORACLE_EDGE) - ORB_ORACLE_EDGE;
+    if (cols < 1 || rows < 1) {
+        /* levelCols == 0 (a quota below 5*ratio) or levelRows == 0 (portrait images): the reference's cell
+         * vectors are empty, both loops over rows do nothing and the level yields no keypoints (:549-703);
+         * the other levels are unaffected.  An empty grid, not an error. */
+        g->cols = 0; g->rows = 0; g->Wd = Wd; g->Hd = Hd;
+        g->cell_w = 1; g->cell_h = 1; g->n_cells = 0; g->nf_cell = 0;
+        return 0;
+    }
     if (Wd < 1 || Hd < 1) return -2;
     g->cols = cols;
     g->rows = rows;

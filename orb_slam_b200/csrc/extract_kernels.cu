@@ -598,6 +598,7 @@ int fast_tma_setup() {
 }
 
 void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+    if (hp.nftiles_total == 0) return;  // every level has an empty cell grid: nothing to detect
     if (w.tmaps) {
         const int nwork = hp.nftiles_total * nf;
         const int grid = min(nwork, w.fast_grid);
@@ -766,6 +767,7 @@ __global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restr
 }
 
 void launch_cell_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
+    if (hp.ncells_total == 0) return;
     dim3 grid(hp.ncells_total, nf);
     if (w.cand_keys64) { cell_select_harris_kernel<<<grid, 128, 0, s>>>(d_plan, w, f0); return; }
     cell_select_kernel<<<grid, 128, 0, s>>>(d_plan, w, f0);

@@ -190,24 +190,34 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         L.cols = (int)std::sqrt((float)L.quota / (5.0f * ratio));
         L.rows = (int)(ratio * (float)L.cols);
         const int Wd = L.w - 2 * ORBFE_EDGE, Hd = L.h - 2 * ORBFE_EDGE;
-        if (L.cols < 1 || L.rows < 1 || Wd < 1 || Hd < 1)
-            return fail(ORBFE_ERR_UNSUPPORTED, "level %d (%dx%d, quota %d): degenerate cell grid %dx%d", l, L.w, L.h,
-                        L.quota, L.cols, L.rows);
-        L.cw = (int)std::ceil((float)Wd / (float)L.cols);
-        L.ch = (int)std::ceil((float)Hd / (float)L.rows);
-        if (L.cw < 2 || L.ch < 2)
-            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %dx%d-pixel cells (image too small for %d features)", l, L.cw, L.ch, L.quota);
-        L.cw_rcp = (uint32_t)((0x100000000ull + (unsigned)L.cw - 1) / (unsigned)L.cw);
-        L.ch_rcp = (uint32_t)((0x100000000ull + (unsigned)L.ch - 1) / (unsigned)L.ch);
-        L.ncells = L.rows * L.cols;
-        L.nfc = (int)std::ceil((float)L.quota / (float)L.ncells);
-        if ((L.cols - 1) * L.cw > Wd || (L.rows - 1) * L.ch > Hd)
-            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cell grid does not tile the detect area (image too small)", l);
-        // a FAST tile (ORBFE_FT_W x ORBFE_FT_H) may overlap at most 64 cells (shared-memory counters)
-        if (((ORBFE_FT_W + L.cw - 2) / L.cw + 1) * ((ORBFE_FT_H + L.ch - 2) / L.ch + 1) > 64)
-            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cells of %dx%d are too small for the FAST tile", l, L.cw, L.ch);
-        if (L.ncells > 4096 || (long long)L.cw * L.ch > (1 << 24))
-            return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %d cells of %dx%d exceed the key layout", l, L.ncells, L.cw, L.ch);
+        // levelCols == 0 (a quota below 5*ratio) or levelRows == 0 (portrait images): the reference's cell vectors are
+        // empty, its loops over the rows do nothing and the level yields no keypoints while the others run (:549-703)
+        const bool empty_level = L.cols < 1 || L.rows < 1;
+        if (empty_level) {
+            L.cols = L.rows = 0;
+            L.cw = L.ch = 1;
+            L.cw_rcp = L.ch_rcp = 1;
+            L.ncells = 0;
+            L.nfc = 0;
+        } else {
+            if (Wd < 1 || Hd < 1)
+                return fail(ORBFE_ERR_UNSUPPORTED, "level %d (%dx%d): no pixels inside the 16-px detection border", l, L.w, L.h);
+            L.cw = (int)std::ceil((float)Wd / (float)L.cols);
+            L.ch = (int)std::ceil((float)Hd / (float)L.rows);
+            if (L.cw < 2 || L.ch < 2)
+                return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %dx%d-pixel cells (image too small for %d features)", l, L.cw, L.ch, L.quota);
+            L.cw_rcp = (uint32_t)((0x100000000ull + (unsigned)L.cw - 1) / (unsigned)L.cw);
+            L.ch_rcp = (uint32_t)((0x100000000ull + (unsigned)L.ch - 1) / (unsigned)L.ch);
+            L.ncells = L.rows * L.cols;
+            L.nfc = (int)std::ceil((float)L.quota / (float)L.ncells);
+            if ((L.cols - 1) * L.cw > Wd || (L.rows - 1) * L.ch > Hd)
+                return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cell grid does not tile the detect area (image too small)", l);
+            // a FAST tile (ORBFE_FT_W x ORBFE_FT_H) may overlap at most 64 cells (shared-memory counters)
+            if (((ORBFE_FT_W + L.cw - 2) / L.cw + 1) * ((ORBFE_FT_H + L.ch - 2) / L.ch + 1) > 64)
+                return fail(ORBFE_ERR_UNSUPPORTED, "level %d: cells of %dx%d are too small for the FAST tile", l, L.cw, L.ch);
+            if (L.ncells > 4096 || (long long)L.cw * L.ch > (1 << 24))
+                return fail(ORBFE_ERR_UNSUPPORTED, "level %d: %d cells of %dx%d exceed the key layout", l, L.ncells, L.cw, L.ch);
+        }
         L.cell_base = cell_base;
         cell_base += L.ncells;
         L.kp_base = kp_base;
@@ -216,8 +226,8 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         L.kept_cap = L.quota + 2 * L.ncells + 64;
         kept_base += L.kept_cap;
         max_kept = std::max(max_kept, L.kept_cap);
-        L.ftiles_x = (Wd + ORBFE_FT_W - 1) / ORBFE_FT_W;
-        L.ftiles_y = (Hd + ORBFE_FT_H - 1) / ORBFE_FT_H;
+        L.ftiles_x = empty_level ? 0 : (Wd + ORBFE_FT_W - 1) / ORBFE_FT_W;
+        L.ftiles_y = empty_level ? 0 : (Hd + ORBFE_FT_H - 1) / ORBFE_FT_H;
         L.ftile_base = ft_base;
         ft_base += L.ftiles_x * L.ftiles_y;
         L.btiles_x = (L.w + ORBFE_BT_W - 1) / ORBFE_BT_W;
@@ -875,6 +885,7 @@ extern "C" int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, co
     if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large for the device matcher", cap);
     P.smem_fixed = (int)fixed;
     P.smem_entries = (int)((total - fixed) / sizeof(uint32_t));
+    if (getenv("ORBFE_SBP_FORCE_SCRATCH")) P.smem_entries = 0;  // test knob: candidate entries always in the global scratch
     const size_t need = (size_t)npairs * P.scratch_per_pair;
     if (m->scratch_entries < need) {
         if (m->scratch) cudaFree(m->scratch);

@@ -5,6 +5,8 @@
 // (include/orbfe.h); this file only adapts cv:: types.
 #include "ORBextractor.h"
 
+#include <cstring>
+
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>

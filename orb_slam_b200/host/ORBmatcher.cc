@@ -10,6 +10,7 @@
 // (tests/test_gpu_matchers.py); the Sim3 / Fuse ones gather through KeyFrame's public API and use orbfe_hamming_csr.
 #include "ORBmatcher.h"
 
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -30,25 +31,39 @@ namespace {
 
 int g_match_device = 0;
 
+// Error policy.  The reference's matchers cannot fail, liborbfe's calls can (a transient cudaMalloc failure in a
+// scratch regrow, a launch error, an unsupported geometry).  Every failure goes through one handler: the default
+// logs the code and message and the calling method returns 0 matches with the map untouched, so that a SLAM node
+// survives a transient device error (Tracking treats 0 matches as a lost frame); ORBFE_ABORT_ON_ERROR=1 or
+// ORBmatcher::SetErrorHandler() select another policy (e.g. abort, as round 1 did unconditionally).
+void default_error_handler(int code, const char *msg) {
+    std::fprintf(stderr, "ORBmatcher: liborbfe error %d: %s (there is no CPU path; returning 0 matches)\n", code, msg);
+    const char *e = std::getenv("ORBFE_ABORT_ON_ERROR");
+    if (e && *e && *e != '0') std::abort();
+}
+ORBmatcher::ErrorHandler g_error_handler = default_error_handler;
+
 // ORBmatcher objects are stack temporaries used from three threads (Tracking.cc:352,488,556,...):
-// each calling thread lazily gets its own device handle (stream + scratch buffers).
+// each calling thread lazily gets its own device handle (stream + scratch buffers), destroyed when the thread exits.
+struct ThreadMatcher {
+    OrbfeMatcher *m;
+    ThreadMatcher() : m(NULL) {}
+    ~ThreadMatcher() { if (m) orbfe_matcher_destroy(m); }
+};
 OrbfeMatcher *thread_matcher() {
-    static thread_local OrbfeMatcher *m = NULL;
-    if (!m) {
-        const int rc = orbfe_matcher_create(g_match_device, &m);
-        if (rc != ORBFE_OK) {
-            std::fprintf(stderr, "ORBmatcher: liborbfe error %d: %s (there is no CPU path)\n", rc, orbfe_last_error());
-            std::abort();
-        }
+    static thread_local ThreadMatcher holder;
+    if (!holder.m) {
+        const int rc = orbfe_matcher_create(g_match_device, &holder.m);
+        if (rc != ORBFE_OK) { holder.m = NULL; g_error_handler(rc, orbfe_last_error()); }
     }
-    return m;
+    return holder.m;  // NULL after a failed create: the C-ABI call then reports ORBFE_ERR_ARG and the method returns 0
 }
 
-void check(int rc) {
-    if (rc != ORBFE_OK) {
-        std::fprintf(stderr, "ORBmatcher: liborbfe error %d: %s\n", rc, orbfe_last_error());
-        std::abort();
-    }
+// true if the call succeeded; otherwise reports through the handler (which may abort) and returns false
+bool ok(int rc) {
+    if (rc == ORBFE_OK) return true;
+    g_error_handler(rc, orbfe_last_error());
+    return false;
 }
 
 // contiguous copy of a frame's descriptors (cv::Mat rows may be strided)
@@ -82,6 +97,8 @@ OrbfeFrameView make_view(const Frame &F, const DescBuf &d) {
 }  // namespace
 
 ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+void ORBmatcher::SetErrorHandler(ErrorHandler h) { g_error_handler = h ? h : default_error_handler; }
 
 // A single pair is 8 XOR+popcount on the host: shipping 64 bytes to the GPU for one distance would only add
 // latency.  Every *batched* distance computation below goes to the device.
@@ -139,8 +156,8 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     const float *wp = nl ? &world[0] : NULL, *tp = T;
     int *mpp = nc ? &mp[0] : NULL;
     int nmatches = 0;
-    check(orbfe_search_by_projection_frames(thread_matcher(), 1, &cur, &last, &hp, &op, &wp, &tp, Frame::fx, Frame::fy,
-                                            Frame::cx, Frame::cy, th, mbCheckOrientation ? 1 : 0, &mpp, &nmatches));
+    if (!ok(orbfe_search_by_projection_frames(thread_matcher(), 1, &cur, &last, &hp, &op, &wp, &tp, Frame::fx, Frame::fy,
+                                            Frame::cx, Frame::cy, th, mbCheckOrientation ? 1 : 0, &mpp, &nmatches))) return 0;
     for (int i = 0; i < nc; i++)
         if (mp[i] >= 0 && mp[i] != INT_MAX) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[mp[i]];
     return nmatches;
@@ -159,8 +176,8 @@ int ORBmatcher::WindowSearch(Frame &F1, Frame &F2, int windowSize, std::vector<M
     }
     std::vector<int> m21(v2.n > 0 ? v2.n : 1, -1);
     int nmatches = 0;
-    check(orbfe_window_search(thread_matcher(), &v1, &v2, v1.n ? &has[0] : NULL, windowSize, minScaleLevel, maxScaleLevel,
-                              mfNNratio, mbCheckOrientation ? 1 : 0, &m21[0], &nmatches));
+    if (!ok(orbfe_window_search(thread_matcher(), &v1, &v2, v1.n ? &has[0] : NULL, windowSize, minScaleLevel, maxScaleLevel,
+                              mfNNratio, mbCheckOrientation ? 1 : 0, &m21[0], &nmatches))) return 0;
     vpMapPointMatches2 = std::vector<MapPoint *>(F2.mvpMapPoints.size(), static_cast<MapPoint *>(NULL));  // :412
     for (int i2 = 0; i2 < v2.n; i2++)
         if (m21[i2] >= 0) vpMapPointMatches2[i2] = F1.mvpMapPoints[m21[i2]];
@@ -177,8 +194,8 @@ int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Po
     vnMatches12 = std::vector<int>(F1.mvKeysUn.size(), -1);  // :601
     int nmatches = 0;
     if (v1.n == 0) return 0;
-    check(orbfe_search_for_initialization(thread_matcher(), &v1, &v2, reinterpret_cast<float *>(&vbPrevMatched[0]), windowSize,
-                                          mfNNratio, mbCheckOrientation ? 1 : 0, &vnMatches12[0], &nmatches));
+    if (!ok(orbfe_search_for_initialization(thread_matcher(), &v1, &v2, reinterpret_cast<float *>(&vbPrevMatched[0]), windowSize,
+                                          mfNNratio, mbCheckOrientation ? 1 : 0, &vnMatches12[0], &nmatches))) return 0;
     return nmatches;
 }
 
@@ -205,8 +222,8 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMa
     for (int i = 0; i < fv.n; i++)
         if (F.mvpMapPoints[i]) mp[i] = INT_MAX;
     int nmatches = 0;
-    check(orbfe_search_local_points(thread_matcher(), &fv, np, np ? &in_view[0] : NULL, &proj[0], &level[0], &vcos[0], &desc[0], th,
-                                    mfNNratio, &mp[0], &nmatches));
+    if (!ok(orbfe_search_local_points(thread_matcher(), &fv, np, np ? &in_view[0] : NULL, &proj[0], &level[0], &vcos[0], &desc[0], th,
+                                    mfNNratio, &mp[0], &nmatches))) return 0;
     for (int i = 0; i < fv.n; i++)
         if (mp[i] >= 0 && mp[i] != INT_MAX) F.mvpMapPoints[i] = vpMapPoints[mp[i]];
     return nmatches;
@@ -235,8 +252,8 @@ int ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, int windowSize, std::ve
     for (int i = 0; i < v2.n; i++)
         if (vpMapPointMatches2[i]) mp[i] = INT_MAX;
     int nmatches = 0;
-    check(orbfe_search_by_projection_f1f2(thread_matcher(), &v1, &v2, &valid[0], &world[0], T, Frame::fx, Frame::fy, Frame::cx,
-                                          Frame::cy, windowSize, mfNNratio, &mp[0], &nmatches));
+    if (!ok(orbfe_search_by_projection_f1f2(thread_matcher(), &v1, &v2, &valid[0], &world[0], T, Frame::fx, Frame::fy, Frame::cx,
+                                          Frame::cy, windowSize, mfNNratio, &mp[0], &nmatches))) return 0;
     for (int i = 0; i < v2.n; i++)
         if (mp[i] >= 0 && mp[i] != INT_MAX) vpMapPointMatches2[i] = F1.mvpMapPoints[mp[i]];
     return nmatches;
@@ -269,7 +286,7 @@ std::vector<unsigned short> distances(const Csr &c, const cv::Mat &targetDesc)
     std::vector<unsigned short> dist(c.cols.empty() ? 1 : c.cols.size());
     if (c.cols.empty()) return dist;
     const DescBuf t(targetDesc);
-    check(orbfe_hamming_csr(thread_matcher(), &c.qdesc[0], c.rows(), t.ptr, targetDesc.rows, &c.row_ptr[0], &c.cols[0], &dist[0]));
+    if (!ok(orbfe_hamming_csr(thread_matcher(), &c.qdesc[0], c.rows(), t.ptr, targetDesc.rows, &c.row_ptr[0], &c.cols[0], &dist[0]))) std::fill(dist.begin(), dist.end(), (unsigned short)0xFFFF);  // no candidate is accepted
     return dist;
 }
 
@@ -385,8 +402,8 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std
     for (int i = 0; i < cur.n; i++)
         if (CurrentFrame.mvpMapPoints[i]) mp[i] = INT_MAX;
     int nmatches = 0;
-    check(orbfe_search_by_projection_kf(thread_matcher(), &cur, np, &valid[0], &world[0], &mind[0], &desc[0], &ang[0], T, Frame::fx,
-                                        Frame::fy, Frame::cx, Frame::cy, th, ORBdist, mbCheckOrientation ? 1 : 0, &mp[0], &nmatches));
+    if (!ok(orbfe_search_by_projection_kf(thread_matcher(), &cur, np, &valid[0], &world[0], &mind[0], &desc[0], &ang[0], T, Frame::fx,
+                                        Frame::fy, Frame::cx, Frame::cy, th, ORBdist, mbCheckOrientation ? 1 : 0, &mp[0], &nmatches))) return 0;
     for (int i = 0; i < cur.n; i++)
         if (mp[i] >= 0 && mp[i] != INT_MAX) CurrentFrame.mvpMapPoints[i] = vpMPs[mp[i]];
     return nmatches;
@@ -504,9 +521,9 @@ int ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint *> &vp
     const DescBuf d1(pKF->GetDescriptors()), d2(F.mDescriptors);
     std::vector<int> out(n2 + 1, -1);
     int nmatches = 0;
-    check(orbfe_search_by_bow(thread_matcher(), 0, n1, d1.ptr, &valid1[0], &a1[0], (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1),
+    if (!ok(orbfe_search_by_bow(thread_matcher(), 0, n1, d1.ptr, &valid1[0], &a1[0], (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1),
                               n2, d2.ptr, &valid2[0], &a2[0], (int)ids2.size(), ptr_or_null(ids2), &ptr2[0], ptr_or_null(it2), mfNNratio,
-                              mbCheckOrientation ? 1 : 0, &out[0], &nmatches));
+                              mbCheckOrientation ? 1 : 0, &out[0], &nmatches))) return 0;
     for (int i2 = 0; i2 < n2; i2++)
         if (out[i2] >= 0) vpMapPointMatches[i2] = vpMapPointsKF[out[i2]];
     return nmatches;
@@ -528,9 +545,9 @@ int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint
     const DescBuf d1(pKF1->GetDescriptors()), d2(pKF2->GetDescriptors());
     std::vector<int> out(n1 + 1, -1);
     int nmatches = 0;
-    check(orbfe_search_by_bow(thread_matcher(), 1, n1, d1.ptr, &valid1[0], &a1[0], (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1),
+    if (!ok(orbfe_search_by_bow(thread_matcher(), 1, n1, d1.ptr, &valid1[0], &a1[0], (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1),
                               n2, d2.ptr, &valid2[0], &a2[0], (int)ids2.size(), ptr_or_null(ids2), &ptr2[0], ptr_or_null(it2), mfNNratio,
-                              mbCheckOrientation ? 1 : 0, &out[0], &nmatches));
+                              mbCheckOrientation ? 1 : 0, &out[0], &nmatches))) return 0;
     for (int i1 = 0; i1 < n1; i1++)
         if (out[i1] >= 0) vpMatches12[i1] = vp2[out[i1]];
     return nmatches;
@@ -568,11 +585,11 @@ int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F
     const DescBuf d1(pKF1->GetDescriptors()), d2(pKF2->GetDescriptors());
     std::vector<int> m12(n1 + 1, -1);
     int nmatches = 0;
-    check(orbfe_search_for_triangulation(thread_matcher(), n1, n1 ? reinterpret_cast<const OrbfeKeyPoint *>(&k1[0]) : NULL, d1.ptr, &has1[0],
+    if (!ok(orbfe_search_for_triangulation(thread_matcher(), n1, n1 ? reinterpret_cast<const OrbfeKeyPoint *>(&k1[0]) : NULL, d1.ptr, &has1[0],
                                          (int)ids1.size(), ptr_or_null(ids1), &ptr1[0], ptr_or_null(it1), n2,
                                          n2 ? reinterpret_cast<const OrbfeKeyPoint *>(&k2[0]) : NULL, d2.ptr, &has2[0], (int)ids2.size(),
                                          ptr_or_null(ids2), &ptr2[0], ptr_or_null(it2), F, &sigma2[0], mbCheckOrientation ? 1 : 0, &m12[0],
-                                         &nmatches));
+                                         &nmatches))) return 0;
     vMatchedKeys1.clear(); vMatchedKeys2.clear(); vMatchedPairs.clear();  // :994-1011
     for (int i = 0; i < n1; i++) {
         if (m12[i] < 0) continue;

@@ -32,15 +32,25 @@ extern "C" int orbfe_guided_via_device(OrbfeMatcher *m, const OrbfeFrameView *f,
                                        const float *qr, const int *qlo, const int *qhi, const uint8_t *const *qdesc,
                                        const float *qangle, int rule, float nnratio, int th_dist, int check_orientation,
                                        const int *slot_owner, int *slot_new, int *nmatches_out);
-static bool g_force_host_replay = false;
+static std::atomic<bool> g_force_host_replay(false);  // test hook, read from several matcher threads
 // test hook: 1 = always use host candidate lists + device distances + host greedy replay
-extern "C" void orbfe_matcher_force_host_replay(int on) { g_force_host_replay = on != 0; }
+extern "C" void orbfe_matcher_force_host_replay(int on) { g_force_host_replay.store(on != 0); }
 
 namespace {
 
 constexpr int kGridCols = 64;  // FRAME_GRID_COLS, Frame.h:36
 constexpr int kGridRows = 48;  // FRAME_GRID_ROWS, Frame.h:35
 constexpr int kThHigh = 100, kThLow = 50, kHisto = 30;  // ORBmatcher.cc:40-42
+
+// A view is well formed when its arrays are present and every keypoint octave indexes scale_factors (a malformed
+// view is rejected with ORBFE_ERR_ARG instead of being read out of bounds; octave < 0 never occurs in extractor output).
+bool view_ok(const OrbfeFrameView &v) {
+    if (v.n < 0 || v.nlevels < 1 || v.nlevels > ORBFE_MAX_LEVELS || !v.scale_factors) return false;
+    if (v.n > 0 && (!v.keys_un || !v.desc)) return false;
+    for (int i = 0; i < v.n; i++)
+        if ((unsigned)v.keys_un[i].octave >= (unsigned)v.nlevels) return false;
+    return true;
+}
 
 struct Grid {
     std::vector<int> start;  // kGridCols*kGridRows + 1, cell id = ix*kGridRows + iy
@@ -181,8 +191,10 @@ extern "C" int orbfe_search_by_projection_frames(OrbfeMatcher *m, int npairs, co
     if (!m || npairs < 0 || (npairs > 0 && (!cur || !last || !last_has_mp || !last_outlier || !last_world || !Tcw ||
                                             !cur_mp_inout || !nmatches_out)))
         return ORBFE_ERR_ARG;
+    for (int j = 0; j < npairs; j++)
+        if (!view_ok(cur[j]) || !view_ok(last[j])) return ORBFE_ERR_ARG;
     // fast path: everything (grid, candidates, distances, greedy, rotation filter) in ONE device kernel
-    if (!g_force_host_replay) {
+    if (!g_force_host_replay.load()) {
         const int rc = orbfe_sbp_frames_via_device(m, npairs, cur, last, last_has_mp, last_outlier, last_world, Tcw, fx, fy, cx,
                                                    cy, th, check_orientation, cur_mp_inout, nmatches_out);
         if (rc != 1) return rc;  // 1 = not applicable (mixed geometry / overflow): exact host replay below
@@ -266,6 +278,7 @@ extern "C" int orbfe_search_for_initialization(OrbfeMatcher *m, const OrbfeFrame
                                                float *prev_matched, int window, float nnratio, int check_orientation,
                                                int *match12_out, int *nmatches_out) {
     if (!m || !f1 || !f2 || !prev_matched || !match12_out || !nmatches_out) return ORBFE_ERR_ARG;
+    if (!view_ok(*f1) || !view_ok(*f2)) return ORBFE_ERR_ARG;
     std::vector<Job> jobs(1);
     Job &J = jobs[0];
     build_grid(*f2, J.grid);
@@ -347,7 +360,7 @@ struct GuidedQuery { float u, v, r; int lo, hi; const uint8_t *desc; float angle
 
 int guided_search(OrbfeMatcher *m, const OrbfeFrameView &f, const std::vector<GuidedQuery> &Q, int rule, float nnratio,
                   int th_dist, int hist_mode, int *slot_owner, const std::vector<int> &owner_id, int *nmatches_out) {
-    if (!g_force_host_replay && !Q.empty() && f.n > 0) {
+    if (!g_force_host_replay.load() && !Q.empty() && f.n > 0) {
         // fused device kernel (grid, candidates, distances, greedy accept loop, rotation histogram in one launch)
         const size_t nq = Q.size();
         std::vector<float> qu(nq), qv(nq), qr(nq), qa(nq);
@@ -434,6 +447,7 @@ extern "C" int orbfe_window_search(OrbfeMatcher *m, const OrbfeFrameView *f1, co
                                    const uint8_t *f1_has_mp, int window, int min_level, int max_level, float nnratio,
                                    int check_orientation, int *match21_out, int *nmatches_out) {
     if (!m || !f1 || !f2 || !f1_has_mp || !match21_out || !nmatches_out) return ORBFE_ERR_ARG;
+    if (!view_ok(*f1) || !view_ok(*f2)) return ORBFE_ERR_ARG;
     const bool bMin = min_level > 0, bMax = max_level < INT_MAX;
     std::vector<GuidedQuery> Q;
     std::vector<int> id;
@@ -458,6 +472,9 @@ extern "C" int orbfe_search_local_points(OrbfeMatcher *m, const OrbfeFrameView *
                                          float th, float nnratio, int *f_mp_inout, int *nmatches_out) {
     if (!m || !f || npts < 0 || !f_mp_inout || !nmatches_out || (npts > 0 && (!in_view || !proj_xy || !level || !view_cos || !desc)))
         return ORBFE_ERR_ARG;
+    if (!view_ok(*f)) return ORBFE_ERR_ARG;
+    for (int i = 0; i < npts; i++)
+        if (in_view[i] && (unsigned)level[i] >= (unsigned)f->nlevels) return ORBFE_ERR_ARG;  // level indexes scale_factors
     const bool bFactor = th != 1.0f;
     std::vector<GuidedQuery> Q;
     std::vector<int> id;
@@ -482,6 +499,7 @@ extern "C" int orbfe_search_by_projection_kf(OrbfeMatcher *m, const OrbfeFrameVi
     if (!m || !cur || npts < 0 || !Tcw || !cur_mp_inout || !nmatches_out ||
         (npts > 0 && (!valid || !world || !min_dist || !desc || !kf_angle)))
         return ORBFE_ERR_ARG;
+    if (!view_ok(*cur)) return ORBFE_ERR_ARG;
     float Ow[3];  // Ow = -Rcw.t()*tcw (:1628): gemm, double accumulation, alpha = -1
     for (int k = 0; k < 3; k++) {
         const double s = (double)Tcw[k] * (double)Tcw[3] + (double)Tcw[4 + k] * (double)Tcw[7] + (double)Tcw[8 + k] * (double)Tcw[11];
@@ -515,6 +533,7 @@ extern "C" int orbfe_search_by_projection_f1f2(OrbfeMatcher *m, const OrbfeFrame
                                                const uint8_t *valid1, const float *world1, const float *Tc2w, float fx, float fy,
                                                float cx, float cy, int window, float nnratio, int *f2_mp_inout, int *nmatches_out) {
     if (!m || !f1 || !f2 || !Tc2w || !f2_mp_inout || !nmatches_out || (f1->n > 0 && (!valid1 || !world1))) return ORBFE_ERR_ARG;
+    if (!view_ok(*f1) || !view_ok(*f2)) return ORBFE_ERR_ARG;
     std::vector<GuidedQuery> Q;
     std::vector<int> id;
     for (int i1 = 0; i1 < f1->n; i1++) {

@@ -21,8 +21,9 @@ def test_reference_arm_prints_one_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
-    assert cb["single_thread_value"] > 0
+    assert cb["kind"] == "port" and 1 <= cb["cores"] <= (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    assert cb["single_thread_value"] > 0 and 0 < cb["parallel_efficiency"] <= 1.5
+    assert d["config"]["frames_per_step_per_gpu"] == 256 and "semantics" in d["config"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0

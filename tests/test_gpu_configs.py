@@ -142,3 +142,18 @@ def test_config4_cross_camera_initialization(gpu_required):
     n_o, m12_o, pv_o = O.search_for_initialization(o0, o1, prev, 100, nnratio=0.9, check_orientation=True)
     assert n == n_o and np.array_equal(m12, m12_o) and np.array_equal(pv, pv_o) and n > 50
     m.close()
+
+
+@pytest.mark.parametrize("nf", [100, 60, 20])
+def test_levels_with_an_empty_cell_grid(gpu_required, nf):
+    """ORBextractor.cc:533-547: a level whose quota gives levelCols == 0 has empty cell vectors and yields no keypoints;
+    the other levels run (the reference does not fail).  nfeatures=100 empties the last level, 60 the last four, 20 all."""
+    img = textured_frame(640, 480, seed=3)
+    p = O.make_params(nf, 1.2, 8, 1, 20)
+    rc, ok, od, _ = O.extract(p, img)
+    assert rc == 0
+    ex = fe.ORBextractor(nf, 1.2, 8)
+    gk, gd = ex(img)
+    _same(gk, gd, ok, od)
+    assert len(gk) == {100: 94, 60: 41, 20: 0}[nf]
+    ex.close()

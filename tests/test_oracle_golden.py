@@ -364,3 +364,16 @@ def test_extract_composition_against_live_cv2():
             bits = (vals[:, 0] < vals[:, 1]).astype(np.uint8)
             ref = np.packbits(bits.reshape(32, 8)[:, ::-1], axis=1).ravel()
             assert np.array_equal(od[q], ref), q
+
+
+def test_levels_with_an_empty_cell_grid():
+    """ORBextractor.cc:533-547: levelCols == 0 (quota below 5*imageRatio) leaves the level's cell vectors empty; the
+    reference yields no keypoints there and keeps going.  The oracle must do the same (it used to reject the input)."""
+    from orb_slam_b200.synth import textured_frame
+    img = textured_frame(640, 480, seed=3)
+    for nf, want in ((100, [22, 18, 15, 13, 10, 9, 7, 0]), (60, [13, 11, 9, 8, 0, 0, 0, 0]), (20, [0] * 8)):
+        p = O.make_params(nf, 1.2, 8, 1, 20)
+        rc, k, d, _ = O.extract(p, img)
+        assert rc == 0 and list(np.bincount(k["octave"], minlength=8)) == want
+        g = O.cell_grid(p, 7, 640, 480, *O.level_size(p, 7, 640, 480))
+        assert g is not None

@@ -1,0 +1,191 @@
+#!/usr/bin/env python3
+"""Measurement harness for the configurations that are not the bench line (run on ONE B200 through gpurun):
+
+  --what config3   BASELINE configs[2]: 3840x2160, 4000 kp, 12 levels -- per-stage CUDA-event times of the extractor on a
+                   device-resident batch, achieved GB/s against the 130.86 MB/frame of SURVEY.md 8(d)
+  --what config5   BASELINE configs[4]: 2000 query descriptors x (ngroups keyframes x 2000 descriptors): the brute-force
+                   best/second sweep (knn2 kernel), Gpairs/s, HBM GB/s, POPC-pipe estimate
+  --what small     the latency-bound kernels once each (bow_descend, distinctive, undistort, hamming_csr, sbp single pair)
+                   so that an `ncu -k regex:` capture finds them
+
+Prints one JSON object per --what; never a bench value when run under ncu."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def level_sizes(W, H, nlevels, scale=1.2):
+    inv = np.float32(np.float32(1.0) / np.float64(np.float32(scale)))
+    s = np.float32(1.0)
+    out = []
+    for _ in range(nlevels):
+        out.append((int(np.rint(np.float32(W) * s)), int(np.rint(np.float32(H) * s))))
+        s = np.float32(s * inv)
+    return out
+
+
+def config3(args):
+    import torch
+    import orb_slam_b200 as fe
+    from orb_slam_b200.synth import textured_frame, shifted_frame
+    W, H, NF, NL = 3840, 2160, 4000, 12
+    B = args.batch
+    base = textured_frame(W, H, seed=33)
+    frames = np.stack([base] + [shifted_frame(base, 3 * i, 2 * i, seed=i) for i in range(1, B)])
+    dev = torch.device("cuda", 0)
+    d_frames = torch.from_numpy(frames).to(dev)
+    d_kps = torch.empty((B, NF, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((B, NF, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    ex = fe.ORBextractor(NF, 1.2, NL, fe.FAST_SCORE, 20)
+    stream = torch.cuda.Stream(device=dev)
+    ex.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run(n):
+        for _ in range(n):
+            ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(),
+                                    stream.cuda_stream)
+    run(args.warmup)
+    stream.synchronize()
+    ex.stage_times()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        run(args.iters)
+        e1.record(stream)
+    stream.synchronize()
+    total_ms = e0.elapsed_time(e1) / args.iters
+    acc = {}
+    for name, ms in ex.stage_times():
+        acc[name] = acc.get(name, 0.0) + ms / args.iters
+    ls = level_sizes(W, H, NL)
+    P = sum(w * h for w, h in ls)
+    reads = sum(w * h for w, h in ls[:-1]) + 2 * P
+    writes = (P - W * H) + P
+    alg = reads + writes + NF * (749 + 512) + NF * 60
+    peak = 6582.5
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    kern_ms = sum(v for k, v in acc.items() if k != "ingest")
+    out = {"what": "config3: 3840x2160, 4000 kp, 12 levels, batch %d device-resident" % B, "counts": d_cnt.cpu().numpy().tolist(),
+           "ms_per_batch": total_ms, "ms_per_frame": total_ms / B, "stage_ms_per_batch": acc,
+           "algorithmic_MB_per_frame": alg / 1e6, "P_px": P,
+           "extract_kernels": {"ms_per_batch": kern_ms, "achieved_GBs": alg * B / (kern_ms * 1e-3) / 1e9,
+                               "frac_of_measured_hbm_peak": alg * B / (kern_ms * 1e-3) / 1e9 / peak},
+           "fast_nms": {"achieved_GBs": P * B / (acc.get("fast_nms", 1e9) * 1e-3) / 1e9,
+                        "frac_of_measured_hbm_peak": P * B / (acc.get("fast_nms", 1e9) * 1e-3) / 1e9 / peak},
+           "pyramid": {"achieved_GBs": (sum(w * h for w, h in ls[:-1]) + P - W * H) * B / (acc.get("pyramid", 1e9) * 1e-3) / 1e9},
+           "Mkp_per_s": NF * B / (total_ms * 1e-3) / 1e6, "hbm_peak_GBs": peak}
+    ex.close()
+    return out
+
+
+def config5(args):
+    import torch
+    import orb_slam_b200 as fe
+    from orb_slam_b200.synth import random_descriptors
+    nq, per, ng = 2000, 2000, args.groups
+    dev = torch.device("cuda", 0)
+    q = torch.from_numpy(random_descriptors(nq, 1)).to(dev)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    db = torch.randint(0, 256, (ng * per, 32), dtype=torch.uint8, device=dev, generator=g)
+    best = torch.empty((ng, nq), dtype=torch.uint16, device=dev)
+    idx = torch.empty((ng, nq), dtype=torch.int32, device=dev)
+    second = torch.empty((ng, nq), dtype=torch.uint16, device=dev)
+    m = fe.ORBmatcher()
+    L = fe.lib()
+    stream = torch.cuda.Stream(device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run(n):
+        for _ in range(n):
+            rc = L.orbfe_knn2_groups_device(m.handle, C.c_void_p(q.data_ptr()), nq, C.c_void_p(db.data_ptr()), ng, per,
+                                            C.c_void_p(best.data_ptr()), C.c_void_p(idx.data_ptr()), C.c_void_p(second.data_ptr()),
+                                            C.c_void_p(stream.cuda_stream))
+            assert rc == 0, L.orbfe_last_error()
+    run(args.warmup)
+    stream.synchronize()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        run(args.iters)
+        e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    pairs = float(nq) * ng * per
+    # spot check against the oracle on one group (outside the timed region)
+    chk = None
+    try:
+        import oracle as O
+        gsel = ng // 2
+        bd, bi, sd = O.knn2(q.cpu().numpy(), db[gsel * per:(gsel + 1) * per].cpu().numpy())
+        chk = bool(np.array_equal(best[gsel].cpu().numpy(), bd) and np.array_equal(idx[gsel].cpu().numpy(), bi)
+                   and np.array_equal(second[gsel].cpu().numpy(), np.minimum(sd, 65535)))
+    except Exception as e:
+        chk = "oracle unavailable: %r" % e
+    out = {"what": "config5: %d queries x %d keyframes x %d descriptors, 256-bit Hamming best/second per keyframe" % (nq, ng, per),
+           "ms_per_query_set": ms, "Gpairs_per_s": pairs / (ms * 1e-3) / 1e9, "db_MB": ng * per * 32 / 1e6,
+           "hbm_GBs": (ng * per * 32 + ng * nq * 8) / (ms * 1e-3) / 1e9,
+           "word_ops_per_s_T": pairs * 8 / (ms * 1e-3) / 1e12, "oracle_spot_check": chk}
+    m.close()
+    return out
+
+
+def small(args):
+    """One call of every latency-bound kernel (for `ncu -k`), sizes of the reference's usage."""
+    import torch
+    import orb_slam_b200 as fe
+    from orb_slam_b200 import matching as M, bow as BW
+    from orb_slam_b200.synth import textured_frame, shifted_frame, random_vocabulary, random_descriptors
+    W, H = 1920, 1080
+    f0 = textured_frame(W, H, seed=9)
+    f1 = shifted_frame(f0, 5, -3, seed=1)
+    ex = fe.ORBextractor(2000, 1.2, 8)
+    (k0, d0), (k1, d1) = ex(f0), ex(f1)
+    m = fe.ORBmatcher(0.9, True)
+    v0, v1 = M.FrameView(k0, d0, W, H), M.FrameView(k1, d1, W, H)
+    world = np.empty((len(k0), 3), np.float32)
+    world[:, 0] = (k0["x"] - 960.0) / 1000.0 * 5.0; world[:, 1] = (k0["y"] - 540.0) / 1000.0 * 5.0; world[:, 2] = 5.0
+    T = np.zeros((3, 4), np.float32); T[0, 0] = T[1, 1] = T[2, 2] = 1; T[0, 3] = 5 * 5.0 / 1000.0; T[1, 3] = -3 * 5.0 / 1000.0
+    lat = []
+    for _ in range(12):
+        t0 = time.perf_counter()
+        nm, _ = M.search_by_projection_frames(m, [v1], [v0], [np.ones(len(k0), np.uint8)], [np.zeros(len(k0), np.uint8)], [world], [T],
+                                              1000.0, 1000.0, 960.0, 540.0, 15.0)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    prev = np.stack([k0["x"], k0["y"]], axis=1).astype(np.float32)
+    n8, _, _ = M.search_for_initialization(m, v0, v1, prev, 100)
+    n7, _ = M.window_search(m, v0, v1, np.ones(len(k0), np.uint8), 50)
+    out = {"sbp_single_pair_host_call_ms_median": float(np.median(lat[2:])), "sbp_matches": int(nm[0]), "init_matches": int(n8),
+           "window_matches": int(n7)}
+    try:
+        V = BW.Vocabulary(random_vocabulary(10, 4, seed=3))
+        out["bow_words"] = int(len(V.transform(d0, 2)[0][0]))
+        gp = np.arange(0, len(d0) + 1, 20, dtype=np.int32)
+        out["distinctive_groups"] = int(len(BW.distinctive_descriptors(m, d0[:gp[-1]], gp)))
+        V.close()
+    except Exception as e:
+        out["bow"] = "skipped: %r" % e
+    ex.close(); m.close()
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="config3,config5")
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--groups", type=int, default=10000)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    args = ap.parse_args()
+    for w in args.what.split(","):
+        print(json.dumps({"config3": config3, "config5": config5, "small": small}[w](args)))
