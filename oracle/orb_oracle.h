@@ -145,6 +145,8 @@ typedef struct {
 } OrbOracleFrame;
 
 /* Frame.cc:116-123 + PosInGrid :267-277 */
+/* cv::Mat `R*x + t` for CV_32F 3x3 / 3x1 (OpenCV's small-matrix gemm path: float accumulation); T = 3x4 row-major [R|t] */
+void orb_oracle_cv_Rx_plus_t(const float *T, const float *X, float out[3]);
 void orb_oracle_frame_grid(OrbOracleFrame *f);
 /* Frame::GetFeaturesInArea, Frame.cc:200-265; returns count */
 int orb_oracle_features_in_area(const OrbOracleFrame *f, float x, float y, float r, int min_level,

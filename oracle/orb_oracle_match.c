@@ -153,14 +153,10 @@ int orb_oracle_search_by_projection_ff(const OrbOracleFrame *cur, const OrbOracl
     int *cand = (int *)malloc(sizeof(int) * (size_t)(cur->n > 0 ? cur->n : 1));
     for (int i = 0; i < last->n; i++) {
         if (!last_has_mp[i] || last_outlier[i]) continue;
-        /* :1527-1528: x3Dc = Rcw*x3Dw+tcw -- cv::gemm on CV_32F accumulates in double, adds tcw in double */
+        /* :1527-1528: x3Dc = Rcw*x3Dw+tcw -- one cv::gemm(Rcw, x3Dw, 1, tcw, 1) on CV_32F 3x3 * 3x1 (see cv_Rx_plus_t) */
         const float *X = last_world + 3 * i;
         float xc3[3];
-        for (int k = 0; k < 3; k++) {
-            double s = (double)Tcw[4 * k + 0] * (double)X[0] + (double)Tcw[4 * k + 1] * (double)X[1] +
-                       (double)Tcw[4 * k + 2] * (double)X[2];
-            xc3[k] = (float)(s + (double)Tcw[4 * k + 3]);
-        }
+        orb_oracle_cv_Rx_plus_t(Tcw, X, xc3);
         const float xc = xc3[0], yc = xc3[1];
         const float invzc = (float)(1.0 / (double)xc3[2]); /* :1532 */
         const float u = fx * xc * invzc + cx;              /* :1534-1535 */
@@ -331,17 +327,23 @@ void orb_oracle_knn2(const uint8_t *q, int nq, const uint8_t *db, long ndb,
 
 /* ------------------------------------------------------------------------------------------------
  * cv::Mat float algebra used by the projecting matchers (OpenCV 2.4 core semantics):
- *   A*x + t  (MatExpr -> one cv::gemm, CV_32F): every output element is accumulated in double,
- *            the addend joins in double, then one rounding to float;
- *   -R.t()*t (gemm with alpha = -1 on the transposed left operand): double accumulate, * alpha, round;
- *   cv::norm(v) for CV_32F: sqrt of the double sum of squares.
+ *   A*x + t  (MatExpr -> ONE cv::gemm(A, x, 1, t, 1), CV_32F, 3x3 * 3x1, flags 0): matmul.cpp takes its unrolled
+ *            small-matrix branch (inner length 2..4, result as wide or as high as that length): the three products
+ *            are summed in FLOAT, left to right, and the result is (float)((double)sum*alpha + (double)t*beta).
+ *            Pinned to python-cv2's cv2.gemm by tests/test_oracle_vs_ref.py (golden vectors tests/golden/opencv_gemm.npz);
+ *            round 1 restated this from memory as a double accumulation, which cv2 contradicts on ~85 % of random inputs;
+ *   -R.t()*t (gemm with GEMM_1_T, alpha = -1): the general path, double accumulation, * alpha, round (also pinned);
+ *   cv::norm(v) for CV_32F: sqrt of the double sum of squares (also pinned).
  * ---------------------------------------------------------------------------------------------- */
-static void cv_Rx_plus_t(const float *T /*3x4 row-major [R|t]*/, const float *X, float out[3]) {
+void orb_oracle_cv_Rx_plus_t(const float *T /*3x4 row-major [R|t]*/, const float *X, float out[3]) {
     for (int k = 0; k < 3; k++) {
-        double s = (double)T[4 * k + 0] * (double)X[0] + (double)T[4 * k + 1] * (double)X[1] + (double)T[4 * k + 2] * (double)X[2];
-        out[k] = (float)(s + (double)T[4 * k + 3]);
+        float s = T[4 * k + 0] * X[0];       /* -ffp-contract=off: every product and sum individually rounded */
+        s = s + T[4 * k + 1] * X[1];
+        s = s + T[4 * k + 2] * X[2];
+        out[k] = (float)((double)s * 1.0 + (double)T[4 * k + 3] * 1.0);
     }
 }
+static void cv_Rx_plus_t(const float *T, const float *X, float out[3]) { orb_oracle_cv_Rx_plus_t(T, X, out); }
 static void cv_camera_centre(const float *T, float Ow[3]) { /* Ow = -Rcw.t()*tcw */
     for (int k = 0; k < 3; k++) {
         double s = (double)T[0 * 4 + k] * (double)T[3] + (double)T[1 * 4 + k] * (double)T[7] + (double)T[2 * 4 + k] * (double)T[11];

@@ -1,0 +1,168 @@
+"""ctypes binding of oracle/_ref/libref_orbslam.so (and libfacade_orbslam.so): the reference's OWN sources
+(/root/reference/src/ORBextractor.cc, ORBmatcher.cc, Frame.cc, KeyFrame.cc, MapPoint.cc, Map.cc, KeyFrameDatabase.cc,
+Thirdparty/DBoW2) compiled unmodified against the stand-in headers of oracle/ref_shim/ (recipe: oracle/Makefile, `make ref`).
+
+TEST INFRASTRUCTURE ONLY (like everything under oracle/): used by tests/ to validate the oracle restatement against the
+reference's real control flow, and optionally by bench.py's CPU arm.  /root/reference does not exist on the GPU box: there
+the prebuilt library travels with the snapshot and `available()` only reports whether it can be loaded."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import KP_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DIR = os.path.join(_HERE, "_ref")
+REFERENCE_ROOT = os.environ.get("ORB_REFERENCE_ROOT", "/root/reference")
+_libs = {}
+
+
+def build(force=False):
+    """Build oracle/_ref/*.so from the reference sources when they are present (this container); otherwise keep what is there."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        from . import build as build_oracle
+        build_oracle()
+        if force:
+            subprocess.call(["rm", "-rf", _DIR])
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REF=" + REFERENCE_ROOT], env={**os.environ, "CC": "gcc", "CXX": "g++"})
+    return os.path.join(_DIR, "libref_orbslam.so")
+
+
+def available(which="ref"):
+    return os.path.exists(os.path.join(_DIR, "lib%s_orbslam.so" % which))
+
+
+def lib(which="ref"):
+    """which = "ref" (reference ORBextractor.cc / ORBmatcher.cc) or "facade" (the product's facades over liborbfe.so)."""
+    if which in _libs:
+        return _libs[which]
+    path = os.path.join(_DIR, "lib%s_orbslam.so" % which)
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path, mode=os.RTLD_NOW | os.RTLD_LOCAL)
+    vp, f, i = C.c_void_p, C.c_float, C.c_int
+    L.ref_extract.argtypes = [i, f, i, i, i, vp, i, i, C.c_size_t, vp, vp, i]
+    L.ref_frame_from_image.argtypes = [vp, i, i, C.c_size_t, f, f, f, f, vp, i, f, i, i, i]
+    L.ref_frame_from_image.restype = vp
+    L.ref_frame_from_arrays.argtypes = [vp, vp, i, i, i, f, f, f, f, f, i]
+    L.ref_frame_from_arrays.restype = vp
+    L.ref_frame_free.argtypes = [vp]
+    L.ref_frame_n.argtypes = [vp]
+    L.ref_frame_get.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ref_frame_grid.argtypes = [vp, vp, vp]
+    L.ref_frame_features_in_area.argtypes = [vp, f, f, f, i, i, vp, i]
+    L.ref_search_by_projection_ff.argtypes = [vp, vp, vp, vp, vp, vp, f, f, i, vp]
+    L.ref_window_search.argtypes = [vp, vp, vp, i, i, i, f, i, vp]
+    L.ref_search_for_initialization.argtypes = [vp, vp, vp, i, f, i, vp]
+    L.ref_search_local_points.argtypes = [vp, i, vp, vp, vp, vp, vp, f, f, vp]
+    L.ref_search_by_projection_f1f2.argtypes = [vp, vp, vp, vp, vp, i, f, vp]
+    L.ref_descriptor_distance.argtypes = [vp, vp]
+    _libs[which] = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, score_type=1, fast_th=20, which="ref"):
+    """ORB_SLAM::ORBextractor(...)(img, cv::Mat(), keys, desc) of the reference build."""
+    img = np.ascontiguousarray(img, np.uint8)
+    H, W = img.shape
+    cap = max(2 * nfeatures, 16)
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = lib(which).ref_extract(nfeatures, scale_factor, nlevels, score_type, fast_th, _p(img), W, H, img.strides[0], _p(kps), _p(desc), cap)
+    assert n <= cap
+    return kps[:n].copy(), desc[:n].copy()
+
+
+class RefFrame:
+    """A real ORB_SLAM::Frame.  from_image runs the reference constructor (Frame.cc:56-125); from_arrays fills the public
+    members from given keypoints (zero distortion) and bins them with the reference's own Frame::PosInGrid."""
+
+    def __init__(self, handle, which):
+        self.h, self.which = handle, which
+        self.n = lib(which).ref_frame_n(handle)
+
+    @classmethod
+    def from_image(cls, img, fx, fy, cx, cy, dist4=None, nfeatures=1000, scale_factor=1.2, nlevels=8, score_type=1, fast_th=20, which="ref"):
+        img = np.ascontiguousarray(img, np.uint8)
+        H, W = img.shape
+        d = None if dist4 is None else np.ascontiguousarray(dist4, np.float32)
+        return cls(lib(which).ref_frame_from_image(_p(img), W, H, img.strides[0], fx, fy, cx, cy, _p(d), nfeatures, scale_factor, nlevels,
+                                                   score_type, fast_th), which)
+
+    @classmethod
+    def from_arrays(cls, kps, desc, W, H, fx=500.0, fy=500.0, cx=None, cy=None, scale_factor=1.2, nlevels=8, which="ref"):
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        cx = W / 2.0 if cx is None else cx
+        cy = H / 2.0 if cy is None else cy
+        return cls(lib(which).ref_frame_from_arrays(_p(kps), _p(desc), len(kps), W, H, fx, fy, cx, cy, scale_factor, nlevels), which)
+
+    def get(self):
+        keys, keys_un = np.zeros(self.n, KP_DTYPE), np.zeros(self.n, KP_DTYPE)
+        desc = np.zeros((self.n, 32), np.uint8)
+        bounds, ginv = np.zeros(4, np.float32), np.zeros(2, np.float32)
+        lib(self.which).ref_frame_get(self.h, _p(keys), _p(keys_un), _p(desc), _p(bounds), _p(ginv))
+        return keys, keys_un, desc, bounds, ginv
+
+    def grid(self):
+        start, items = np.zeros(64 * 48 + 1, np.int32), np.zeros(max(self.n, 1), np.int32)
+        lib(self.which).ref_frame_grid(self.h, _p(start), _p(items))
+        return start, items[:start[-1]]
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(max(self.n, 1), np.int32)
+        n = lib(self.which).ref_frame_features_in_area(self.h, x, y, r, min_level, max_level, _p(out), self.n)
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            lib(self.which).ref_frame_free(self.h)
+            self.h = None
+
+
+def search_by_projection_ff(cur, last, last_has_mp, last_outlier, last_world, Tcw, th, nnratio=0.9, check_orientation=True, cur_mp=None):
+    mp = np.full(cur.n, -1, np.int32) if cur_mp is None else np.ascontiguousarray(cur_mp, np.int32).copy()
+    has, outl = np.ascontiguousarray(last_has_mp, np.uint8), np.ascontiguousarray(last_outlier, np.uint8)
+    world, T = np.ascontiguousarray(last_world, np.float32), np.ascontiguousarray(Tcw, np.float32)
+    n = lib(cur.which).ref_search_by_projection_ff(cur.h, last.h, _p(has), _p(outl), _p(world), _p(T), th, nnratio, int(check_orientation), _p(mp))
+    return n, mp
+
+
+def window_search(f1, f2, f1_has_mp, window, min_level=-1, max_level=2 ** 31 - 1, nnratio=0.6, check_orientation=True):
+    has = np.ascontiguousarray(f1_has_mp, np.uint8)
+    m21 = np.full(max(f2.n, 1), -1, np.int32)
+    n = lib(f1.which).ref_window_search(f1.h, f2.h, _p(has), window, min_level, max_level, nnratio, int(check_orientation), _p(m21))
+    return n, m21[:f2.n]
+
+
+def search_for_initialization(f1, f2, prev_matched, window, nnratio=0.9, check_orientation=True):
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.full(max(f1.n, 1), -1, np.int32)
+    n = lib(f1.which).ref_search_for_initialization(f1.h, f2.h, _p(prev), window, nnratio, int(check_orientation), _p(m12))
+    return n, m12[:f1.n], prev
+
+
+def search_local_points(f, in_view, proj_xy, level, view_cos, desc, th, nnratio=0.8, f_mp=None):
+    mp = np.full(f.n, -1, np.int32) if f_mp is None else np.ascontiguousarray(f_mp, np.int32).copy()
+    iv, pxy = np.ascontiguousarray(in_view, np.uint8), np.ascontiguousarray(proj_xy, np.float32)
+    lv, vc, d = np.ascontiguousarray(level, np.int32), np.ascontiguousarray(view_cos, np.float32), np.ascontiguousarray(desc, np.uint8)
+    n = lib(f.which).ref_search_local_points(f.h, len(iv), _p(iv), _p(pxy), _p(lv), _p(vc), _p(d), th, nnratio, _p(mp))
+    return n, mp
+
+
+def search_by_projection_f1f2(f1, f2, valid1, world1, Tc2w, window, nnratio=0.9, f2_mp=None):
+    mp = np.full(f2.n, -1, np.int32) if f2_mp is None else np.ascontiguousarray(f2_mp, np.int32).copy()
+    v, w, T = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(world1, np.float32), np.ascontiguousarray(Tc2w, np.float32)
+    n = lib(f1.which).ref_search_by_projection_f1f2(f1.h, f2.h, _p(v), _p(w), _p(T), window, nnratio, _p(mp))
+    return n, mp
+
+
+def descriptor_distance(a, b, which="ref"):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return lib(which).ref_descriptor_distance(_p(a), _p(b))

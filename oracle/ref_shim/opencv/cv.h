@@ -1,0 +1,2 @@
+// oracle/ref_shim: every OpenCV header the reference includes resolves to the one stand-in header (test infrastructure only)
+#include "../opencv2/core/core.hpp"

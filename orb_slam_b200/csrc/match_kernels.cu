@@ -114,7 +114,7 @@ void launch_knn2_groups(const uint8_t *q, int nq, const uint8_t *db, int ngroups
 // the device.  One CTA per (Current, Last) pair:
 //   A  grid of the Current frame: counting sort of the keypoints into the 64x48 cells, ascending index
 //      inside a cell (= push_back order, Frame.cc:116-123; PosInGrid rounds with round(), :269-270);
-//   B  one thread per Last feature: project its map point with Tcw (double accumulation like cv::gemm),
+//   B  one thread per Last feature: project its map point with Tcw (float accumulation: cv::gemm's small-matrix path),
 //      enumerate the candidates exactly in GetFeaturesInArea order (ix outer, iy inner, cell order; octave
 //      and |dx|,|dy| <= r filters) and compute every 256-bit Hamming distance (XOR + POPC);
 //   C  the sequential accept loop, replayed by one warp over the precomputed (candidate, distance) lists:
@@ -186,9 +186,10 @@ __device__ __forceinline__ SbpQuery sbp_project(const SbpParams &P, const OrbfeK
     float xc3[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)T[4 * k], (double)X[0]), __dmul_rn((double)T[4 * k + 1], (double)X[1])),
-                                   __dmul_rn((double)T[4 * k + 2], (double)X[2]));
-        xc3[k] = (float)__dadd_rn(s, (double)T[4 * k + 3]);
+        // x3Dc = Rcw*x3Dw + tcw: one cv::gemm on CV_32F 3x3 * 3x1 (flags 0) = OpenCV's unrolled small-matrix path: the three
+        // products summed in FLOAT left to right, then (float)((double)sum + (double)t)  (pinned to cv2.gemm golden vectors)
+        const float s = __fadd_rn(__fadd_rn(__fmul_rn(T[4 * k], X[0]), __fmul_rn(T[4 * k + 1], X[1])), __fmul_rn(T[4 * k + 2], X[2]));
+        xc3[k] = (float)__dadd_rn((double)s, (double)T[4 * k + 3]);
     }
     const float invzc = (float)(1.0 / (double)xc3[2]);
     q.u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, xc3[0]), invzc), P.cx);

@@ -267,7 +267,8 @@ int ORBmatcher::SearchByProjection(Frame &F1, Frame &F2, int windowSize, std::ve
 // one orbfe_hamming_csr launch (or to the array-level matchers of include/orbfe_match.h), and the reference's
 // accept loop -- including its map mutations -- is replayed on the host in the original order.
 // The cv::Mat algebra of the projections is written out element-wise with OpenCV 2.4's float/double semantics
-// (gemm on CV_32F accumulates in double; Mat/scalar scales by the reciprocal).
+// (a 3x3 * 3x1 gemm with flags 0 sums in float -- OpenCV's small-matrix path, pinned to cv2.gemm -- every other product
+// in double; Mat/scalar scales by the float reciprocal).
 // =================================================================================================
 namespace ORB_SLAM {
 
@@ -290,12 +291,16 @@ std::vector<unsigned short> distances(const Csr &c, const cv::Mat &targetDesc)
     return dist;
 }
 
-// y = R*x + t for 3x3 / 3x1 CV_32F Mats (cv::gemm: double accumulation, one rounding)
+// y = R*x + t for 3x3 / 3x1 CV_32F Mats: one cv::gemm(R, x, 1, t, 1) with flags 0 -> OpenCV's unrolled small-matrix branch:
+// the three products are summed in FLOAT, left to right, then (float)(sum + t) in double (pinned to cv2.gemm golden vectors,
+// tests/golden/opencv_gemm.npz; this file is compiled with -ffp-contract=off)
 void transform(const cv::Mat &R, const cv::Mat &t, const float x[3], float y[3])
 {
     for (int k = 0; k < 3; k++) {
-        const double s = (double)R.at<float>(k, 0) * x[0] + (double)R.at<float>(k, 1) * x[1] + (double)R.at<float>(k, 2) * x[2];
-        y[k] = (float)(s + (double)t.at<float>(k, 0));
+        float s = R.at<float>(k, 0) * x[0];
+        s = s + R.at<float>(k, 1) * x[1];
+        s = s + R.at<float>(k, 2) * x[2];
+        y[k] = (float)((double)s + (double)t.at<float>(k, 0));
     }
 }
 void mat3(const cv::Mat &m, float out[3]) { for (int k = 0; k < 3; k++) out[k] = m.at<float>(k, 0); }
@@ -610,10 +615,11 @@ int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoin
     const float inv_s = (float)(1.0 / (double)s12);
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) { sR12.at<float>(r, c) = R12.at<float>(r, c) * s12; sR21.at<float>(r, c) = R12.at<float>(c, r) * inv_s; }
-    for (int k = 0; k < 3; k++) {
-        const double s = (double)sR21.at<float>(k, 0) * t12.at<float>(0, 0) + (double)sR21.at<float>(k, 1) * t12.at<float>(1, 0) +
-                         (double)sR21.at<float>(k, 2) * t12.at<float>(2, 0);
-        t21.at<float>(k, 0) = (float)(s * -1.0);
+    for (int k = 0; k < 3; k++) {   // -sR21*t12: gemm(sR21, t12, -1) with flags 0 -> the float small-matrix path, then * alpha
+        float s = sR21.at<float>(k, 0) * t12.at<float>(0, 0);
+        s = s + sR21.at<float>(k, 1) * t12.at<float>(1, 0);
+        s = s + sR21.at<float>(k, 2) * t12.at<float>(2, 0);
+        t21.at<float>(k, 0) = (float)((double)s * -1.0);
     }
     const std::vector<MapPoint *> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
     const int N1 = (int)vp1.size(), N2 = (int)vp2.size();

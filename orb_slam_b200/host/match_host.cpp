@@ -52,6 +52,18 @@ bool view_ok(const OrbfeFrameView &v) {
     return true;
 }
 
+// cv::Mat `R*x + t` of the reference's projections (CV_32F, 3x3 * 3x1, one cv::gemm with flags 0): OpenCV's unrolled
+// small-matrix branch sums the three products in FLOAT, left to right, then (float)(sum*alpha + t*beta) in double.
+// Verified against python-cv2 (tests/golden/opencv_gemm.npz); this file is compiled with -ffp-contract=off.
+inline void Rx_plus_t(const float *T, const float *X, float out[3]) {
+    for (int k = 0; k < 3; k++) {
+        float s = T[4 * k] * X[0];
+        s = s + T[4 * k + 1] * X[1];
+        s = s + T[4 * k + 2] * X[2];
+        out[k] = (float)((double)s + (double)T[4 * k + 3]);
+    }
+}
+
 struct Grid {
     std::vector<int> start;  // kGridCols*kGridRows + 1, cell id = ix*kGridRows + iy
     std::vector<int> items;
@@ -210,13 +222,10 @@ extern "C" int orbfe_search_by_projection_frames(OrbfeMatcher *m, int npairs, co
         const float *T = Tcw[j];
         for (int i = 0; i < L.n; i++) {
             if (!last_has_mp[j][i] || last_outlier[j][i]) continue;
-            // x3Dc = Rcw*x3Dw + tcw: cv::gemm on CV_32F accumulates in double and adds tcw in double (:1527-1528)
+            // x3Dc = Rcw*x3Dw + tcw (:1527-1528): one cv::gemm on CV_32F 3x3 * 3x1 -> OpenCV's small-matrix path (Rx_plus_t)
             const float *X = last_world[j] + 3 * (size_t)i;
             float xc3[3];
-            for (int k = 0; k < 3; k++) {
-                const double s = (double)T[4 * k] * (double)X[0] + (double)T[4 * k + 1] * (double)X[1] + (double)T[4 * k + 2] * (double)X[2];
-                xc3[k] = (float)(s + (double)T[4 * k + 3]);
-            }
+            Rx_plus_t(T, X, xc3);
             const float invzc = (float)(1.0 / (double)xc3[2]);
             const float u = fx * xc3[0] * invzc + cx;
             const float v = fy * xc3[1] * invzc + cy;
@@ -429,14 +438,6 @@ int guided_search(OrbfeMatcher *m, const OrbfeFrameView &f, const std::vector<Gu
     }
     *nmatches_out = nmatches;
     return ORBFE_OK;
-}
-
-// cv::Mat float algebra of the reference's projections (OpenCV 2.4 gemm on CV_32F accumulates in double)
-inline void Rx_plus_t(const float *T, const float *X, float out[3]) {
-    for (int k = 0; k < 3; k++) {
-        const double s = (double)T[4 * k] * (double)X[0] + (double)T[4 * k + 1] * (double)X[1] + (double)T[4 * k + 2] * (double)X[2];
-        out[k] = (float)(s + (double)T[4 * k + 3]);
-    }
 }
 
 }  // namespace
