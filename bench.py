@@ -4,8 +4,8 @@
 Workload (BASELINE.json configs[1]): a stream of synthetic 1920x1080 u8 frames, ORBextractor(2000, 1.2, 8,
 FAST_SCORE, 20), frame-to-frame ORBmatcher(0.9, true).SearchByProjection(Current, Last, 15).
 One "step" = `--frames` DISTINCT consecutive frames of the stream per GPU (default 256 = 531 MB of pixels, 4.2x the
-126 MB L2), processed as `--frames / --batch` batches of `--batch` frames and `--repeat` passes over them (default 2:
-a step is then 512 frame extractions + matches, ~25 ms of GPU work): extract every frame, match every frame against
+126 MB L2), processed as `--frames / --batch` batches of `--batch` frames and `--repeat` passes over them (default 4:
+a step is then 1024 frame extractions + matches, ~51 ms of GPU work, 20 steps time >= 1 s): extract every frame, match every frame against
 its predecessor.  Mkeypoints/s = keypoints extracted-and-matched / time.
 
   value : inputs already resident in HBM when the timed region starts (device API of liborbfe.so),
@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--impl", default="orbfe", choices=["orbfe", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="distinct frames per step per GPU")
     ap.add_argument("--batch", type=int, default=64, help="frames per library call")
-    ap.add_argument("--repeat", type=int, default=2, help="passes over the step's frames inside one step")
+    ap.add_argument("--repeat", type=int, default=4, help="passes over the step's frames inside one step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle cross-check of the step's results (ncu runs)")
     args = ap.parse_args()

@@ -166,3 +166,159 @@ def search_by_projection_f1f2(f1, f2, valid1, world1, Tc2w, window, nnratio=0.9,
 def descriptor_distance(a, b, which="ref"):
     a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
     return lib(which).ref_descriptor_distance(_p(a), _p(b))
+
+
+# ---- KeyFrame-level scenes (M4, M5, M9-M12, N4): thin wrappers over the id-based driver API ------------------------------
+def _bind_scene(L):
+    if getattr(L, "_scene_bound", False):
+        return L
+    vp, f, i = C.c_void_p, C.c_float, C.c_int
+    L.ref_frame_set_pose.argtypes = [vp, vp]
+    L.ref_frame_set_feature_vector.argtypes = [vp, i, vp, vp, vp]
+    L.ref_frame_set_map_points.argtypes = [vp, vp]
+    L.ref_frame_get_map_points.argtypes = [vp, vp]
+    L.ref_kf_create.argtypes = [vp, vp]
+    L.ref_kf_set_feature_vector.argtypes = [i, i, vp, vp, vp]
+    L.ref_mp_create.argtypes = [vp, vp, vp, f, f, i]
+    L.ref_mp_set_bad.argtypes = [i]
+    L.ref_kf_add_map_point.argtypes = [i, i, i]
+    L.ref_kf_get_map_points.argtypes = [i, vp]
+    L.ref_kf_n.argtypes = [i]
+    L.ref_mp_state.argtypes = [i, vp, vp, vp, i]
+    L.ref_search_by_projection_frame_kf.argtypes = [vp, i, vp, i, f, i, f, i, vp]
+    L.ref_search_by_projection_sim3.argtypes = [i, vp, vp, i, vp, i, f]
+    L.ref_search_by_bow_kf_frame.argtypes = [i, vp, f, i, vp]
+    L.ref_search_by_bow_kf_kf.argtypes = [i, i, f, i, vp]
+    L.ref_search_for_triangulation.argtypes = [i, i, vp, f, i, vp, i]
+    L.ref_search_by_sim3.argtypes = [i, i, vp, f, vp, vp, f]
+    L.ref_fuse.argtypes = [i, vp, i, f]
+    L.ref_fuse_sim3.argtypes = [i, vp, vp, i, f]
+    L.ref_mp_compute_distinctive.argtypes = [i, vp]
+    L.ref_world_counts.argtypes = [vp, vp]
+    L._scene_bound = True
+    return L
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+class Scene:
+    """Composes keyframes / map points in one build ("ref" or "facade") of the reference's map model."""
+
+    def __init__(self, which="ref"):
+        self.which = which
+        self.L = _bind_scene(lib(which))
+
+    def frame(self, kps, desc, W, H, fx, fy, cx, cy, scale_factor=1.2, nlevels=8):
+        return RefFrame.from_arrays(kps, desc, W, H, fx, fy, cx, cy, scale_factor, nlevels, which=self.which)
+
+    def keyframe(self, frame, Tcw):
+        T = _f32(Tcw)
+        return self.L.ref_kf_create(frame.h, _p(T))
+
+    def set_pose(self, frame, Tcw):
+        T = _f32(Tcw)
+        self.L.ref_frame_set_pose(frame.h, _p(T))
+
+    def map_point(self, world, desc=None, normal=None, min_dist=0.0, max_dist=0.0, ref_kf=-1):
+        w = _f32(world)
+        d = None if desc is None else np.ascontiguousarray(desc, np.uint8)
+        n = None if normal is None else _f32(normal)
+        return self.L.ref_mp_create(_p(w), _p(d), _p(n), float(min_dist), float(max_dist), int(ref_kf))
+
+    def set_bad(self, mp):
+        self.L.ref_mp_set_bad(int(mp))
+
+    def observe(self, kf, mp, idx):
+        self.L.ref_kf_add_map_point(int(kf), int(mp), int(idx))
+
+    def kf_map_points(self, kf):
+        out = np.zeros(max(self.L.ref_kf_n(kf), 1), np.int32)
+        self.L.ref_kf_get_map_points(kf, _p(out))
+        return out[:self.L.ref_kf_n(kf)]
+
+    def mp_state(self, mp, cap=64):
+        bad = C.c_int(0)
+        ok, oi = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        n = self.L.ref_mp_state(int(mp), C.byref(bad), _p(ok), _p(oi), cap)
+        return bool(bad.value), [(int(ok[k]), int(oi[k])) for k in range(min(n, cap))]
+
+    def counts(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self.L.ref_world_counts(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def set_feature_vector(self, target, fv):
+        """target: RefFrame or keyframe id; fv = (node ids, ptr, items) CSR as orb_slam_b200.matching.feature_vector() returns."""
+        ids, ptr, items = (_i32(x) for x in fv)
+        if isinstance(target, RefFrame):
+            self.L.ref_frame_set_feature_vector(target.h, len(ids), _p(ids), _p(ptr), _p(items))
+        else:
+            self.L.ref_kf_set_feature_vector(int(target), len(ids), _p(ids), _p(ptr), _p(items))
+
+    def frame_map_points(self, frame, ids=None):
+        if ids is not None:
+            a = _i32(ids)
+            self.L.ref_frame_set_map_points(frame.h, _p(a))
+            return None
+        out = np.zeros(max(frame.n, 1), np.int32)
+        self.L.ref_frame_get_map_points(frame.h, _p(out))
+        return out[:frame.n]
+
+    # M4
+    def search_by_projection_frame_kf(self, cur, kf, already_found, th, orb_dist, nnratio=0.9, check_orientation=True, cur_mp=None):
+        mp = np.full(cur.n, -1, np.int32) if cur_mp is None else _i32(cur_mp).copy()
+        af = _i32(already_found)
+        n = self.L.ref_search_by_projection_frame_kf(cur.h, int(kf), _p(af), len(af), th, int(orb_dist), nnratio, int(check_orientation), _p(mp))
+        return n, mp
+
+    # M5
+    def search_by_projection_sim3(self, kf, Scw, points, matched, th, nnratio=0.75):
+        S, pts, m = _f32(Scw), _i32(points), _i32(matched).copy()
+        n = self.L.ref_search_by_projection_sim3(int(kf), _p(S), _p(pts), len(pts), _p(m), int(th), nnratio)
+        return n, m
+
+    # M9
+    def search_by_bow_kf_frame(self, kf, frame, nnratio=0.75, check_orientation=True):
+        out = np.full(max(frame.n, 1), -1, np.int32)
+        n = self.L.ref_search_by_bow_kf_frame(int(kf), frame.h, nnratio, int(check_orientation), _p(out))
+        return n, out[:frame.n]
+
+    def search_by_bow_kf_kf(self, kf1, kf2, nnratio=0.75, check_orientation=True):
+        out = np.full(max(self.L.ref_kf_n(kf1), 1), -1, np.int32)
+        n = self.L.ref_search_by_bow_kf_kf(int(kf1), int(kf2), nnratio, int(check_orientation), _p(out))
+        return n, out[:self.L.ref_kf_n(kf1)]
+
+    # M10
+    def search_for_triangulation(self, kf1, kf2, F12, nnratio=0.6, check_orientation=True):
+        F = _f32(F12)
+        cap = self.L.ref_kf_n(kf1) + 8
+        pairs = np.zeros((cap, 2), np.int32)
+        n = self.L.ref_search_for_triangulation(int(kf1), int(kf2), _p(F), nnratio, int(check_orientation), _p(pairs), cap)
+        return n, pairs[:min(n, cap)]
+
+    # M11
+    def search_by_sim3(self, kf1, kf2, matches12, s12, R12, t12, th):
+        m, R_, t_ = _i32(matches12).copy(), _f32(R12), _f32(t12)
+        n = self.L.ref_search_by_sim3(int(kf1), int(kf2), _p(m), float(s12), _p(R_), _p(t_), float(th))
+        return n, m
+
+    # M12
+    def fuse(self, kf, points, th=2.5):
+        pts = _i32(points)
+        return self.L.ref_fuse(int(kf), _p(pts), len(pts), float(th))
+
+    def fuse_sim3(self, kf, Scw, points, th=2.5):
+        S, pts = _f32(Scw), _i32(points)
+        return self.L.ref_fuse_sim3(int(kf), _p(S), _p(pts), len(pts), float(th))
+
+    # N4
+    def compute_distinctive(self, mp):
+        d = np.zeros(32, np.uint8)
+        self.L.ref_mp_compute_distinctive(int(mp), _p(d))
+        return d

@@ -348,3 +348,189 @@ extern "C" void ref_shim_gemm(const float *A, int ar, int ac, const float *B, in
     for (int i = 0; i < n; i++) std::memcpy(out + (size_t)i * m, d.ptr(i), sizeof(float) * (size_t)m);
 }
 extern "C" double ref_shim_norm(const float *v, int n) { return cv::norm(cv::Mat(n, 1, CV_32F, const_cast<float *>(v))); }
+
+// =====================================================================================================================
+// KeyFrame-level scenes: keyframes with poses, map points with observations, FeatureVectors -- composed from Python, then
+// the KeyFrame-level matchers (M4, M5, M9-M12) run on them.  Map points and keyframes are addressed by their index in
+// the driver's lists (deterministic for a given call sequence, so the same script gives the same ids in both builds).
+// =====================================================================================================================
+namespace {
+MapPoint *mp_at(int id) { return id < 0 ? NULL : world().mps[(size_t)id]; }
+KeyFrame *kf_at(int id) { return world().kfs[(size_t)id]; }
+int mp_id(MapPoint *p) {
+    if (!p) return -1;
+    World &w = world();
+    for (size_t i = w.mps.size(); i-- > 0;) if (w.mps[i] == p) return (int)i;
+    return -2;
+}
+DBoW2::FeatureVector feature_vector(int nn, const int *ids, const int *ptr, const int *items) {
+    DBoW2::FeatureVector fv;
+    for (int k = 0; k < nn; k++)
+        for (int j = ptr[k]; j < ptr[k + 1]; j++) fv.addFeature((DBoW2::NodeId)ids[k], (unsigned int)items[j]);
+    return fv;
+}
+cv::Mat mat_from(const float *v, int r, int c) {
+    cv::Mat m(r, c, CV_32F);
+    for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) m.at<float>(i, j) = v[i * c + j];
+    return m;
+}
+}  // namespace
+
+extern "C" {
+
+int ref_world_counts(int *n_mps, int *n_kfs) { *n_mps = (int)world().mps.size(); *n_kfs = (int)world().kfs.size(); return 0; }
+
+void ref_frame_set_pose(void *f, const float *Tcw12) { static_cast<Frame *>(f)->mTcw = pose_from(Tcw12); }
+void ref_frame_set_feature_vector(void *f, int nn, const int *ids, const int *ptr, const int *items) {
+    static_cast<Frame *>(f)->mFeatVec = feature_vector(nn, ids, ptr, items);
+}
+// Frame::mvpMapPoints from map-point ids (-1 = NULL)
+void ref_frame_set_map_points(void *f, const int *ids) {
+    Frame &F = *static_cast<Frame *>(f);
+    for (int i = 0; i < F.N; i++) F.mvpMapPoints[i] = mp_at(ids[i]);
+}
+void ref_frame_get_map_points(void *f, int *ids) {
+    Frame &F = *static_cast<Frame *>(f);
+    for (int i = 0; i < F.N; i++) ids[i] = mp_id(F.mvpMapPoints[i]);
+}
+
+// KeyFrame(Frame &F, Map*, KeyFrameDatabase*) with F.mTcw = Tcw (KeyFrame.cc:30-53); returns the keyframe id
+int ref_kf_create(void *f, const float *Tcw12) {
+    Frame &F = *static_cast<Frame *>(f);
+    F.mTcw = pose_from(Tcw12);
+    World &w = world();
+    std::vector<MapPoint *> keep = F.mvpMapPoints;
+    F.mvpMapPoints = std::vector<MapPoint *>(F.N, static_cast<MapPoint *>(NULL));   // map points are attached explicitly below
+    KeyFrame *kf = new KeyFrame(F, &w.map, &w.db);
+    F.mvpMapPoints = keep;
+    w.kfs.push_back(kf);
+    return (int)w.kfs.size() - 1;
+}
+void ref_kf_set_feature_vector(int kf, int nn, const int *ids, const int *ptr, const int *items) {
+    kf_at(kf)->mFeatVec = feature_vector(nn, ids, ptr, items);
+}
+
+// a map point with everything the matchers read: position, representative descriptor (MapPoint::GetDescriptor), mean
+// viewing direction (GetNormal) and the scale-invariance distance range (GetMin/MaxDistanceInvariance)
+int ref_mp_create(const float *world3, const uint8_t *desc32, const float *normal3, float min_dist, float max_dist, int ref_kf) {
+    MapPoint *p = new_map_point(world3, ref_kf >= 0 ? kf_at(ref_kf) : NULL);
+    if (desc32) p->mDescriptor = desc_row(desc32);
+    if (normal3) p->mNormalVector = point3(normal3);
+    p->mfMinDistance = min_dist;
+    p->mfMaxDistance = max_dist;
+    return (int)world().mps.size() - 1;
+}
+void ref_mp_set_bad(int mp) { mp_at(mp)->mbBad = true; }
+// observation both ways, as LocalMapping does (pKF->AddMapPoint + pMP->AddObservation)
+void ref_kf_add_map_point(int kf, int mp, int idx) {
+    kf_at(kf)->AddMapPoint(mp_at(mp), (size_t)idx);
+    mp_at(mp)->AddObservation(kf_at(kf), (size_t)idx);
+}
+void ref_kf_get_map_points(int kf, int *ids /*N*/) {
+    const std::vector<MapPoint *> v = kf_at(kf)->GetMapPointMatches();
+    for (size_t i = 0; i < v.size(); i++) ids[i] = mp_id(v[i]);
+}
+int ref_kf_n(int kf) { return (int)kf_at(kf)->GetMapPointMatches().size(); }
+// state of a map point after a mutating call: bad flag, number of observations, and (keyframe id, feature index) pairs
+int ref_mp_state(int mp, int *is_bad, int *obs_kf /*cap*/, int *obs_idx /*cap*/, int cap) {
+    MapPoint *p = mp_at(mp);
+    *is_bad = p->isBad() ? 1 : 0;
+    const std::map<KeyFrame *, size_t> obs = p->GetObservations();
+    World &w = world();
+    std::vector<std::pair<int, int> > out;
+    for (std::map<KeyFrame *, size_t>::const_iterator it = obs.begin(); it != obs.end(); ++it) {
+        int kid = -1;
+        for (size_t k = 0; k < w.kfs.size(); k++) if (w.kfs[k] == it->first) kid = (int)k;
+        out.push_back(std::make_pair(kid, (int)it->second));
+    }
+    std::sort(out.begin(), out.end());   // the std::map is ordered by pointer value: report in keyframe-id order
+    for (size_t k = 0; k < out.size() && (int)k < cap; k++) { obs_kf[k] = out[k].first; obs_idx[k] = out[k].second; }
+    return (int)out.size();
+}
+
+// ---- M4: SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist), :1622-1746
+int ref_search_by_projection_frame_kf(void *cur, int kf, const int *already_found, int n_found, float th, int orb_dist, float nnratio,
+                                      int check_orientation, int *cur_mp_ids_inout) {
+    Frame &C = *static_cast<Frame *>(cur);
+    for (int i = 0; i < C.N; i++) C.mvpMapPoints[i] = mp_at(cur_mp_ids_inout[i]);
+    std::set<MapPoint *> found;
+    for (int k = 0; k < n_found; k++) found.insert(mp_at(already_found[k]));
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    const int n = matcher.SearchByProjection(C, kf_at(kf), found, th, orb_dist);
+    for (int i = 0; i < C.N; i++) cur_mp_ids_inout[i] = mp_id(C.mvpMapPoints[i]);
+    return n;
+}
+
+// ---- M5: SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th), :286-407
+int ref_search_by_projection_sim3(int kf, const float *Scw16, const int *points, int npts, int *matched_ids_inout, int th, float nnratio) {
+    KeyFrame *K = kf_at(kf);
+    std::vector<MapPoint *> pts(npts), matched(K->GetMapPointMatches().size());
+    for (int i = 0; i < npts; i++) pts[i] = mp_at(points[i]);
+    for (size_t i = 0; i < matched.size(); i++) matched[i] = mp_at(matched_ids_inout[i]);
+    ORBmatcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(K, mat_from(Scw16, 4, 4), pts, matched, th);
+    for (size_t i = 0; i < matched.size(); i++) matched_ids_inout[i] = mp_id(matched[i]);
+    return n;
+}
+
+// ---- M9: SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) :155-284 and SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) :715-850
+int ref_search_by_bow_kf_frame(int kf, void *f, float nnratio, int check_orientation, int *out_ids /*F.N*/) {
+    Frame &F = *static_cast<Frame *>(f);
+    std::vector<MapPoint *> m;
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    const int n = matcher.SearchByBoW(kf_at(kf), F, m);
+    for (int i = 0; i < F.N; i++) out_ids[i] = mp_id(i < (int)m.size() ? m[i] : NULL);
+    return n;
+}
+int ref_search_by_bow_kf_kf(int kf1, int kf2, float nnratio, int check_orientation, int *out_ids /*N1*/) {
+    std::vector<MapPoint *> m;
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    const int n = matcher.SearchByBoW(kf_at(kf1), kf_at(kf2), m);
+    for (size_t i = 0; i < m.size(); i++) out_ids[i] = mp_id(m[i]);
+    return n;
+}
+
+// ---- M10: SearchForTriangulation :852-1014 -------------------------------------------------------------------------
+int ref_search_for_triangulation(int kf1, int kf2, const float *F12_9, float nnratio, int check_orientation, int *pairs /*2 x cap*/, int cap) {
+    std::vector<cv::KeyPoint> k1, k2;
+    std::vector<std::pair<size_t, size_t> > pr;
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    const int n = matcher.SearchForTriangulation(kf_at(kf1), kf_at(kf2), mat_from(F12_9, 3, 3), k1, k2, pr);
+    for (size_t i = 0; i < pr.size() && (int)i < cap; i++) { pairs[2 * i] = (int)pr[i].first; pairs[2 * i + 1] = (int)pr[i].second; }
+    return n;
+}
+
+// ---- M11: SearchBySim3 :1267-1505 ----------------------------------------------------------------------------------
+int ref_search_by_sim3(int kf1, int kf2, int *matches12_ids_inout /*N1*/, float s12, const float *R12_9, const float *t12_3, float th) {
+    KeyFrame *K1 = kf_at(kf1);
+    std::vector<MapPoint *> m(K1->GetMapPointMatches().size());
+    for (size_t i = 0; i < m.size(); i++) m[i] = mp_at(matches12_ids_inout[i]);
+    ORBmatcher matcher(0.9f, true);
+    const int n = matcher.SearchBySim3(K1, kf_at(kf2), m, s12, mat_from(R12_9, 3, 3), mat_from(t12_3, 3, 1), th);
+    for (size_t i = 0; i < m.size(); i++) matches12_ids_inout[i] = mp_id(m[i]);
+    return n;
+}
+
+// ---- M12: Fuse(KeyFrame*, vector<MapPoint*>&, th) :1016-1134 and Fuse(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, th) :1136-1265
+int ref_fuse(int kf, const int *points, int npts, float th) {
+    std::vector<MapPoint *> pts(npts);
+    for (int i = 0; i < npts; i++) pts[i] = mp_at(points[i]);
+    ORBmatcher matcher(0.6f, true);
+    return matcher.Fuse(kf_at(kf), pts, th);
+}
+int ref_fuse_sim3(int kf, const float *Scw16, const int *points, int npts, float th) {
+    std::vector<MapPoint *> pts(npts);
+    for (int i = 0; i < npts; i++) pts[i] = mp_at(points[i]);
+    ORBmatcher matcher(0.6f, true);
+    return matcher.Fuse(kf_at(kf), mat_from(Scw16, 4, 4), pts, th);
+}
+
+// ---- N4: MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:185-250) on the map point's observations ----------------
+void ref_mp_compute_distinctive(int mp, uint8_t *desc_out) {
+    MapPoint *p = mp_at(mp);
+    p->ComputeDistinctiveDescriptors();
+    cv::Mat d = p->GetDescriptor();
+    std::memcpy(desc_out, d.ptr(0), 32);
+}
+
+}  // extern "C"

@@ -225,3 +225,82 @@ def test_oracle_projection_primitive_against_cv2_golden_vectors():
         out = np.zeros(3, np.float32)
         L.orb_oracle_cv_Rx_plus_t(T.ctypes.data, X.ctypes.data, out.ctypes.data)
         assert np.array_equal(out, want.reshape(3))
+
+
+# ---- KeyFrame-level matchers: the scripted scene of tests/ref_scenarios.py in the reference build vs the oracle's arrays ---
+@pytest.fixture(scope="module")
+def scene():
+    import ref_scenarios as RS
+    return RS, RS.run("ref")
+
+
+def _index_of_id(ids):
+    """map-point id (relative) -> feature index of the keyframe that owns it"""
+    m = {}
+    for i, v in enumerate(ids):
+        if v >= 0:
+            m[int(v)] = i
+    return lambda arr: np.array([m.get(int(v), -1) if v >= 0 else int(v) for v in arr], np.int32)
+
+
+def test_reloc_projection_against_keyframe(scene):
+    """M4: SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist), ORBmatcher.cc:1622-1746."""
+    RS, out = scene
+    (k1, d1), (k2, d2) = RS.features()
+    idsA, idsB, _, _ = out["ids"]
+    hasA, bad, found, occupied, world, min_dist, T_B = out["m4_inputs"]
+    to_idx = _index_of_id(idsA)
+    o2 = O.OracleFrame(k2, d2, RS.W, RS.H)
+    skip = set(int(b) for b in bad) | set(int(f) for f in found)      # isBad() or already found (:1643)
+    valid = np.array([hasA[i] and int(idsA[i]) not in skip for i in range(len(k1))])
+    pre = np.where(occupied, 7, -1).astype(np.int32)
+    for key, th, od, ori in (("m4_a", 10.0, 100, True), ("m4_b", 3.0, 64, True), ("m4_c", 10.0, 100, False)):
+        n_r, mp_r = out[key]
+        n_o, mp_o = O.search_by_projection_kf(o2, valid.astype(np.uint8), world, min_dist, d1, k1["angle"], T_B, RS.FX, RS.FY, RS.CX, RS.CY,
+                                              th, od, ori, cur_mp=pre)
+        got = to_idx(mp_r)
+        got[occupied] = 7
+        assert n_r == n_o and np.array_equal(got, mp_o), key
+        assert n_r > 200
+
+
+def test_search_by_bow_both_overloads(scene):
+    """M9: SearchByBoW(KeyFrame*, Frame&, ...) :155-284 and SearchByBoW(KeyFrame*, KeyFrame*, ...) :715-850."""
+    RS, out = scene
+    (k1, d1), (k2, d2) = RS.features()
+    idsA, idsB, _, _ = out["ids"]
+    hasA, bad, _, _, _, _, _ = out["m4_inputs"]
+    fvA, fvB = out["m9_inputs"]
+    badset = set(int(b) for b in bad)
+    valid1 = np.array([idsA[i] >= 0 and int(idsA[i]) not in badset for i in range(len(k1))], np.uint8)
+    valid2 = (idsB >= 0).astype(np.uint8)
+    a_idx, b_idx = _index_of_id(idsA), _index_of_id(idsB)
+    for key, nnr, ori in (("m9_kf_f_a", 0.75, True), ("m9_kf_f_b", 0.6, False)):
+        n_r, m_r = out[key]
+        n_o, m_o = O.search_by_bow(0, d1, valid1, k1["angle"], fvA, d2, np.ones(len(k2), np.uint8), k2["angle"], fvB, nnratio=nnr, check_orientation=ori)
+        assert n_r == n_o and np.array_equal(a_idx(m_r), m_o), key
+        assert n_r > 200
+    for key, nnr, ori in (("m9_kf_kf_a", 0.75, True), ("m9_kf_kf_b", 0.6, False)):
+        n_r, m_r = out[key]
+        n_o, m_o = O.search_by_bow(1, d1, valid1, k1["angle"], fvA, d2, valid2, k2["angle"], fvB, nnratio=nnr, check_orientation=ori)
+        assert n_r == n_o and np.array_equal(b_idx(m_r), m_o), key
+        assert n_r > 50
+
+
+def test_search_for_triangulation(scene):
+    """M10: SearchForTriangulation :852-1014 + CheckDistEpipolarLine :136-153."""
+    RS, out = scene
+    (k1, d1), (k2, d2) = RS.features()
+    idsA, idsB, _, _ = out["ids"]
+    fvA, fvB = out["m9_inputs"]
+    (F12,) = out["m10_inputs"]
+    sf = np.empty(8, np.float32)
+    O.lib().orb_oracle_frame_scale_factors(np.float32(1.2), 8, sf.ctypes.data_as(__import__("ctypes").c_void_p))
+    sigma2 = sf * sf     # Frame.cc:95-103: mvLevelSigma2[i] = mvScaleFactors[i]^2
+    for key, ori in (("m10_a", True), ("m10_b", False)):
+        n_r, pairs = out[key]
+        n_o, m12 = O.search_for_triangulation(k1, d1, (idsA >= 0).astype(np.uint8), fvA, k2, d2, (idsB >= 0).astype(np.uint8), fvB, F12, sigma2,
+                                              check_orientation=ori)
+        want = np.array([(i, m12[i]) for i in range(len(m12)) if m12[i] >= 0], np.int32).reshape(-1, 2)
+        assert n_r == n_o and np.array_equal(pairs, want), key
+        assert n_r > 20
