@@ -66,6 +66,20 @@ int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, const OrbfeKe
                                       float fx, float fy, float cx, float cy, float th, int check_orientation,
                                       int *d_cur_mp, int *d_nmatches, void *stream);
 
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:598-713; call
+ * pattern Tracking.cc:352-353 and, across cameras of a rig, BASELINE config 4) with everything device-resident: pair j
+ * searches the level-0 features of frame d_f1_idx[j] in frame d_f2_idx[j] (frames as laid out by
+ * orbfe_extract_batch_device / the rig exchange: frame f at f*cap).  d_prev_matched: npairs x cap x 2 floats, the
+ * vbPrevMatched vector of each pair (x, y per F1 feature), updated in place for the matched features (:706-710).
+ * d_match12 (npairs x cap ints) receives vnMatches12, d_nmatches[j] the return value.  The candidate walk
+ * (Frame::GetFeaturesInArea order), the skip of candidates whose current match is at least as close (:637), the
+ * re-assignment of an already matched F2 feature (:656-663) and the rotation histogram (entries of features that were
+ * unmatched later still count, as in the reference) run in one kernel, one thread block per pair.  Not synchronised. */
+int orbfe_search_for_initialization_device(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                           const int *d_counts, int cap, const int *d_f1_idx, const int *d_f2_idx,
+                                           float *d_prev_matched, float min_x, float min_y, float max_x, float max_y, int window,
+                                           float nnratio, int check_orientation, int *d_match12, int *d_nmatches, void *stream);
+
 /* Guided search (the skeleton shared by ORBmatcher.cc:49-125, :519-594, :1622-1746 and WindowSearch-style loops) with
  * EVERYTHING device-resident: job j searches frame d_frame_idx[j] (layout as above) with the explicit query windows
  * [d_q_base[j], d_q_base[j] + d_q_cnt[j]) of the concatenated arrays: centre (qu, qv), half-size qr, octave filter

@@ -39,11 +39,18 @@ ABI_SYMBOLS = [
     "orbfe_matcher_counters",
     # include/orbfe_match.h
     "orbfe_frame_scale_factors", "orbfe_search_by_projection_frames", "orbfe_search_by_projection_device", "orbfe_guided_search_device",
+    "orbfe_search_for_initialization_device",
     "orbfe_matcher_force_host_replay", "orbfe_search_local_points", "orbfe_search_by_projection_kf",
     "orbfe_search_by_projection_f1f2", "orbfe_search_by_bow", "orbfe_guided_search", "orbfe_guided_best", "orbfe_search_for_triangulation",
     "orbfe_window_search",
     "orbfe_search_for_initialization",
     "orbfe_undistort_keypoints_device", "orbfe_undistort_keypoints", "orbfe_image_bounds",
+    # include/orbfe_comm.h
+    "orbfe_comm_unique_id", "orbfe_comm_create", "orbfe_comm_destroy", "orbfe_comm_world", "orbfe_comm_rank", "orbfe_comm_nccl_version",
+    "orbfe_comm_sync", "orbfe_comm_barrier", "orbfe_allgather_desc", "orbfe_comm_broadcast", "orbfe_comm_allgather", "orbfe_shard_range",
+    "orbfe_knn2_sweep_sharded", "orbfe_rig_exchange_create", "orbfe_rig_exchange_destroy", "orbfe_extract_batch_device_exchange",
+    "orbfe_rig_exchange_wait", "orbfe_rig_exchange_release", "orbfe_rig_exchange_buffers", "orbfe_rig_exchange_check",
+    "orbfe_rig_exchange_bytes",
     # include/orbfe_bow.h
     "orbfe_vocabulary_create", "orbfe_vocabulary_destroy", "orbfe_bow_descend_device", "orbfe_bow_descend", "orbfe_bow_transform",
     "orbfe_distinctive_descriptors", "orbfe_bow_db_detect",

@@ -10,10 +10,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liborbfe.so")
-SOURCES = ["orbfe_api.cu", "extract_kernels.cu", "match_kernels.cu", "bow_kernels.cu",
+SOURCES = ["orbfe_api.cu", "extract_kernels.cu", "match_kernels.cu", "bow_kernels.cu", "comm.cu",
            os.path.join("..", "host", "match_host.cpp"), os.path.join("..", "host", "bow_host.cpp")]
 DEPS = SOURCES + ["orbfe_internal.h", os.path.join("..", "..", "include", "orbfe.h"),
-                  os.path.join("..", "..", "include", "orbfe_match.h"), os.path.join("..", "..", "include", "orbfe_bow.h"),
+                  os.path.join("..", "..", "include", "orbfe_match.h"), os.path.join("..", "..", "include", "orbfe_bow.h"), os.path.join("..", "..", "include", "orbfe_comm.h"),
                   os.path.join("..", "..", "include", "orbfe_brief_pattern.inc")]
 
 NVCC_FLAGS = [
@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
     "-cudart", "static",
     "-shared",
+    "-ldl",
 ]
 
 

@@ -1247,10 +1247,15 @@ __device__ __forceinline__ int brief_byte_fused(const __half2 *pp, float a, floa
     return val;
 }
 
-__global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
-                                                             const int8_t *__restrict__ g_pattern,
-                                                             OrbfeKeyPoint *__restrict__ out_kps,
-                                                             uint8_t *__restrict__ out_desc, int *__restrict__ out_counts, int f0) {
+// PEERS: the exchange of a camera rig fused into the kernel (include/orbfe_comm.h): every keypoint / descriptor / count is
+// stored into slot [rank] of EVERY rank's gather buffer (st.global on peer pointers over NVLink) instead of one local
+// output, and the last thread block to finish publishes the epoch to every rank's flag word (release at system scope).
+template <bool PEERS>
+__device__ __forceinline__ void describe_fused_body(const PlanDev *__restrict__ plan, const WorkDev &wk,
+                                                    const int8_t *__restrict__ g_pattern,
+                                                    OrbfeKeyPoint *__restrict__ out_kps,
+                                                    uint8_t *__restrict__ out_desc, int *__restrict__ out_counts, int f0,
+                                                    const PeerOut &po) {
     // the pattern as fp16 (x, y) pairs: small integers are exact, and fp16 -> fp32 is a full-rate conversion
     __shared__ __align__(16) __half2 pat[512];
     __shared__ __align__(16) uint32_t patch[8 * DF_WARP_WORDS];
@@ -1268,7 +1273,8 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int tot = 0;
         for (int k = 0; k < nlev; k++) tot += lcnt[k];
-        out_counts[f] = tot;
+        if (PEERS) { for (int p = 0; p < po.n; p++) po.counts[p][f] = tot; }
+        else out_counts[f] = tot;
     }
     if (slot >= plan->nfeatures) return;
     // level of this slot and its position in the frame's output, warp-cooperatively: lane k holds level k's slot
@@ -1402,7 +1408,10 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 2) << 16;
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 3) << 24;
     const size_t o = (size_t)f * plan->nfeatures + out_idx;
-    if ((lane & 3) == 0) reinterpret_cast<uint32_t *>(out_desc + o * 32)[lane >> 2] = word;
+    if ((lane & 3) == 0) {
+        if (PEERS) { for (int p = 0; p < po.n; p++) reinterpret_cast<uint32_t *>(po.desc[p] + o * 32)[lane >> 2] = word; }
+        else reinterpret_cast<uint32_t *>(out_desc + o * 32)[lane >> 2] = word;
+    }
     if (lane == 0) {
         OrbfeKeyPoint r;
         r.x = l ? __fmul_rn((float)x, L.scale) : (float)x;  // :768-775
@@ -1412,14 +1421,45 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
         r.response = wk.cand_keys64 ? __int_as_float(kp.y) : (float)kp.y;  // Harris response or FAST score
         r.octave = l;
         r.class_id = -1;
-        out_kps[o] = r;
+        if (PEERS) { for (int p = 0; p < po.n; p++) po.kps[p][o] = r; }
+        else out_kps[o] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
+                                                             const int8_t *__restrict__ g_pattern,
+                                                             OrbfeKeyPoint *__restrict__ out_kps,
+                                                             uint8_t *__restrict__ out_desc, int *__restrict__ out_counts, int f0) {
+    PeerOut none;
+    none.n = 0;
+    describe_fused_body<false>(plan, wk, g_pattern, out_kps, out_desc, out_counts, f0, none);
+}
+
+__global__ void __launch_bounds__(256) describe_fused_exchange_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
+                                                                      const int8_t *__restrict__ g_pattern, int f0,
+                                                                      const __grid_constant__ PeerOut po) {
+    describe_fused_body<true>(plan, wk, g_pattern, nullptr, nullptr, nullptr, f0, po);
+    // ---- publish: every thread's remote stores are ordered before the block's arrival, the last block to arrive
+    //      (all others' stores are therefore visible system-wide) writes the epoch into every rank's flag word ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned prev = atomicAdd(po.done, 1u);
+        if (prev == total - 1) {
+            __threadfence_system();
+            *po.done = 0;   // ready for the next launch (stream order separates them)
+            for (int p = 0; p < po.n; p++)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(po.flag[p]), "r"(po.epoch) : "memory");
+        }
     }
 }
 
 void launch_describe_fused(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, const int8_t *d_pattern,
-                           OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s) {
+                           OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s, const PeerOut *peers) {
     dim3 grid((hp.nfeatures + 7) / 8, nf);
     if (grid.x == 0) grid.x = 1;
+    if (peers && peers->n > 0) { describe_fused_exchange_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, f0, *peers); return; }
     describe_fused_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, d_kps, d_desc, d_counts, f0);
 }
 

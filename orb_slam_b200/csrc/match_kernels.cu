@@ -235,7 +235,14 @@ __device__ __forceinline__ bool octave_ok(int o, int lo, int hi) {
     return (lo == -1 && hi == -1) || (o >= lo && o <= hi);
 }
 
-template <bool EXPLICIT>
+// MODE 0: SearchByProjection(Frame, Frame) -- queries = projections of the Last frame's map points;
+// MODE 1: guided search -- explicit query windows (M3, M4, M6, M7 and the KeyFrame-level routines);
+// MODE 2: SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:598-713) -- queries = the
+//         level-0 features of F1 (= frame last_idx[pair]) searched in F2 (= frame cur_idx[pair]) inside a `th`-pixel window
+//         around their previously matched position (`world` holds vbPrevMatched, 2 floats per F1 feature, updated in place,
+//         :708-710); an F2 feature can be RE-assigned to a later, closer F1 feature (:637, :656-663); cur_mp receives
+//         vnMatches12 (per F1 feature).
+template <int MODE>
 __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, const OrbfeKeyPoint *__restrict__ kps,
                                                                  const uint8_t *__restrict__ desc, const int *__restrict__ counts,
                                                                  const int *__restrict__ cur_idx, const int *__restrict__ last_idx,
@@ -254,6 +261,10 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     uint16_t *items = reinterpret_cast<uint16_t *>(taken + (cap + 31) / 32);  // [cap]
     uint8_t *newbin = reinterpret_cast<uint8_t *>(items + cap);      // [cap]
     uint8_t *koct = newbin + cap;                                    // [cap] Current keypoint octave
+    uint16_t *mdist = reinterpret_cast<uint16_t *>(koct + cap + (cap & 1));   // MODE 2: [cap] vMatchedDistance (0xFFFF = INT_MAX)
+    uint16_t *owner = mdist + cap;                                   // MODE 2: [cap] vnMatches21 (0xFFFF = -1)
+    constexpr bool EXPLICIT = MODE == 1;
+    constexpr bool INIT = MODE == 2;
     __shared__ int s_warp[SBP_WARPS], s_hist[32], s_keep[3], s_removed, s_nm;
     uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem + P.smem_fixed);  // entry staging area
 
@@ -267,9 +278,10 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     const uint4 *__restrict__ dc = reinterpret_cast<const uint4 *>(desc + (size_t)fc * cap * 32);
     const uint4 *__restrict__ dl = EXPLICIT ? reinterpret_cast<const uint4 *>(GQ.qdesc + (size_t)qb * 32)
                                             : reinterpret_cast<const uint4 *>(desc + (size_t)fl * cap * 32);
-    const float *__restrict__ wl = EXPLICIT ? nullptr : world + (size_t)fl * cap * 3;
+    const float *__restrict__ wl = EXPLICIT ? nullptr : INIT ? world + (size_t)pair * cap * 2 /* vbPrevMatched of this pair */
+                                                            : world + (size_t)fl * cap * 3;
     const uint8_t *__restrict__ fll = EXPLICIT ? nullptr : flags + (size_t)fl * cap;
-    const float *__restrict__ T = EXPLICIT ? nullptr : Tcw + (size_t)pair * 12;
+    const float *__restrict__ T = (EXPLICIT || INIT) ? nullptr : Tcw + (size_t)pair * 12;
     int *__restrict__ mp = cur_mp + (size_t)pair * cap;
     const int tid = threadIdx.x;
     // query q of this job (projection of a Last feature, or an explicit (u, v, r, lo, hi) window)
@@ -278,6 +290,15 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
             SbpQuery Q;
             Q.u = GQ.qu[qb + q]; Q.v = GQ.qv[qb + q]; Q.r = GQ.qr[qb + q];
             Q.lo = GQ.qlo[qb + q]; Q.hi = GQ.qhi[qb + q];
+            Q.ok = sbp_cell_range(P, Q);
+            return Q;
+        }
+        if (INIT) {   // :609-618: level-0 features only, window around the previously matched position, same level
+            SbpQuery Q;
+            Q.ok = false;
+            if (kl[q].octave > 0) return Q;
+            Q.u = wl[2 * q]; Q.v = wl[2 * q + 1]; Q.r = P.th;
+            Q.lo = 0; Q.hi = 0;
             Q.ok = sbp_cell_range(P, Q);
             return Q;
         }
@@ -300,7 +321,11 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
         if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS) cell = (int)px * SBP_GROWS + (int)py;
         newbin[i] = 0xFF;
         if (cell >= 0) atomicAdd(&cell_cur[cell], 1);
-        if (mp[i] >= 0) atomicOr(&taken[i >> 5], 1u << (i & 31));  // slot occupied on entry (:1562)
+        if (INIT) { mdist[i] = 0xFFFF; owner[i] = 0xFFFF; }
+        else if (mp[i] >= 0) atomicOr(&taken[i >> 5], 1u << (i & 31));  // slot occupied on entry (:1562)
+    }
+    if (INIT) {
+        for (int i = tid; i < cap; i += SBP_THREADS) { mp[i] = -1; if (i >= nc) newbin[i] = 0xFF; }   // vnMatches12 = -1 (:601); newbin = rotation bin per F1 feature
     }
     __syncthreads();
     {   // exclusive scan of the 3072 cell counts: 3 cells per thread
@@ -340,7 +365,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     for (int it = 0; it < nq_iter; it++) {
         const int q = it * SBP_THREADS + tid;
         int cnt = 0;
-        if (q < nl && (EXPLICIT || fll[q])) {
+        if (q < nl && (EXPLICIT || INIT || fll[q])) {
             const SbpQuery Q = get_query(q);
             if (Q.ok) {
                 for (int ix = Q.x0; ix <= Q.x1; ix++) {
@@ -400,7 +425,53 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
             // prefetch query q+1
             const int nb = e, ne = (q + 1 < nl) ? q_off[q + 2] : e;
             const uint32_t nen = (q + 1 < nl && nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
-            if (b != e) {
+            if (INIT && b != e) {
+                // best / second over the candidates whose current match is worse than this distance (:637); strict-< update
+                // order = first minimum wins, the second best is the minimum over the remaining candidates
+                uint32_t best = 0xFFFFFFFFu, cur = en;
+                for (int p0 = b; p0 < e; p0 += 32) {
+                    const int p = p0 + lane;
+                    if (p0 != b) cur = (p < e) ? ent[p] : 0xFFFFFFFFu;
+                    uint32_t key = 0xFFFFFFFFu;
+                    if (p < e && (uint32_t)mdist[cur & 0xFFFF] > (cur >> 16)) key = (cur & 0xFFFF0000u) | (uint32_t)(p - b);
+                    best = min(best, __reduce_min_sync(0xffffffffu, key));
+                }
+                if (best != 0xFFFFFFFFu) {
+                    const int bpos = (int)(best & 0xFFFF), bd = (int)(best >> 16);
+                    uint32_t second = 0xFFFFFFFFu;
+                    for (int p0 = b; p0 < e; p0 += 32) {
+                        const int p = p0 + lane;
+                        uint32_t key = 0xFFFFFFFFu;
+                        if (p < e && p - b != bpos) {
+                            const uint32_t c2 = ent[p];
+                            if ((uint32_t)mdist[c2 & 0xFFFF] > (c2 >> 16)) key = c2 >> 16;
+                        }
+                        second = min(second, __reduce_min_sync(0xffffffffu, key));
+                    }
+                    const float sd = second == 0xFFFFFFFFu ? 2147483648.0f : (float)(int)second;   // (float)INT_MAX
+                    if (bd <= 50 /* TH_LOW, :652 */ && (float)bd < __fmul_rn(sd, P.nnratio)) {
+                        const int i2 = (int)(ent[b + bpos] & 0xFFFF);
+                        const int prev_owner = owner[i2];
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (prev_owner != 0xFFFF) mp[prev_owner] = -1;   // :656-660 re-assignment
+                            mp[q] = i2;
+                            owner[i2] = (uint16_t)q;
+                            mdist[i2] = (uint16_t)bd;
+                            if (P.check_ori) {   // :666-676; the histogram keeps entries of features that get unmatched later
+                                float rot = __fsub_rn(kl[q].angle, kc[i2].angle);
+                                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                                int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+                                if (bin == 30) bin = 0;
+                                newbin[q] = (uint8_t)bin;
+                                s_hist[bin]++;
+                            }
+                        }
+                        nm += prev_owner != 0xFFFF ? 0 : 1;
+                        __syncwarp();
+                    }
+                }
+            } else if (b != e) {
                 uint32_t best = 0xFFFFFFFFu;  // dist << 16 | position: strict-< argmin, first minimum wins
                 uint32_t cur = en;
                 for (int p0 = b; p0 < e; p0 += 32) {
@@ -457,6 +528,36 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     __syncthreads();
 
     // ---- D: rotation consistency ----
+    if (INIT) {
+        if (P.check_ori) {
+            if (tid == 0) {
+                int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+                for (int i = 0; i < 30; i++) {
+                    const int s = s_hist[i];
+                    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                    else if (s > max3) { max3 = s; ind3 = i; }
+                }
+                if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+                else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+                s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+            }
+            __syncthreads();
+            int removed = 0;
+            for (int q = tid; q < nl; q += SBP_THREADS) {   // :691-702: only features that are still matched lose their match
+                const int bb = newbin[q];
+                if (bb != 0xFF && bb != s_keep[0] && bb != s_keep[1] && bb != s_keep[2] && mp[q] >= 0) { mp[q] = -1; removed++; }
+            }
+            if (removed) atomicAdd(&s_removed, removed);
+            __syncthreads();
+        }
+        // :706-710 vbPrevMatched[i1] = F2.mvKeysUn[vnMatches12[i1]].pt
+        float *wout = const_cast<float *>(wl);
+        for (int q = tid; q < nl; q += SBP_THREADS)
+            if (mp[q] >= 0) { wout[2 * q] = kx[mp[q]]; wout[2 * q + 1] = ky[mp[q]]; }
+        if (tid == 0) nmatches[pair] = s_nm - s_removed;
+        return;
+    }
     if (P.check_ori) {
         // rotation histogram of the new matches (:1583-1590), in parallel: bin = round((aLast - aCur [+360]) / 30)
         for (int i = tid; i < nc; i += SBP_THREADS) {
@@ -496,7 +597,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
 size_t sbp_smem_fixed_bytes(int cap, int qcap) {
     size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)qcap + 1) +
                2 * sizeof(float) * (size_t)cap + sizeof(uint32_t) * (((size_t)cap + 31) / 32) + sizeof(uint16_t) * (size_t)cap +
-               2 * (size_t)cap;
+               2 * (size_t)cap + ((size_t)cap & 1) + 2 * sizeof(uint16_t) * (size_t)cap /* MODE 2: matched distance + owner */;
     return (b + 15) / 16 * 16;
 }
 
@@ -504,13 +605,28 @@ int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const O
                       const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
                       const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s) {
     if (smem_bytes > 48 * 1024) {  // per device/context attribute: set on every call (cheap), never cached process-wide
-        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return (int)e;
     }
     GuidedQueries none;
     memset(&none, 0, sizeof(none));
-    sbp_device_kernel<false><<<npairs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, cur_idx, last_idx, world, flags, Tcw, none,
+    sbp_device_kernel<0><<<npairs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, cur_idx, last_idx, world, flags, Tcw, none,
                                                              scratch, cur_mp, nmatches, err);
+    return 0;
+}
+
+int launch_init_device(const SbpParams &P, size_t smem_bytes, int npairs, const OrbfeKeyPoint *kps, const uint8_t *desc,
+                       const int *counts, const int *f1_idx, const int *f2_idx, float *prev_matched, uint32_t *scratch, int *match12,
+                       int *nmatches, int *err, cudaStream_t s) {
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    GuidedQueries none;
+    memset(&none, 0, sizeof(none));
+    // cur = F2 (the searched frame), last = F1 (the querying frame)
+    sbp_device_kernel<2><<<npairs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, f2_idx, f1_idx, prev_matched, nullptr, nullptr, none,
+                                                            scratch, match12, nmatches, err);
     return 0;
 }
 
@@ -519,12 +635,12 @@ int launch_guided_device(const SbpParams &P, size_t smem_bytes, int njobs, const
                          const int *qlo, const int *qhi, const uint8_t *qdesc, const float *qangle, const int *q_base,
                          const int *q_cnt, uint32_t *scratch, int *slot_owner, int *nmatches, int *err, cudaStream_t s) {
     if (smem_bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(sbp_device_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return (int)e;
     }
     GuidedQueries G;
     G.qu = qu; G.qv = qv; G.qr = qr; G.qangle = qangle; G.qlo = qlo; G.qhi = qhi; G.qdesc = qdesc; G.q_base = q_base; G.q_cnt = q_cnt;
-    sbp_device_kernel<true><<<njobs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, frame_idx, nullptr, nullptr, nullptr, nullptr, G,
+    sbp_device_kernel<1><<<njobs, SBP_THREADS, smem_bytes, s>>>(P, kps, desc, counts, frame_idx, nullptr, nullptr, nullptr, nullptr, G,
                                                             scratch, slot_owner, nmatches, err);
     return 0;
 }

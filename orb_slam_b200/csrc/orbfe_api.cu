@@ -537,7 +537,7 @@ static void enqueue_pyramid(OrbfeExtractor *ex, int f0, int nf, cudaStream_t s) 
 }
 
 static int enqueue_pipeline(OrbfeExtractor *ex, int f0, int nf, OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts,
-                            cudaStream_t s, bool with_pyramid = true) {
+                            cudaStream_t s, bool with_pyramid = true, const PeerOut *peers = nullptr) {
     const PlanDev &hp = ex->hplan;
     int launches = 0;
     if (with_pyramid) enqueue_pyramid(ex, f0, nf, s);
@@ -555,7 +555,7 @@ static int enqueue_pipeline(OrbfeExtractor *ex, int f0, int nf, OrbfeKeyPoint *d
         stage_mark(ex, s, "blur7");
         launch_describe(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, f0, nf, s); launches++;
     } else {
-        launch_describe_fused(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, f0, nf, s); launches++;
+        launch_describe_fused(ex->dplan, hp, ex->work, ex->d_pattern, d_kps, d_desc, d_counts, f0, nf, s, peers); launches++;
     }
     stage_mark(ex, s, "describe");
     CU_TRY(cudaGetLastError());
@@ -611,6 +611,34 @@ extern "C" int orbfe_extract_batch_device(OrbfeExtractor *ex, const uint8_t *d_i
     rc = zero_counters(ex, s);
     if (rc) return rc;
     return enqueue_pipeline(ex, 0, batch, d_kps, d_desc, d_counts, s);
+}
+
+// The device-resident extract with the descriptor kernel's outputs redirected into the gather buffers of a rig exchange
+// (include/orbfe_comm.h; called by orbfe_extract_batch_device_exchange in comm.cu)
+int orbfe_extract_batch_device_peers(OrbfeExtractor *ex, const uint8_t *d_imgs, int width, int height, size_t stride, size_t frame_stride,
+                                     int batch, const PeerOut &po, int cap, void *stream) {
+    if (!ex || !d_imgs) return fail(ORBFE_ERR_ARG, "NULL argument");
+    if (width <= 0 || height <= 0 || batch <= 0 || stride < (size_t)width) return fail(ORBFE_ERR_ARG, "bad geometry");
+    if (ex->blur_planes) return fail(ORBFE_ERR_UNSUPPORTED, "the fused exchange needs the fused descriptor kernel (ORBFE_BLUR_PLANES is set)");
+    CU_TRY(cudaSetDevice(ex->device));
+    int rc = build_plan(ex, width, height, batch);
+    if (rc) return rc;
+    if (cap != ex->hplan.nfeatures) return fail(ORBFE_ERR_ARG, "exchange capacity %d != keypoint slots per frame %d", cap, ex->hplan.nfeatures);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ex->stream;
+    const LevelDev &L0 = ex->hplan.lv[0];
+    profiling_begin(ex, s);
+    if (frame_stride == stride * (size_t)height && L0.plane == (size_t)L0.pitch * height) {
+        CU_TRY(cudaMemcpy2DAsync(L0.pyr, L0.pitch, d_imgs, stride, width, (size_t)height * batch, cudaMemcpyDeviceToDevice, s));
+    } else {
+        for (int f = 0; f < batch; f++)
+            CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, d_imgs + f * frame_stride, stride, width, height,
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+    stage_mark(ex, s, "ingest");
+    ex->last_launches = 0;
+    rc = zero_counters(ex, s);
+    if (rc) return rc;
+    return enqueue_pipeline(ex, 0, batch, nullptr, nullptr, nullptr, s, true, &po);
 }
 
 extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int width, int height, size_t stride,
@@ -896,6 +924,52 @@ extern "C" int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, co
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
     int rc = launch_sbp_device(P, total, npairs, d_kps, d_desc, d_counts, d_cur_idx, d_last_idx, d_world, d_flags, d_Tcw,
                                m->scratch, d_cur_mp, d_nmatches, m->d_err, s);
+    if (rc) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)rc));
+    CU_TRY(cudaGetLastError());
+    m->launches += 1;
+    return ORBFE_OK;
+}
+
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) for `npairs` (F1, F2) pairs, device-resident
+// (ORBmatcher.cc:598-713; the fused kernel's MODE 2).  d_prev_matched: npairs x cap x 2 floats, in/out.
+extern "C" int orbfe_search_for_initialization_device(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                                      const int *d_counts, int cap, const int *d_f1_idx, const int *d_f2_idx,
+                                                      float *d_prev_matched, float min_x, float min_y, float max_x, float max_y,
+                                                      int window, float nnratio, int check_orientation, int *d_match12,
+                                                      int *d_nmatches, void *stream) {
+    if (!m || npairs < 0 || cap < 1 || cap > 65534 || window < 0) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (npairs == 0) return ORBFE_OK;
+    if (!d_kps || !d_desc || !d_counts || !d_f1_idx || !d_f2_idx || !d_prev_matched || !d_match12 || !d_nmatches)
+        return fail(ORBFE_ERR_ARG, "NULL argument");
+    if (!(max_x > min_x) || !(max_y > min_y)) return fail(ORBFE_ERR_ARG, "bad image bounds");
+    CU_TRY(cudaSetDevice(m->device));
+    SbpParams P;
+    memset(&P, 0, sizeof(P));
+    P.min_x = min_x; P.min_y = min_y; P.max_x = max_x; P.max_y = max_y;
+    P.gw = (float)64 / (float)(max_x - min_x);   // Frame.cc:77
+    P.gh = (float)48 / (float)(max_y - min_y);   // Frame.cc:78
+    P.th = (float)window;                        // GetFeaturesInArea(x, y, windowSize, 0, 0), :618
+    P.nlevels = 1; P.cap = cap; P.check_ori = check_orientation ? 1 : 0;
+    P.qcap = cap; P.rule = 3; P.th_dist = 50 /* TH_LOW, :652 */; P.nnratio = nnratio;
+    // a 100-px window at 720p holds a few hundred level-0 candidates per query: entries live in the global scratch
+    const size_t per_pair = (size_t)256 * cap;
+    if (per_pair > (size_t)INT_MAX) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large", cap);
+    P.scratch_per_pair = (int)per_pair;
+    const size_t fixed = sbp_smem_fixed_bytes(cap, cap);
+    const size_t total = std::max<size_t>(fixed + 16 * 1024, 100 * 1024);
+    if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large for the device matcher", cap);
+    P.smem_fixed = (int)fixed;
+    P.smem_entries = (int)((total - fixed) / sizeof(uint32_t));
+    const size_t need = (size_t)npairs * P.scratch_per_pair;
+    if (m->scratch_entries < need) {
+        if (m->scratch) cudaFree(m->scratch);
+        m->scratch = nullptr; m->scratch_entries = 0;
+        CU_TRY(cudaMalloc((void **)&m->scratch, need * sizeof(uint32_t)));
+        m->scratch_entries = need;
+    }
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    int rc = launch_init_device(P, total, npairs, d_kps, d_desc, d_counts, d_f1_idx, d_f2_idx, d_prev_matched, m->scratch, d_match12,
+                                d_nmatches, m->d_err, s);
     if (rc) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString((cudaError_t)rc));
     CU_TRY(cudaGetLastError());
     m->launches += 1;

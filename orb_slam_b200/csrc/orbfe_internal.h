@@ -86,6 +86,20 @@ struct WorkDev {
     int *err_flag;                    // [1]
 };
 
+// Destinations of the descriptor kernel's outputs when the exchange is fused into it (include/orbfe_comm.h, OrbfeRigExchange):
+// slot [rank] of every rank's gather buffer (peer pointers over NVLink, own buffer included), plus the flag words the
+// kernel's last thread block publishes the epoch to.  n == 0: plain single destination (the kernel's pointer arguments).
+#define ORBFE_MAX_PEERS 16
+struct PeerOut {
+    int n;
+    unsigned epoch;
+    unsigned *done;                          // local counter of finished thread blocks (reset by the last one)
+    OrbfeKeyPoint *kps[ORBFE_MAX_PEERS];     // [nslots x nfeatures] of this rank inside peer p's buffer
+    uint8_t *desc[ORBFE_MAX_PEERS];
+    int *counts[ORBFE_MAX_PEERS];
+    unsigned *flag[ORBFE_MAX_PEERS];         // &flags[rank] in peer p's memory
+};
+
 // ---- launchers (extract_kernels.cu): every launch covers frames [f0, f0 + nf) of the batch ----
 void launch_resize_level(const PlanDev *d_plan, const PlanDev &h_plan, int level, int f0, int nf, cudaStream_t s);
 void launch_fast_nms(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, int f0, int nf, cudaStream_t s);
@@ -96,7 +110,7 @@ void launch_blur(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, int f0
 void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, const int8_t *d_pattern,
                      OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s);
 void launch_describe_fused(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, const int8_t *d_pattern,
-                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s);
+                     OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s, const PeerOut *peers = nullptr);
 int fast_tma_setup();
 int level_select_smem_bytes(int max_kept);
 int level_select_harris_smem_bytes(int max_kept);
@@ -121,6 +135,9 @@ int launch_guided_device(const SbpParams &P, size_t smem_bytes, int njobs, const
                          const int *counts, const int *frame_idx, const float *qu, const float *qv, const float *qr,
                          const int *qlo, const int *qhi, const uint8_t *qdesc, const float *qangle, const int *q_base,
                          const int *q_cnt, uint32_t *scratch, int *slot_owner, int *nmatches, int *err, cudaStream_t s);
+int launch_init_device(const SbpParams &P, size_t smem_bytes, int npairs, const OrbfeKeyPoint *kps, const uint8_t *desc,
+                       const int *counts, const int *f1_idx, const int *f2_idx, float *prev_matched, uint32_t *scratch, int *match12,
+                       int *nmatches, int *err, cudaStream_t s);
 int launch_sbp_device(const SbpParams &P, size_t smem_bytes, int npairs, const OrbfeKeyPoint *kps, const uint8_t *desc,
                       const int *counts, const int *cur_idx, const int *last_idx, const float *world, const uint8_t *flags,
                       const float *Tcw, uint32_t *scratch, int *cur_mp, int *nmatches, int *err, cudaStream_t s);

@@ -66,13 +66,16 @@ bool ok(int rc) {
     return false;
 }
 
-// contiguous copy of a frame's descriptors (cv::Mat rows may be strided)
+// contiguous view of a descriptor matrix (cv::Mat rows may be strided).  Holds a reference on the Mat's buffer: KeyFrame::
+// GetDescriptors() returns a CLONE (KeyFrame.cc), i.e. a temporary whose storage would otherwise die with the full expression
+// -- found by tests/test_gpu_facade_vs_ref.py, which runs this file against the reference's real KeyFrame.cc.
 struct DescBuf {
+    cv::Mat keep;
     std::vector<unsigned char> own;
     const unsigned char *ptr;
-    explicit DescBuf(const cv::Mat &d) : ptr(NULL) {
+    explicit DescBuf(const cv::Mat &d) : keep(d), ptr(NULL) {
         if (d.empty()) return;
-        if (d.isContinuous()) { ptr = d.ptr(0); return; }
+        if (d.isContinuous()) { ptr = keep.ptr(0); return; }
         own.resize((size_t)d.rows * 32);
         for (int i = 0; i < d.rows; i++) std::memcpy(&own[(size_t)i * 32], d.ptr(i), 32);
         ptr = &own[0];

@@ -40,6 +40,8 @@ def _bind():
     L.orbfe_guided_search_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int,
                                              C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
                                              vp, vp, vp]
+    L.orbfe_search_for_initialization_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_float, C.c_float,
+                                                         C.c_float, C.c_int, C.c_float, C.c_int, vp, vp, vp]
     L.orbfe_undistort_keypoints_device.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     L.orbfe_undistort_keypoints.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     L.orbfe_image_bounds.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
@@ -288,3 +290,14 @@ def image_bounds(matcher: ORBmatcher, cols, rows, fx, fy, cx, cy, dist):
     b = np.zeros(4, np.float32)
     _check(L.orbfe_image_bounds(matcher.handle, cols, rows, fx, fy, cx, cy, _p(d), _p(b)))
     return b
+
+
+def search_for_initialization_device(matcher: ORBmatcher, npairs, d_kps, d_desc, d_counts, cap, d_f1_idx, d_f2_idx, d_prev_matched,
+                                     width, height, window, d_match12, d_nmatches, stream=0):
+    """orbfe_search_for_initialization_device on raw device addresses (ints); zero distortion: bounds = [0,W] x [0,H]."""
+    L = _bind()
+    vp = C.c_void_p
+    _check(L.orbfe_search_for_initialization_device(matcher.handle, npairs, vp(d_kps), vp(d_desc), vp(d_counts), cap, vp(d_f1_idx), vp(d_f2_idx),
+                                                    vp(d_prev_matched), 0.0, 0.0, float(width), float(height), int(window),
+                                                    float(matcher.mfNNratio), int(matcher.mbCheckOrientation), vp(d_match12), vp(d_nmatches),
+                                                    vp(stream)))

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     names = set()
-    for h in ("orbfe.h", "orbfe_match.h", "orbfe_bow.h"):
+    for h in ("orbfe.h", "orbfe_match.h", "orbfe_bow.h", "orbfe_comm.h"):
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         names |= set(re.findall(r"\b(orbfe_[a-z0-9_]+)\s*\(", txt))
@@ -91,7 +91,7 @@ def test_headers_are_plain_c(tmp_path):
     """The boundary is a C ABI: the three headers compile as C99 (-pedantic) and a C program links against liborbfe.so."""
     import subprocess
     src = tmp_path / "abi.c"
-    src.write_text('#include "orbfe.h"\n#include "orbfe_match.h"\n#include "orbfe_bow.h"\n'
+    src.write_text('#include "orbfe.h"\n#include "orbfe_match.h"\n#include "orbfe_bow.h"\n#include "orbfe_comm.h"\n'
                    'int main(void) { return (sizeof(OrbfeKeyPoint) == 28 && orbfe_version() == ORBFE_VERSION) ? 0 : 1; }\n')
     exe = tmp_path / "abi.bin"
     so_dir = os.path.dirname(fe.library_path())
