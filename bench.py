@@ -99,6 +99,27 @@ def usable_cores():
     return n
 
 
+def pin_to_gpu_numa_node(torch, local_rank):
+    """Restrict this rank's host threads to the CPUs of the NUMA node its GPU hangs off (sysfs local_cpulist of the PCI
+    device): pinned-memory uploads and the ctypes worker threads then stay on the socket with the PCIe root port.  Best
+    effort: returns a short description, never fails."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus |= set(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return "no local cpus in the affinity mask"
+        os.sched_setaffinity(0, cpus)
+        return "%s: %d cpus (%s)" % (bdf, len(cpus), txt)
+    except Exception as e:
+        return "not pinned (%r)" % (e,)
+
+
 def cgroup_cpu_quota():
     for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
         try:
@@ -357,7 +378,22 @@ def main():
     ap.add_argument("--repeat", type=int, default=4, help="passes over the step's frames inside one step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle cross-check of the step's results (ncu runs)")
+    ap.add_argument("--workload", default="stream", choices=["stream", "rig8", "dbsweep"],
+                    help="stream = BASELINE configs[1] (the headline line); rig8 = configs[3] (one camera per GPU, exchange + cross-camera "
+                         "SearchForInitialization); dbsweep = configs[4] (sharded keyframe-database sweep): the last two print their own line")
+    ap.add_argument("--slots", type=int, default=8, help="rig8: time steps per exchange")
+    ap.add_argument("--groups", type=int, default=10000, help="dbsweep: keyframes in the database")
     args = ap.parse_args()
+    if args.workload != "stream" and args.impl == "orbfe":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import multi_gpu
+        ctx = multi_gpu._setup()
+        out = (multi_gpu.run_rig if args.workload == "rig8" else multi_gpu.run_dbsweep)(args, ctx)
+        if ctx[3] == 0:
+            print(json.dumps(out))
+        if ctx[2] > 1:
+            ctx[1].destroy_process_group()
+        return 0
     args.frames = max(args.batch, args.frames // args.batch * args.batch)
     if args.impl == "reference":
         return run_reference(args)
@@ -377,6 +413,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(torch, local_rank) if world > 1 else "single rank: not pinned"
 
     B = args.batch
     NB = args.frames // B                      # batches per pass
@@ -746,7 +783,7 @@ def main():
                 "keypoints_per_step": r_dev["kp"] / args.steps,
                 "wall_ms_per_step": r_dev["wall_ms"] / args.steps,
                 "host_ms_per_batch": {k: 1e3 * v / max(host_t["n"], 1) for k, v in host_t.items() if k != "n"},
-                "single_frame_latency_ms": single_ms,
+                "single_frame_latency_ms": single_ms, "host_numa_pinning_rank0": numa,
                 "parity_checked": parity,
                 "roofline": roof, "clocks": clocks}
         if not args.no_cpu_baseline:

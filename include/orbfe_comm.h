@@ -84,10 +84,19 @@ int orbfe_rig_exchange_create(OrbfeComm *c, int cap, int nslots, OrbfeRigExchang
 int orbfe_rig_exchange_destroy(OrbfeRigExchange *x);
 int orbfe_extract_batch_device_exchange(OrbfeExtractor *ex, const uint8_t *d_imgs, int width, int height, size_t stride,
                                         size_t frame_stride, int batch, OrbfeRigExchange *x, void *stream);
+/* config 4's consumer, fused as well: orbfe_search_for_initialization_device (include/orbfe_match.h) on the gathered arrays
+ * of the epoch just produced; the matcher kernel polls the local epoch flags before its first read and its last thread
+ * block publishes the release -- neither orbfe_rig_exchange_wait nor _release is needed around it. */
+int orbfe_search_for_initialization_exchange(OrbfeMatcher *m, OrbfeRigExchange *x, int npairs, const int *d_f1_idx, const int *d_f2_idx,
+                                             float *d_prev_matched, float min_x, float min_y, float max_x, float max_y, int window,
+                                             float nnratio, int check_orientation, int *d_match12, int *d_nmatches, void *stream);
 int orbfe_rig_exchange_wait(OrbfeRigExchange *x, void *stream);
 int orbfe_rig_exchange_release(OrbfeRigExchange *x, void *stream);
 /* gathered views of the epoch last waited for: world x nslots x cap keypoints / descriptors, world x nslots counts */
 int orbfe_rig_exchange_buffers(OrbfeRigExchange *x, OrbfeKeyPoint **d_all_kps, uint8_t **d_all_desc, int **d_all_counts);
+/* the same views for the epoch just PRODUCED by orbfe_extract_batch_device_exchange (before any wait): only this rank's own
+ * slot [rank] is valid there without waiting (it was written locally, in stream order) */
+int orbfe_rig_exchange_buffers_produced(OrbfeRigExchange *x, OrbfeKeyPoint **d_all_kps, uint8_t **d_all_desc, int **d_all_counts);
 /* synchronises `stream` and reports a timed-out wait (ORBFE_ERR_INTERNAL) */
 int orbfe_rig_exchange_check(OrbfeRigExchange *x, void *stream);
 /* bytes this rank pushed to its peers over NVLink in the last exchange (capacity-based upper bound: nslots x cap x 60 x (world-1)) */

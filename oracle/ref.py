@@ -322,3 +322,75 @@ class Scene:
         d = np.zeros(32, np.uint8)
         self.L.ref_mp_compute_distinctive(int(mp), _p(d))
         return d
+
+
+# ---- N2 / N3: the reference's DBoW2 vocabulary and KeyFrameDatabase -----------------------------------------------------
+def write_vocabulary_text(voc, path, scoring=0, weighting=0):
+    """A synthetic vocabulary (orb_slam_b200.synth.random_vocabulary: nodes in creation order, children consecutive) in the text
+    format TemplatedVocabulary::loadFromTextFile reads (Data/ORBvoc.txt: header `k L scoring weighting`, then one line per
+    node `parent isLeaf b0 .. b31 weight`): the loader numbers nodes by line and words by leaf order, exactly like the arrays."""
+    nd, cp, ch = voc["node_desc"], voc["child_ptr"], voc["children"]
+    n = len(nd)
+    parent = np.zeros(n, np.int32)
+    for i in range(n):
+        parent[ch[cp[i]:cp[i + 1]]] = i
+    with open(path, "w") as f:
+        f.write("%d %d %d %d\n" % (voc["k"], voc["L"], scoring, weighting))
+        for i in range(1, n):
+            leaf = 1 if cp[i + 1] == cp[i] else 0
+            f.write("%d %d %s %r\n" % (parent[i], leaf, " ".join(str(int(b)) for b in nd[i]), float(voc["weight"][i])))
+    # loadFromTextFile reads until eof: the file must not end with an empty line that would create a phantom node
+    data = open(path).read().rstrip("\n")
+    open(path, "w").write(data)
+
+
+class RefVocabulary:
+    def __init__(self, path, which="ref"):
+        L = lib(which)
+        vp, i = C.c_void_p, C.c_int
+        L.ref_voc_load.argtypes = [C.c_char_p]
+        L.ref_voc_load.restype = vp
+        L.ref_voc_words.argtypes = [vp]
+        L.ref_bow_transform.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
+        L.ref_db_add.argtypes = [vp, vp, vp, i]
+        L.ref_db_set_covisibles.argtypes = [vp, i, vp, i]
+        L.ref_db_detect_loop.argtypes = [vp, vp, vp, i, vp, i, C.c_float, vp, i]
+        L.ref_db_detect_reloc.argtypes = [vp, vp, vp, i, vp, i]
+        self.L = L
+        self.h = L.ref_voc_load(path.encode())
+        assert self.h, "loadFromTextFile failed"
+        self.nkf = 0
+
+    def words(self):
+        return self.L.ref_voc_words(self.h)
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        cap = max(n, 1)
+        bi, bv = np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+        fi, fp, ff = np.zeros(cap, np.int32), np.zeros(cap + 1, np.int32), np.zeros(cap, np.int32)
+        nw, nn = C.c_int(0), C.c_int(0)
+        self.L.ref_bow_transform(self.h, _p(desc), n, levelsup, C.byref(nw), _p(bi), _p(bv), C.byref(nn), _p(fi), _p(fp), _p(ff))
+        return (bi[:nw.value], bv[:nw.value]), (fi[:nn.value], fp[:nn.value + 1], ff[:fp[nn.value]])
+
+    def db_add(self, ids, vals):
+        ids, vals = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(vals, np.float64)
+        self.nkf += 1
+        return self.L.ref_db_add(self.h, _p(ids), _p(vals), len(ids))
+
+    def db_set_covisibles(self, k, others):
+        o = np.ascontiguousarray(others, np.int32)
+        self.L.ref_db_set_covisibles(self.h, int(k), _p(o), len(o))
+
+    def detect_loop(self, q_ids, q_vals, connected, min_score):
+        qi, qv, cn = np.ascontiguousarray(q_ids, np.int32), np.ascontiguousarray(q_vals, np.float64), np.ascontiguousarray(connected, np.int32)
+        out = np.zeros(max(self.nkf, 1), np.int32)
+        n = self.L.ref_db_detect_loop(self.h, _p(qi), _p(qv), len(qi), _p(cn), len(cn), float(min_score), _p(out), len(out))
+        return out[:n]
+
+    def detect_reloc(self, q_ids, q_vals):
+        qi, qv = np.ascontiguousarray(q_ids, np.int32), np.ascontiguousarray(q_vals, np.float64)
+        out = np.zeros(max(self.nkf, 1), np.int32)
+        n = self.L.ref_db_detect_reloc(self.h, _p(qi), _p(qv), len(qi), _p(out), len(out))
+        return out[:n]

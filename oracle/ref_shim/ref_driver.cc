@@ -534,3 +534,107 @@ void ref_mp_compute_distinctive(int mp, uint8_t *desc_out) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// N2 / N3: the reference's vocabulary (Thirdparty/DBoW2 TemplatedVocabulary, loaded from the text format of
+// Data/ORBvoc.txt) and its KeyFrameDatabase (src/KeyFrameDatabase.cc)
+// =====================================================================================================================
+namespace {
+struct VocDb {
+    ORBVocabulary voc;
+    KeyFrameDatabase *db;
+    std::vector<KeyFrame *> kfs;
+    VocDb() : db(NULL) {}
+};
+KeyFrame *bare_keyframe() {
+    World &w = world();
+    Frame *F = frame_from_arrays(NULL, NULL, 0, 64, 48, 50.f, 50.f, 32.f, 24.f, 1.2f, 8);
+    KeyFrame *kf = new KeyFrame(*F, &w.map, &w.db);
+    delete F;
+    return kf;
+}
+DBoW2::BowVector bow_from(const int *ids, const double *vals, int n) {
+    DBoW2::BowVector v;
+    for (int i = 0; i < n; i++) v.addWeight((DBoW2::WordId)ids[i], vals[i]);
+    return v;
+}
+}  // namespace
+
+extern "C" {
+
+void *ref_voc_load(const char *text_path) {
+    VocDb *V = new VocDb();
+    if (!V->voc.loadFromTextFile(text_path)) { delete V; return NULL; }
+    V->db = new KeyFrameDatabase(V->voc);
+    return V;
+}
+int ref_voc_words(void *v) { return (int)static_cast<VocDb *>(v)->voc.size(); }
+
+// Frame::ComputeBoW / KeyFrame::ComputeBoW: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) (Frame.cc:280-287)
+// outputs: BowVector as (word id, value) in map order; FeatureVector as CSR (node id, ptr, feature indices)
+int ref_bow_transform(void *v, const uint8_t *desc, int n, int levelsup, int *nwords_out, int *bow_ids, double *bow_vals, int *nnodes_out,
+                      int *fv_ids, int *fv_ptr, int *fv_feats) {
+    VocDb *V = static_cast<VocDb *>(v);
+    cv::Mat D(std::max(n, 1), 32, CV_8UC1);
+    if (n) std::memcpy(D.data, desc, (size_t)n * 32);
+    std::vector<cv::Mat> rows;
+    for (int i = 0; i < n; i++) rows.push_back(D.row(i));
+    DBoW2::BowVector bv;
+    DBoW2::FeatureVector fv;
+    V->voc.transform(rows, bv, fv, levelsup);
+    int k = 0;
+    for (DBoW2::BowVector::const_iterator it = bv.begin(); it != bv.end(); ++it, ++k) { bow_ids[k] = (int)it->first; bow_vals[k] = it->second; }
+    *nwords_out = k;
+    int nn = 0, o = 0;
+    fv_ptr[0] = 0;
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it, ++nn) {
+        fv_ids[nn] = (int)it->first;
+        for (size_t j = 0; j < it->second.size(); j++) fv_feats[o++] = (int)it->second[j];
+        fv_ptr[nn + 1] = o;
+    }
+    *nnodes_out = nn;
+    return 0;
+}
+
+// keyframe `k` of the database = the k-th ref_db_add call: BowVector given, KeyFrameDatabase::add (KeyFrameDatabase.cc:37-44)
+int ref_db_add(void *v, const int *ids, const double *vals, int n) {
+    VocDb *V = static_cast<VocDb *>(v);
+    KeyFrame *kf = bare_keyframe();
+    kf->mBowVec = bow_from(ids, vals, n);
+    V->db->add(kf);
+    V->kfs.push_back(kf);
+    return (int)V->kfs.size() - 1;
+}
+// GetBestCovisibilityKeyFrames(10) of keyframe k returns `others` in this order (strictly decreasing weights)
+void ref_db_set_covisibles(void *v, int k, const int *others, int n) {
+    VocDb *V = static_cast<VocDb *>(v);
+    for (int i = 0; i < n; i++) V->kfs[k]->AddConnection(V->kfs[others[i]], 1000 - i);
+}
+// DetectLoopCandidates(pKF, minScore) (KeyFrameDatabase.cc:72-204) for a fresh query keyframe connected to `connected`
+int ref_db_detect_loop(void *v, const int *q_ids, const double *q_vals, int nq, const int *connected, int nconn, float min_score, int *out, int cap) {
+    VocDb *V = static_cast<VocDb *>(v);
+    KeyFrame *q = bare_keyframe();
+    q->mBowVec = bow_from(q_ids, q_vals, nq);
+    for (int i = 0; i < nconn; i++) q->AddConnection(V->kfs[connected[i]], 100);
+    const std::vector<KeyFrame *> c = V->db->DetectLoopCandidates(q, min_score);
+    for (size_t i = 0; i < c.size() && (int)i < cap; i++) {
+        out[i] = -1;
+        for (size_t k = 0; k < V->kfs.size(); k++) if (V->kfs[k] == c[i]) out[i] = (int)k;
+    }
+    return (int)c.size();
+}
+// DetectRelocalisationCandidates(Frame *F) (KeyFrameDatabase.cc:206-308)
+int ref_db_detect_reloc(void *v, const int *q_ids, const double *q_vals, int nq, int *out, int cap) {
+    VocDb *V = static_cast<VocDb *>(v);
+    Frame *F = frame_from_arrays(NULL, NULL, 0, 64, 48, 50.f, 50.f, 32.f, 24.f, 1.2f, 8);
+    F->mBowVec = bow_from(q_ids, q_vals, nq);
+    const std::vector<KeyFrame *> c = V->db->DetectRelocalisationCandidates(F);
+    for (size_t i = 0; i < c.size() && (int)i < cap; i++) {
+        out[i] = -1;
+        for (size_t k = 0; k < V->kfs.size(); k++) if (V->kfs[k] == c[i]) out[i] = (int)k;
+    }
+    delete F;
+    return (int)c.size();
+}
+
+}  // extern "C"

@@ -32,6 +32,8 @@ def _bind():
     L.orbfe_rig_exchange_create.argtypes = [vp, i, i, C.POINTER(vp)]
     L.orbfe_rig_exchange_destroy.argtypes = [vp]
     L.orbfe_extract_batch_device_exchange.argtypes = [vp, vp, i, i, sz, sz, i, vp, vp]
+    L.orbfe_search_for_initialization_exchange.argtypes = [vp, vp, i, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, i, C.c_float, i,
+                                                           vp, vp, vp]
     L.orbfe_rig_exchange_wait.argtypes = [vp, vp]
     L.orbfe_rig_exchange_release.argtypes = [vp, vp]
     L.orbfe_rig_exchange_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -122,6 +124,14 @@ class RigExchange:
         _check(_bind().orbfe_extract_batch_device_exchange(extractor._h, C.c_void_p(d_imgs), W, H, stride, frame_stride, self.nslots,
                                                            self.h, C.c_void_p(stream)))
 
+    def search_for_initialization(self, matcher, npairs, d_f1_idx, d_f2_idx, d_prev_matched, width, height, window, d_match12, d_nmatches,
+                                  stream=0):
+        """orbfe_search_for_initialization_exchange: the matcher waits for the epoch's data and releases it itself."""
+        vp = C.c_void_p
+        _check(_bind().orbfe_search_for_initialization_exchange(matcher.handle, self.h, npairs, vp(d_f1_idx), vp(d_f2_idx), vp(d_prev_matched),
+                                                                0.0, 0.0, float(width), float(height), int(window), float(matcher.mfNNratio),
+                                                                int(matcher.mbCheckOrientation), vp(d_match12), vp(d_nmatches), vp(stream)))
+
     def wait(self, stream=0):
         _check(_bind().orbfe_rig_exchange_wait(self.h, C.c_void_p(stream)))
 
@@ -131,6 +141,14 @@ class RigExchange:
     def buffers(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(_bind().orbfe_rig_exchange_buffers(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def buffers_of_current_epoch(self):
+        """Gathered views of the epoch just PRODUCED (before any wait): only this rank's own slot is valid without waiting."""
+        L = _bind()
+        L.orbfe_rig_exchange_buffers_produced.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(L.orbfe_rig_exchange_buffers_produced(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
     def check(self, stream=0):

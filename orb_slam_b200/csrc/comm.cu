@@ -259,6 +259,7 @@ struct OrbfeRigExchange {
     size_t half_bytes = 0, kps_off = 0, desc_off = 0, cnt_off = 0, flags_off = 0, total_bytes = 0;
     uint8_t *peer_base[ORBFE_MAX_RANKS] = {nullptr};
     unsigned *done = nullptr;   // local block counter of the publishing kernel
+    unsigned *done2 = nullptr;  // local block counter of the consuming (matcher) kernel
     int *d_err = nullptr;
     int *h_err = nullptr;
     unsigned epoch = 0;         // last epoch produced
@@ -306,8 +307,9 @@ extern "C" int orbfe_rig_exchange_create(OrbfeComm *c, int cap, int nslots, Orbf
     x->total_bytes = x->flags_off + up(2 * ORBFE_MAX_RANKS * sizeof(unsigned));
     cudaError_t e = cudaMalloc((void **)&x->base, x->total_bytes);
     if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->total_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&x->done, sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemset(x->done, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&x->done, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(x->done, 0, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) x->done2 = x->done + 1;
     if (e == cudaSuccess) e = cudaMalloc((void **)&x->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(x->d_err, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&x->h_err, sizeof(int), cudaHostAllocDefault);
@@ -373,16 +375,16 @@ extern "C" int orbfe_extract_batch_device_exchange(OrbfeExtractor *ex, const uin
     const unsigned epoch = x->epoch + 1;
     const int half = (int)(epoch & 1u);
     unsigned *flags = (unsigned *)(x->base + x->flags_off);
-    // a buffer half is overwritten only after EVERY rank has released the epoch that last used it (epoch - 2)
-    if (epoch > 2 && x->world > 1) {
-        wait_flags_kernel<<<1, 32, 0, s>>>(flags + ORBFE_MAX_RANKS, x->world, epoch - 2, x->d_err, 2);
-        CU_TRY(cudaGetLastError());
-    }
+    // a buffer half is overwritten only after EVERY rank has released the epoch that last used it (epoch - 2): the
+    // descriptor kernel polls the acknowledgement flags (local memory) before its first remote store
     PeerOut po;
     memset(&po, 0, sizeof(po));
     po.n = x->world;
     po.epoch = epoch;
     po.done = x->done;
+    po.ack = flags + ORBFE_MAX_RANKS;
+    po.ack_epoch = (epoch > 2 && x->world > 1) ? epoch - 2 : 0;
+    po.err = x->d_err;
     const size_t slot = (size_t)x->rank * x->nslots * x->cap;
     for (int p = 0; p < x->world; p++) {
         uint8_t *hb = x->peer_base[p] + (size_t)half * x->half_bytes;
@@ -396,6 +398,38 @@ extern "C" int orbfe_extract_batch_device_exchange(OrbfeExtractor *ex, const uin
     x->epoch = epoch;
     x->last_bytes = (size_t)x->nslots * x->cap * 60 * (size_t)(x->world - 1);
     return ORBFE_OK;
+}
+
+// declared in orbfe_api.cu
+int orbfe_search_for_initialization_hooked(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                           const int *d_counts, int cap, const int *d_f1_idx, const int *d_f2_idx,
+                                           float *d_prev_matched, float min_x, float min_y, float max_x, float max_y,
+                                           int window, float nnratio, int check_orientation, int *d_match12,
+                                           int *d_nmatches, void *stream, const SbpParams *hooks);
+
+// Cross-camera SearchForInitialization on the epoch just produced: the matcher kernel itself waits for every rank's data
+// (polling the local epoch flags) and its last thread block releases the epoch to every rank -- together with
+// orbfe_extract_batch_device_exchange a rig step is two library calls and not a single extra kernel launch.
+extern "C" int orbfe_search_for_initialization_exchange(OrbfeMatcher *m, OrbfeRigExchange *x, int npairs, const int *d_f1_idx,
+                                                        const int *d_f2_idx, float *d_prev_matched, float min_x, float min_y, float max_x,
+                                                        float max_y, int window, float nnratio, int check_orientation, int *d_match12,
+                                                        int *d_nmatches, void *stream) {
+    if (!m || !x) return set_error(ORBFE_ERR_ARG, "NULL argument");
+    CU_TRY(cudaSetDevice(x->c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : x->c->stream;
+    x->waited = x->epoch;
+    uint8_t *hb = x->base + (size_t)(x->waited & 1u) * x->half_bytes;
+    SbpParams H;
+    memset(&H, 0, sizeof(H));
+    H.xw_flags = (unsigned *)(x->base + x->flags_off);
+    H.xw_done = x->done2;
+    H.xw_err = x->d_err;
+    H.xw_n = x->world;
+    H.xw_epoch = x->epoch;
+    for (int p = 0; p < x->world; p++) H.xw_ack[p] = (unsigned *)(x->peer_base[p] + x->flags_off) + ORBFE_MAX_RANKS + x->rank;
+    return orbfe_search_for_initialization_hooked(m, npairs, (const OrbfeKeyPoint *)(hb + x->kps_off), hb + x->desc_off, (const int *)(hb + x->cnt_off),
+                                                  x->cap, d_f1_idx, d_f2_idx, d_prev_matched, min_x, min_y, max_x, max_y, window, nnratio,
+                                                  check_orientation, d_match12, d_nmatches, s, &H);
 }
 
 extern "C" int orbfe_rig_exchange_wait(OrbfeRigExchange *x, void *stream) {
@@ -423,6 +457,15 @@ extern "C" int orbfe_rig_exchange_release(OrbfeRigExchange *x, void *stream) {
 extern "C" int orbfe_rig_exchange_buffers(OrbfeRigExchange *x, OrbfeKeyPoint **d_all_kps, uint8_t **d_all_desc, int **d_all_counts) {
     if (!x) return set_error(ORBFE_ERR_ARG, "x is NULL");
     uint8_t *hb = x->base + (size_t)(x->waited & 1u) * x->half_bytes;
+    if (d_all_kps) *d_all_kps = (OrbfeKeyPoint *)(hb + x->kps_off);
+    if (d_all_desc) *d_all_desc = hb + x->desc_off;
+    if (d_all_counts) *d_all_counts = (int *)(hb + x->cnt_off);
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_rig_exchange_buffers_produced(OrbfeRigExchange *x, OrbfeKeyPoint **d_all_kps, uint8_t **d_all_desc, int **d_all_counts) {
+    if (!x) return set_error(ORBFE_ERR_ARG, "x is NULL");
+    uint8_t *hb = x->base + (size_t)(x->epoch & 1u) * x->half_bytes;
     if (d_all_kps) *d_all_kps = (OrbfeKeyPoint *)(hb + x->kps_off);
     if (d_all_desc) *d_all_desc = hb + x->desc_off;
     if (d_all_counts) *d_all_counts = (int *)(hb + x->cnt_off);

@@ -1408,10 +1408,22 @@ __device__ __forceinline__ void describe_fused_body(const PlanDev *__restrict__ 
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 2) << 16;
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 3) << 24;
     const size_t o = (size_t)f * plan->nfeatures + out_idx;
-    if ((lane & 3) == 0) {
-        if (PEERS) { for (int p = 0; p < po.n; p++) reinterpret_cast<uint32_t *>(po.desc[p] + o * 32)[lane >> 2] = word; }
-        else reinterpret_cast<uint32_t *>(out_desc + o * 32)[lane >> 2] = word;
+    if (PEERS) {
+        // remote stores over NVLink: 16-byte descriptor halves from lanes 0 and 16, the seven keypoint fields from lanes 0..6
+        // (one coalesced 28-byte segment per destination) -- every lane holds the same keypoint values
+        const uint32_t w1 = __shfl_down_sync(0xffffffffu, word, 4), w2 = __shfl_down_sync(0xffffffffu, word, 8);
+        const uint32_t w3 = __shfl_down_sync(0xffffffffu, word, 12);
+        const float kx = l ? __fmul_rn((float)x, L.scale) : (float)x, ky = l ? __fmul_rn((float)y, L.scale) : (float)y;  // :768-775
+        const float resp = wk.cand_keys64 ? __int_as_float(kp.y) : (float)kp.y;
+        const uint32_t field = lane == 0 ? __float_as_uint(kx) : lane == 1 ? __float_as_uint(ky) : lane == 2 ? __float_as_uint(L.patch_size)
+                             : lane == 3 ? __float_as_uint(angle) : lane == 4 ? __float_as_uint(resp) : lane == 5 ? (uint32_t)l : 0xFFFFFFFFu;
+        for (int p = 0; p < po.n; p++) {
+            if ((lane & 15) == 0) reinterpret_cast<uint4 *>(po.desc[p] + o * 32)[lane >> 4] = make_uint4(word, w1, w2, w3);
+            if (lane < 7) reinterpret_cast<uint32_t *>(po.kps[p] + o)[lane] = field;
+        }
+        return;
     }
+    if ((lane & 3) == 0) reinterpret_cast<uint32_t *>(out_desc + o * 32)[lane >> 2] = word;
     if (lane == 0) {
         OrbfeKeyPoint r;
         r.x = l ? __fmul_rn((float)x, L.scale) : (float)x;  // :768-775
@@ -1421,8 +1433,7 @@ __device__ __forceinline__ void describe_fused_body(const PlanDev *__restrict__ 
         r.response = wk.cand_keys64 ? __int_as_float(kp.y) : (float)kp.y;  // Harris response or FAST score
         r.octave = l;
         r.class_id = -1;
-        if (PEERS) { for (int p = 0; p < po.n; p++) po.kps[p][o] = r; }
-        else out_kps[o] = r;
+        out_kps[o] = r;
     }
 }
 
@@ -1438,6 +1449,19 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
 __global__ void __launch_bounds__(256) describe_fused_exchange_kernel(const PlanDev *__restrict__ plan, WorkDev wk,
                                                                       const int8_t *__restrict__ g_pattern, int f0,
                                                                       const __grid_constant__ PeerOut po) {
+    // a half of the peers' gather buffers is reused every second epoch: before the first remote store, every rank must have
+    // released the epoch that last used it (their acknowledgement flags live in THIS rank's memory: local polling)
+    if (po.ack_epoch && (int)threadIdx.x < po.n) {
+        const long long t0 = clock64();
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(po.ack + threadIdx.x) : "memory");
+            if ((int)(v - po.ack_epoch) >= 0) break;
+            if (clock64() - t0 > 4000000000ll) { atomicExch(po.err, 2); break; }   // ~2 s: a peer is gone
+            __nanosleep(100);
+        } while (true);
+    }
+    __syncthreads();
     describe_fused_body<true>(plan, wk, g_pattern, nullptr, nullptr, nullptr, f0, po);
     // ---- publish: every thread's remote stores are ordered before the block's arrival, the last block to arrive
     //      (all others' stores are therefore visible system-wide) writes the epoch into every rank's flag word ----

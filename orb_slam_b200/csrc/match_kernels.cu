@@ -306,6 +306,35 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     };
     auto query_angle = [&](int q) -> float { return EXPLICIT ? GQ.qangle[qb + q] : kl[q].angle; };
 
+    // rig exchange: the gathered keypoints / descriptors of the other ranks arrive by remote stores; wait for every rank's
+    // epoch flag (local polling) before the first read
+    if (P.xw_flags) {
+        if (tid < P.xw_n) {
+            const long long t0 = clock64();
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(P.xw_flags + tid) : "memory");
+                if ((int)(v - P.xw_epoch) >= 0) break;
+                if (clock64() - t0 > 4000000000ll) { atomicExch(P.xw_err, 1); break; }
+                __nanosleep(100);
+            } while (true);
+        }
+        __syncthreads();
+    }
+    // ... and the last thread block to finish tells every rank that this one has read the epoch (called by ALL threads)
+    auto publish_ack = [&]() {
+        if (!P.xw_done) return;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(P.xw_done, 1u) == gridDim.x - 1) {
+                *P.xw_done = 0;
+                __threadfence_system();
+                for (int r = 0; r < P.xw_n; r++)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xw_ack[r]), "r"(P.xw_epoch) : "memory");
+            }
+        }
+    };
     // ---- A: grid of the Current frame ----
     for (int i = tid; i < SBP_NCELL; i += SBP_THREADS) cell_cur[i] = 0;
     for (int i = tid; i < (cap + 31) / 32; i += SBP_THREADS) taken[i] = 0;
@@ -390,6 +419,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     const int T_total = run_total;
     if (T_total > P.scratch_per_pair) {
         if (tid == 0) { atomicExch(err, 1); nmatches[pair] = -1; }
+        publish_ack();
         return;
     }
     uint32_t *ent = (T_total <= P.smem_entries) ? s_ent : scratch + (size_t)pair * P.scratch_per_pair;
@@ -556,6 +586,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
         for (int q = tid; q < nl; q += SBP_THREADS)
             if (mp[q] >= 0) { wout[2 * q] = kx[mp[q]]; wout[2 * q + 1] = ky[mp[q]]; }
         if (tid == 0) nmatches[pair] = s_nm - s_removed;
+        publish_ack();
         return;
     }
     if (P.check_ori) {

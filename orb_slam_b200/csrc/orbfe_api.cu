@@ -932,11 +932,27 @@ extern "C" int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, co
 
 // SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) for `npairs` (F1, F2) pairs, device-resident
 // (ORBmatcher.cc:598-713; the fused kernel's MODE 2).  d_prev_matched: npairs x cap x 2 floats, in/out.
+int orbfe_search_for_initialization_hooked(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                           const int *d_counts, int cap, const int *d_f1_idx, const int *d_f2_idx,
+                                           float *d_prev_matched, float min_x, float min_y, float max_x, float max_y,
+                                           int window, float nnratio, int check_orientation, int *d_match12,
+                                           int *d_nmatches, void *stream, const SbpParams *hooks);
+
 extern "C" int orbfe_search_for_initialization_device(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
                                                       const int *d_counts, int cap, const int *d_f1_idx, const int *d_f2_idx,
                                                       float *d_prev_matched, float min_x, float min_y, float max_x, float max_y,
                                                       int window, float nnratio, int check_orientation, int *d_match12,
                                                       int *d_nmatches, void *stream) {
+    return orbfe_search_for_initialization_hooked(m, npairs, d_kps, d_desc, d_counts, cap, d_f1_idx, d_f2_idx, d_prev_matched, min_x, min_y,
+                                                  max_x, max_y, window, nnratio, check_orientation, d_match12, d_nmatches, stream, nullptr);
+}
+
+// `hooks`: only the xw_* fields are read (rig exchange: wait for the epoch's data at kernel start, publish the release at its end)
+int orbfe_search_for_initialization_hooked(OrbfeMatcher *m, int npairs, const OrbfeKeyPoint *d_kps, const uint8_t *d_desc,
+                                           const int *d_counts, int cap, const int *d_f1_idx, const int *d_f2_idx,
+                                           float *d_prev_matched, float min_x, float min_y, float max_x, float max_y,
+                                           int window, float nnratio, int check_orientation, int *d_match12,
+                                           int *d_nmatches, void *stream, const SbpParams *hooks) {
     if (!m || npairs < 0 || cap < 1 || cap > 65534 || window < 0) return fail(ORBFE_ERR_ARG, "bad arguments");
     if (npairs == 0) return ORBFE_OK;
     if (!d_kps || !d_desc || !d_counts || !d_f1_idx || !d_f2_idx || !d_prev_matched || !d_match12 || !d_nmatches)
@@ -951,6 +967,10 @@ extern "C" int orbfe_search_for_initialization_device(OrbfeMatcher *m, int npair
     P.th = (float)window;                        // GetFeaturesInArea(x, y, windowSize, 0, 0), :618
     P.nlevels = 1; P.cap = cap; P.check_ori = check_orientation ? 1 : 0;
     P.qcap = cap; P.rule = 3; P.th_dist = 50 /* TH_LOW, :652 */; P.nnratio = nnratio;
+    if (hooks) {
+        P.xw_flags = hooks->xw_flags; P.xw_done = hooks->xw_done; P.xw_err = hooks->xw_err; P.xw_n = hooks->xw_n; P.xw_epoch = hooks->xw_epoch;
+        for (int r = 0; r < 16; r++) P.xw_ack[r] = hooks->xw_ack[r];
+    }
     // a 100-px window at 720p holds a few hundred level-0 candidates per query: entries live in the global scratch
     const size_t per_pair = (size_t)256 * cap;
     if (per_pair > (size_t)INT_MAX) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large", cap);

@@ -94,6 +94,9 @@ struct PeerOut {
     int n;
     unsigned epoch;
     unsigned *done;                          // local counter of finished thread blocks (reset by the last one)
+    const unsigned *ack;                     // local flags: last epoch each rank finished READING (buffer-half reuse)
+    unsigned ack_epoch;                      // wait until ack[r] >= ack_epoch for all r before the first remote store (0 = no wait)
+    int *err;                                // device error flag (a wait timed out)
     OrbfeKeyPoint *kps[ORBFE_MAX_PEERS];     // [nslots x nfeatures] of this rank inside peer p's buffer
     uint8_t *desc[ORBFE_MAX_PEERS];
     int *counts[ORBFE_MAX_PEERS];
@@ -129,6 +132,14 @@ struct SbpParams {
     int scratch_per_pair;                      // global scratch entries per pair
     int smem_entries;                          // entries that fit in the dynamic shared-memory staging area
     int smem_fixed;                            // bytes of the fixed shared-memory part
+    // rig exchange hooks (include/orbfe_comm.h): wait for every rank's data of `xw_epoch` before the first read of the
+    // gathered arrays, and let the last thread block tell every rank that this one is done reading (0 / NULL = unused)
+    const unsigned *xw_flags;
+    unsigned *xw_ack[16];
+    unsigned *xw_done;
+    int *xw_err;
+    int xw_n;
+    unsigned xw_epoch;
 };
 size_t sbp_smem_fixed_bytes(int cap, int qcap);
 int launch_guided_device(const SbpParams &P, size_t smem_bytes, int njobs, const OrbfeKeyPoint *kps, const uint8_t *desc,

@@ -90,6 +90,24 @@ def test_rig_exchange_and_sharded_sweep_world1(gpu_required):
         x.check()
         assert torch.equal(gc, d_cnt) and torch.equal(gk, d_kps) and torch.equal(gd, d_desc), epoch
     assert x.bytes_pushed() == 0
+    # the exchange-aware matcher call (waits for the epoch inside the kernel, releases it at its end) == the plain device call
+    mm = fe.ORBmatcher(0.9, True)
+    f1 = torch.tensor([0, 1], dtype=torch.int32, device=dev); f2 = torch.tensor([1, 2], dtype=torch.int32, device=dev)
+    res = []
+    for use_exchange in (False, True):
+        prev = d_kps.view(torch.float32).view(T, nf, 7)[:2, :, 0:2].contiguous()
+        m12 = torch.full((2, nf), -5, dtype=torch.int32, device=dev); nm = torch.zeros(2, dtype=torch.int32, device=dev)
+        if use_exchange:
+            x.extract(ex, d_frames.data_ptr(), W, H, W, W * H)
+            x.search_for_initialization(mm, 2, f1.data_ptr(), f2.data_ptr(), prev.data_ptr(), W, H, 100, m12.data_ptr(), nm.data_ptr())
+            x.check()
+        else:
+            M.search_for_initialization_device(mm, 2, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), nf, f1.data_ptr(), f2.data_ptr(),
+                                               prev.data_ptr(), W, H, 100, m12.data_ptr(), nm.data_ptr())
+            mm.sync()
+        res.append((m12.cpu().numpy(), nm.cpu().numpy(), prev.cpu().numpy()))
+    assert all(np.array_equal(a, b) for a, b in zip(res[0], res[1]))
+    mm.close()
     # plain all-gather of one rank = copy
     g2 = torch.zeros_like(d_kps); gd2 = torch.zeros_like(d_desc); gc2 = torch.zeros_like(d_cnt)
     comm.allgather_desc(d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), nf, T, g2.data_ptr(), gd2.data_ptr(), gc2.data_ptr())

@@ -304,3 +304,75 @@ def test_search_for_triangulation(scene):
         want = np.array([(i, m12[i]) for i in range(len(m12)) if m12[i] >= 0], np.int32).reshape(-1, 2)
         assert n_r == n_o and np.array_equal(pairs, want), key
         assert n_r > 20
+
+
+# ---- (f) rows against the reference's own code: Frame's undistortion, DBoW2's transform, KeyFrameDatabase ------------------
+def test_frame_constructor_with_lens_distortion():
+    """N1: Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:289-350) through the reference's Frame constructor: mvKeysUn,
+    the image bounds, the grid constants and the grid itself vs the oracle's arrays."""
+    img = textured_frame(640, 480, seed=9)
+    fx, fy, cx, cy, dist = 520.0, 515.0, 318.0, 243.0, np.array([-0.25, 0.09, 0.001, -0.0007], np.float32)
+    f = R.RefFrame.from_image(img, fx, fy, cx, cy, dist, 800, 1.2, 8, 1, 20)
+    keys, keys_un, desc, bounds, ginv = f.get()
+    assert not np.array_equal(keys["x"], keys_un["x"])
+    d5 = np.concatenate([dist, [0]]).astype(np.float32)
+    assert np.array_equal(keys_un, O.undistort_keypoints(keys, fx, fy, cx, cy, d5))
+    b = O.image_bounds(640, 480, fx, fy, cx, cy, d5)
+    assert np.array_equal(bounds, b)
+    assert ginv[0] == np.float32(64) / np.float32(b[2] - b[0]) and ginv[1] == np.float32(48) / np.float32(b[3] - b[1])
+    f.close()
+
+
+@pytest.mark.parametrize("k,L,ragged,levelsup", [(10, 3, False, 2), (6, 4, True, 3), (10, 3, False, 0)])
+def test_vocabulary_transform_against_dbow2(tmp_path, k, L, ragged, levelsup):
+    """N2: DBoW2::TemplatedVocabulary::transform (TemplatedVocabulary.h:1126-1262, the tree descent with FORB::distance and the
+    TF-IDF / L1 weighting) itself, loaded from the text format of Data/ORBvoc.txt, vs the oracle's BowVector / FeatureVector."""
+    from orb_slam_b200.synth import random_vocabulary, random_descriptors, noisy_copies
+    voc = random_vocabulary(k, L, seed=5, ragged=ragged)
+    path = str(tmp_path / "voc.txt")
+    R.write_vocabulary_text(voc, path)
+    V = R.RefVocabulary(path)
+    assert V.words() == int((voc["word_id"] >= 0).sum())
+    leaves = voc["node_desc"][voc["word_id"] >= 0]
+    desc = np.concatenate([noisy_copies(leaves[np.random.default_rng(1).integers(0, len(leaves), 700)], 0.08, 2), random_descriptors(300, 3)])
+    (bi, bv), (fi, fp, ff) = V.transform(desc, levelsup)
+    (obi, obv), (ofi, ofp, off) = O.bow_transform(voc, desc, levelsup=levelsup, weighting=0, norm=1)
+    assert np.array_equal(bi, obi) and np.array_equal(bv, obv)            # float64 values bit for bit (same summation order)
+    assert np.array_equal(fi, ofi) and np.array_equal(fp, ofp) and np.array_equal(ff, off)
+    assert len(bi) > 50
+
+
+def test_keyframe_database_against_the_reference(tmp_path):
+    """N3: KeyFrameDatabase::DetectLoopCandidates (:72-204) and DetectRelocalisationCandidates (:206-308) with the reference's own
+    inverted file, covisibility accumulation and DBoW2 L1 score vs the oracle's candidate lists (order included)."""
+    from orb_slam_b200.synth import random_keyframe_db
+    # a flat-enough vocabulary that only has to own the word ids: 10^4 words
+    n_nodes = 1 + 10 + 100 + 1000 + 10000
+    path = str(tmp_path / "flat.txt")
+    with open(path, "w") as f:
+        f.write("10 4 0 0\n")
+        lines, first_child = [], 1
+        for nid in range(1, n_nodes):
+            parent = (nid - 1) // 10
+            leaf = 1 if nid >= 1111 else 0
+            lines.append("%d %d %s 1.0" % (parent, leaf, " ".join(["0"] * 32)))
+        f.write("\n".join(lines))
+    for seed in (0, 1):
+        V = R.RefVocabulary(path)
+        assert V.words() == 10000
+        db = random_keyframe_db(nkf=120 + 30 * seed, nwords=3000, words_per_kf=200, seed=seed, loop_at=20 + seed)
+        nkf = len(db["kf_ptr"]) - 1
+        for kf in range(nkf):
+            a, b = db["kf_ptr"][kf], db["kf_ptr"][kf + 1]
+            assert V.db_add(db["db_ids"][a:b], db["db_vals"][a:b]) == kf
+        for kf in range(nkf):
+            V.db_set_covisibles(kf, db["covis"][db["covis_ptr"][kf]:db["covis_ptr"][kf + 1]])
+        for min_score in (0.0, 0.02):
+            cand, _, _ = O.bow_db_detect(0, db["q_ids"], db["q_vals"], db["kf_ptr"], db["db_ids"], db["db_vals"], db["connected"],
+                                         db["covis_ptr"], db["covis"], min_score)
+            got = V.detect_loop(db["q_ids"], db["q_vals"], np.flatnonzero(db["connected"]), min_score)
+            assert np.array_equal(got, cand), (seed, min_score)
+        cand, _, _ = O.bow_db_detect(1, db["q_ids"], db["q_vals"], db["kf_ptr"], db["db_ids"], db["db_vals"], db["connected"],
+                                     db["covis_ptr"], db["covis"], 0.0)
+        got = V.detect_reloc(db["q_ids"], db["q_vals"])
+        assert np.array_equal(got, cand) and len(cand) > 0, seed

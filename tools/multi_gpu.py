@@ -99,16 +99,15 @@ def run_rig(args, ctx=None):
             match(g_kps.data_ptr(), g_desc.data_ptr(), g_cnt.data_ptr(), g_kps)
 
     def step_fused():
+        # two library calls, no extra launch: the descriptor kernel stores into every rank's buffer and publishes the epoch;
+        # the matcher kernel polls the epoch flags before its first read and releases the epoch when its last block is done
         with torch.cuda.stream(stream):
             xch.extract(ex, d_frames.data_ptr(), RW, RH, RW, RW * RH, s)
-            xch.wait(s)
-            a, b, c = xch.buffers()
-            # prev-matched from this rank's own slot of the gathered keypoints (device-to-device, strided)
-            own = _as_tensor(torch, a + rank * T * RNF * 28, (T, RNF, 28), dev)
+            a, _, _ = xch.buffers_of_current_epoch()
+            own = _as_tensor(torch, a + rank * T * RNF * 28, (T, RNF, 28), dev)      # this rank's own slot: written locally, stream-ordered
             d_prev.copy_(own.view(torch.float32).view(T, RNF, 7)[:, :, 0:2])
-            M.search_for_initialization_device(mt, T, a, b, c, RNF, d_f1.data_ptr(), d_f2.data_ptr(), d_prev.data_ptr(), RW, RH, 100,
-                                               d_m12.data_ptr(), d_nm.data_ptr(), s)
-            xch.release(s)
+            xch.search_for_initialization(mt, T, d_f1.data_ptr(), d_f2.data_ptr(), d_prev.data_ptr(), RW, RH, 100, d_m12.data_ptr(),
+                                          d_nm.data_ptr(), s)
 
     def timed(fn, steps, warm):
         for _ in range(warm):
