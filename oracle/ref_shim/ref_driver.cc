@@ -10,6 +10,7 @@
 #include <boost/thread.hpp>
 #include <cstdint>
 #include <map>
+#include <new>
 #include <numeric>
 #define protected public   // the drivers set a few protected MapPoint fields (descriptor, normal, distance range) directly
 #define private public
@@ -43,6 +44,21 @@ struct World {
 };
 World *g_world = NULL;
 
+// KeyFrames and MapPoints are placed in one arena in creation order.  The reference keys several containers by POINTER
+// (std::map<KeyFrame*, size_t> mObservations, std::set<MapPoint*>): MapPoint::ComputeDistinctiveDescriptors, for one, breaks
+// median ties by iteration order, i.e. by the addresses malloc happened to return.  With addresses ascending in creation
+// order the reference's behaviour is reproducible, and identical between the two builds of this driver.
+void *arena_alloc(size_t bytes) {
+    static char *base = NULL;
+    static size_t used = 0, cap = (size_t)1 << 30;
+    if (!base) base = static_cast<char *>(std::malloc(cap));   // untouched pages cost nothing
+    used = (used + 63) / 64 * 64;
+    if (!base || used + bytes > cap) { std::fprintf(stderr, "ref_driver: object arena exhausted\n"); std::abort(); }
+    void *p = base + used;
+    used += bytes;
+    return p;
+}
+
 cv::Mat pose_from(const float *T12) {   // 3x4 row-major [R|t] -> 4x4 CV_32F
     cv::Mat T = cv::Mat::eye(4, 4, CV_32F);
     if (T12)
@@ -68,7 +84,7 @@ World &world();
 MapPoint *new_map_point(const float *pos3, KeyFrame *ref = NULL) {
     static const float zero[3] = {0, 0, 0};
     World &w = world();
-    MapPoint *p = new MapPoint(point3(pos3 ? pos3 : zero), ref ? ref : w.anchor, &w.map);
+    MapPoint *p = new (arena_alloc(sizeof(MapPoint))) MapPoint(point3(pos3 ? pos3 : zero), ref ? ref : w.anchor, &w.map);
     w.mps.push_back(p);
     return p;
 }
@@ -130,7 +146,7 @@ World &world() {
         g_world = new World();
         // anchor keyframe: built from an empty 64x48 frame
         Frame *F = frame_from_arrays(NULL, NULL, 0, 64, 48, 50.f, 50.f, 32.f, 24.f, 1.2f, 8);
-        g_world->anchor = new KeyFrame(*F, &g_world->map, &g_world->db);
+        g_world->anchor = new (arena_alloc(sizeof(KeyFrame))) KeyFrame(*F, &g_world->map, &g_world->db);
         g_world->kfs.push_back(g_world->anchor);
         delete F;
     }
@@ -401,7 +417,7 @@ int ref_kf_create(void *f, const float *Tcw12) {
     World &w = world();
     std::vector<MapPoint *> keep = F.mvpMapPoints;
     F.mvpMapPoints = std::vector<MapPoint *>(F.N, static_cast<MapPoint *>(NULL));   // map points are attached explicitly below
-    KeyFrame *kf = new KeyFrame(F, &w.map, &w.db);
+    KeyFrame *kf = new (arena_alloc(sizeof(KeyFrame))) KeyFrame(F, &w.map, &w.db);
     F.mvpMapPoints = keep;
     w.kfs.push_back(kf);
     return (int)w.kfs.size() - 1;
@@ -549,7 +565,7 @@ struct VocDb {
 KeyFrame *bare_keyframe() {
     World &w = world();
     Frame *F = frame_from_arrays(NULL, NULL, 0, 64, 48, 50.f, 50.f, 32.f, 24.f, 1.2f, 8);
-    KeyFrame *kf = new KeyFrame(*F, &w.map, &w.db);
+    KeyFrame *kf = new (arena_alloc(sizeof(KeyFrame))) KeyFrame(*F, &w.map, &w.db);
     delete F;
     return kf;
 }
@@ -638,3 +654,19 @@ int ref_db_detect_reloc(void *v, const int *q_ids, const double *q_vals, int nq,
 }
 
 }  // extern "C"
+
+// N4 helper: the keyframes observing a map point in the ITERATION order of its std::map<KeyFrame*, size_t> (pointer order --
+// the order MapPoint::ComputeDistinctiveDescriptors collects the descriptors in, MapPoint.cc:204-210), as (keyframe id, index)
+extern "C" int ref_mp_observation_order(int mp, int *obs_kf, int *obs_idx, int cap) {
+    MapPoint *p = mp_at(mp);
+    const std::map<KeyFrame *, size_t> obs = p->GetObservations();
+    World &w = world();
+    int n = 0;
+    for (std::map<KeyFrame *, size_t>::const_iterator it = obs.begin(); it != obs.end(); ++it, ++n) {
+        if (n >= cap) continue;
+        obs_kf[n] = -1;
+        for (size_t k = 0; k < w.kfs.size(); k++) if (w.kfs[k] == it->first) obs_kf[n] = (int)k;
+        obs_idx[n] = (int)it->second;
+    }
+    return n;
+}

@@ -376,3 +376,39 @@ def test_keyframe_database_against_the_reference(tmp_path):
                                      db["covis_ptr"], db["covis"], 0.0)
         got = V.detect_reloc(db["q_ids"], db["q_vals"])
         assert np.array_equal(got, cand) and len(cand) > 0, seed
+
+
+def test_distinctive_descriptor_against_the_reference():
+    """N4: MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:185-250): the observed descriptor with the least median distance
+    to the others, first minimum in the std::map's iteration order, vs the oracle on the same order."""
+    import ctypes as C
+    from orb_slam_b200.synth import random_descriptors, noisy_copies
+    S = R.Scene("ref")
+    L = S.L
+    L.ref_mp_observation_order.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(4)
+    nkf, nfeat = 9, 40
+    base = random_descriptors(nfeat, 11)
+    kps = np.zeros(nfeat, O.KP_DTYPE)
+    kps["x"], kps["y"] = rng.uniform(20, 600, nfeat), rng.uniform(20, 440, nfeat)
+    descs, kfs = [], []
+    for k in range(nkf):
+        d = noisy_copies(base, 0.10, 100 + k)
+        descs.append(d)
+        f = S.frame(kps, d, 640, 480, 500.0, 500.0, 320.0, 240.0)
+        kfs.append(S.keyframe(f, np.eye(4, dtype=np.float32)[:3]))
+        f.close()
+    groups, got = [], []
+    for i in range(nfeat):
+        mp = S.map_point(np.array([0, 0, 4], np.float32), descs[0][i], None, 1.0, 30.0, kfs[0])
+        seen = [k for k in range(nkf) if rng.random() < 0.7] or [0]
+        for k in seen:
+            S.observe(kfs[k], mp, i)
+        got.append(S.compute_distinctive(mp))
+        ok_, oi_ = np.zeros(16, np.int32), np.zeros(16, np.int32)
+        n = L.ref_mp_observation_order(mp, ok_.ctypes.data, oi_.ctypes.data, 16)
+        groups.append(np.stack([descs[kfs.index(int(ok_[j]))][oi_[j]] for j in range(n)]))
+    ptr = np.concatenate([[0], np.cumsum([len(g) for g in groups])]).astype(np.int32)
+    best = O.distinctive_descriptors(np.concatenate(groups), ptr)
+    for i in range(nfeat):
+        assert np.array_equal(got[i], groups[i][best[i]]), i

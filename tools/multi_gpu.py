@@ -98,14 +98,17 @@ def run_rig(args, ctx=None):
                                 g_cnt.data_ptr(), s)
             match(g_kps.data_ptr(), g_desc.data_ptr(), g_cnt.data_ptr(), g_kps)
 
+    own_view = {}
+
     def step_fused():
         # two library calls, no extra launch: the descriptor kernel stores into every rank's buffer and publishes the epoch;
         # the matcher kernel polls the epoch flags before its first read and releases the epoch when its last block is done
         with torch.cuda.stream(stream):
             xch.extract(ex, d_frames.data_ptr(), RW, RH, RW, RW * RH, s)
             a, _, _ = xch.buffers_of_current_epoch()
-            own = _as_tensor(torch, a + rank * T * RNF * 28, (T, RNF, 28), dev)      # this rank's own slot: written locally, stream-ordered
-            d_prev.copy_(own.view(torch.float32).view(T, RNF, 7)[:, :, 0:2])
+            if a not in own_view:   # this rank's own slot of each buffer half: written locally, stream-ordered (views cached: two halves)
+                own_view[a] = _as_tensor(torch, a + rank * T * RNF * 28, (T, RNF, 28), dev).view(torch.float32).view(T, RNF, 7)[:, :, 0:2]
+            d_prev.copy_(own_view[a])
             xch.search_for_initialization(mt, T, d_f1.data_ptr(), d_f2.data_ptr(), d_prev.data_ptr(), RW, RH, 100, d_m12.data_ptr(),
                                           d_nm.data_ptr(), s)
 
@@ -154,6 +157,21 @@ def run_rig(args, ctx=None):
     ms_ex = timed(only_extract, args.steps, args.warmup)
     ms_exf = timed(only_extract_fused, args.steps, args.warmup)
     xch.check(s)
+    # the descriptor kernel itself, plain vs with the remote stores + publish (CUDA events around the stage, extractor alone)
+    stage = {}
+    ex.set_profiling(True)
+    for name, fn in (("plain", only_extract), ("exchange", only_extract_fused)):
+        ex.stage_times()
+        for _ in range(args.steps):
+            fn()
+        stream.synchronize()
+        acc = {}
+        for k, v in ex.stage_times():
+            acc[k] = acc.get(k, 0.0) + v / args.steps
+        stage[name] = acc
+    ex.set_profiling(False)
+    xch.check(s)
+    desc_ms = _max_over_ranks(torch, dist, dev, [stage["plain"].get("describe", 0.0), stage["exchange"].get("describe", 0.0)])
 
     # ---- checks (outside the timed regions) ----
     same_gather = bool(np.array_equal(gc_nccl, gc_f) and np.array_equal(gk_nccl, gk_f) and np.array_equal(gd_nccl, gd_f))
@@ -182,7 +200,9 @@ def run_rig(args, ctx=None):
                "n_gpus": world, "nccl_version": CM.nccl_version(),
                "ms_per_step": {"extract+ncclAllGather+match": ms_nccl, "extract(fused exchange)+match": ms_fused,
                                "ncclAllGather alone": ms_ag, "extract alone": ms_ex, "extract with fused exchange + wait + release": ms_exf},
-               "exchange_cost_ms": {"nccl": ms_ag, "fused (extra time over a plain extract)": ms_exf - ms_ex},
+               "exchange_cost_ms": {"nccl": ms_ag, "fused (extra time over a plain extract)": ms_exf - ms_ex,
+                                    "fused (whole step vs whole nccl step)": ms_fused - ms_nccl},
+               "describe_kernel_ms": {"plain": desc_ms[0], "with remote stores + publish": desc_ms[1]},
                "Mkeypoints_per_s": {"nccl": kp_step / (ms_nccl * 1e-3) / 1e6, "fused": kp_step / (ms_fused * 1e-3) / 1e6},
                "nvlink_bytes_per_step_per_gpu": T * RNF * 60 * (world - 1),
                "matches_rank0": int(nm_fused.sum()), "gathered_identical_nccl_vs_fused_all_ranks": flags[0] == 0.0,
