@@ -1463,11 +1463,12 @@ __global__ void __launch_bounds__(256) describe_fused_exchange_kernel(const Plan
     }
     __syncthreads();
     describe_fused_body<true>(plan, wk, g_pattern, nullptr, nullptr, nullptr, f0, po);
-    // ---- publish: every thread's remote stores are ordered before the block's arrival, the last block to arrive
-    //      (all others' stores are therefore visible system-wide) writes the epoch into every rank's flag word ----
-    __threadfence_system();
+    // ---- publish: the block barrier orders every warp's remote stores before thread 0, whose system-scope fence is
+    //      cumulative over them (the pattern of a cooperative-groups grid barrier: bar.sync, then ONE fencing thread); the
+    //      last block to arrive -- all others' stores are then visible system-wide -- writes the epoch into every rank's flag ----
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned total = gridDim.x * gridDim.y;
         const unsigned prev = atomicAdd(po.done, 1u);
         if (prev == total - 1) {

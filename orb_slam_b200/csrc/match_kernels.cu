@@ -148,6 +148,7 @@ namespace orbfe {
 #define SBP_GROWS 48
 #define SBP_NCELL (SBP_GCOLS * SBP_GROWS)
 
+#define SBP_MAX_ROUNDS 48
 #define SBP_THREADS 1024
 #define SBP_WARPS (SBP_THREADS / 32)
 
@@ -261,11 +262,15 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     uint16_t *items = reinterpret_cast<uint16_t *>(taken + (cap + 31) / 32);  // [cap]
     uint8_t *newbin = reinterpret_cast<uint8_t *>(items + cap);      // [cap]
     uint8_t *koct = newbin + cap;                                    // [cap] Current keypoint octave
-    uint16_t *mdist = reinterpret_cast<uint16_t *>(koct + cap + (cap & 1));   // MODE 2: [cap] vMatchedDistance (0xFFFF = INT_MAX)
+    // (items, newbin, koct together are 4 * cap bytes after a 4-byte aligned start: what follows stays 4-byte aligned)
+    uint16_t *mdist = reinterpret_cast<uint16_t *>(koct + cap);      // MODE 2: [cap] vMatchedDistance (0xFFFF = INT_MAX)
     uint16_t *owner = mdist + cap;                                   // MODE 2: [cap] vnMatches21 (0xFFFF = -1)
+    int *firstq = reinterpret_cast<int *>(owner + cap);              // rule 0: [cap] lowest unresolved query that can still take the slot
+    uint16_t *choice = reinterpret_cast<uint16_t *>(firstq + cap);   // rule 0: [qcap] the slot a query wants this round
+    uint32_t *resolved = reinterpret_cast<uint32_t *>(choice + P.qcap + (P.qcap & 1));  // [(qcap + 31) / 32] query has been decided
     constexpr bool EXPLICIT = MODE == 1;
     constexpr bool INIT = MODE == 2;
-    __shared__ int s_warp[SBP_WARPS], s_hist[32], s_keep[3], s_removed, s_nm;
+    __shared__ int s_warp[SBP_WARPS], s_hist[32], s_keep[3], s_removed, s_nm, s_unres;
     uint32_t *s_ent = reinterpret_cast<uint32_t *>(smem + P.smem_fixed);  // entry staging area
 
     const int pair = blockIdx.x;
@@ -444,9 +449,62 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     __threadfence_block();
     __syncthreads();
 
-    // ---- C: sequential accept loop (one warp); the next query's entries are prefetched while the
-    //         current one is resolved (only the `taken` test depends on earlier queries) ----
-    if (tid < 32) {
+    // ---- C: the accept loop.  In the reference it is sequential: query q takes the best candidate that no EARLIER query
+    //         took.  For the best-only rule (rule 0: SearchByProjection(Frame,Frame) and the best-only guided searches) it is
+    //         resolved in parallel rounds of deterministic reservations: every undecided query picks its best free slot and
+    //         stamps its index (atomicMin) on every free slot of its list; a query commits iff its own stamp survived on the
+    //         slot it picked, i.e. no earlier undecided query can still take that slot -- its pick cannot change any more
+    //         (earlier queries can only remove slots it ranks lower).  The outcome equals the sequential loop's; almost every
+    //         query commits in the first round, the rest within a few.  A chain longer than SBP_MAX_ROUNDS finishes in the
+    //         sequential loop below, which skips decided queries. ----
+    for (int i = tid; i < (P.qcap + 31) / 32; i += SBP_THREADS) resolved[i] = 0;
+    __syncthreads();
+    const bool par_rule0 = !INIT && P.rule == 0;
+    if (par_rule0) {
+        for (int round = 0; round < SBP_MAX_ROUNDS; round++) {
+            for (int c = tid; c < nc; c += SBP_THREADS) firstq[c] = 0x7FFFFFFF;
+            if (tid == 0) s_unres = 0;
+            __syncthreads();
+            for (int q = tid; q < nl; q += SBP_THREADS) {
+                if ((resolved[q >> 5] >> (q & 31)) & 1u) continue;
+                const int b = q_off[q], e = q_off[q + 1];
+                uint32_t best = 0xFFFFFFFFu;   // dist << 16 | position: strict-< argmin, first minimum wins
+                for (int p = b; p < e; p++) {
+                    const uint32_t cur = ent[p];
+                    const int i2 = (int)(cur & 0xFFFF);
+                    if (!((taken[i2 >> 5] >> (i2 & 31)) & 1u)) best = min(best, (cur & 0xFFFF0000u) | (uint32_t)(p - b));
+                }
+                if (best == 0xFFFFFFFFu || (int)(best >> 16) > P.th_dist) {   // nothing acceptable now, and the free set only shrinks
+                    atomicOr(&resolved[q >> 5], 1u << (q & 31));
+                    choice[q] = 0xFFFF;
+                    continue;
+                }
+                choice[q] = (uint16_t)(ent[b + (int)(best & 0xFFFF)] & 0xFFFF);
+                for (int p = b; p < e; p++) {
+                    const int i2 = (int)(ent[p] & 0xFFFF);
+                    if (!((taken[i2 >> 5] >> (i2 & 31)) & 1u)) atomicMin(&firstq[i2], q);
+                }
+            }
+            __syncthreads();
+            for (int q = tid; q < nl; q += SBP_THREADS) {
+                if ((resolved[q >> 5] >> (q & 31)) & 1u) continue;
+                const int i2 = choice[q];
+                if (firstq[i2] == q) {
+                    atomicOr(&taken[i2 >> 5], 1u << (i2 & 31));
+                    mp[i2] = q;
+                    newbin[i2] = 0xFE;  // matched in this call; the rotation bin is filled in phase D
+                    atomicOr(&resolved[q >> 5], 1u << (q & 31));
+                    atomicAdd(&s_nm, 1);
+                } else {
+                    s_unres = 1;
+                }
+            }
+            __syncthreads();
+            if (!s_unres) break;
+            __syncthreads();   // everybody has read s_unres before the next round clears it
+        }
+    }
+    if (tid < 32 && !(par_rule0 && !s_unres)) {
         const int lane = tid;
         int nm = 0;
         int b = q_off[0], e = (nl > 0) ? q_off[1] : 0;
@@ -455,6 +513,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
             // prefetch query q+1
             const int nb = e, ne = (q + 1 < nl) ? q_off[q + 2] : e;
             const uint32_t nen = (q + 1 < nl && nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
+            if (par_rule0 && ((resolved[q >> 5] >> (q & 31)) & 1u)) { b = nb; e = ne; en = nen; continue; }   // decided in the parallel rounds
             if (INIT && b != e) {
                 // best / second over the candidates whose current match is worse than this distance (:637); strict-< update
                 // order = first minimum wins, the second best is the minimum over the remaining candidates
@@ -553,7 +612,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
             }
             b = nb; e = ne; en = nen;
         }
-        if (lane == 0) s_nm = nm;
+        if (lane == 0) s_nm += nm;
     }
     __syncthreads();
 
@@ -626,9 +685,12 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
 }
 
 size_t sbp_smem_fixed_bytes(int cap, int qcap) {
-    size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)qcap + 1) +
-               2 * sizeof(float) * (size_t)cap + sizeof(uint32_t) * (((size_t)cap + 31) / 32) + sizeof(uint16_t) * (size_t)cap +
-               2 * (size_t)cap + ((size_t)cap & 1) + 2 * sizeof(uint16_t) * (size_t)cap /* MODE 2: matched distance + owner */;
+    size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)qcap + 1) +   // cell_start, cell_cur, q_off
+               2 * sizeof(float) * (size_t)cap + sizeof(uint32_t) * (((size_t)cap + 31) / 32) +              // kx, ky, taken
+               sizeof(uint16_t) * (size_t)cap + 2 * (size_t)cap +                                             // items, newbin, koct
+               2 * sizeof(uint16_t) * (size_t)cap +                                                           // MODE 2: matched distance, owner
+               sizeof(int) * (size_t)cap + sizeof(uint16_t) * ((size_t)qcap + ((size_t)qcap & 1)) +           // rule 0: stamps, picks
+               sizeof(uint32_t) * (((size_t)qcap + 31) / 32);                                                 // rule 0: decided bits
     return (b + 15) / 16 * 16;
 }
 
