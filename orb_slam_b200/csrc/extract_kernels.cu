@@ -682,10 +682,11 @@ void launch_cell_quota(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int 
 // Survivors are appended (order irrelevant) to the level's kept list as 64-bit selection keys
 //   score(8) << 36 | (4095 - cell)(12) << 24 | (0xFFFFFF - raster)(24).
 // ------------------------------------------------------------------------------------------------
+#define CS_LIST 256   // candidates sharing the score at the cut that are ranked directly
 __global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
     __shared__ int hist[256];
-    __shared__ uint32_t s_prefix, s_mask;
-    __shared__ int s_k, s_base, s_fill;
+    __shared__ uint32_t s_prefix, s_mask, s_list[CS_LIST];
+    __shared__ int s_k, s_base, s_fill, s_bin_cnt, s_ln;
 
     const int gcell = blockIdx.x, f = blockIdx.y + f0;
     const size_t fc = (size_t)f * plan->ncells_total + gcell;
@@ -729,19 +730,40 @@ __global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restr
                 }
                 const int fl = __ffs(__ballot_sync(0xffffffffu, incl >= k)) - 1;  // the bins are known to hold >= k keys
                 if (tid == fl) {
-                    int cum = incl - sum, b = 255 - 8 * tid;
+                    int cum = incl - sum, b = 255 - 8 * tid, t = 0;
 #pragma unroll
-                    for (int t = 0; t < 8; t++) {
+                    for (; t < 8; t++) {
                         if (cum + hb[t] >= k) break;
                         cum += hb[t];
                         b--;
                     }
                     s_k = k - cum;  // rank inside bin b
+                    s_bin_cnt = hb[min(t, 7)];
                     s_prefix = prefix | ((uint32_t)b << shift);
                     s_mask = mask | (0xFFu << shift);
+                    s_ln = 0;
                 }
             }
             __syncthreads();
+            // after the score byte the cut falls inside ONE score value: when few candidates share it (the usual case), rank
+            // them directly instead of three more radix passes over all keys
+            if (shift == 24 && s_bin_cnt <= CS_LIST) {
+                const uint32_t prefix2 = s_prefix;
+                for (int i = tid; i < n; i += blockDim.x) {
+                    const uint32_t k = keys[i];
+                    if (k >= min_key && (k & 0xFF000000u) == prefix2) s_list[atomicAdd(&s_ln, 1)] = k;
+                }
+                __syncthreads();
+                const int ln = s_ln, kk = s_k;
+                for (int t = tid; t < ln; t += blockDim.x) {
+                    const uint32_t mine = s_list[t];
+                    int rank = 0;
+                    for (int j = 0; j < ln; j++) rank += s_list[j] > mine;
+                    if (rank == kk - 1) s_prefix = mine;   // keys are unique: exactly one thread
+                }
+                __syncthreads();
+                break;
+            }
         }
         cut = s_prefix;  // the keep-th largest eligible key
     }
