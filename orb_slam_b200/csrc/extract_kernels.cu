@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
             uint32_t out = 0;
             for (int i = 0; i < 4; i++) {
                 const int a0 = (int)(as[i] & 0xFFFF), a1 = (int)(as[i] >> 16);
-                const int r0 = (int)__ldg(s0 + xs[i]) * a0 + (int)__ldg(s0 + xs[i] + 1) * a1;
-                const int r1 = (int)__ldg(s1 + xs[i]) * a0 + (int)__ldg(s1 + xs[i] + 1) * a1;
+                const int xn = min(xs[i] + 1, S.w - 1);   // the right tap of the last column has weight 0: keep its address inside the row
+                const int r0 = (int)__ldg(s0 + xs[i]) * a0 + (int)__ldg(s0 + xn) * a1;
+                const int r1 = (int)__ldg(s1 + xs[i]) * a0 + (int)__ldg(s1 + xn) * a1;
                 int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
                 out |= (uint32_t)min(max(v, 0), 255) << (8 * i);
             }
@@ -93,13 +94,17 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__rest
         rr[ry] = __ldg(&D.yrows[y]);
         bb[ry] = __ldg(&D.yab[y]);
     }
+    // the three words may reach past the last pixel of the row (those bytes only meet zero weights); when level 0 is the
+    // caller's buffer there is no slack behind the last row: keep the word addresses inside the row
+    const int wlim = max((spitch - 4 - sbase) >> 2, 0);
+    const int w1 = min(1, wlim), w2 = min(2, wlim);
     uint32_t u[RZ_ROWS][3], v[RZ_ROWS][3];
 #pragma unroll
     for (int ry = 0; ry < RZ_ROWS; ry++) {
         const uint32_t *p0 = reinterpret_cast<const uint32_t *>(src + (size_t)rr[ry].x * spitch);
         const uint32_t *p1 = reinterpret_cast<const uint32_t *>(src + (size_t)rr[ry].y * spitch);
-        u[ry][0] = __ldg(p0); u[ry][1] = __ldg(p0 + 1); u[ry][2] = __ldg(p0 + 2);
-        v[ry][0] = __ldg(p1); v[ry][1] = __ldg(p1 + 1); v[ry][2] = __ldg(p1 + 2);
+        u[ry][0] = __ldg(p0); u[ry][1] = __ldg(p0 + w1); u[ry][2] = __ldg(p0 + w2);
+        v[ry][0] = __ldg(p1); v[ry][1] = __ldg(p1 + w1); v[ry][2] = __ldg(p1 + w2);
     }
 #pragma unroll
     for (int ry = 0; ry < RZ_ROWS; ry++) {

@@ -96,6 +96,12 @@ struct OrbfeExtractor {
     size_t counters_bytes = 0;
     size_t ls_smem = 0;
     int8_t *d_pattern = nullptr;
+    // level 0 either lives in the plan's own pitched planes or IS the caller's device buffer (no ingest copy)
+    uint8_t *own_pyr0 = nullptr;
+    int own_pitch0 = 0;
+    size_t own_plane0 = 0;
+    void *tma_encode = nullptr;      // cuTensorMapEncodeTiled
+    CUtensorMap *d_maps = nullptr;   // [nlevels] in device memory
     // own outputs (host-API path)
     OrbfeKeyPoint *d_kps = nullptr;
     uint8_t *d_desc = nullptr;
@@ -118,6 +124,7 @@ static void free_plan(OrbfeExtractor *ex) {
     for (void *p : ex->allocs) cudaFree(p);
     ex->allocs.clear();
     ex->dplan = nullptr;
+    ex->own_pyr0 = nullptr; ex->d_maps = nullptr;
     ex->counters = nullptr;
     ex->d_kps = nullptr;
     ex->d_desc = nullptr;
@@ -386,6 +393,8 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         CU_TRY(dmalloc(ex, &d_maps, maps.size()));
         CU_TRY(cudaMemcpy(d_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice));
         Wk.tmaps = d_maps;
+        ex->tma_encode = fn;
+        ex->d_maps = d_maps;
         cudaError_t e = (cudaError_t)fast_tma_setup();
         if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(fast_nms_tma_kernel): %s", cudaGetErrorString(e));
         int nsm = 148;
@@ -424,6 +433,51 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     }
     CU_TRY(cudaStreamSynchronize(ex->stream));
     ex->W = W; ex->H = H; ex->Bcap = B;
+    ex->own_pyr0 = P.lv[0].pyr; ex->own_pitch0 = P.lv[0].pitch; ex->own_plane0 = P.lv[0].plane;
+    return ORBFE_OK;
+}
+
+// Point level 0 of the plan at `ptr` (the plan's own planes, or the caller's device frames when they can be read in place:
+// 16-byte aligned base and strides, as the level-0 tensor map requires).  Stream-ordered: the device copy of the level
+// descriptor and the level-0 tensor map are rewritten on `s` before the kernels that read them.
+static int set_level0(OrbfeExtractor *ex, uint8_t *ptr, int pitch, size_t plane, int batch, cudaStream_t s) {
+    LevelDev &L0 = ex->hplan.lv[0];
+    if (L0.pyr == ptr && L0.pitch == pitch && L0.plane == plane) return ORBFE_OK;
+    L0.pyr = ptr; L0.pitch = pitch; L0.plane = plane;
+    CU_TRY(cudaMemcpyAsync(&ex->dplan->lv[0], &L0, sizeof(LevelDev), cudaMemcpyHostToDevice, s));
+    if (ex->d_maps && ex->tma_encode) {
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        CUtensorMap m;
+        const cuuint64_t dims[3] = {(cuuint64_t)L0.w, (cuuint64_t)L0.h, (cuuint64_t)std::max(batch, ex->Bcap)};
+        const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)plane};
+        const cuuint32_t box[3] = {160, ORBFE_FT_H + 8, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ((EncodeFn)ex->tma_encode)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled(level 0, in place) failed: %d", (int)r);
+        CU_TRY(cudaMemcpyAsync(&ex->d_maps[0], &m, sizeof(m), cudaMemcpyHostToDevice, s));
+    }
+    return ORBFE_OK;
+}
+
+// Level 0 = the caller's device frames (no copy) when base and strides are 16-byte aligned; else a 2-D copy into the plan's planes.
+static int ingest_device(OrbfeExtractor *ex, const uint8_t *d_imgs, int width, int height, size_t stride, size_t frame_stride, int batch,
+                         cudaStream_t s) {
+    const bool in_place = !getenv("ORBFE_INGEST_COPY") && ((uintptr_t)d_imgs % 16 == 0) && stride % 16 == 0 && frame_stride % 16 == 0 &&
+                          stride <= (size_t)INT_MAX && frame_stride >= stride * (size_t)height;
+    if (in_place) return set_level0(ex, const_cast<uint8_t *>(d_imgs), (int)stride, frame_stride, batch, s);
+    int rc = set_level0(ex, ex->own_pyr0, ex->own_pitch0, ex->own_plane0, batch, s);
+    if (rc) return rc;
+    const LevelDev &L0 = ex->hplan.lv[0];
+    if (frame_stride == stride * (size_t)height && L0.plane == (size_t)L0.pitch * height) {
+        CU_TRY(cudaMemcpy2DAsync(L0.pyr, L0.pitch, d_imgs, stride, width, (size_t)height * batch, cudaMemcpyDeviceToDevice, s));
+    } else {
+        for (int f = 0; f < batch; f++)
+            CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, d_imgs + f * frame_stride, stride, width, height,
+                                     cudaMemcpyDeviceToDevice, s));
+    }
     return ORBFE_OK;
 }
 
@@ -596,16 +650,9 @@ extern "C" int orbfe_extract_batch_device(OrbfeExtractor *ex, const uint8_t *d_i
     int rc = build_plan(ex, width, height, batch);
     if (rc) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : ex->stream;
-    const LevelDev &L0 = ex->hplan.lv[0];
     profiling_begin(ex, s);
-    if (frame_stride == stride * (size_t)height && L0.plane == (size_t)L0.pitch * height) {
-        // frames are stacked: one 2-D copy of batch*height rows
-        CU_TRY(cudaMemcpy2DAsync(L0.pyr, L0.pitch, d_imgs, stride, width, (size_t)height * batch, cudaMemcpyDeviceToDevice, s));
-    } else {
-        for (int f = 0; f < batch; f++)
-            CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, d_imgs + f * frame_stride, stride, width, height,
-                                     cudaMemcpyDeviceToDevice, s));
-    }
+    rc = ingest_device(ex, d_imgs, width, height, stride, frame_stride, batch, s);
+    if (rc) return rc;
     stage_mark(ex, s, "ingest");
     ex->last_launches = 0;
     rc = zero_counters(ex, s);
@@ -625,15 +672,9 @@ int orbfe_extract_batch_device_peers(OrbfeExtractor *ex, const uint8_t *d_imgs, 
     if (rc) return rc;
     if (cap != ex->hplan.nfeatures) return fail(ORBFE_ERR_ARG, "exchange capacity %d != keypoint slots per frame %d", cap, ex->hplan.nfeatures);
     cudaStream_t s = stream ? (cudaStream_t)stream : ex->stream;
-    const LevelDev &L0 = ex->hplan.lv[0];
     profiling_begin(ex, s);
-    if (frame_stride == stride * (size_t)height && L0.plane == (size_t)L0.pitch * height) {
-        CU_TRY(cudaMemcpy2DAsync(L0.pyr, L0.pitch, d_imgs, stride, width, (size_t)height * batch, cudaMemcpyDeviceToDevice, s));
-    } else {
-        for (int f = 0; f < batch; f++)
-            CU_TRY(cudaMemcpy2DAsync(L0.pyr + f * L0.plane, L0.pitch, d_imgs + f * frame_stride, stride, width, height,
-                                     cudaMemcpyDeviceToDevice, s));
-    }
+    rc = ingest_device(ex, d_imgs, width, height, stride, frame_stride, batch, s);
+    if (rc) return rc;
     stage_mark(ex, s, "ingest");
     ex->last_launches = 0;
     rc = zero_counters(ex, s);
@@ -652,6 +693,8 @@ extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int 
     int rc = build_plan(ex, width, height, batch);
     if (rc) return rc;
     cudaStream_t s = ex->stream;
+    rc = set_level0(ex, ex->own_pyr0, ex->own_pitch0, ex->own_plane0, batch, s);   // the uploads land in the plan's own planes
+    if (rc) return rc;
     const PlanDev &P = ex->hplan;
     const LevelDev &L0 = P.lv[0];
     profiling_begin(ex, s);

@@ -179,6 +179,54 @@ def small(args):
     return out
 
 
+def exchange1(args):
+    """The exchange variant of the descriptor kernel with a world of ONE rank (its peer table holds only this GPU): what the
+    remote-store code path, the acknowledgement poll and the publish cost by themselves, without NVLink or a second rank."""
+    import torch
+    import torch.distributed as dist
+    import orb_slam_b200 as fe
+    from orb_slam_b200 import comm as CM
+    from orb_slam_b200.synth import textured_frame
+    W, H, NF, T = 1280, 720, 2000, 8
+    dev = torch.device("cuda", 0)
+    frames = np.stack([textured_frame(W, H, seed=40 + t) for t in range(T)])
+    d_frames = torch.from_numpy(frames).to(dev)
+    ex = fe.ORBextractor(NF, 1.2, 8)
+    comm = CM.Comm.create(torch, dist, 0)
+    x = CM.RigExchange(comm, NF, T)
+    d_kps = torch.zeros((T, NF, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((T, NF, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros((T,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    s = stream.cuda_stream
+
+    def plain():
+        ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, T, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), s)
+
+    def exch():
+        x.extract(ex, d_frames.data_ptr(), W, H, W, W * H, s)
+
+    out = {"what": "exchange variant of describe_fused with world = 1 (8 x 1280x720, 2000 kp)"}
+    ex.set_profiling(True)
+    for name, fn in (("plain", plain), ("exchange_self", exch), ("plain_again", plain)):
+        for _ in range(args.warmup):
+            fn()
+        stream.synchronize()
+        ex.stage_times()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.iters):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+        acc = {}
+        for k, v in ex.stage_times():
+            acc[k] = acc.get(k, 0.0) + v / args.iters
+        out[name] = {"ms_per_call": e0.elapsed_time(e1) / args.iters, "describe_ms": acc.get("describe")}
+    x.close(); comm.close(); ex.close()
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="config3,config5")
@@ -188,4 +236,4 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     for w in args.what.split(","):
-        print(json.dumps({"config3": config3, "config5": config5, "small": small}[w](args)))
+        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1}[w](args)))
