@@ -1490,19 +1490,21 @@ __global__ void __launch_bounds__(256) describe_fused_exchange_kernel(const Plan
     }
     __syncthreads();
     describe_fused_body<true>(plan, wk, g_pattern, nullptr, nullptr, nullptr, f0, po);
-    // ---- publish: the block barrier orders every warp's remote stores before thread 0, whose system-scope fence is
-    //      cumulative over them (the pattern of a cooperative-groups grid barrier: bar.sync, then ONE fencing thread); the
-    //      last block to arrive -- all others' stores are then visible system-wide -- writes the epoch into every rank's flag ----
+    // ---- publish.  The block barrier orders every warp's remote stores before thread 0, whose RELEASE increment of the arrival
+    //      counter (gpu scope: the counter is only read by this GPU's blocks) is cumulative over them.  The last block to
+    //      arrive has read the counter after all the others' releases; its acq_rel fence at SYSTEM scope then orders all of that
+    //      before the epoch words it stores into every rank's flag array.  (A seq_cst system fence per block, which is what
+    //      __threadfence_system() is, cost 20 us per 16 k keypoints even with a single local destination.)
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
         const unsigned total = gridDim.x * gridDim.y;
-        const unsigned prev = atomicAdd(po.done, 1u);
+        unsigned prev;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(po.done) : "memory");
         if (prev == total - 1) {
-            __threadfence_system();
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             *po.done = 0;   // ready for the next launch (stream order separates them)
             for (int p = 0; p < po.n; p++)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(po.flag[p]), "r"(po.epoch) : "memory");
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(po.flag[p]), "r"(po.epoch) : "memory");   // fence above + relaxed store = release
         }
     }
 }

@@ -331,12 +331,13 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
         if (!P.xw_done) return;
         __syncthreads();
         if (tid == 0) {
-            __threadfence();
-            if (atomicAdd(P.xw_done, 1u) == gridDim.x - 1) {
+            unsigned prev;
+            asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(P.xw_done) : "memory");
+            if (prev == gridDim.x - 1) {
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
                 *P.xw_done = 0;
-                __threadfence_system();
                 for (int r = 0; r < P.xw_n; r++)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xw_ack[r]), "r"(P.xw_epoch) : "memory");
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(P.xw_ack[r]), "r"(P.xw_epoch) : "memory");
             }
         }
     };
@@ -450,17 +451,20 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     __syncthreads();
 
     // ---- C: the accept loop.  In the reference it is sequential: query q takes the best candidate that no EARLIER query
-    //         took.  For the best-only rule (rule 0: SearchByProjection(Frame,Frame) and the best-only guided searches) it is
-    //         resolved in parallel rounds of deterministic reservations: every undecided query picks its best free slot and
-    //         stamps its index (atomicMin) on every free slot of its list; a query commits iff its own stamp survived on the
-    //         slot it picked, i.e. no earlier undecided query can still take that slot -- its pick cannot change any more
-    //         (earlier queries can only remove slots it ranks lower).  The outcome equals the sequential loop's; almost every
-    //         query commits in the first round, the rest within a few.  A chain longer than SBP_MAX_ROUNDS finishes in the
-    //         sequential loop below, which skips decided queries. ----
+    //         took.  Here it is resolved in parallel rounds of deterministic reservations: every undecided query picks its
+    //         best free slot and stamps its index (atomicMin) on every free slot of its list.  Best-only rule (rule 0:
+    //         SearchByProjection(Frame,Frame) and the best-only guided searches): a query commits iff its own stamp survived on
+    //         the slot it picked -- no earlier undecided query can still take that slot, and earlier queries can only remove
+    //         slots it ranks lower, so the pick is final.  Second-best rules (1, 2): the runner-up matters too, so a query
+    //         decides (accept OR reject) only once its stamp survived on EVERY free slot of its list.  The outcome equals the
+    //         sequential loop's; almost every query is decided in the first round, the rest within a few.  A chain longer
+    //         than SBP_MAX_ROUNDS finishes in the sequential loop below, which skips decided queries.
+    //         SearchForInitialization (MODE 2) re-assigns slots by distance and keeps the sequential warp. ----
     for (int i = tid; i < (P.qcap + 31) / 32; i += SBP_THREADS) resolved[i] = 0;
     __syncthreads();
-    const bool par_rule0 = !INIT && P.rule == 0;
+    const bool par_rule0 = !INIT;   // rules 0, 1, 2 (SearchForInitialization's re-assignment rule keeps the sequential warp)
     if (par_rule0) {
+        const bool needs_all = P.rule != 0;   // the second-best rules read EVERY free slot of the list, not just the pick
         for (int round = 0; round < SBP_MAX_ROUNDS; round++) {
             for (int c = tid; c < nc; c += SBP_THREADS) firstq[c] = 0x7FFFFFFF;
             if (tid == 0) s_unres = 0;
@@ -474,12 +478,13 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
                     const int i2 = (int)(cur & 0xFFFF);
                     if (!((taken[i2 >> 5] >> (i2 & 31)) & 1u)) best = min(best, (cur & 0xFFFF0000u) | (uint32_t)(p - b));
                 }
-                if (best == 0xFFFFFFFFu || (int)(best >> 16) > P.th_dist) {   // nothing acceptable now, and the free set only shrinks
+                // no free slot, or (best-only rule) a best that is already too far: final, because the free set only shrinks
+                if (best == 0xFFFFFFFFu || (!needs_all && (int)(best >> 16) > P.th_dist)) {
                     atomicOr(&resolved[q >> 5], 1u << (q & 31));
                     choice[q] = 0xFFFF;
                     continue;
                 }
-                choice[q] = (uint16_t)(ent[b + (int)(best & 0xFFFF)] & 0xFFFF);
+                choice[q] = (uint16_t)(best & 0xFFFF);   // POSITION of the pick inside the list
                 for (int p = b; p < e; p++) {
                     const int i2 = (int)(ent[p] & 0xFFFF);
                     if (!((taken[i2 >> 5] >> (i2 & 31)) & 1u)) atomicMin(&firstq[i2], q);
@@ -488,15 +493,41 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
             __syncthreads();
             for (int q = tid; q < nl; q += SBP_THREADS) {
                 if ((resolved[q >> 5] >> (q & 31)) & 1u) continue;
-                const int i2 = choice[q];
-                if (firstq[i2] == q) {
+                const int b = q_off[q], e = q_off[q + 1];
+                const int bpos = choice[q];
+                const uint32_t bent = ent[b + bpos];
+                const int i2 = (int)(bent & 0xFFFF), bd = (int)(bent >> 16);
+                bool mine = firstq[i2] == q, accept = true;
+                if (needs_all && mine) {
+                    // every free slot of the list must carry this query's stamp: then no earlier undecided query can change the
+                    // second best either, and the decision -- accept OR reject -- is final
+                    uint32_t second = 0xFFFFFFFFu;
+                    for (int p = b; p < e; p++) {
+                        const uint32_t c2 = ent[p];
+                        const int j2 = (int)(c2 & 0xFFFF);
+                        if ((taken[j2 >> 5] >> (j2 & 31)) & 1u) continue;
+                        if (firstq[j2] != q) { mine = false; break; }
+                        if (p - b != bpos) second = min(second, (c2 & 0xFFFF0000u) | (uint32_t)(p - b));
+                    }
+                    if (mine) {
+                        // INT_MAX stands for "no second candidate": (float)INT_MAX in the reference's comparisons
+                        const float sd = second == 0xFFFFFFFFu ? 2147483648.0f : (float)(int)(second >> 16);
+                        if (P.rule == 1) {
+                            accept = (float)bd <= __fmul_rn(sd, P.nnratio) && bd <= 100;
+                        } else {
+                            const int lb = koct[i2];
+                            const int ls = second == 0xFFFFFFFFu ? -1 : (int)koct[ent[b + (int)(second & 0xFFFF)] & 0xFFFF];
+                            accept = bd <= 100 && !(lb == ls && (float)bd > __fmul_rn(P.nnratio, sd));
+                        }
+                    }
+                }
+                if (!mine) { s_unres = 1; continue; }
+                atomicOr(&resolved[q >> 5], 1u << (q & 31));
+                if (accept) {
                     atomicOr(&taken[i2 >> 5], 1u << (i2 & 31));
                     mp[i2] = q;
                     newbin[i2] = 0xFE;  // matched in this call; the rotation bin is filled in phase D
-                    atomicOr(&resolved[q >> 5], 1u << (q & 31));
                     atomicAdd(&s_nm, 1);
-                } else {
-                    s_unres = 1;
                 }
             }
             __syncthreads();

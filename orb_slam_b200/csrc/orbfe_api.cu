@@ -702,7 +702,7 @@ extern "C" int orbfe_extract_batch(OrbfeExtractor *ex, const uint8_t *imgs, int 
     rc = zero_counters(ex, s);
     if (rc) return rc;
     // H2D of chunk k+1 (copy stream) overlaps the kernels of chunk k (compute stream)
-    int nchunks = batch >= 32 ? 8 : batch >= 8 ? 4 : 1;
+    int nchunks = batch >= 8 ? 4 : 1;   // measured on B200 (64 x 1080p, two handles): 4 chunks 32-33, 8 chunks 31.4, 2 chunks 30.7, 1 chunk 28.1 Mkp/s end to end
     if (const char *e = getenv("ORBFE_CHUNKS")) nchunks = std::max(1, std::min(batch, atoi(e)));  // tuning knob
     if (!ex->copy_stream) CU_TRY(cudaStreamCreateWithFlags(&ex->copy_stream, cudaStreamNonBlocking));
     while ((int)ex->chunk_ev.size() < nchunks + 1) {
