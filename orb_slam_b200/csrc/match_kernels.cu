@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     }
     if (INIT) {
         for (int i = tid; i < cap; i += SBP_THREADS) { mp[i] = -1; if (i >= nc) newbin[i] = 0xFF; }   // vnMatches12 = -1 (:601); newbin = rotation bin per F1 feature
+        for (int i = tid; i < P.qcap; i += SBP_THREADS) choice[i] = 0xFFFF;                            // slot accepted for each F1 feature
     }
     __syncthreads();
     {   // exclusive scan of the 3072 cell counts: 3 cells per thread
@@ -578,14 +579,10 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
                             mp[q] = i2;
                             owner[i2] = (uint16_t)q;
                             mdist[i2] = (uint16_t)bd;
-                            if (P.check_ori) {   // :666-676; the histogram keeps entries of features that get unmatched later
-                                float rot = __fsub_rn(kl[q].angle, kc[i2].angle);
-                                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                                int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
-                                if (bin == 30) bin = 0;
-                                newbin[q] = (uint8_t)bin;
-                                s_hist[bin]++;
-                            }
+                            // :666-676 the rotation histogram keeps the entries of features that get unmatched later: remember
+                            // the slot accepted for q (a query is accepted at most once); the bins are filled in parallel after
+                            // the loop -- two dependent global angle loads per accept were most of this loop's time
+                            choice[q] = (uint16_t)i2;
                         }
                         nm += prev_owner != 0xFFFF ? 0 : 1;
                         __syncwarp();
@@ -650,6 +647,17 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     // ---- D: rotation consistency ----
     if (INIT) {
         if (P.check_ori) {
+            for (int q = tid; q < nl; q += SBP_THREADS) {   // :666-676, one entry per ACCEPTED feature, unmatched later or not
+                const int i2 = choice[q];
+                if (i2 == 0xFFFF) continue;
+                float rot = __fsub_rn(kl[q].angle, kc[i2].angle);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+                if (bin == 30) bin = 0;
+                newbin[q] = (uint8_t)bin;
+                atomicAdd(&s_hist[bin], 1);
+            }
+            __syncthreads();
             if (tid == 0) {
                 int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
                 for (int i = 0; i < 30; i++) {

@@ -179,6 +179,83 @@ def small(args):
     return out
 
 
+def matchers(args):
+    """Device-resident matcher calls timed with CUDA events: SearchByProjection(Frame,Frame) for 1 and 64 pairs at 1080p / 2000 kp,
+    SearchForInitialization for 8 pairs at 720p (config 4's matcher)."""
+    import torch
+    import orb_slam_b200 as fe
+    from orb_slam_b200 import matching as M
+    from orb_slam_b200.synth import textured_frame, shifted_frame
+    dev = torch.device("cuda", 0)
+    out = {}
+    stream = torch.cuda.Stream(device=dev)
+    s = stream.cuda_stream
+
+    def timed(fn, iters=20, warm=5):
+        for _ in range(warm):
+            fn()
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1) / iters
+    # ---- M2 at the bench geometry
+    W, H, NF = 1920, 1080, 2000
+    f0 = textured_frame(W, H, seed=9)
+    frames = np.stack([f0] + [shifted_frame(f0, 3 * (i % 3) - 3, 2 * (i % 2) - 1, seed=i) for i in range(1, 9)])
+    ex = fe.ORBextractor(NF, 1.2, 8)
+    kps, desc, cnt = ex.extract_batch(frames)
+    ex.close()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    world = np.zeros((9, NF, 3), np.float32)
+    world[:, :, 0] = (kps["x"] - 960.0) / 1000.0 * 5.0; world[:, :, 1] = (kps["y"] - 540.0) / 1000.0 * 5.0; world[:, :, 2] = 5.0
+    d_kps, d_desc, d_cnt = t(kps.view(np.uint8).reshape(9, NF, 28)), t(desc), t(cnt)
+    d_world, d_flags = t(world), torch.ones((9, NF), dtype=torch.uint8, device=dev)
+    m = fe.ORBmatcher(0.9, True)
+    for npairs in (1, 8, 64):
+        cur = np.array([1 + (j % 8) for j in range(npairs)], np.int32)
+        last = cur - 1
+        T = np.tile(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32), (npairs, 1))
+        d_cur, d_last, d_T = t(cur), t(last), t(T)
+        d_mp = torch.full((npairs, NF), -1, dtype=torch.int32, device=dev)
+        d_nm = torch.zeros(npairs, dtype=torch.int32, device=dev)
+
+        def call():
+            d_mp.fill_(-1)
+            M.search_by_projection_device(m, npairs, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), NF, d_cur.data_ptr(), d_last.data_ptr(),
+                                          d_world.data_ptr(), d_flags.data_ptr(), d_T.data_ptr(), W, H, 1.2, 8, 1000.0, 1000.0, 960.0, 540.0, 15.0,
+                                          d_mp.data_ptr(), d_nm.data_ptr(), s)
+        with torch.cuda.stream(stream):
+            out["sbp_ff_%d_pairs_ms" % npairs] = timed(call)
+        out["sbp_ff_%d_pairs_matches" % npairs] = int(d_nm.sum().item())
+    # ---- M8 at the rig geometry
+    W2, H2 = 1280, 720
+    g0 = textured_frame(W2, H2, seed=40)
+    fr2 = np.stack([g0, shifted_frame(g0, 12, 4, seed=1)])
+    ex2 = fe.ORBextractor(NF, 1.2, 8)
+    k2, dd2, c2 = ex2.extract_batch(fr2)
+    ex2.close()
+    d_k2, d_d2, d_c2 = t(k2.view(np.uint8).reshape(2, NF, 28)), t(dd2), t(c2)
+    for npairs in (1, 8):
+        f1 = t(np.zeros(npairs, np.int32)); f2 = t(np.ones(npairs, np.int32))
+        prev0 = np.tile(np.stack([k2[0]["x"], k2[0]["y"]], axis=1).astype(np.float32)[None], (npairs, 1, 1))
+        d_prev0, d_prev = t(prev0), t(prev0)
+        d_m12 = torch.full((npairs, NF), -1, dtype=torch.int32, device=dev); d_nm2 = torch.zeros(npairs, dtype=torch.int32, device=dev)
+
+        def call2():
+            d_prev.copy_(d_prev0)
+            M.search_for_initialization_device(m, npairs, d_k2.data_ptr(), d_d2.data_ptr(), d_c2.data_ptr(), NF, f1.data_ptr(), f2.data_ptr(),
+                                               d_prev.data_ptr(), W2, H2, 100, d_m12.data_ptr(), d_nm2.data_ptr(), s)
+        with torch.cuda.stream(stream):
+            out["init_%d_pairs_ms" % npairs] = timed(call2)
+        out["init_%d_pairs_matches" % npairs] = int(d_nm2.sum().item())
+    m.close()
+    return out
+
+
 def exchange1(args):
     """The exchange variant of the descriptor kernel with a world of ONE rank (its peer table holds only this GPU): what the
     remote-store code path, the acknowledgement poll and the publish cost by themselves, without NVLink or a second rank."""
@@ -236,4 +313,4 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     for w in args.what.split(","):
-        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1}[w](args)))
+        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1, "matchers": matchers}[w](args)))
