@@ -464,8 +464,63 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     for (int i = tid; i < (P.qcap + 31) / 32; i += SBP_THREADS) resolved[i] = 0;
     __syncthreads();
     const bool par_rule0 = !INIT;   // rules 0, 1, 2 (SearchForInitialization's re-assignment rule keeps the sequential warp)
-    if (par_rule0) {
-        const bool needs_all = P.rule != 0;   // the second-best rules read EVERY free slot of the list, not just the pick
+    if (par_rule0 && P.rule == 0) {
+        // Best-only rule: "query q takes its best slot no earlier query took" is the serial dictatorship of the queries over
+        // the slots, which is the unique stable assignment when every slot prefers the lower query index -- so deferred
+        // acceptance reaches it in any proposal order.  firstq[c] = lowest query that proposed to slot c so far (it only
+        // decreases, and the lowest proposer is never displaced); a query whose pick is held by a lower index moves to its
+        // next best slot (distance, then list position) that no lower index holds.  The block iterates until a pass changes
+        // nothing: ~half the passes of the reservation rounds below and a fraction of their work per pass.
+        for (int c = tid; c < nc; c += SBP_THREADS) firstq[c] = ((taken[c >> 5] >> (c & 31)) & 1u) ? -1 : 0x7FFFFFFF;
+        for (int q = tid; q < nl; q += SBP_THREADS) choice[q] = 0xFFFE;   // not started
+        volatile int *holder = firstq;
+        for (;;) {
+            if (tid == 0) s_unres = 0;
+            __syncthreads();
+            bool changed = false;
+            for (int q = tid; q < nl; q += SBP_THREADS) {
+                int pos = choice[q];
+                if (pos == 0xFFFF) continue;   // list exhausted: no match
+                const int b = q_off[q], e = q_off[q + 1];
+                for (;;) {
+                    uint32_t lower = 0;   // keys are compared as key + 1, so 0 = "nothing picked yet"
+                    if (pos != 0xFFFE) {
+                        const uint32_t cur = ent[b + pos];
+                        const int c = (int)(cur & 0xFFFF), h = holder[c];
+                        if (h == q) break;
+                        if (h > q) { atomicMin(&firstq[c], q); changed = true; break; }
+                        lower = ((cur & 0xFFFF0000u) | (uint32_t)pos) + 1u;
+                    }
+                    uint32_t next = 0xFFFFFFFFu;
+                    for (int p = b; p < e; p++) {
+                        const uint32_t cur = ent[p];
+                        const uint32_t key = ((cur & 0xFFFF0000u) | (uint32_t)(p - b)) + 1u;
+                        if (key > lower && key < next && (int)(cur >> 16) <= P.th_dist && holder[cur & 0xFFFF] > q) next = key;
+                    }
+                    changed = true;
+                    pos = next == 0xFFFFFFFFu ? 0xFFFF : (int)((next - 1u) & 0xFFFF);
+                    choice[q] = (uint16_t)pos;
+                    if (pos == 0xFFFF) break;
+                }
+            }
+            if (changed) s_unres = 1;
+            __syncthreads();
+            if (!s_unres) break;
+            __syncthreads();   // everybody has read s_unres before the next pass clears it
+        }
+        for (int q = tid; q < nl; q += SBP_THREADS) {
+            const int pos = choice[q];
+            if (pos == 0xFFFF) continue;
+            const int i2 = (int)(ent[q_off[q] + pos] & 0xFFFF);
+            if (firstq[i2] != q) continue;
+            atomicOr(&taken[i2 >> 5], 1u << (i2 & 31));
+            mp[i2] = q;
+            newbin[i2] = 0xFE;  // matched in this call; the rotation bin is filled in phase D
+            atomicAdd(&s_nm, 1);
+        }
+        __syncthreads();
+    } else if (par_rule0) {
+        const bool needs_all = true;   // the second-best rules read EVERY free slot of the list, not just the pick
         for (int round = 0; round < SBP_MAX_ROUNDS; round++) {
             for (int c = tid; c < nc; c += SBP_THREADS) firstq[c] = 0x7FFFFFFF;
             if (tid == 0) s_unres = 0;
@@ -539,13 +594,26 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     if (tid < 32 && !(par_rule0 && !s_unres)) {
         const int lane = tid;
         int nm = 0;
-        int b = q_off[0], e = (nl > 0) ? q_off[1] : 0;
-        uint32_t en = (nl > 0 && b + lane < e) ? ent[b + lane] : 0xFFFFFFFFu;
-        for (int q = 0; q < nl; q++) {
-            // prefetch query q+1
-            const int nb = e, ne = (q + 1 < nl) ? q_off[q + 2] : e;
-            const uint32_t nen = (q + 1 < nl && nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
-            if (par_rule0 && ((resolved[q >> 5] >> (q & 31)) & 1u)) { b = nb; e = ne; en = nen; continue; }   // decided in the parallel rounds
+        // 32 queries per step: one ballot finds the queries that have candidates and are still undecided, so the empty
+        // ones (4 of 5 in SearchForInitialization: only level-0 features ask) cost no dependent shared-memory round trip
+        for (int q0 = 0; q0 < nl; q0 += 32) {
+            const int ql = q0 + lane;
+            int bb = 0, ee = 0;
+            if (ql < nl) { bb = q_off[ql]; ee = q_off[ql + 1]; }
+            if (par_rule0 && ql < nl && ((resolved[ql >> 5] >> (ql & 31)) & 1u)) ee = bb;   // decided in the parallel rounds
+            unsigned todo = __ballot_sync(0xffffffffu, ee != bb);
+            int jn = todo ? __ffs(todo) - 1 : 0;
+            int nb = __shfl_sync(0xffffffffu, bb, jn), ne = __shfl_sync(0xffffffffu, ee, jn);
+            uint32_t nen = (todo && nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
+            while (todo) {
+            const int q = q0 + jn, b = nb, e = ne;
+            const uint32_t en = nen;
+            todo &= todo - 1;
+            if (todo) {   // prefetch the next query that has work
+                jn = __ffs(todo) - 1;
+                nb = __shfl_sync(0xffffffffu, bb, jn); ne = __shfl_sync(0xffffffffu, ee, jn);
+                nen = (nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
+            }
             if (INIT && b != e) {
                 // best / second over the candidates whose current match is worse than this distance (:637); strict-< update
                 // order = first minimum wins, the second best is the minimum over the remaining candidates
@@ -638,7 +706,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
                     __syncwarp();
                 }
             }
-            b = nb; e = ne; en = nen;
+            }
         }
         if (lane == 0) s_nm += nm;
     }
