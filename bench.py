@@ -436,28 +436,39 @@ def main():
     ones_u8, zeros_u8 = np.ones(NFEAT, np.uint8), np.zeros(NFEAT, np.uint8)
     checks = {"device": None, "e2e": None}    # last finished sub-step of each path, for the oracle cross-check
 
+    Tcws_arr = np.ascontiguousarray(np.stack(Tcws).reshape(args.frames, 12), np.float32)
+    ones_ptr, zeros_ptr = np.uint64(ones_u8.ctypes.data), np.uint64(zeros_u8.ctypes.data)
+
     def prepare_views(kps_a, desc_a, cnt_a):
-        """Frame views + synthetic map points of one batch's host results, plus a private copy of the batch's last frame
-        (it is the Last frame of the next batch's first pair, and the pinned result buffers are reused)."""
+        """Frame views + synthetic map points of one batch's host results (array operations over the whole batch: this glue
+        stands for the reference's C++ Frame construction and must not be what the pipeline waits for), plus a private
+        copy of the batch's last frame (the Last frame of the next batch's first pair; the pinned buffers are reused)."""
         t0 = time.perf_counter()
-        views = [M.FrameView(kps_a[i, :cnt_a[i]], desc_a[i, :cnt_a[i]], W, H, SCALE, NLEVELS) for i in range(B)]
-        wpts = [backproject(f.kps) for f in views]
-        tail = (M.FrameView(views[B - 1].kps.copy(), views[B - 1].desc.copy(), W, H, SCALE, NLEVELS), wpts[B - 1].copy())
+        batch = M.FrameViewBatch(kps_a, desc_a, cnt_a, W, H, SCALE, NLEVELS)
+        wpts = np.empty((B, NFEAT, 3), np.float32)            # same float32 ops as backproject()
+        wpts[:, :, 0] = (kps_a["x"] - np.float32(CX)) / np.float32(FX) * np.float32(DEPTH)
+        wpts[:, :, 1] = (kps_a["y"] - np.float32(CY)) / np.float32(FY) * np.float32(DEPTH)
+        wpts[:, :, 2] = DEPTH
+        tail_view, tail_keep = batch.tail()
+        tail = (tail_view, wpts[B - 1].copy(), tail_keep)
         host_t["views"] += time.perf_counter() - t0
-        return views, wpts, tail
+        return batch, wpts, tail
 
     def match_step(sb, prepared, prev_prepared, matcher):
-        views, world_cur, tail = prepared
+        batch, world_cur, tail = prepared
         t1 = time.perf_counter()
-        pv, pw = prev_prepared[2] if prev_prepared is not None else tail
-        lasts = [pv] + views[:-1]
-        wl = [pw] + world_cur[:-1]
-        has = [ones_u8[:f.n] for f in lasts]
-        outl = [zeros_u8[:f.n] for f in lasts]
-        nm, mp = M.search_by_projection_frames(matcher, views, lasts, has, outl, wl, Tcws[sb * B:(sb + 1) * B], FX, FY, CX, CY, MATCH_TH)
+        pv, pw, _keep = prev_prepared[2] if prev_prepared is not None else tail
+        views_last = np.concatenate([pv, batch.views[:-1]])
+        wrows = M.row_pointers(world_cur)
+        world_ptrs = np.concatenate([np.array([pw.ctypes.data], np.uint64), wrows[:-1]])
+        mp = np.full((B, NFEAT), -1, np.int32)
+        nm = M.search_by_projection_views(matcher, batch.views, views_last, np.full(B, ones_ptr, np.uint64), np.full(B, zeros_ptr, np.uint64),
+                                          world_ptrs, Tcws_arr[sb * B:(sb + 1) * B], FX, FY, CX, CY, MATCH_TH, mp)
         host_t["match_call"] += time.perf_counter() - t1
         host_t["n"] += 1
-        checks["e2e"] = (sb, [v.kps.copy() for v in views[:4]], [v.desc.copy() for v in views[:4]], [m.copy() for m in mp[:4]])
+        cn = batch.counts
+        checks["e2e"] = (sb, [batch.kps[i, :cn[i]].copy() for i in range(4)], [batch.desc[i, :cn[i]].copy() for i in range(4)],
+                         [mp[i].copy() for i in range(4)])
         return int(nm.sum())
 
     def collect_stages():

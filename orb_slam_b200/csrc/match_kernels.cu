@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     // (items, newbin, koct together are 4 * cap bytes after a 4-byte aligned start: what follows stays 4-byte aligned)
     uint16_t *mdist = reinterpret_cast<uint16_t *>(koct + cap);      // MODE 2: [cap] vMatchedDistance (0xFFFF = INT_MAX)
     uint16_t *owner = mdist + cap;                                   // MODE 2: [cap] vnMatches21 (0xFFFF = -1)
-    int *firstq = reinterpret_cast<int *>(owner + cap);              // rule 0: [cap] lowest unresolved query that can still take the slot
+    int *firstq = reinterpret_cast<int *>(mdist);                    // rules 0-2 (never MODE 2): [cap] lowest query holding / stamping the slot -- same bytes as mdist + owner
     uint16_t *choice = reinterpret_cast<uint16_t *>(firstq + cap);   // rule 0: [qcap] the slot a query wants this round
     uint32_t *resolved = reinterpret_cast<uint32_t *>(choice + P.qcap + (P.qcap & 1));  // [(qcap + 31) / 32] query has been decided
     constexpr bool EXPLICIT = MODE == 1;
@@ -353,7 +353,9 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
         const float px = roundf(__fmul_rn(__fsub_rn(k.x, P.min_x), P.gw));
         const float py = roundf(__fmul_rn(__fsub_rn(k.y, P.min_y), P.gh));
         int cell = -1;
-        if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS) cell = (int)px * SBP_GROWS + (int)py;
+        // MODE 2 asks for level-0 features only (:618): the other levels never enter the grid, so the window walks touch
+        // one keypoint in five
+        if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS && !(INIT && k.octave != 0)) cell = (int)px * SBP_GROWS + (int)py;
         newbin[i] = 0xFF;
         if (cell >= 0) atomicAdd(&cell_cur[cell], 1);
         if (INIT) { mdist[i] = 0xFFFF; owner[i] = 0xFFFF; }
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     for (int i = tid; i < nc; i += SBP_THREADS) {
         const float px = roundf(__fmul_rn(__fsub_rn(kx[i], P.min_x), P.gw));
         const float py = roundf(__fmul_rn(__fsub_rn(ky[i], P.min_y), P.gh));
-        if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS) {
+        if (px >= 0.f && px < (float)SBP_GCOLS && py >= 0.f && py < (float)SBP_GROWS && !(INIT && koct[i] != 0)) {
             const int cell = (int)px * SBP_GROWS + (int)py;
             items[atomicAdd(&cell_cur[cell], 1)] = (uint16_t)i;
         }
@@ -431,22 +433,31 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
     }
     uint32_t *ent = (T_total <= P.smem_entries) ? s_ent : scratch + (size_t)pair * P.scratch_per_pair;
 
-    // ---- B2: fill (candidate index | distance << 16) in enumeration order ----
+    // ---- B2: candidate indices in enumeration order (query index in the upper half for now) ----
     for (int q = tid; q < nl; q += SBP_THREADS) {
         int o = q_off[q];
         if (q_off[q + 1] == o) continue;
         const SbpQuery Q = get_query(q);
-        const uint4 a0 = __ldg(&dl[2 * q]), a1 = __ldg(&dl[2 * q + 1]);
         for (int ix = Q.x0; ix <= Q.x1; ix++) {
             const int kb = cell_start[ix * SBP_GROWS + Q.y0], ke = cell_start[ix * SBP_GROWS + Q.y1 + 1];
             for (int k = kb; k < ke; k++) {
                 const int i2 = items[k];
                 if (!octave_ok(koct[i2], Q.lo, Q.hi)) continue;
                 if (fabsf(__fsub_rn(kx[i2], Q.u)) > Q.r || fabsf(__fsub_rn(ky[i2], Q.v)) > Q.r) continue;
-                const int d = ham256(a0, a1, __ldg(&dc[2 * i2]), __ldg(&dc[2 * i2 + 1]));
-                ent[o++] = (uint32_t)i2 | ((uint32_t)d << 16);
+                ent[o++] = (uint32_t)i2 | ((uint32_t)q << 16);
             }
         }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- B3: one 256-bit distance per ENTRY (balanced over the block whatever the list lengths are; the descriptor loads
+    //          of independent entries overlap): entry = candidate index | distance << 16 ----
+#pragma unroll 4
+    for (int p = tid; p < T_total; p += SBP_THREADS) {
+        const uint32_t v = ent[p];
+        const int i2 = (int)(v & 0xFFFF), q = (int)(v >> 16);
+        const int d = ham256(__ldg(&dl[2 * q]), __ldg(&dl[2 * q + 1]), __ldg(&dc[2 * i2]), __ldg(&dc[2 * i2 + 1]));
+        ent[p] = (uint32_t)i2 | ((uint32_t)d << 16);
     }
     __threadfence_block();
     __syncthreads();
@@ -605,54 +616,71 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
             int jn = todo ? __ffs(todo) - 1 : 0;
             int nb = __shfl_sync(0xffffffffu, bb, jn), ne = __shfl_sync(0xffffffffu, ee, jn);
             uint32_t nen = (todo && nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
+            // MODE 2: vMatchedDistance of this lane's candidate rides along with the prefetch (patched below when the query
+            // in between changes that slot)
+            uint32_t nmd = (INIT && todo && nb + lane < ne) ? mdist[nen & 0xFFFF] : 0;
             while (todo) {
             const int q = q0 + jn, b = nb, e = ne;
-            const uint32_t en = nen;
+            const uint32_t en = nen, md = nmd;
             todo &= todo - 1;
             if (todo) {   // prefetch the next query that has work
                 jn = __ffs(todo) - 1;
-                nb = __shfl_sync(0xffffffffu, bb, jn); ne = __shfl_sync(0xffffffffu, ee, jn);
+                // MODE 2 skips only empty lists, so the next list starts where this one ends
+                nb = INIT ? ne : __shfl_sync(0xffffffffu, bb, jn);
+                ne = __shfl_sync(0xffffffffu, ee, jn);
                 nen = (nb + lane < ne) ? ent[nb + lane] : 0xFFFFFFFFu;
+                if (INIT) nmd = (nb + lane < ne) ? mdist[nen & 0xFFFF] : 0;
             }
             if (INIT && b != e) {
                 // best / second over the candidates whose current match is worse than this distance (:637); strict-< update
                 // order = first minimum wins, the second best is the minimum over the remaining candidates
-                uint32_t best = 0xFFFFFFFFu, cur = en;
-                for (int p0 = b; p0 < e; p0 += 32) {
-                    const int p = p0 + lane;
-                    if (p0 != b) cur = (p < e) ? ent[p] : 0xFFFFFFFFu;
+                uint32_t best = 0xFFFFFFFFu, second = 0xFFFFFFFFu;
+                if (e - b <= 32) {
+                    // the usual case, one candidate per lane: keys are unique (lane in the low half), so the second best is
+                    // the minimum with the winner's key masked out -- two REDUX, no second trip through shared memory
                     uint32_t key = 0xFFFFFFFFu;
-                    if (p < e && (uint32_t)mdist[cur & 0xFFFF] > (cur >> 16)) key = (cur & 0xFFFF0000u) | (uint32_t)(p - b);
-                    best = min(best, __reduce_min_sync(0xffffffffu, key));
+                    if (b + lane < e && md > (en >> 16)) key = (en & 0xFFFF0000u) | (uint32_t)lane;
+                    best = __reduce_min_sync(0xffffffffu, key);
+                    second = __reduce_min_sync(0xffffffffu, key == best ? 0xFFFFFFFFu : key);
+                    if (second != 0xFFFFFFFFu) second >>= 16;
+                } else {
+                    uint32_t cur = en;
+                    for (int p0 = b; p0 < e; p0 += 32) {
+                        const int p = p0 + lane;
+                        if (p0 != b) cur = (p < e) ? ent[p] : 0xFFFFFFFFu;
+                        uint32_t key = 0xFFFFFFFFu;
+                        if (p < e && (uint32_t)mdist[cur & 0xFFFF] > (cur >> 16)) key = (cur & 0xFFFF0000u) | (uint32_t)(p - b);
+                        best = min(best, __reduce_min_sync(0xffffffffu, key));
+                    }
+                    if (best != 0xFFFFFFFFu) {
+                        const int bpos = (int)(best & 0xFFFF);
+                        for (int p0 = b; p0 < e; p0 += 32) {
+                            const int p = p0 + lane;
+                            uint32_t key = 0xFFFFFFFFu;
+                            if (p < e && p - b != bpos) {
+                                const uint32_t c2 = ent[p];
+                                if ((uint32_t)mdist[c2 & 0xFFFF] > (c2 >> 16)) key = c2 >> 16;
+                            }
+                            second = min(second, __reduce_min_sync(0xffffffffu, key));
+                        }
+                    }
                 }
                 if (best != 0xFFFFFFFFu) {
                     const int bpos = (int)(best & 0xFFFF), bd = (int)(best >> 16);
-                    uint32_t second = 0xFFFFFFFFu;
-                    for (int p0 = b; p0 < e; p0 += 32) {
-                        const int p = p0 + lane;
-                        uint32_t key = 0xFFFFFFFFu;
-                        if (p < e && p - b != bpos) {
-                            const uint32_t c2 = ent[p];
-                            if ((uint32_t)mdist[c2 & 0xFFFF] > (c2 >> 16)) key = c2 >> 16;
-                        }
-                        second = min(second, __reduce_min_sync(0xffffffffu, key));
-                    }
                     const float sd = second == 0xFFFFFFFFu ? 2147483648.0f : (float)(int)second;   // (float)INT_MAX
                     if (bd <= 50 /* TH_LOW, :652 */ && (float)bd < __fmul_rn(sd, P.nnratio)) {
-                        const int i2 = (int)(ent[b + bpos] & 0xFFFF);
-                        const int prev_owner = owner[i2];
-                        __syncwarp();
+                        // the winner's lane still holds its entry when the list fits one pass
+                        const int i2 = (e - b <= 32) ? (int)(__shfl_sync(0xffffffffu, en, bpos) & 0xFFFF) : (int)(ent[b + bpos] & 0xFFFF);
+                        // :656-660 re-assignment: the slot changes owner.  Only shared memory is touched here -- which feature
+                        // owns the slot at the END decides vnMatches12 (filled in parallel after the loop), and the slot
+                        // accepted for q is remembered for the rotation histogram (:666-676 keeps the entries of features
+                        // that get unmatched later; a query is accepted at most once)
                         if (lane == 0) {
-                            if (prev_owner != 0xFFFF) mp[prev_owner] = -1;   // :656-660 re-assignment
-                            mp[q] = i2;
                             owner[i2] = (uint16_t)q;
                             mdist[i2] = (uint16_t)bd;
-                            // :666-676 the rotation histogram keeps the entries of features that get unmatched later: remember
-                            // the slot accepted for q (a query is accepted at most once); the bins are filled in parallel after
-                            // the loop -- two dependent global angle loads per accept were most of this loop's time
                             choice[q] = (uint16_t)i2;
                         }
-                        nm += prev_owner != 0xFFFF ? 0 : 1;
+                        if (nb + lane < ne && (int)(nen & 0xFFFF) == i2) nmd = (uint32_t)bd;   // the prefetched distance of that slot is stale now
                         __syncwarp();
                     }
                 }
@@ -714,6 +742,14 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
 
     // ---- D: rotation consistency ----
     if (INIT) {
+        {   // vnMatches12: feature q keeps its slot iff it still owns it after every re-assignment
+            int matched = 0;
+            for (int q = tid; q < nl; q += SBP_THREADS) {
+                const int i2 = choice[q];
+                if (i2 != 0xFFFF && owner[i2] == q) { mp[q] = i2; matched++; }
+            }
+            if (matched) atomicAdd(&s_nm, matched);
+        }
         if (P.check_ori) {
             for (int q = tid; q < nl; q += SBP_THREADS) {   // :666-676, one entry per ACCEPTED feature, unmatched later or not
                 const int i2 = choice[q];
@@ -751,6 +787,7 @@ __global__ void __launch_bounds__(SBP_THREADS) sbp_device_kernel(SbpParams P, co
         float *wout = const_cast<float *>(wl);
         for (int q = tid; q < nl; q += SBP_THREADS)
             if (mp[q] >= 0) { wout[2 * q] = kx[mp[q]]; wout[2 * q + 1] = ky[mp[q]]; }
+        __syncthreads();
         if (tid == 0) nmatches[pair] = s_nm - s_removed;
         publish_ack();
         return;
@@ -795,8 +832,8 @@ size_t sbp_smem_fixed_bytes(int cap, int qcap) {
     size_t b = sizeof(int) * (SBP_NCELL + 1) + sizeof(int) * SBP_NCELL + sizeof(int) * ((size_t)qcap + 1) +   // cell_start, cell_cur, q_off
                2 * sizeof(float) * (size_t)cap + sizeof(uint32_t) * (((size_t)cap + 31) / 32) +              // kx, ky, taken
                sizeof(uint16_t) * (size_t)cap + 2 * (size_t)cap +                                             // items, newbin, koct
-               2 * sizeof(uint16_t) * (size_t)cap +                                                           // MODE 2: matched distance, owner
-               sizeof(int) * (size_t)cap + sizeof(uint16_t) * ((size_t)qcap + ((size_t)qcap & 1)) +           // rule 0: stamps, picks
+               sizeof(int) * (size_t)cap +                       // MODE 2: matched distance, owner (u16 each); otherwise the stamps (int)
+               sizeof(uint16_t) * ((size_t)qcap + ((size_t)qcap & 1)) +                                       // picks
                sizeof(uint32_t) * (((size_t)qcap + 31) / 32);                                                 // rule 0: decided bits
     return (b + 15) / 16 * 16;
 }

@@ -837,6 +837,7 @@ extern "C" int orbfe_debug_read_level(OrbfeExtractor *ex, int frame, int level, 
 // ------------------------------------------------------------------------------------------------
 struct OrbfeMatcher {
     int device = 0;
+    int nsm = 148;
     cudaStream_t stream = nullptr;
     // grow-only device scratch for the host-pointer entry points
     void *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -851,6 +852,17 @@ struct OrbfeMatcher {
     unsigned char *d_stage = nullptr;
     size_t stage_cap = 0;
 };
+
+// Dynamic shared memory of the fused matcher (one thread block per pair / job).  What is left after the fixed arrays
+// holds the candidate entries; lists that do not fit go to the global scratch, which costs the accept loop an L2 round
+// trip per list.  Up to one block per SM nothing else of this launch could use the space, so the block takes most of the
+// carve-out; larger launches keep 100 KB so that two blocks share an SM.  ORBFE_SBP_SMEM_KB overrides (measurement knob).
+static size_t sbp_smem_total(const OrbfeMatcher *m, size_t fixed, int nblocks) {
+    size_t total = nblocks <= m->nsm ? 200 * 1024 : 100 * 1024;
+    if (const char *e = getenv("ORBFE_SBP_SMEM_KB")) total = (size_t)std::max(0, atoi(e)) * 1024;
+    total = std::max(total, fixed + 16 * 1024);
+    return total;
+}
 
 static cudaError_t mreserve(OrbfeMatcher *m, int i, size_t bytes) {
     if (m->cap[i] >= bytes) return cudaSuccess;
@@ -882,6 +894,7 @@ extern "C" int orbfe_matcher_create(int device, OrbfeMatcher **out) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         e = cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, hi);
     }
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->nsm, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(m->d_err, 0, sizeof(int));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&m->h_err, sizeof(int), cudaHostAllocDefault);
@@ -952,7 +965,7 @@ extern "C" int orbfe_search_by_projection_device(OrbfeMatcher *m, int npairs, co
     P.qcap = cap; P.rule = 0; P.th_dist = 100 /* TH_HIGH, ORBmatcher.cc:1576 */; P.nnratio = 0.f;
     P.scratch_per_pair = 64 * cap;
     const size_t fixed = sbp_smem_fixed_bytes(cap, cap);
-    const size_t total = std::max<size_t>(fixed + 16 * 1024, 100 * 1024);
+    const size_t total = sbp_smem_total(m, fixed, npairs);
     if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large for the device matcher", cap);
     P.smem_fixed = (int)fixed;
     P.smem_entries = (int)((total - fixed) / sizeof(uint32_t));
@@ -1019,7 +1032,7 @@ int orbfe_search_for_initialization_hooked(OrbfeMatcher *m, int npairs, const Or
     if (per_pair > (size_t)INT_MAX) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large", cap);
     P.scratch_per_pair = (int)per_pair;
     const size_t fixed = sbp_smem_fixed_bytes(cap, cap);
-    const size_t total = std::max<size_t>(fixed + 16 * 1024, 100 * 1024);
+    const size_t total = sbp_smem_total(m, fixed, npairs);
     if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d too large for the device matcher", cap);
     P.smem_fixed = (int)fixed;
     P.smem_entries = (int)((total - fixed) / sizeof(uint32_t));
@@ -1047,7 +1060,7 @@ extern "C" int orbfe_guided_search_device(OrbfeMatcher *m, int njobs, const Orbf
                                           const int *d_q_cnt, int qcap, float min_x, float min_y, float max_x, float max_y,
                                           int rule, float nnratio, int th_dist, int check_orientation, int *d_slot_owner,
                                           int *d_nmatches, void *stream) {
-    if (!m || njobs < 0 || cap < 1 || cap > 65535 || qcap < 1 || rule < 0 || rule > 2) return fail(ORBFE_ERR_ARG, "bad arguments");
+    if (!m || njobs < 0 || cap < 1 || cap > 65535 || qcap < 1 || qcap > 65535 || rule < 0 || rule > 2) return fail(ORBFE_ERR_ARG, "bad arguments");
     if (njobs == 0) return ORBFE_OK;
     if (!d_kps || !d_desc || !d_counts || !d_frame_idx || !d_qu || !d_qv || !d_qr || !d_qlo || !d_qhi || !d_qdesc || !d_q_base ||
         !d_q_cnt || !d_slot_owner || !d_nmatches || (check_orientation && !d_qangle))
@@ -1065,7 +1078,7 @@ extern "C" int orbfe_guided_search_device(OrbfeMatcher *m, int njobs, const Orbf
     if (per_job > (size_t)INT_MAX) return fail(ORBFE_ERR_UNSUPPORTED, "too many queries per job");
     P.scratch_per_pair = (int)per_job;
     const size_t fixed = sbp_smem_fixed_bytes(cap, qcap);
-    const size_t total = std::max<size_t>(fixed + 16 * 1024, 100 * 1024);
+    const size_t total = sbp_smem_total(m, fixed, njobs);
     if (total > 220 * 1024) return fail(ORBFE_ERR_UNSUPPORTED, "cap %d / qcap %d too large for the device matcher", cap, qcap);
     P.smem_fixed = (int)fixed;
     P.smem_entries = (int)((total - fixed) / sizeof(uint32_t));
@@ -1454,7 +1467,7 @@ extern "C" int orbfe_guided_via_device(OrbfeMatcher *m, const OrbfeFrameView *f,
     if (f->n < 1 || f->n > 65535 || nq < 1) return 1;
     if (f->grid_inv_w != (float)64 / (float)(f->max_x - f->min_x) || f->grid_inv_h != (float)48 / (float)(f->max_y - f->min_y)) return 1;
     const int cap = f->n, qcap = nq;
-    if (std::max<size_t>(sbp_smem_fixed_bytes(cap, qcap) + 16 * 1024, 100 * 1024) > 220 * 1024) return 1;
+    if (sbp_smem_fixed_bytes(cap, qcap) + 16 * 1024 > 220 * 1024) return 1;
     CU_TRY(cudaSetDevice(m->device));
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };

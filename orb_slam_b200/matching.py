@@ -86,6 +86,72 @@ class FrameView:
         self.c = c
 
 
+# numpy mirror of OrbfeFrameView (include/orbfe_match.h): lets a whole batch of views be filled with array operations
+FRAME_VIEW_DTYPE = np.dtype([("n", "<i4"), ("keys_un", "<u8"), ("desc", "<u8"), ("min_x", "<f4"), ("min_y", "<f4"),
+                             ("max_x", "<f4"), ("max_y", "<f4"), ("grid_inv_w", "<f4"), ("grid_inv_h", "<f4"),
+                             ("nlevels", "<i4"), ("scale_factors", "<u8")], align=True)
+assert FRAME_VIEW_DTYPE.itemsize == C.sizeof(_FrameViewC)
+assert all(FRAME_VIEW_DTYPE.fields[f][1] == getattr(_FrameViewC, f).offset for f, _ in _FrameViewC._fields_)
+
+
+class FrameViewBatch:
+    """The views of a batch of frames that live in one (B, cap) keypoint array and one (B, cap, 32) descriptor array --
+    the layout orbfe_extract_batch writes.  Same content as B `FrameView`s, built without a Python loop."""
+
+    def __init__(self, kps, desc, counts, width, height, scale_factor=1.2, nlevels=8):
+        L = _bind()
+        assert kps.dtype == KP_DTYPE and kps.ndim == 2 and kps.strides[1] == KP_DTYPE.itemsize
+        assert desc.dtype == np.uint8 and desc.shape[:2] == kps.shape and desc.strides[1] == 32
+        self.kps, self.desc = kps, desc
+        self.counts = np.ascontiguousarray(counts, np.int32)
+        B = kps.shape[0]
+        self.sf = np.empty(nlevels, np.float32)
+        L.orbfe_frame_scale_factors(scale_factor, nlevels, _p(self.sf))
+        v = np.zeros(B, FRAME_VIEW_DTYPE)
+        idx = np.arange(B, dtype=np.uint64)
+        v["n"] = self.counts
+        v["keys_un"] = np.uint64(kps.ctypes.data) + idx * np.uint64(kps.strides[0])
+        v["desc"] = np.uint64(desc.ctypes.data) + idx * np.uint64(desc.strides[0])
+        v["max_x"], v["max_y"] = float(width), float(height)                        # Frame.cc:342-348
+        v["grid_inv_w"] = np.float32(GRID_COLS) / np.float32(width)                 # Frame.cc:77
+        v["grid_inv_h"] = np.float32(GRID_ROWS) / np.float32(height)                # Frame.cc:78
+        v["nlevels"] = nlevels
+        v["scale_factors"] = self.sf.ctypes.data
+        self.views = v
+
+    def __len__(self):
+        return len(self.views)
+
+    def tail(self):
+        """A private copy of the last frame (for the next batch's first pair): (view[1], keep-alive tuple)."""
+        i = len(self.views) - 1
+        k, d = self.kps[i].copy(), self.desc[i].copy()
+        v = self.views[i:i + 1].copy()
+        v["keys_un"], v["desc"] = k.ctypes.data, d.ctypes.data
+        return v, (k, d, self.sf)
+
+
+def row_pointers(a):
+    """Host addresses of the rows of a 2-D+ array (uint64), for the pointer-array arguments of the batched entry points."""
+    return np.uint64(a.ctypes.data) + np.arange(a.shape[0], dtype=np.uint64) * np.uint64(a.strides[0])
+
+
+def search_by_projection_views(matcher: ORBmatcher, views_cur, views_last, has_ptrs, outlier_ptrs, world_ptrs, Tcws,
+                               fx, fy, cx, cy, th, cur_mp):
+    """orbfe_search_by_projection_frames on prebuilt argument arrays: `views_*` are FRAME_VIEW_DTYPE arrays, `*_ptrs`
+    uint64 arrays of host addresses (one per pair), `Tcws` a contiguous (n, 12) float32 array, `cur_mp` a (n, cap) int32
+    array (in: occupied slots >= 0, out: matches).  Returns nmatches[n]."""
+    L = _bind()
+    n = len(views_cur)
+    vc, vl = np.ascontiguousarray(views_cur), np.ascontiguousarray(views_last)
+    ptrs = [np.ascontiguousarray(a, np.uint64) for a in (has_ptrs, outlier_ptrs, world_ptrs, row_pointers(Tcws), row_pointers(cur_mp))]
+    assert all(len(a) == n for a in ptrs) and len(vl) == n and Tcws.dtype == np.float32 and cur_mp.dtype == np.int32
+    nm = np.zeros(n, np.int32)
+    _check(L.orbfe_search_by_projection_frames(matcher.handle, n, _p(vc), _p(vl), _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]),
+                                               _p(ptrs[3]), fx, fy, cx, cy, th, int(matcher.mbCheckOrientation), _p(ptrs[4]), _p(nm)))
+    return nm
+
+
 def _check(rc):
     if rc != 0:
         raise OrbfeError(rc, lib().orbfe_last_error().decode("utf-8", "replace") or "matcher call failed")

@@ -304,6 +304,60 @@ def exchange1(args):
     return out
 
 
+def h2d(args):
+    """Raw pinned-host -> device copy bandwidth of this box (64 frames of 1080p per copy burst), with the pinned buffer
+    allocated from wherever the process runs and again after moving the process to the GPU's NUMA node: what the e2e
+    number of bench.py can reach at best on this host."""
+    import os
+    import torch
+    dev = torch.device("cuda", 0)
+    out = {}
+    n = 64 * 1920 * 1080
+    dst = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def probe(tag):
+        src = torch.empty(n, dtype=torch.uint8).pin_memory()
+        src.fill_(3)
+        res = torch.empty(4 << 20, dtype=torch.uint8).pin_memory()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dst.copy_(src, non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        out["h2d_GBps_" + tag] = 10 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        e0.record()
+        for _ in range(10):
+            for f in range(64):
+                dst[f * 1920 * 1080:(f + 1) * 1920 * 1080].copy_(src[f * 1920 * 1080:(f + 1) * 1920 * 1080], non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        out["h2d_GBps_per_frame_copies_" + tag] = 10 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        e0.record()
+        for _ in range(10):
+            res.copy_(dst[:4 << 20], non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        out["d2h_GBps_4MB_" + tag] = 10 * (4 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    probe("as_started")
+    try:
+        pr = torch.cuda.get_device_properties(0)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        out["gpu_numa_node"] = open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip()
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        out["gpu_local_cpulist"] = txt
+        out["started_on_cpu"] = os.sched_getcpu() if hasattr(os, "sched_getcpu") else None
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus |= set(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus & set(os.sched_getaffinity(0)))
+        probe("on_gpu_node")
+    except Exception as e:
+        out["numa_probe_error"] = repr(e)
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="config3,config5")
@@ -313,4 +367,4 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     for w in args.what.split(","):
-        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1, "matchers": matchers}[w](args)))
+        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1, "matchers": matchers, "h2d": h2d}[w](args)))
