@@ -179,6 +179,9 @@ void launch_resize_level(const PlanDev *d_plan, const PlanDev &hp, int level, in
 #define F2_PWORDS 35               // words actually loaded per row (x0-8 .. x0+131)
 #define F2_PH (F2_H + 8)           // 70 staged rows: y0-4 .. y0+65
 #define F2_MS 128                  // m tile row stride (32 groups x 4)
+#ifndef ORBFE_FAST_ARC_DEFAULT
+#define ORBFE_FAST_ARC_DEFAULT 12   // arc-network variant of the non-TMA kernel (fast_m_arc): second form, 12 (min, max) pairs on the FMA pipe
+#endif
 #define F2_MH (F2_H + 2)           // 64 m rows
 
 __device__ __forceinline__ uint32_t max16_u16x2(const uint32_t *w) {
@@ -211,6 +214,73 @@ __device__ __forceinline__ uint32_t fast_m_u16x2(const uint32_t (&r)[16], uint32
     const uint32_t bright = __vmaxu2(mb, c) - c;  // per half >= 0: no borrow across halves
     const uint32_t dark = c - __vminu2(md, c);
     return __vmaxu2(bright, dark);
+}
+
+// ---- arc network, second form (default).  For even k the two 9-arcs starting at k and k+1 share the 8 ring pixels
+// k+1 .. k+8; with c_k their minimum,  max(min(c_k, r_k), min(c_k, r_k+9)) = min(c_k, max(r_k, r_k+9)), so
+//     p_j  = min(r_2j+1, r_2j+2)              8 pair minima
+//     pp_j = min(p_j, p_j+1)                  8 quad minima  (r_2j+1 .. r_2j+4)
+//     e_i  = max(r_2i, r_2i+9)                8 arc-end maxima
+//     v_i  = min3(pp_i, pp_i+2, e_i)          the better of arcs 2i and 2i+1
+//     mb   = max(v_0 .. v_7, centre)          4 three-input maxima (the centre clamp rides in the tree)
+// and the dual for the dark arcs: 36 operations per polarity instead of 40.  NPAIR of the 16 (min, max) pairs
+// (p_j / P_j and e_i / E_i take the minimum AND the maximum of the same two registers) are computed on the FMA pipe
+// instead of the integer ALU pipe the rest of the kernel saturates: pixel values 0..255 in a 16-bit half are fp16
+// subnormals, on which HFMA2 is exact, so  t = relu(a - b), min = a - t, max = b + t  is three FMA-pipe
+// instructions per pair, bit-identical to VIMNMX.U16x2.
+__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// fma_pipe is a compile-time constant at every call site once the callers' loops are unrolled
+__device__ __forceinline__ void minmax_u16x2(bool fma_pipe, uint32_t a, uint32_t b, uint32_t &mn, uint32_t &mx) {
+    if (fma_pipe) {
+        const uint32_t NEG1 = 0xBC00BC00u, ONE = 0x3C003C00u;
+        const uint32_t t = hfma2_relu(b, NEG1, a);   // relu(a - b)
+        mn = hfma2(t, NEG1, a);                      // a - relu(a - b)
+        mx = hfma2(t, ONE, b);                       // b + relu(a - b)
+    } else {
+        mn = __vminu2(a, b);
+        mx = __vmaxu2(a, b);
+    }
+}
+template <int NPAIR>
+__device__ __forceinline__ uint32_t fast_m2_u16x2(const uint32_t (&r)[16], uint32_t c) {
+    uint32_t p[8], P[8], e[8], E[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        // pairs are handed to the FMA pipe interleaved (p_0, e_0, p_1, e_1, ...) so that any NPAIR spreads over the network
+        minmax_u16x2(2 * j < NPAIR, r[2 * j + 1], r[(2 * j + 2) & 15], p[j], P[j]);
+        minmax_u16x2(2 * j + 1 < NPAIR, r[2 * j], r[(2 * j + 9) & 15], E[j], e[j]);
+    }
+    uint32_t pp[8], PP[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        pp[j] = __vminu2(p[j], p[(j + 1) & 7]);
+        PP[j] = __vmaxu2(P[j], P[(j + 1) & 7]);
+    }
+    uint32_t v[8], V[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        v[i] = __vimin3_u16x2(pp[i], pp[(i + 2) & 7], e[i]);
+        V[i] = __vimax3_u16x2(PP[i], PP[(i + 2) & 7], E[i]);
+    }
+    // mb >= c and md <= c by construction: the differences need no clamp and cannot borrow across halves
+    const uint32_t mb = __vimax3_u16x2(__vimax3_u16x2(v[0], v[1], v[2]), __vimax3_u16x2(v[3], v[4], v[5]), __vimax3_u16x2(v[6], v[7], c));
+    const uint32_t md = __vimin3_u16x2(__vimin3_u16x2(V[0], V[1], V[2]), __vimin3_u16x2(V[3], V[4], V[5]), __vimin3_u16x2(V[6], V[7], c));
+    return __vmaxu2(mb - c, c - md);
+}
+// ARC < 0: the first form (16 triple minima + 16 nine-arc minima per polarity); ARC >= 0: the second form with ARC pairs on the FMA pipe
+template <int ARC>
+__device__ __forceinline__ uint32_t fast_m_arc(const uint32_t (&r)[16], uint32_t c) {
+    if (ARC < 0) return fast_m_u16x2(r, c);
+    return fast_m2_u16x2<(ARC < 0 ? 0 : ARC)>(r, c);
 }
 
 __device__ __forceinline__ void fast_load_row(const uint8_t *row /* smem, word aligned at the group's b0 */, uint32_t (&P)[8]) {
@@ -293,7 +363,7 @@ __device__ __forceinline__ void cell_window(const LevelDev &L, int xmax, int yma
 
 // Everything after the pixel tile is staged: m map, NMS passes, candidate conversion and flush.
 // pix: staged pixel rows (stride F2_PW); mt: 16 KB m tile; s_cand: candidate list (F2_MAXC entries).
-template <int PSTRIDE>
+template <int PSTRIDE, int ARC>
 __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ plan, const WorkDev &wk, const LevelDev &L,
                                                   const FTileInfo &ti, int f, int x0, int y0, const uint8_t *pix, uint32_t *mt,
                                                   uint32_t *s_cand, int &s_n, int *s_cnt_lo, int *s_cnt_hi, int *s_base) {
@@ -324,12 +394,12 @@ __device__ __forceinline__ void fast_tile_compute(const PlanDev *__restrict__ pl
             {
                 const uint32_t r[16] = {FROW(3)[3], FROW(3)[4], FROW(2)[5], FROW(1)[6], FROW(0)[6], FROW(-1)[6], FROW(-2)[5], FROW(-3)[4],
                                         FROW(-3)[3], FROW(-3)[2], FROW(-2)[1], FROW(-1)[0], FROW(0)[0], FROW(1)[0], FROW(2)[1], FROW(3)[2]};
-                mA = fast_m_u16x2(r, FROW(0)[3]);
+                mA = fast_m_arc<ARC>(r, FROW(0)[3]);
             }
             {
                 const uint32_t r[16] = {FROW(3)[4], FROW(3)[5], FROW(2)[6], FROW(1)[7], FROW(0)[7], FROW(-1)[7], FROW(-2)[6], FROW(-3)[5],
                                         FROW(-3)[4], FROW(-3)[3], FROW(-2)[2], FROW(-1)[1], FROW(0)[1], FROW(1)[1], FROW(2)[2], FROW(3)[3]};
-                mB = fast_m_u16x2(r, FROW(0)[4]);
+                mB = fast_m_arc<ARC>(r, FROW(0)[4]);
             }
 #undef FROW
             const int mr = seg * 8 + i;
@@ -507,7 +577,7 @@ __global__ void __launch_bounds__(256, 2) fast_nms_kernel(const PlanDev *__restr
         }
     }
     __syncthreads();
-    fast_tile_compute<F2_PW>(plan, wk, L, ti, f, x0, y0, pix, mt, s_cand, s_n, s_cnt_lo, s_cnt_hi, s_base);
+    fast_tile_compute<F2_PW, ORBFE_FAST_ARC_DEFAULT>(plan, wk, L, ti, f, x0, y0, pix, mt, s_cand, s_n, s_cnt_lo, s_cnt_hi, s_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -552,6 +622,7 @@ static_assert(F2_MAXC * 4 <= F2_PIXSLOT, "the candidate queue lives in the pixel
 #ifndef ORBFE_FAST_MINBLOCKS
 #define ORBFE_FAST_MINBLOCKS 4   // resident CTAs per SM the register budget is sized for (64 registers)
 #endif
+template <int ARC>
 __global__ void __launch_bounds__(256, ORBFE_FAST_MINBLOCKS) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint8_t *pixbuf0 = dsm, *pixbuf1 = dsm + F2_PIXSLOT;
@@ -592,14 +663,28 @@ __global__ void __launch_bounds__(256, ORBFE_FAST_MINBLOCKS) fast_nms_tma_kernel
         // the candidate queue reuses the current pixel slot (dead once m is computed; the next TMA into it is
         // only issued after the __syncthreads that ends this iteration)
         uint8_t *slot_cur = cur ? pixbuf1 : pixbuf0;
-        fast_tile_compute<F2_TW>(plan, wk, L, ti, f, x0, y0, slot_cur + ((x0 - 8) & 15), mt, reinterpret_cast<uint32_t *>(slot_cur),
+        fast_tile_compute<F2_TW, ARC>(plan, wk, L, ti, f, x0, y0, slot_cur + ((x0 - 8) & 15), mt, reinterpret_cast<uint32_t *>(slot_cur),
                                  s_n, s_cnt_lo, s_cnt_hi, s_base);
         __syncthreads();  // mt / s_cand / counters and the pixel buffer are reused by the next item
     }
 }
 
+// arc-network variants compiled in (WorkDev::fast_arc; ORBFE_FAST_ARC=n picks one, see orbfe_api.cu)
+#define FAST_ARC_VARIANTS(X) X(-1) X(0) X(4) X(8) X(12) X(16)
+typedef void (*FastTmaKernel)(const PlanDev *, WorkDev, int, int);
+static FastTmaKernel fast_tma_variant(int arc) {
+#define X(a) if (arc == (a)) return fast_nms_tma_kernel<(a)>;
+    FAST_ARC_VARIANTS(X)
+#undef X
+    return nullptr;
+}
+int fast_arc_supported(int arc) { return fast_tma_variant(arc) != nullptr; }
+
 int fast_tma_setup() {
-    return (int)cudaFuncSetAttribute(fast_nms_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_TMA_SMEM);
+#define X(a) { cudaError_t e = cudaFuncSetAttribute(fast_nms_tma_kernel<(a)>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_TMA_SMEM); if (e != cudaSuccess) return (int)e; }
+    FAST_ARC_VARIANTS(X)
+#undef X
+    return 0;
 }
 
 void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
@@ -607,7 +692,7 @@ void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0
     if (w.tmaps) {
         const int nwork = hp.nftiles_total * nf;
         const int grid = min(nwork, w.fast_grid);
-        fast_nms_tma_kernel<<<grid, 256, F2_TMA_SMEM, s>>>(d_plan, w, f0, nwork);
+        fast_tma_variant(w.fast_arc)<<<grid, 256, F2_TMA_SMEM, s>>>(d_plan, w, f0, nwork);
         return;
     }
     dim3 grid(hp.nftiles_total, nf);

@@ -368,6 +368,11 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     // ---- TMA tensor maps (one per level: x, y, frame) for the FAST kernel's pixel tiles ----
     Wk.tmaps = nullptr;
     Wk.fast_grid = 0;
+    Wk.fast_arc = ORBFE_FAST_ARC_RUNTIME_DEFAULT;
+    if (const char *a = getenv("ORBFE_FAST_ARC")) {
+        if (!fast_arc_supported(atoi(a))) return fail(ORBFE_ERR_ARG, "ORBFE_FAST_ARC=%s is not a compiled arc-network variant", a);
+        Wk.fast_arc = atoi(a);
+    }
     if (!getenv("ORBFE_FAST_NO_TMA")) {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -96,10 +96,13 @@ def test_strided_input_and_empty(gpu_required):
     ex.close()
 
 
-@pytest.mark.parametrize("env", [{"ORBFE_BLUR_PLANES": "1"}, {"ORBFE_FAST_NO_TMA": "1"}, {"ORBFE_BLUR_PLANES": "1", "ORBFE_FAST_NO_TMA": "1"}])
+@pytest.mark.parametrize("env", [{"ORBFE_BLUR_PLANES": "1"}, {"ORBFE_FAST_NO_TMA": "1"}, {"ORBFE_BLUR_PLANES": "1", "ORBFE_FAST_NO_TMA": "1"}] +
+                         [{"ORBFE_FAST_ARC": str(a)} for a in (-1, 0, 4, 8, 12, 16)])
 def test_alternate_kernel_paths(gpu_required, env, monkeypatch):
     """The variants behind environment switches (whole-level blur7 + describe instead of the fused descriptor kernel;
-    plain staged FAST tiles instead of the TMA pipeline) produce the same bits as the default path and the oracle."""
+    plain staged FAST tiles instead of the TMA pipeline; every compiled form of the FAST arc network, integer-ALU-only
+    and with 4..16 (min, max) pairs on the FMA pipe as exact fp16-subnormal arithmetic) produce the same bits as the
+    oracle."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     _compare(textured_frame(752, 480, seed=3), 1000, 8)

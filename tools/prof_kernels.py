@@ -358,6 +358,49 @@ def h2d(args):
     return out
 
 
+def fastarc(args):
+    """BASELINE configs[1] geometry (1920x1080, 2000 kp, 8 levels), 64-frame device-resident batches: per-stage CUDA-event
+    times for every compiled FAST arc-network variant (ORBFE_FAST_ARC is read when the extractor plans a geometry)."""
+    import torch
+    import orb_slam_b200 as fe
+    from orb_slam_b200.synth import textured_frame, shifted_frame
+    W, H, NF, NL, B = 1920, 1080, 2000, 8, 64
+    bases = [textured_frame(W, H, seed=100 + i) for i in range(4)]
+    frames = np.stack([shifted_frame(bases[i % 4], 2 * i, i, seed=i) for i in range(B)])
+    dev = torch.device("cuda", 0)
+    d_frames = torch.from_numpy(frames).to(dev)
+    d_kps = torch.empty((B, NF, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((B, NF, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    out = {"what": "FAST arc-network variants, 1080p x 64 frames, ms per batch"}
+    ref = None
+    variants = [int(v) for v in os.environ.get("FASTARC_VARIANTS", "-1,0,4,8,12,16").split(",")]
+    for rep in range(2):
+        for arc in variants:
+            os.environ["ORBFE_FAST_ARC"] = str(arc)
+            ex = fe.ORBextractor(NF, 1.2, NL, fe.FAST_SCORE, 20)
+            ex.set_profiling(True)
+            for _ in range(3):
+                ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), stream.cuda_stream)
+            stream.synchronize()
+            ex.stage_times()
+            n = 10
+            for _ in range(n):
+                ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), stream.cuda_stream)
+            stream.synchronize()
+            acc = {}
+            for name, ms in ex.stage_times():
+                acc[name] = acc.get(name, 0.0) + ms / n
+            sig = (d_kps.cpu().numpy().tobytes(), d_desc.cpu().numpy().tobytes())
+            if ref is None:
+                ref = sig
+            out["arc%d_rep%d" % (arc, rep)] = {"fast_nms": round(acc.get("fast_nms", -1), 4), "all": round(sum(acc.values()), 4), "same_bits": sig == ref}
+            ex.close()
+    os.environ.pop("ORBFE_FAST_ARC", None)
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="config3,config5")
@@ -367,4 +410,4 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     for w in args.what.split(","):
-        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1, "matchers": matchers, "h2d": h2d}[w](args)))
+        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1, "matchers": matchers, "h2d": h2d, "fastarc": fastarc}[w](args)))

@@ -5,6 +5,8 @@
 #define ITERS 4096
 __device__ __forceinline__ unsigned hmax2u(unsigned a, unsigned b) { unsigned d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 __device__ __forceinline__ unsigned hmin2u(unsigned a, unsigned b) { unsigned d; asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ unsigned hfma2u(unsigned a, unsigned b, unsigned c) { unsigned d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ unsigned hfma2relu(unsigned a, unsigned b, unsigned c) { unsigned d; asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 __global__ void denorm_check(unsigned *o) {
     // u16 values 0..255 are fp16 subnormals: max/min must order them like integers and return them unflushed
@@ -42,6 +44,11 @@ __global__ void k(unsigned *out, unsigned seed) {
             if (OP == 13) a[i] = (i & 1) ? a[i] * b + c : __vimax3_u16x2(a[i], b, c);     // VIMNMX3 + IMAD (ALU + FMA pipe)
             if (OP == 14) a[i] = __float_as_uint(fmax3(__uint_as_float(a[i]), __uint_as_float(b), __uint_as_float(c)));
             if (OP == 15) a[i] = (i % 3 == 2) ? hmax2u(a[i], b) : __vimax3_u16x2(a[i], b, c);  // 5-6 VIMNMX3 + 2-3 HMNMX2
+            if (OP == 17) a[i] = hfma2u(a[i], 0xBC00BC00u, b);                          // HFMA2 (FMA pipe), fp16 subnormal operands
+            if (OP == 18) a[i] = (i & 1) ? hfma2relu(a[i], 0xBC00BC00u, b) : __vimax3_u16x2(a[i], b, c);   // 4 VIMNMX3 + 4 HFMA2
+            if (OP == 19) a[i] = (i % 3 == 2) ? hfma2relu(a[i], 0xBC00BC00u, b) : __vimax3_u16x2(a[i], b, c);   // ~5.3 VIMNMX3 + 2.7 HFMA2
+            if (OP == 20) a[i] = (i & 1) ? hfma2u(hfma2relu(a[i], 0xBC00BC00u, b), 0x3C003C00u, c) : __vimax3_u16x2(a[i], b, c);   // 4 VIMNMX3 + 8 HFMA2
+            if (OP == 21) a[i] = (i & 3) ? __vimax3_u16x2(a[i], b, c) : hfma2relu(a[i], 0xBC00BC00u, b);   // 6 VIMNMX3 + 2 HFMA2
             if (OP == 16) a[i] = (i & 1) ? hmin2u(hmax2u(a[i], b), c) : __vimax3_u16x2(a[i], b, c);   // 4 VIMNMX3 + 8 HMNMX2
         }
         b += 0x00010001u;
@@ -63,7 +70,7 @@ void run(const char *name) {
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    double ops = (double)148 * 4 * 512 * ITERS * 8;  // thread-ops of the op under test
+    double ops = (double)148 * 4 * 512 * ITERS * (OP == 20 ? 12 : 8);  // thread-ops of the op under test (all pipes)
     printf("%-22s %8.3f ms  %7.2f Tthread-op/s  %6.2f thread-ops/clk/SM (at 1.965 GHz)\n", name, ms, ops / ms / 1e9,
            ops / (ms * 1e-3) / 148 / 1.965e9);
     cudaFree(out);
@@ -79,6 +86,7 @@ int main() {
     }
     run<11>("hmnmx2"); run<12>("4 vimnmx3 + 4 hmnmx2"); run<13>("4 vimnmx3 + 4 imad"); run<14>("fmnmx3"); run<15>("vimnmx3:hmnmx2 ~2:1");
     run<16>("4 vimnmx3 + 8 hmnmx2");
+    run<17>("hfma2 (subnormal)"); run<18>("4 vimnmx3 + 4 hfma2"); run<19>("~5.3 vimnmx3 + 2.7 hfma2"); run<20>("4 vimnmx3 + 8 hfma2"); run<21>("6 vimnmx3 + 2 hfma2");
     run<5>("lop3"); run<6>("iadd3"); run<7>("imad"); run<8>("vimax_s16x2"); run<9>("popc+iadd"); run<10>("shf");
     return 0;
 }
