@@ -575,10 +575,11 @@ def main():
         hd = torch.empty((B, NFEAT, 32), dtype=torch.uint8).pin_memory()
         hc = torch.empty((B,), dtype=torch.int32).pin_memory()
         e2e_bufs.append((hk, hd, hc, hk.numpy().view(fe.KP_DTYPE).reshape(B, NFEAT), hd.numpy(), hc.numpy()))
-    e2e_ex = [ex] + [fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank) for _ in range(NEX - 1)]
+    USE_PY_E2E = os.environ.get("ORBFE_E2E_PY") == "1"           # Python-thread pipeline instead of the C++ driver (below)
+    e2e_ex = [ex] + [fe.ORBextractor(NFEAT, SCALE, NLEVELS, fe.FAST_SCORE, FAST_TH, device=local_rank) for _ in range(NEX - 1 if USE_PY_E2E else 0)]
     e2e_ex_pool = [ThreadPoolExecutor(max_workers=1) for _ in range(NEX)]
     E2E_MODE = int(os.environ.get("ORBFE_E2E_BATCH_MODE", "0"))   # measured: chunked 28.7 vs phased 26.8 Mkp/s with two handles
-    e2e_mt = (mt, fe.ORBmatcher(0.9, True, device=local_rank))
+    e2e_mt = (mt, fe.ORBmatcher(0.9, True, device=local_rank)) if USE_PY_E2E else (mt,)
     e2e_match_pool = (ThreadPoolExecutor(max_workers=1), ThreadPoolExecutor(max_workers=1))
     e2e_views_pool = ThreadPoolExecutor(max_workers=2)
     e2e_state = {"step": 0}
@@ -593,7 +594,7 @@ def main():
         host_t["e2e_extract_call"] += time.perf_counter() - t0
         return x.last_launches(), int(c_np.sum())
 
-    def run_e2e(steps):
+    def run_e2e_python(steps):
         nm = 0
         ex_futs, m_futs, v_futs = {}, {}, {}
         s0 = e2e_state["step"]
@@ -625,10 +626,66 @@ def main():
         e2e_state["step"] = s0 + nsub
         return nm
 
+    # The same pipeline on C++ threads (tools/e2e_driver.cpp -> orb_slam_b200/libe2e_driver.so; default): a C++ host -- what the
+    # reference's Tracking thread is -- calling orbfe_extract_batch / orbfe_search_by_projection_frames of liborbfe.so, nothing
+    # else.  The Python-thread version above is kept behind ORBFE_E2E_PY=1: its GIL hand-offs cost more than the calls themselves.
+    import ctypes as C
+    drv = {"lib": None, "h": None, "mh2d": 0, "md2h": 0, "mlaunch": 0}
+    if not USE_PY_E2E:
+        from orb_slam_b200.build import E2E_SO
+        if not os.path.exists(E2E_SO):
+            raise SystemExit("libe2e_driver.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        dl = C.CDLL(E2E_SO)
+
+        class E2eConfig(C.Structure):
+            _fields_ = [(n, C.c_int) for n in ("W", "H", "nfeat", "nlevels", "fast_th", "B", "NB", "nex", "nmatch", "nbuf", "device")] + \
+                       [(n, C.c_float) for n in ("scale", "fx", "fy", "cx", "cy", "depth", "th")]
+        dl.e2e_create.restype = C.c_void_p
+        dl.e2e_create.argtypes = [C.POINTER(E2eConfig)] + [C.c_void_p] * 6
+        dl.e2e_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+        dl.e2e_last_matches.argtypes = [C.c_void_p, C.c_void_p]
+        dl.e2e_destroy.argtypes = [C.c_void_p]
+        dl.e2e_error.restype = C.c_char_p
+        dl.e2e_error.argtypes = [C.c_void_p]
+        Lfe = fe.lib()
+        fn_names = ["orbfe_extractor_create", "orbfe_extractor_destroy", "orbfe_extract_batch", "orbfe_extractor_last_launches",
+                    "orbfe_matcher_create", "orbfe_matcher_destroy", "orbfe_matcher_counters", "orbfe_search_by_projection_frames",
+                    "orbfe_frame_scale_factors", "orbfe_last_error"]
+        fns = (C.c_void_p * len(fn_names))(*[C.cast(getattr(Lfe, n), C.c_void_p).value for n in fn_names])
+        cfg = E2eConfig(W, H, NFEAT, NLEVELS, FAST_TH, B, NB, NEX, 2, NBUF, local_rank, SCALE, FX, FY, CX, CY, DEPTH, MATCH_TH)
+        arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        drv["keep"] = (fns, cfg, Tcws_arr)
+        drv["h"] = dl.e2e_create(C.byref(cfg), fns, h_frames.data_ptr(), Tcws_arr.ctypes.data, arr([b_[0] for b_ in e2e_bufs]),
+                                 arr([b_[1] for b_ in e2e_bufs]), arr([b_[2] for b_ in e2e_bufs]))
+        if not drv["h"]:
+            raise SystemExit("e2e_create failed: " + fe.lib().orbfe_last_error().decode())
+        drv["lib"] = dl
+
+    def run_e2e_driver(steps):
+        out = (C.c_longlong * 7)()
+        hs = (C.c_double * 3)()
+        if drv["lib"].e2e_run(drv["h"], steps * SUB, out, hs) != 0:
+            raise SystemExit("e2e driver failed: " + drv["lib"].e2e_error(drv["h"]).decode())
+        kp_total[0] += out[0]
+        launches[0] += out[2] + out[5]
+        drv["mh2d"] += out[3]
+        drv["md2h"] += out[4]
+        host_t["e2e_extract_call"] += hs[0]; host_t["views"] += hs[1]; host_t["match_call"] += hs[2]; host_t["n"] += steps * SUB
+        # the last matched batch, for the oracle cross-check: its keypoints / descriptors still sit in their pinned output set
+        st = int(out[6])
+        _, _, _, k_np, d_np, c_np = e2e_bufs[st % NBUF]
+        mp4 = np.empty((4, NFEAT), np.int32)
+        drv["lib"].e2e_last_matches(drv["h"], mp4.ctypes.data)
+        checks["e2e"] = (st % NB, [k_np[i, :c_np[i]].copy() for i in range(4)], [d_np[i, :c_np[i]].copy() for i in range(4)], list(mp4))
+        return int(out[1])
+
+    run_e2e = run_e2e_python if USE_PY_E2E else run_e2e_driver
+
     def timed(run_fn, steps):
         kp_total[0] = 0
         launches[0] = 0
         c0 = [sum(x) for x in zip(*(m_.counters() for m_ in e2e_mt))]
+        d0 = (drv["mh2d"], drv["md2h"])
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -649,7 +706,7 @@ def main():
             dist.all_reduce(k, op=dist.ReduceOp.SUM)
             dist.barrier()
         return {"ms": float(t[0]), "wall_ms": float(t[1]), "kp": float(k[0]), "matches": float(k[1]),
-                "launches": launches[0] + (c1[2] - c0[2]), "mh2d": c1[0] - c0[0], "md2h": c1[1] - c0[1]}
+                "launches": launches[0] + (c1[2] - c0[2]), "mh2d": c1[0] - c0[0] + drv["mh2d"] - d0[0], "md2h": c1[1] - c0[1] + drv["md2h"] - d0[1]}
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -800,6 +857,8 @@ def main():
         if not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline_dict(frames_np, shifts, 1, True)
         print(json.dumps(line))
+    if drv["h"]:
+        drv["lib"].e2e_destroy(drv["h"])
     for x in e2e_ex:
         x.close()
     for m_ in e2e_mt:

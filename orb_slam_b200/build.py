@@ -41,7 +41,27 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+E2E_SRC = os.path.join(HERE, "..", "tools", "e2e_driver.cpp")
+E2E_SO = os.path.join(HERE, "libe2e_driver.so")
+
+
+def build_e2e_driver(force=False):
+    """bench.py's end-to-end stream pipeline on C++ threads (tools/e2e_driver.cpp): bench harness over the public C-ABI,
+    not part of liborbfe.so; plain g++, no CUDA."""
+    if not force and os.path.exists(E2E_SO) and os.path.getmtime(E2E_SO) >= max(
+            os.path.getmtime(E2E_SRC), os.path.getmtime(os.path.join(HERE, "..", "include", "orbfe_match.h"))):
+        return E2E_SO
+    cmd = ["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-ffp-contract=off", "-pthread", "-I", os.path.join(HERE, "..", "include"),
+           E2E_SRC, "-o", E2E_SO]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("g++ failed building libe2e_driver.so")
+    return E2E_SO
+
+
 def build_native(force=False, verbose=False):
+    build_e2e_driver(force)
     if not force and not is_stale():
         return SO
     extra = os.environ.get("ORBFE_NVCC_EXTRA", "").split()   # experiments, e.g. -DORBFE_FAST_MINBLOCKS=3

@@ -619,11 +619,8 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, ui
 #define F2_TMA_SMEM (2 * F2_PIXSLOT + F2_MH * 32 * 2 * 4 + 128)
 static_assert(F2_MAXC * 4 <= F2_PIXSLOT, "the candidate queue lives in the pixel slot that was just consumed");
 
-#ifndef ORBFE_FAST_MINBLOCKS
-#define ORBFE_FAST_MINBLOCKS 4   // resident CTAs per SM the register budget is sized for (64 registers)
-#endif
-template <int ARC>
-__global__ void __launch_bounds__(256, ORBFE_FAST_MINBLOCKS) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
+template <int ARC, int MINB>
+__global__ void __launch_bounds__(256, MINB) fast_nms_tma_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0, int nwork) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint8_t *pixbuf0 = dsm, *pixbuf1 = dsm + F2_PIXSLOT;
     uint32_t *mt = reinterpret_cast<uint32_t *>(dsm + 2 * F2_PIXSLOT);
@@ -670,18 +667,19 @@ __global__ void __launch_bounds__(256, ORBFE_FAST_MINBLOCKS) fast_nms_tma_kernel
 }
 
 // arc-network variants compiled in (WorkDev::fast_arc; ORBFE_FAST_ARC=n picks one, see orbfe_api.cu)
-#define FAST_ARC_VARIANTS(X) X(-1) X(0) X(4) X(8) X(12) X(16)
+// (arc variant, resident CTAs per SM the register budget is sized for: 4 -> 64 registers, 3 -> 80)
+#define FAST_ARC_VARIANTS(X) X(-1, 4) X(0, 4) X(4, 4) X(8, 4) X(12, 4) X(16, 4) X(12, 3) X(16, 3)
 typedef void (*FastTmaKernel)(const PlanDev *, WorkDev, int, int);
-static FastTmaKernel fast_tma_variant(int arc) {
-#define X(a) if (arc == (a)) return fast_nms_tma_kernel<(a)>;
+static FastTmaKernel fast_tma_variant(int arc, int minb) {
+#define X(a, b) if (arc == (a) && minb == (b)) return fast_nms_tma_kernel<(a), (b)>;
     FAST_ARC_VARIANTS(X)
 #undef X
     return nullptr;
 }
-int fast_arc_supported(int arc) { return fast_tma_variant(arc) != nullptr; }
+int fast_arc_supported(int arc, int ctas_per_sm) { return fast_tma_variant(arc, ctas_per_sm <= 3 ? 3 : 4) != nullptr; }
 
 int fast_tma_setup() {
-#define X(a) { cudaError_t e = cudaFuncSetAttribute(fast_nms_tma_kernel<(a)>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_TMA_SMEM); if (e != cudaSuccess) return (int)e; }
+#define X(a, b) { cudaError_t e = cudaFuncSetAttribute(fast_nms_tma_kernel<(a), (b)>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_TMA_SMEM); if (e != cudaSuccess) return (int)e; }
     FAST_ARC_VARIANTS(X)
 #undef X
     return 0;
@@ -692,7 +690,7 @@ void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0
     if (w.tmaps) {
         const int nwork = hp.nftiles_total * nf;
         const int grid = min(nwork, w.fast_grid);
-        fast_tma_variant(w.fast_arc)<<<grid, 256, F2_TMA_SMEM, s>>>(d_plan, w, f0, nwork);
+        fast_tma_variant(w.fast_arc, w.fast_ctas <= 3 ? 3 : 4)<<<grid, 256, F2_TMA_SMEM, s>>>(d_plan, w, f0, nwork);
         return;
     }
     dim3 grid(hp.nftiles_total, nf);

@@ -369,10 +369,10 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     Wk.tmaps = nullptr;
     Wk.fast_grid = 0;
     Wk.fast_arc = ORBFE_FAST_ARC_RUNTIME_DEFAULT;
-    if (const char *a = getenv("ORBFE_FAST_ARC")) {
-        if (!fast_arc_supported(atoi(a))) return fail(ORBFE_ERR_ARG, "ORBFE_FAST_ARC=%s is not a compiled arc-network variant", a);
-        Wk.fast_arc = atoi(a);
-    }
+    Wk.fast_ctas = getenv("ORBFE_FAST_CTAS") ? std::max(1, atoi(getenv("ORBFE_FAST_CTAS"))) : 3;  // 3 CTAs x 80 registers (no spills; default), or 4 x 64
+    if (const char *a = getenv("ORBFE_FAST_ARC")) Wk.fast_arc = atoi(a);
+    if (!fast_arc_supported(Wk.fast_arc, Wk.fast_ctas))
+        return fail(ORBFE_ERR_ARG, "ORBFE_FAST_ARC=%d with ORBFE_FAST_CTAS=%d is not a compiled variant of the FAST kernel", Wk.fast_arc, Wk.fast_ctas);
     if (!getenv("ORBFE_FAST_NO_TMA")) {
         typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -404,7 +404,7 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
         if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(fast_nms_tma_kernel): %s", cudaGetErrorString(e));
         int nsm = 148;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ex->device);
-        Wk.fast_grid = (getenv("ORBFE_FAST_CTAS") ? atoi(getenv("ORBFE_FAST_CTAS")) : 4) * nsm;  // resident persistent CTAs per SM (64 registers, 39 KB smem each)
+        Wk.fast_grid = Wk.fast_ctas * nsm;  // resident persistent CTAs (39 KB smem each)
     }
     CU_TRY(dmalloc(ex, &Wk.cand_keys, (size_t)cand_total * B));
     if (ex->score_type == 0) {

@@ -13,7 +13,7 @@
 // FAST/NMS tile (detect-area pixels per CTA) and blur tile
 #define ORBFE_FT_W 120
 #define ORBFE_FT_H 62
-#define ORBFE_FAST_ARC_RUNTIME_DEFAULT 12  // WorkDev::fast_arc unless ORBFE_FAST_ARC overrides it
+#define ORBFE_FAST_ARC_RUNTIME_DEFAULT 16  // WorkDev::fast_arc unless ORBFE_FAST_ARC overrides it (measured best with 3 CTAs x 80 registers per SM)
 #define ORBFE_BT_W 120
 #define ORBFE_BT_H 64
 
@@ -73,6 +73,7 @@ struct WorkDev {
     const BTileInfo *btile_info;      // [nbtiles_total]
     const CUtensorMap *tmaps;         // [nlevels] 3-D (x, y, frame) tensor maps of the unblurred levels; NULL = no TMA
     int fast_grid;                    // persistent CTAs of the TMA FAST kernel
+    int fast_ctas;                    // resident persistent CTAs per SM (fast_grid = fast_ctas x SMs)
     int fast_arc;                     // arc-network variant of the TMA FAST kernel (extract_kernels.cu, fast_m_arc)
     uint32_t *cand_keys;              // [batch][cand_total]   (score<<24 | 0xFFFFFF - raster)
     unsigned long long *cand_keys64;  // HARRIS_SCORE only: order(resp)<<32 | (0xFFFFFF - raster)<<8 | score; NULL otherwise
@@ -117,7 +118,7 @@ void launch_describe(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, co
 void launch_describe_fused(const PlanDev *d_plan, const PlanDev &h_plan, WorkDev w, const int8_t *d_pattern,
                      OrbfeKeyPoint *d_kps, uint8_t *d_desc, int *d_counts, int f0, int nf, cudaStream_t s, const PeerOut *peers = nullptr);
 int fast_tma_setup();
-int fast_arc_supported(int arc);
+int fast_arc_supported(int arc, int ctas_per_sm);
 int level_select_smem_bytes(int max_kept);
 int level_select_harris_smem_bytes(int max_kept);
 int set_level_select_harris_smem(int bytes);

@@ -375,10 +375,17 @@ def fastarc(args):
     stream = torch.cuda.Stream(device=dev)
     out = {"what": "FAST arc-network variants, 1080p x 64 frames, ms per batch"}
     ref = None
-    variants = [int(v) for v in os.environ.get("FASTARC_VARIANTS", "-1,0,4,8,12,16").split(",")]
+    # "arc" or "arc:ctas" (ctas = resident CTAs per SM, 4 x 64 registers or 3 x 80)
+    variants = [v for v in os.environ.get("FASTARC_VARIANTS", "-1,0,4,8,12,16,12:3,16:3").split(",")]
     for rep in range(2):
-        for arc in variants:
+        for var in variants:
+            arc, _, ctas = var.partition(":")
+            arc = int(arc)
             os.environ["ORBFE_FAST_ARC"] = str(arc)
+            if ctas:
+                os.environ["ORBFE_FAST_CTAS"] = ctas
+            else:
+                os.environ.pop("ORBFE_FAST_CTAS", None)
             ex = fe.ORBextractor(NF, 1.2, NL, fe.FAST_SCORE, 20)
             ex.set_profiling(True)
             for _ in range(3):
@@ -395,9 +402,10 @@ def fastarc(args):
             sig = (d_kps.cpu().numpy().tobytes(), d_desc.cpu().numpy().tobytes())
             if ref is None:
                 ref = sig
-            out["arc%d_rep%d" % (arc, rep)] = {"fast_nms": round(acc.get("fast_nms", -1), 4), "all": round(sum(acc.values()), 4), "same_bits": sig == ref}
+            out["arc%s_rep%d" % (var, rep)] = {"fast_nms": round(acc.get("fast_nms", -1), 4), "all": round(sum(acc.values()), 4), "same_bits": sig == ref}
             ex.close()
     os.environ.pop("ORBFE_FAST_ARC", None)
+    os.environ.pop("ORBFE_FAST_CTAS", None)
     return out
 
 
