@@ -471,9 +471,13 @@ def main():
                          [mp[i].copy() for i in range(4)])
         return int(nm.sum())
 
+    stage_cnt = {}
+
     def collect_stages():
+        # per-stage sums AND occurrence counts: the per-batch figure is sum / count, whatever number of intervals came back
         for name, ms in ex.stage_times():
             stage_acc[name] = stage_acc.get(name, 0.0) + ms
+            stage_cnt[name] = stage_cnt.get(name, 0) + 1
         stage_n[0] += 1
 
     # ---- device-resident pipeline (value path).  Two buffer sets: while batch t is matched and read back on
@@ -567,8 +571,10 @@ def main():
     # a last thread matches finished batches in order (orbfe_search_by_projection_frames on host views).
     # ctypes releases the GIL inside the calls.  Outputs rotate through four pinned buffer sets.
     from concurrent.futures import ThreadPoolExecutor
-    NEX = max(1, int(os.environ.get("ORBFE_E2E_EXTRACTORS", "2")))   # extractor handles in flight
-    NBUF = NEX + 2
+    NEX = max(1, int(os.environ.get("ORBFE_E2E_EXTRACTORS", "3")))   # extractor handles in flight
+    os.environ.setdefault("ORBFE_CHUNKS", "2")   # upload chunks per host batch: with three handles in flight two chunks measured best
+    NMATCH = max(1, int(os.environ.get("ORBFE_E2E_MATCHERS", "3")))  # matcher handles in flight (C++ driver)
+    NBUF = NEX + NMATCH
     e2e_bufs = []
     for _ in range(NBUF):
         hk = torch.empty((B, NFEAT, 28), dtype=torch.uint8).pin_memory()
@@ -652,7 +658,7 @@ def main():
                     "orbfe_matcher_create", "orbfe_matcher_destroy", "orbfe_matcher_counters", "orbfe_search_by_projection_frames",
                     "orbfe_frame_scale_factors", "orbfe_last_error"]
         fns = (C.c_void_p * len(fn_names))(*[C.cast(getattr(Lfe, n), C.c_void_p).value for n in fn_names])
-        cfg = E2eConfig(W, H, NFEAT, NLEVELS, FAST_TH, B, NB, NEX, 2, NBUF, local_rank, SCALE, FX, FY, CX, CY, DEPTH, MATCH_TH)
+        cfg = E2eConfig(W, H, NFEAT, NLEVELS, FAST_TH, B, NB, NEX, NMATCH, NBUF, local_rank, SCALE, FX, FY, CX, CY, DEPTH, MATCH_TH)
         arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         drv["keep"] = (fns, cfg, Tcws_arr)
         drv["h"] = dl.e2e_create(C.byref(cfg), fns, h_frames.data_ptr(), Tcws_arr.ctypes.data, arr([b_[0] for b_ in e2e_bufs]),
@@ -717,11 +723,14 @@ def main():
     ex.set_profiling(True)
     ex.stage_times()                 # flush
     stage_acc.clear()
+    stage_cnt.clear()
     stage_n[0] = 0
 
     sampler.t_begin = time.perf_counter()
     r_dev = timed(run_device, args.steps)
-    stages = {k: v / max(args.steps, 1) for k, v in stage_acc.items()}   # ms per step (= SUB library calls)
+    stages = {k: v / max(stage_cnt.get(k, 1), 1) * SUB for k, v in stage_acc.items()}   # ms per step (= SUB library calls)
+    if rank == 0 and stage_cnt and min(stage_cnt.values()) != args.steps * SUB:
+        sys.stderr.write("bench: stage intervals read back for %s of %d batches\n" % (sorted(set(stage_cnt.values())), args.steps * SUB))
     ex.set_profiling(False)
     r_e2e = timed(run_e2e, args.steps)
     sampler.t_end = time.perf_counter()
@@ -817,18 +826,24 @@ def main():
                 t_ncu = tj["duration_us"] * 1e-3 / tj["frames_in_launch"]          # ms per frame under ncu
                 util_hw = tj["alu_pipe_pct_of_peak"] / 100.0 * t_ncu / (dom_ms / B)   # of the hardware peak (64 /clk/SM)
                 a = util_hw * tj["alu_peak_hw_thread_inst_per_clk_sm"]
+                scale_t = t_ncu / (dom_ms / B)
                 alu = {"achieved": a, "peak": tj["alu_peak_measured_thread_inst_per_clk_sm"],
                        "unit": "ALU-pipe thread-instructions/clk/SM", "frac": a / tj["alu_peak_measured_thread_inst_per_clk_sm"],
-                       "peak_source": "tools/ubench_alu.cu on B200: 58.7 (VIMNMX3 / PRMT / LOP3 share one 16-lane pipe per SM "
-                                      "sub-partition; hardware peak 64)",
-                       "how": "ncu sm__inst_executed_pipe_alu %.1f%% of peak at %.1f us per frame, scaled by the live per-frame time"
-                              % (tj["alu_pipe_pct_of_peak"], t_ncu * 1e3), "source": tj.get("source")}
+                       "peak_source": "tools/ubench_alu.cu on B200 (profiles/r2_ubench_alu.txt): 58.7 (VIMNMX3 / VIMNMX / PRMT / LOP3 share one "
+                                      "16-lane pipe per SM sub-partition; hardware peak 64)",
+                       "issue_slots_used": tj.get("issue_active_pct", 0.0) / 100.0 * scale_t,
+                       "fma_pipe_frac_of_hw_peak": tj.get("fma_pipe_pct_of_peak", 0.0) / 100.0 * scale_t,
+                       "issue_note": "warp-instructions issued per cycle per scheduler; the same microbenchmark measures 0.63-0.68 as the most a "
+                                     "mix of ALU-pipe and FMA-pipe instructions issues on this SM, 0.46 for ALU-pipe instructions alone: the "
+                                     "kernel moved its 2-input min/max pairs to the FMA pipe (exact fp16-subnormal HFMA2) until issue, not a pipe, binds",
+                       "how": "ncu sm__inst_executed_pipe_alu %.1f%% of peak, issue active %.1f%%, at %.1f us per frame, scaled by the live per-frame time"
+                              % (tj["alu_pipe_pct_of_peak"], tj.get("issue_active_pct", 0.0), t_ncu * 1e3), "source": tj.get("source")}
         except Exception:
             pass
         roof = {"bound": "alu" if alu else "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                "note": "achieved/peak/frac are the HBM roofline the metric is quoted against; fast_nms is bound by the integer ALU "
-                        "pipe (the `alu` entry), not by memory: see profiles/README.md",
+                "note": "achieved/peak/frac are the HBM roofline the metric is quoted against; fast_nms is bound by instruction issue "
+                        "(integer ALU pipe + FMA pipe, the `alu` entry), not by memory: see profiles/README.md",
                 "alu": alu,
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms, "frames_per_launch": B,
                 "extract_all_kernels": {"algorithmic_bytes": ab["total"] * B, "ms": ext_ms,
@@ -842,6 +857,9 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config_dict(args),
                 "e2e": {"value": e2e_val, "unit": "Mkeypoints/s", "ms_per_step": r_e2e["ms"] / args.steps,
+                        "pipeline": ("python threads (ORBFE_E2E_PY=1)" if USE_PY_E2E else "C++ threads over the public C-ABI (tools/e2e_driver.cpp)") +
+                                    ": %d extractor handles, %d matcher handles, %s upload chunks per batch; pinned host frames in, host keypoints / "
+                                    "descriptors / matches out" % (NEX, NMATCH, os.environ.get("ORBFE_CHUNKS", "4")),
                         # whole job: every rank moves the same amount
                         "h2d_bytes_per_step": world * (SUB * B * W * H + r_e2e["mh2d"] // args.steps),
                         "d2h_bytes_per_step": world * (SUB * B * (NFEAT * 60 + 4) + r_e2e["md2h"] // args.steps)},

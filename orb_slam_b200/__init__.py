@@ -214,7 +214,7 @@ class ORBextractor:
         _check(lib().orbfe_extractor_set_profiling(self._h, int(on)))
 
     def stage_times(self):
-        cap = 1024
+        cap = 32768   # the library keeps at most 16384 intervals between two reads
         names = (C.c_char * 32 * cap)()
         ms = (C.c_float * cap)()
         n = lib().orbfe_extractor_stage_times(self._h, names, ms, cap)

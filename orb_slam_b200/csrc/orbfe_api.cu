@@ -624,7 +624,7 @@ static int enqueue_pipeline(OrbfeExtractor *ex, int f0, int nf, OrbfeKeyPoint *d
 
 static void profiling_begin(OrbfeExtractor *ex, cudaStream_t s) {
     if (!ex->profiling) return;
-    if (ex->timer.names.size() > 4096) { ex->timer.names.clear(); ex->timer.origin_pending = true; }  // never read: recycle
+    if (ex->timer.names.size() > 16384) { ex->timer.names.clear(); ex->timer.origin_pending = true; }  // never read: recycle
     stage_mark(ex, s, nullptr);  // call marker (its interval is ignored)
 }
 

@@ -5,6 +5,7 @@ duration, DRAM bytes, pipe utilisation, issue rate, registers, occupancy.  Usage
 The raw CSV has one header row, one units row and one row per profiled launch."""
 import csv
 import json
+import re
 import sys
 
 KEYS = {
@@ -17,6 +18,7 @@ KEYS = {
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pct",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "xu_pct",
     "sm__issue_active.avg.pct_of_peak_sustained_active": "issue_pct",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_pct",
     "smsp__inst_executed.sum": "warp_inst",
     "smsp__thread_inst_executed.sum": "thread_inst",
     "sm__inst_executed_pipe_alu.sum": "alu_warp_inst",
@@ -46,7 +48,10 @@ def summarise(path):
     name_i = hdr.index("Kernel Name")
     out = []
     for r in data:
-        d = {"kernel": r[name_i].split("(")[0], "file": path}
+        full = r[name_i]
+        m = re.match(r"^(.*?>)\(", full) if "<" in full else None     # template kernels: keep the <...> argument list
+        d = {"kernel": (m.group(1) if m else full.split("(")[0]).replace("void ", "").replace("orbfe::", "").replace("(int)", "").replace(" ", ""),
+             "file": path}
         for key, i in col.items():
             try:
                 v = float(r[i].replace(",", ""))

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "orb_slam_b200", "liborbfe.so")
-WATCH = ["UTMALDG", "UBLKCP", "SYNCS", "VIMNMX3", "VIMNMX", "IDP", "POPC", "LOP3", "PRMT", "IMAD", "SHFL", "LDS", "LDG", "STG", "ATOMS", "ATOMG",
+WATCH = ["UTMALDG", "UBLKCP", "SYNCS", "VIMNMX3", "VIMNMX", "HFMA2", "HADD2", "IDP", "POPC", "LOP3", "PRMT", "IMAD", "SHFL", "LDS", "LDG", "STG", "ATOMS", "ATOMG",
          "RED", "MEMBAR", "HMMA", "UTCHMMA", "UTCQMMA", "LDTM", "DFMA", "DADD", "DMUL"]
 
 
