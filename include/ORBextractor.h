@@ -35,6 +35,12 @@ public:
     // CUDA device used by extractors constructed afterwards (default 0); extension, not in the reference
     static void SetDevice(int device);
 
+    // What a failing liborbfe call does (extension, same contract as ORBmatcher::SetErrorHandler): the handler is called
+    // with the OrbfeStatus code and message, then operator() returns no keypoints.  Default: log to stderr, abort only if
+    // ORBFE_ABORT_ON_ERROR is set.  NULL restores the default.
+    typedef void (*ErrorHandler)(int code, const char *message);
+    static void SetErrorHandler(ErrorHandler handler);
+
 protected:
     int nfeatures;
     double scaleFactor;  // a double initialised from the float argument, exactly like the reference member

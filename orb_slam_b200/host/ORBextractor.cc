@@ -18,18 +18,31 @@ namespace ORB_SLAM {
 static int g_device = 0;
 void ORBextractor::SetDevice(int device) { g_device = device; }
 
+// Error policy, the same as ORBmatcher's (host/ORBmatcher.cc): the reference's extractor cannot fail, liborbfe's calls can
+// (no device, a failed cudaMalloc, an unsupported geometry).  Every failure goes through one handler; the default logs and the
+// call returns NO keypoints and an empty descriptor matrix (Tracking sees a frame without features: a lost frame, not a dead
+// process); ORBFE_ABORT_ON_ERROR=1 or ORBextractor::SetErrorHandler() select another policy.  There is no CPU path.
+static void default_error_handler(int code, const char *msg) {
+    std::fprintf(stderr, "ORBextractor: liborbfe error %d: %s (there is no CPU path; returning no keypoints)\n", code, msg);
+    const char *e = std::getenv("ORBFE_ABORT_ON_ERROR");
+    if (e && *e && *e != '0') std::abort();
+}
+static ORBextractor::ErrorHandler g_error_handler = default_error_handler;
+void ORBextractor::SetErrorHandler(ErrorHandler handler) { g_error_handler = handler ? handler : default_error_handler; }
+
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _scoreType, int _fastTh)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), scoreType(_scoreType), fastTh(_fastTh), mpImpl(NULL)
 {
     const int rc = orbfe_extractor_create(_nfeatures, _scaleFactor, _nlevels, _scoreType, _fastTh, g_device, &mpImpl);
     if (rc != ORBFE_OK) {
-        // the reference constructor cannot fail; there is deliberately no CPU path to fall back to
-        std::fprintf(stderr, "ORBextractor: liborbfe error %d: %s\n", rc, orbfe_last_error());
-        std::abort();
+        // the reference constructor cannot fail; there is deliberately no CPU path to fall back to: the object stays
+        // without a handle and every operator() call reports through the handler again
+        mpImpl = NULL;
+        g_error_handler(rc, orbfe_last_error());
     }
 }
 
-ORBextractor::~ORBextractor() { orbfe_extractor_destroy(mpImpl); }
+ORBextractor::~ORBextractor() { if (mpImpl) orbfe_extractor_destroy(mpImpl); }
 
 void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
                               cv::OutputArray _descriptors)
@@ -54,8 +67,8 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::
                            reinterpret_cast<OrbfeKeyPoint*>(&_keypoints[0]), &desc[0], n, &n);
     }
     if (rc != ORBFE_OK) {
-        std::fprintf(stderr, "ORBextractor: liborbfe error %d: %s\n", rc, orbfe_last_error());
-        std::abort();
+        g_error_handler(rc, orbfe_last_error());
+        n = 0;
     }
     _keypoints.resize(n);
     if (n == 0) {

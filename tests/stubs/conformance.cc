@@ -482,7 +482,26 @@ int main() {
     for (int i = 0; i < 32; i++) { a.at<unsigned char>(0, i) = (unsigned char)(i * 7); b.at<unsigned char>(0, i) = (unsigned char)(i * 7 ^ 0x0F); }
     if (ORBmatcher::DescriptorDistance(a, b) != 32 * 4 || ORBmatcher::DescriptorDistance(a, a) != 0) { std::puts("DescriptorDistance wrong"); return 1; }
     if (ORBmatcher::TH_HIGH != 100 || ORBmatcher::TH_LOW != 50 || ORBmatcher::HISTO_LENGTH != 30) return 1;
-    if (orbfe_device_count() == 0) { std::puts("conformance: compile+link ok (no CUDA device: run skipped)"); return 0; }
+    if (orbfe_device_count() == 0) {
+        // No device: the error policy of the facades is what can be checked here.  The reference's constructor and
+        // operator() cannot fail; ours report through the handler and return no keypoints / 0 matches instead of
+        // aborting the process (ORBFE_ABORT_ON_ERROR=1 restores the abort).
+        static int n_err = 0;
+        struct H { static void on_error(int, const char *) { n_err++; } };
+        ORBextractor::SetErrorHandler(&H::on_error);
+        ORBmatcher::SetErrorHandler(&H::on_error);
+        ORBextractor ex(500, 1.2f, 8, 1, 20);             // create fails: no device
+        cv::Mat im(120, 160, CV_8UC1);
+        for (int y = 0; y < 120; y++) for (int x = 0; x < 160; x++) im.at<unsigned char>(y, x) = (unsigned char)((x * 7) ^ (y * 13));
+        std::vector<cv::KeyPoint> kp(3);
+        cv::Mat desc;
+        ex(im, cv::Mat(), kp, desc);                      // reports again, returns nothing
+        if (n_err < 2 || !kp.empty() || !desc.empty()) { std::printf("error policy: n_err=%d kp=%d\n", n_err, (int)kp.size()); return 9; }
+        ORBextractor::SetErrorHandler(NULL);
+        ORBmatcher::SetErrorHandler(NULL);
+        std::puts("conformance: compile+link ok, error policy ok (no CUDA device: run skipped)");
+        return 0;
+    }
 
     const int nFeatures = 1000, nLevels = 8, Score = 1, fastTh = 20;
     const float fScaleFactor = 1.2f;
