@@ -112,9 +112,37 @@ def run_rig(args, ctx=None):
             xch.search_for_initialization(mt, T, d_f1.data_ptr(), d_f2.data_ptr(), d_prev.data_ptr(), RW, RH, 100, d_m12.data_ptr(),
                                           d_nm.data_ptr(), s)
 
+    # Throughput form of the fused step: the exchange's buffer halves alternate by epoch, so the extraction of time step t+1
+    # (stream) may run while the matcher of step t (stream_m: one CTA per pair, one busy warp each) is still going.  Depth 2:
+    # extract(t+2) rewrites the half of step t and is held back until THIS rank's matcher of step t is done -- its descriptor
+    # kernel would otherwise spin on an acknowledgement that a kernel queued behind it has to produce.
+    stream_m = torch.cuda.Stream(device=dev)
+    ev_x = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_m = [torch.cuda.Event(), torch.cuda.Event()]
+    pipe = {"k": 0}
+
+    def step_fused_pipelined():
+        k = pipe["k"]
+        with torch.cuda.stream(stream):
+            if k >= 2:
+                stream.wait_event(ev_m[k & 1])
+            xch.extract(ex, d_frames.data_ptr(), RW, RH, RW, RW * RH, s)
+            ev_x[k & 1].record(stream)
+            a, _, _ = xch.buffers_of_current_epoch()
+            if a not in own_view:
+                own_view[a] = _as_tensor(torch, a + rank * T * RNF * 28, (T, RNF, 28), dev).view(torch.float32).view(T, RNF, 7)[:, :, 0:2]
+        with torch.cuda.stream(stream_m):
+            stream_m.wait_event(ev_x[k & 1])
+            d_prev.copy_(own_view[a])
+            xch.search_for_initialization(mt, T, d_f1.data_ptr(), d_f2.data_ptr(), d_prev.data_ptr(), RW, RH, 100, d_m12.data_ptr(),
+                                          d_nm.data_ptr(), stream_m.cuda_stream)
+            ev_m[k & 1].record(stream_m)
+        pipe["k"] = k + 1
+
     def timed(fn, steps, warm):
         for _ in range(warm):
             fn()
+        stream.wait_stream(stream_m)
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -122,6 +150,7 @@ def run_rig(args, ctx=None):
         e0.record(stream)
         for _ in range(steps):
             fn()
+        stream.wait_stream(stream_m)
         e1.record(stream)
         stream.synchronize()
         return _max_over_ranks(torch, dist, dev, [e0.elapsed_time(e1) / steps])[0]
@@ -153,6 +182,9 @@ def run_rig(args, ctx=None):
     gk_f = _as_tensor(torch, a, (world, T, RNF, 28), dev).cpu().numpy()
     gd_f = _as_tensor(torch, b, (world, T, RNF, 32), dev).cpu().numpy()
     gc_f = _as_tensor(torch, c, (world, T), dev, torch.int32).cpu().numpy()
+    ms_pipe = timed(step_fused_pipelined, args.steps, args.warmup)
+    xch.check(s)
+    same_pipe = bool(np.array_equal(nm_fused, d_nm.cpu().numpy()) and np.array_equal(m12_fused, d_m12.cpu().numpy()))
     ms_ag = timed(only_allgather, args.steps, args.warmup)
     ms_ex = timed(only_extract, args.steps, args.warmup)
     ms_exf = timed(only_extract_fused, args.steps, args.warmup)
@@ -192,18 +224,21 @@ def run_rig(args, ctx=None):
                 rc, ok, od, _ = O.extract(O.make_params(RNF, 1.2, RNL, 1, 20), frames[0])
                 oracle_ok &= bool(rc == 0 and np.array_equal(od, gd_f[rank, 0][:len(ok)]) and np.array_equal(ok["x"], k1["x"]))
     kp_step = float(world * T * RNF)
-    flags = _max_over_ranks(torch, dist, dev, [0.0 if same_gather else 1.0, 0.0 if same_match else 1.0])
+    flags = _max_over_ranks(torch, dist, dev, [0.0 if same_gather else 1.0, 0.0 if same_match else 1.0, 0.0 if same_pipe else 1.0])
     out = None
     if rank == 0:
         out = {"workload": "configs[3]: %d-camera rig 1280x720, one camera per GPU, %d time steps per exchange, 2000 kp, 8 levels; "
                            "cross-camera SearchForInitialization(window 100) of camera r against camera r+1" % (world, T),
                "n_gpus": world, "nccl_version": CM.nccl_version(),
                "ms_per_step": {"extract+ncclAllGather+match": ms_nccl, "extract(fused exchange)+match": ms_fused,
+                               "extract(fused exchange) of step t+1 overlapping the match of step t": ms_pipe,
                                "ncclAllGather alone": ms_ag, "extract alone": ms_ex, "extract with fused exchange + wait + release": ms_exf},
                "exchange_cost_ms": {"nccl": ms_ag, "fused (extra time over a plain extract)": ms_exf - ms_ex,
                                     "fused (whole step vs whole nccl step)": ms_fused - ms_nccl},
                "describe_kernel_ms": {"plain": desc_ms[0], "with remote stores + publish": desc_ms[1]},
-               "Mkeypoints_per_s": {"nccl": kp_step / (ms_nccl * 1e-3) / 1e6, "fused": kp_step / (ms_fused * 1e-3) / 1e6},
+               "Mkeypoints_per_s": {"nccl": kp_step / (ms_nccl * 1e-3) / 1e6, "fused": kp_step / (ms_fused * 1e-3) / 1e6,
+                                    "fused, pipelined over time steps": kp_step / (ms_pipe * 1e-3) / 1e6},
+               "matches_identical_pipelined_vs_fused_all_ranks": flags[2] == 0.0,
                "nvlink_bytes_per_step_per_gpu": T * RNF * 60 * (world - 1),
                "matches_rank0": int(nm_fused.sum()), "gathered_identical_nccl_vs_fused_all_ranks": flags[0] == 0.0,
                "matches_identical_nccl_vs_fused_all_ranks": flags[1] == 0.0, "oracle_check_rank0": oracle_ok}
