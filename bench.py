@@ -636,54 +636,27 @@ def main():
     # reference's Tracking thread is -- calling orbfe_extract_batch / orbfe_search_by_projection_frames of liborbfe.so, nothing
     # else.  The Python-thread version above is kept behind ORBFE_E2E_PY=1: its GIL hand-offs cost more than the calls themselves.
     import ctypes as C
-    drv = {"lib": None, "h": None, "mh2d": 0, "md2h": 0, "mlaunch": 0}
+    drv = {"d": None, "mh2d": 0, "md2h": 0}
     if not USE_PY_E2E:
-        from orb_slam_b200.build import E2E_SO
-        if not os.path.exists(E2E_SO):
-            raise SystemExit("libe2e_driver.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-        dl = C.CDLL(E2E_SO)
-
-        class E2eConfig(C.Structure):
-            _fields_ = [(n, C.c_int) for n in ("W", "H", "nfeat", "nlevels", "fast_th", "B", "NB", "nex", "nmatch", "nbuf", "device")] + \
-                       [(n, C.c_float) for n in ("scale", "fx", "fy", "cx", "cy", "depth", "th")]
-        dl.e2e_create.restype = C.c_void_p
-        dl.e2e_create.argtypes = [C.POINTER(E2eConfig)] + [C.c_void_p] * 6
-        dl.e2e_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
-        dl.e2e_last_matches.argtypes = [C.c_void_p, C.c_void_p]
-        dl.e2e_destroy.argtypes = [C.c_void_p]
-        dl.e2e_error.restype = C.c_char_p
-        dl.e2e_error.argtypes = [C.c_void_p]
-        Lfe = fe.lib()
-        fn_names = ["orbfe_extractor_create", "orbfe_extractor_destroy", "orbfe_extract_batch", "orbfe_extractor_last_launches",
-                    "orbfe_matcher_create", "orbfe_matcher_destroy", "orbfe_matcher_counters", "orbfe_search_by_projection_frames",
-                    "orbfe_frame_scale_factors", "orbfe_last_error"]
-        fns = (C.c_void_p * len(fn_names))(*[C.cast(getattr(Lfe, n), C.c_void_p).value for n in fn_names])
-        cfg = E2eConfig(W, H, NFEAT, NLEVELS, FAST_TH, B, NB, NEX, NMATCH, NBUF, local_rank, SCALE, FX, FY, CX, CY, DEPTH, MATCH_TH)
-        arr = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
-        drv["keep"] = (fns, cfg, Tcws_arr)
-        drv["h"] = dl.e2e_create(C.byref(cfg), fns, h_frames.data_ptr(), Tcws_arr.ctypes.data, arr([b_[0] for b_ in e2e_bufs]),
-                                 arr([b_[1] for b_ in e2e_bufs]), arr([b_[2] for b_ in e2e_bufs]))
-        if not drv["h"]:
-            raise SystemExit("e2e_create failed: " + fe.lib().orbfe_last_error().decode())
-        drv["lib"] = dl
+        from orb_slam_b200.stream_driver import StreamDriver
+        drv["d"] = StreamDriver(W, H, NFEAT, NLEVELS, SCALE, FAST_TH, B, NB, NEX, NMATCH, local_rank, FX, FY, CX, CY, DEPTH, MATCH_TH,
+                                h_frames.data_ptr(), Tcws_arr, [b_[0].data_ptr() for b_ in e2e_bufs], [b_[1].data_ptr() for b_ in e2e_bufs],
+                                [b_[2].data_ptr() for b_ in e2e_bufs])
 
     def run_e2e_driver(steps):
-        out = (C.c_longlong * 7)()
-        hs = (C.c_double * 3)()
-        if drv["lib"].e2e_run(drv["h"], steps * SUB, out, hs) != 0:
-            raise SystemExit("e2e driver failed: " + drv["lib"].e2e_error(drv["h"]).decode())
-        kp_total[0] += out[0]
-        launches[0] += out[2] + out[5]
-        drv["mh2d"] += out[3]
-        drv["md2h"] += out[4]
-        host_t["e2e_extract_call"] += hs[0]; host_t["views"] += hs[1]; host_t["match_call"] += hs[2]; host_t["n"] += steps * SUB
+        r = drv["d"].run(steps * SUB)
+        kp_total[0] += r["keypoints"]
+        launches[0] += r["extract_launches"] + r["match_launches"]
+        drv["mh2d"] += r["match_h2d"]
+        drv["md2h"] += r["match_d2h"]
+        host_t["e2e_extract_call"] += r["extract_s"]; host_t["views"] += r["views_s"]; host_t["match_call"] += r["match_s"]
+        host_t["n"] += steps * SUB
         # the last matched batch, for the oracle cross-check: its keypoints / descriptors still sit in their pinned output set
-        st = int(out[6])
+        st = int(r["last_batch"])
         _, _, _, k_np, d_np, c_np = e2e_bufs[st % NBUF]
-        mp4 = np.empty((4, NFEAT), np.int32)
-        drv["lib"].e2e_last_matches(drv["h"], mp4.ctypes.data)
+        mp4 = drv["d"].last_matches()
         checks["e2e"] = (st % NB, [k_np[i, :c_np[i]].copy() for i in range(4)], [d_np[i, :c_np[i]].copy() for i in range(4)], list(mp4))
-        return int(out[1])
+        return int(r["matches"])
 
     run_e2e = run_e2e_python if USE_PY_E2E else run_e2e_driver
 
@@ -875,8 +848,8 @@ def main():
         if not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline_dict(frames_np, shifts, 1, True)
         print(json.dumps(line))
-    if drv["h"]:
-        drv["lib"].e2e_destroy(drv["h"])
+    if drv["d"]:
+        drv["d"].close()
     for x in e2e_ex:
         x.close()
     for m_ in e2e_mt:

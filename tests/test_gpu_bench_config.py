@@ -136,3 +136,83 @@ def test_sbp_frames_at_bench_config(stream, entry_placement, replay):
     for j in range(NFRAMES - 1):
         assert nm[j] == ref[j][0] and np.array_equal(mp[j], ref[j][1]), j
     m.close()
+
+
+def test_stream_driver_equals_direct_calls_and_oracle(gpu_required):
+    """bench.py's end-to-end pipeline (tools/e2e_driver.cpp on C++ threads: two extractor handles and two matcher handles
+    alternating batches, frame views and synthetic map points built in C++) produces, for every frame of a small stream, the
+    keypoints / descriptors of a direct orbfe_extract_batch call, and for every consecutive pair -- the pairs that straddle
+    two batches included -- the match vector of the CPU oracle."""
+    import torch
+    from orb_slam_b200.stream_driver import StreamDriver
+    w, h, nf, B, NB = 640, 480, 600, 4, 3
+    fx = fy = 500.0
+    cx, cy, depth, th = w / 2.0, h / 2.0, 4.0, 15.0
+    rng = np.random.default_rng(9)
+    frames, shifts = [textured_frame(w, h, seed=21)], [(0, 0)]
+    for i in range(1, B * NB):
+        dx, dy = int(rng.integers(-5, 6)), int(rng.integers(-3, 4))
+        frames.append(shifted_frame(frames[-1], dx, dy, seed=300 + i))
+        shifts.append((dx, dy))
+    frames = np.stack(frames)
+
+    def tcw(dx, dy):
+        T = np.zeros((3, 4), np.float32)
+        T[0, 0] = T[1, 1] = T[2, 2] = 1
+        T[0, 3], T[1, 3] = dx * depth / fx, dy * depth / fy
+        return T
+    Tcws = np.stack([tcw(*s) for s in shifts]).reshape(-1, 12)
+    h_frames = torch.from_numpy(frames).pin_memory()
+    nex, nmatch = 2, 2
+    bufs = [(torch.zeros((B, nf, 28), dtype=torch.uint8).pin_memory(), torch.zeros((B, nf, 32), dtype=torch.uint8).pin_memory(),
+             torch.zeros((B,), dtype=torch.int32).pin_memory()) for _ in range(nex + nmatch)]
+    drv = StreamDriver(w, h, nf, 8, 1.2, 20, B, NB, nex, nmatch, 0, fx, fy, cx, cy, depth, th, h_frames.data_ptr(), Tcws,
+                       [b[0].data_ptr() for b in bufs], [b[1].data_ptr() for b in bufs], [b[2].data_ptr() for b in bufs])
+    ex = fe.ORBextractor(nf, 1.2, 8)
+    kps, desc, cnt = ex.extract_batch(frames)
+    ex.close()
+
+    def world(k):
+        o = np.empty((len(k), 3), np.float32)
+        o[:, 0] = (k["x"] - np.float32(cx)) / np.float32(fx) * np.float32(depth)
+        o[:, 1] = (k["y"] - np.float32(cy)) / np.float32(fy) * np.float32(depth)
+        o[:, 2] = depth
+        return o
+    total_matches = 0
+    for nb in (1, 2, 3):       # one batch at a time: the last matched batch is then batch nb - 1 of the stream
+        r = drv.run(1)
+        st = int(r["last_batch"])
+        assert st == nb - 1 and r["keypoints"] == int(cnt[st * B:(st + 1) * B].sum()) and r["extract_launches"] > 0
+        bk, bd, bc = bufs[st % len(bufs)]
+        mp4 = drv.last_matches()
+        nm_oracle = 0
+        for i in range(B):
+            f = st * B + i
+            n = int(bc[i])
+            assert n == cnt[f]
+            assert np.array_equal(bk.numpy()[i, :n].reshape(-1).view(fe.KP_DTYPE), kps[f][:n])
+            assert np.array_equal(bd.numpy()[i, :n], desc[f][:n])
+            # pair i of a batch: Current = frame f, Last = frame f - 1; the FIRST batch of a run has no predecessor and matches its
+            # first frame against its own last frame (a scene cut), later runs continue the stream
+            fl = f - 1 if i > 0 else (st * B + B - 1)
+            oc = O.OracleFrame(kps[f][:cnt[f]], desc[f][:cnt[f]], w, h)
+            ol = O.OracleFrame(kps[fl][:cnt[fl]], desc[fl][:cnt[fl]], w, h)
+            n_o, mp_o = O.search_by_projection_ff(oc, ol, np.ones(ol.n, np.uint8), np.zeros(ol.n, np.uint8), world(kps[fl][:cnt[fl]]),
+                                                  Tcws[f].reshape(3, 4), fx, fy, cx, cy, th, True)
+            assert np.array_equal(mp4[i][:oc.n], mp_o), (st, i)
+            nm_oracle += n_o
+        assert r["matches"] == nm_oracle
+        total_matches += nm_oracle
+    assert total_matches > 500
+    # two batches in one run: batch 1 of that run takes the last frame of batch 0 as the Last frame of its first pair
+    r = drv.run(2)
+    st = int(r["last_batch"])
+    assert st == 4 and st % NB == 1
+    mp4 = drv.last_matches()
+    f = (st % NB) * B
+    oc = O.OracleFrame(kps[f][:cnt[f]], desc[f][:cnt[f]], w, h)
+    ol = O.OracleFrame(kps[f - 1][:cnt[f - 1]], desc[f - 1][:cnt[f - 1]], w, h)
+    n_o, mp_o = O.search_by_projection_ff(oc, ol, np.ones(ol.n, np.uint8), np.zeros(ol.n, np.uint8), world(kps[f - 1][:cnt[f - 1]]),
+                                          Tcws[f].reshape(3, 4), fx, fy, cx, cy, th, True)
+    assert np.array_equal(mp4[0][:oc.n], mp_o) and n_o > 50
+    drv.close()
