@@ -409,6 +409,46 @@ def fastarc(args):
     return out
 
 
+def latency(args):
+    """Small-batch shapes, per-stage CUDA-event times of the device-resident extractor: one 1080p frame (the reference's own call
+    shape) and eight 720p frames (one rig step of configs[3])."""
+    import torch
+    import orb_slam_b200 as fe
+    from orb_slam_b200.synth import textured_frame, shifted_frame
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    out = {"what": "per-stage ms of small extractor batches (device-resident)"}
+    for tag, W, H, B in (("1x1080p", 1920, 1080, 1), ("8x720p", 1280, 720, 8)):
+        base = textured_frame(W, H, seed=5)
+        frames = np.stack([shifted_frame(base, 2 * i, i, seed=i) for i in range(B)])
+        d_frames = torch.from_numpy(frames).to(dev)
+        d_kps = torch.empty((B, 2000, 28), dtype=torch.uint8, device=dev)
+        d_desc = torch.empty((B, 2000, 32), dtype=torch.uint8, device=dev)
+        d_cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+        ex = fe.ORBextractor(2000, 1.2, 8, fe.FAST_SCORE, 20)
+        ex.set_profiling(True)
+        call = lambda: ex.extract_batch_device(d_frames.data_ptr(), W, H, W, W * H, B, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(),
+                                               stream.cuda_stream)
+        for _ in range(5):
+            call()
+        stream.synchronize()
+        ex.stage_times()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 50
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(n):
+                call()
+            e1.record(stream)
+        stream.synchronize()
+        acc = {}
+        for name, ms in ex.stage_times():
+            acc[name] = acc.get(name, 0.0) + ms / n
+        out[tag] = {"ms_per_call": e0.elapsed_time(e1) / n, "stages": {k: round(v, 4) for k, v in acc.items()}}
+        ex.close()
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="config3,config5")
@@ -418,4 +458,4 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
     for w in args.what.split(","):
-        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1, "matchers": matchers, "h2d": h2d, "fastarc": fastarc}[w](args)))
+        print(json.dumps({"config3": config3, "config5": config5, "small": small, "exchange1": exchange1, "matchers": matchers, "h2d": h2d, "fastarc": fastarc, "latency": latency}[w](args)))
