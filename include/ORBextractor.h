@@ -26,7 +26,8 @@ public:
     ORBextractor(int nfeatures = 1000, float scaleFactor = 1.2f, int nlevels = 8, int scoreType = FAST_SCORE, int fastTh = 20);
     ~ORBextractor();
 
-    // keypoints + 32-byte descriptors of one CV_8UC1 image; `mask` must be empty (Frame.cc:60 passes cv::Mat())
+    // keypoints + 32-byte descriptors of one CV_8UC1 image.  `mask` has no effect, as in the reference: ORBextractor.cc:601-603
+    // builds a cellMask that no call consumes (cv::FAST runs unmasked, :607), and Frame.cc:60 passes cv::Mat()
     void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors);
 
     int inline GetLevels() { return nlevels; }

@@ -51,7 +51,7 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::
         return;
     cv::Mat image = _image.getMat();
     assert(image.type() == CV_8UC1);  // :725
-    (void)_mask;                      // always empty on the hot path (Frame.cc:60)
+    (void)_mask;                      // never applied by the reference either (:601-603 build a cellMask nothing reads); empty at Frame.cc:60
 
     static_assert(sizeof(cv::KeyPoint) == sizeof(OrbfeKeyPoint), "cv::KeyPoint must be the 28-byte OpenCV 2.4 layout");
     const int cap = nfeatures > 0 ? nfeatures : 1;
