@@ -122,3 +122,39 @@ def test_phased_batch_mode_matches_chunked(gpu_required):
     with pytest.raises(fe.OrbfeError):
         ex.set_batch_mode(7)
     ex.close()
+
+
+def test_random_geometries_and_extreme_contrast(gpu_required):
+    """A seeded sweep over image sizes / feature counts / level counts / thresholds, on content that reaches both ends of the u8
+    range (binary 0/255 noise, saturated blobs on texture): the FAST arc network runs part of its min/max on the FMA pipe as
+    fp16-subnormal arithmetic, which must be exact for every value 0..255 and every difference of two of them."""
+    rng = np.random.default_rng(2024)
+    for it in range(10):
+        W = int(rng.integers(200, 1100))
+        H = int(rng.integers(160, 800))
+        nl = int(rng.integers(2, 9))
+        nf = int(rng.integers(150, 2500))
+        th = int(rng.choice([5, 7, 12, 20, 35]))
+        kind = it % 3
+        if kind == 0:
+            img = textured_frame(W, H, seed=900 + it)
+            for _ in range(6):   # saturated and black blobs
+                x0, y0 = int(rng.integers(0, W - 40)), int(rng.integers(0, H - 40))
+                img[y0:y0 + int(rng.integers(5, 40)), x0:x0 + int(rng.integers(5, 40))] = int(rng.choice([0, 255]))
+        elif kind == 1:
+            img = (rng.integers(0, 2, (H, W), dtype=np.uint8) * 255).astype(np.uint8)   # binary noise: every ring value is 0 or 255
+        else:
+            img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+            img[::7, ::5] = 255
+            img[3::11, 2::9] = 0
+        img = np.ascontiguousarray(img)
+        rc = O.extract(O.make_params(nf, 1.2, nl, 1, th), img)[0]
+        if rc == -2:
+            # a cell grid the reference itself cannot run ((cols-1)*cellW reaches past the image: cv::Mat::colRange throws,
+            # ORBextractor.cc:599): the oracle and the library both refuse it
+            ex = fe.ORBextractor(nf, 1.2, nl, fe.FAST_SCORE, th)
+            with pytest.raises(fe.OrbfeError):
+                ex(img)
+            ex.close()
+            continue
+        _compare(img, nf, nl, fast_th=th, check_levels=False)
