@@ -1338,7 +1338,9 @@ __device__ __forceinline__ int brief_byte_fused(const __half2 *pp, float a, floa
         int t[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const float2 pf = __half22float2(pp[2 * k + e]);
+            // pattern pair 2k+e of this lane's descriptor byte; layout [pair / 4][lane][pair % 4]: the four LDS.128 of a warp
+            // cover 512 contiguous bytes each (the byte-major layout [lane][16] put 16 lanes on the same banks)
+            const float2 pf = __half22float2(pp[(k >> 1) * 128 + ((2 * k + e) & 3)]);
             const float px = pf.x, py = pf.y;
             // cvRound (round half to even) of |v| < 2^22 as one FADD: v + 1.5 * 2^23 has ulp 1
             const float fy = __fadd_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)), 12582912.0f);
@@ -1375,9 +1377,10 @@ __device__ __forceinline__ void describe_fused_body(const PlanDev *__restrict__ 
     // the pattern as fp16 (x, y) pairs: small integers are exact, and fp16 -> fp32 is a full-rate conversion
     __shared__ __align__(16) __half2 pat[512];
     __shared__ __align__(16) uint32_t patch[8 * DF_WARP_WORDS];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {   // i = 16 * descriptor byte (= lane) + pair
         const char2 p = *reinterpret_cast<const char2 *>(g_pattern + 2 * i);
-        pat[i] = __floats2half2_rn((float)p.x, (float)p.y);
+        const int ln = i >> 4, pr = i & 15;
+        pat[((pr >> 2) * 32 + ln) * 4 + (pr & 3)] = __floats2half2_rn((float)p.x, (float)p.y);
     }
     __syncthreads();
 
@@ -1517,8 +1520,8 @@ __device__ __forceinline__ void describe_fused_body(const PlanDev *__restrict__ 
     // outside it: no per-sample bounds test
     const bool inner = (x >= 18) && (x + 18 < w) && (y >= 18) && (y + 18 < h);
     const int xoff = off + DF_R - 3;  // u16 index of the leftmost tap of a sample at rx = 0
-    const int val = inner ? brief_byte_fused<false>(pat + lane * 16, a, b, x, y, w, h, vpW, xoff, ctr)
-                          : brief_byte_fused<true>(pat + lane * 16, a, b, x, y, w, h, vpW, xoff, ctr);
+    const int val = inner ? brief_byte_fused<false>(pat + lane * 4, a, b, x, y, w, h, vpW, xoff, ctr)
+                          : brief_byte_fused<true>(pat + lane * 4, a, b, x, y, w, h, vpW, xoff, ctr);
     uint32_t word = (uint32_t)val;
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 1) << 8;
     word |= __shfl_down_sync(0xffffffffu, (uint32_t)val, 2) << 16;
