@@ -100,3 +100,26 @@ def test_headers_are_plain_c(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_stream_driver_builds_and_fails_loudly_without_a_device():
+    """bench.py's end-to-end pipeline driver (tools/e2e_driver.cpp) is plain C++ over the public C-ABI: it builds with g++, exports
+    its five entry points, links nothing from oracle/, and creating it without a CUDA device fails with the library's message."""
+    import ctypes as C
+    import subprocess
+    from orb_slam_b200.build import build_e2e_driver
+    so = build_e2e_driver()
+    dl = C.CDLL(so)
+    for sym in ("e2e_create", "e2e_run", "e2e_last_matches", "e2e_error", "e2e_destroy"):
+        assert hasattr(dl, sym), sym
+    needed = subprocess.run(["readelf", "-d", so], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in needed and "liborbfe" not in needed     # entry points of liborbfe.so arrive as function pointers
+    src = open(os.path.join(ROOT, "tools", "e2e_driver.cpp")).read()
+    assert "#include <cuda" not in src and "cudaMemcpy" not in src and "cudaMalloc" not in src   # the driver makes no CUDA call of its own
+    if fe.lib().orbfe_device_count() == 0:
+        from orb_slam_b200.stream_driver import StreamDriver
+        frames = np.zeros((2, 48, 64), np.uint8)
+        bufs = [(np.zeros((1, 50, 28), np.uint8), np.zeros((1, 50, 32), np.uint8), np.zeros(1, np.int32)) for _ in range(3)]
+        with pytest.raises(RuntimeError):
+            StreamDriver(64, 48, 50, 2, 1.2, 20, 1, 2, 1, 1, 0, 50.0, 50.0, 32.0, 24.0, 3.0, 15.0, frames.ctypes.data, np.zeros((2, 12), np.float32),
+                         [b[0].ctypes.data for b in bufs], [b[1].ctypes.data for b in bufs], [b[2].ctypes.data for b in bufs])
