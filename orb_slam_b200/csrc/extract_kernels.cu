@@ -35,6 +35,34 @@ __device__ __forceinline__ int find_level_by(const PlanDev *plan, int idx, int w
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): every kernel of the pipeline opens with
+//     griddepcontrol.launch_dependents   -- the NEXT kernel in the stream may be launched as soon as all CTAs of this one run
+//     griddepcontrol.wait                -- ... and this one touches nothing a predecessor wrote until that grid has completed
+// and is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that the launch latency and prologue of kernel
+// n+1 overlap the tail of kernel n.  It matters for the small batches of the reference's own call shape (one frame per call:
+// twelve launches of 5-30 us); with ORBFE_PDL=0 (or for kernels launched without the attribute) both instructions are no-ops.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... P, typename... A>
+static inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pyramid: level l from level l-1.  One thread = 4 adjacent destination pixels (one uchar4 store).
 // Horizontal/vertical tap tables were computed on the host exactly as OpenCV computes them, so the
 // device part is pure integer: r = S[x0]*a0 + S[x1]*a1 ; v = (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.
@@ -42,6 +70,7 @@ __device__ __forceinline__ int find_level_by(const PlanDev *plan, int idx, int w
 #define RZ_ROWS 4  // destination rows per thread (the horizontal taps are loaded once and reused)
 
 __global__ void __launch_bounds__(256) resize_level_kernel(const PlanDev *__restrict__ plan, int level, int f0) {
+    pdl_prologue();
     const LevelDev &D = plan->lv[level];
     const LevelDev &S = plan->lv[level - 1];
     const int f = blockIdx.z + f0;
@@ -151,7 +180,7 @@ void launch_resize_level(const PlanDev *d_plan, const PlanDev &hp, int level, in
     const LevelDev &D = hp.lv[level];
     dim3 block(64, 4);
     dim3 grid((D.w + 255) / 256, (D.h + 4 * RZ_ROWS - 1) / (4 * RZ_ROWS), nf);
-    resize_level_kernel<<<grid, block, 0, s>>>(d_plan, level, f0);
+    launch_k(resize_level_kernel, grid, block, 0, s, hp.pdl != 0, d_plan, level, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -634,6 +663,7 @@ __global__ void __launch_bounds__(256, MINB) fast_nms_tma_kernel(const PlanDev *
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_prologue();   // the barriers above are private to the CTA; the first TMA load reads what the resize kernels wrote
     int wi = blockIdx.x;
     if (wi < nwork && threadIdx.x == 0) {
         const FTileInfo t0 = wk.ftile_info[wi % ntiles];
@@ -690,7 +720,7 @@ void launch_fast_nms(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0
     if (w.tmaps) {
         const int nwork = hp.nftiles_total * nf;
         const int grid = min(nwork, w.fast_grid);
-        fast_tma_variant(w.fast_arc, w.fast_ctas <= 3 ? 3 : 4)<<<grid, 256, F2_TMA_SMEM, s>>>(d_plan, w, f0, nwork);
+        launch_k(fast_tma_variant(w.fast_arc, w.fast_ctas <= 3 ? 3 : 4), dim3(grid), dim3(256), F2_TMA_SMEM, s, hp.pdl != 0, d_plan, w, f0, nwork);
         return;
     }
     dim3 grid(hp.nftiles_total, nf);
@@ -707,6 +737,7 @@ __device__ __forceinline__ int warp_sum(int v) {
 }
 
 __global__ void __launch_bounds__(32) cell_quota_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
+    pdl_prologue();
     __shared__ uint32_t no_more[128];  // bitmap, up to 4096 cells per level
     const int l = blockIdx.x, f = blockIdx.y + f0;
     const LevelDev &L = plan->lv[l];
@@ -760,7 +791,7 @@ __global__ void __launch_bounds__(32) cell_quota_kernel(const PlanDev *__restric
 
 void launch_cell_quota(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int f0, int nf, cudaStream_t s) {
     dim3 grid(hp.nlevels, nf);
-    cell_quota_kernel<<<grid, 32, 0, s>>>(d_plan, w, f0);
+    launch_k(cell_quota_kernel, grid, dim3(32), 0, s, hp.pdl != 0, d_plan, w, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -772,6 +803,7 @@ void launch_cell_quota(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int 
 // ------------------------------------------------------------------------------------------------
 #define CS_LIST 256   // candidates sharing the score at the cut that are ranked directly
 __global__ void __launch_bounds__(128) cell_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
+    pdl_prologue();
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix, s_mask, s_list[CS_LIST];
     __shared__ int s_k, s_base, s_fill, s_bin_cnt, s_ln;
@@ -880,7 +912,7 @@ void launch_cell_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int
     if (hp.ncells_total == 0) return;
     dim3 grid(hp.ncells_total, nf);
     if (w.cand_keys64) { cell_select_harris_kernel<<<grid, 128, 0, s>>>(d_plan, w, f0); return; }
-    cell_select_kernel<<<grid, 128, 0, s>>>(d_plan, w, f0);
+    launch_k(cell_select_kernel, grid, dim3(128), 0, s, hp.pdl != 0, d_plan, w, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -909,6 +941,7 @@ __device__ void bitonic_sort_desc(unsigned long long *a, int n2) {
 }
 
 __global__ void __launch_bounds__(512) level_select_kernel(const PlanDev *__restrict__ plan, WorkDev wk, int f0) {
+    pdl_prologue();
     extern __shared__ unsigned long long skeys[];
     const int l = blockIdx.x, f = blockIdx.y + f0;
     const LevelDev &L = plan->lv[l];
@@ -1088,7 +1121,7 @@ int set_level_select_smem(int bytes) {
 void launch_level_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, size_t smem_bytes, int f0, int nf, cudaStream_t s) {
     dim3 grid(hp.nlevels, nf);
     if (w.cand_keys64) { level_select_harris_kernel<<<grid, 512, smem_bytes, s>>>(d_plan, w, f0); return; }
-    level_select_kernel<<<grid, 512, smem_bytes, s>>>(d_plan, w, f0);
+    launch_k(level_select_kernel, grid, dim3(512), smem_bytes, s, hp.pdl != 0, d_plan, w, f0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1560,6 +1593,7 @@ __global__ void __launch_bounds__(256) describe_fused_kernel(const PlanDev *__re
                                                              const int8_t *__restrict__ g_pattern,
                                                              OrbfeKeyPoint *__restrict__ out_kps,
                                                              uint8_t *__restrict__ out_desc, int *__restrict__ out_counts, int f0) {
+    pdl_prologue();
     PeerOut none;
     none.n = 0;
     describe_fused_body<false>(plan, wk, g_pattern, out_kps, out_desc, out_counts, f0, none);
@@ -1606,7 +1640,7 @@ void launch_describe_fused(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, 
     dim3 grid((hp.nfeatures + 7) / 8, nf);
     if (grid.x == 0) grid.x = 1;
     if (peers && peers->n > 0) { describe_fused_exchange_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, f0, *peers); return; }
-    describe_fused_kernel<<<grid, 256, 0, s>>>(d_plan, w, d_pattern, d_kps, d_desc, d_counts, f0);
+    launch_k(describe_fused_kernel, grid, dim3(256), 0, s, hp.pdl != 0, d_plan, w, d_pattern, d_kps, d_desc, d_counts, f0);
 }
 
 void launch_describe(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, const int8_t *d_pattern,

@@ -171,6 +171,10 @@ static int build_plan(OrbfeExtractor *ex, int W, int H, int B) {
     P.t_hi = std::max(ex->fast_th, 7);
     P.t1_is_lo = ex->fast_th <= 7;
     P.score_type = ex->score_type;
+    {   // programmatic dependent launch of the pipeline's kernels (extract_kernels.cu, pdl_prologue); ORBFE_PDL=0 turns it off
+        const char *e = getenv("ORBFE_PDL");
+        P.pdl = !(e && *e == '0');
+    }
     {   // HarrisResponses scale (ORBextractor.cc:90-92)
         float scale = (float)(1 << 2) * (float)7 * 255.0f;
         scale = 1.0f / scale;

@@ -51,6 +51,7 @@ struct PlanDev {
     int t_lo, t_hi;      // min / max of (fastTh, 7)
     int t1_is_lo;        // fastTh <= 7
     int score_type;
+    int pdl;             // host side only: launch the pipeline's kernels with programmatic stream serialization (ORBFE_PDL, default 1)
     float harris_scale4;   // (1 / (4 * 7 * 255))^4 as the reference computes it (ORBextractor.cc:90-92)
     long long cand_total;  // candidate slots per frame
     LevelDev lv[ORBFE_MAX_LEVELS];

@@ -97,7 +97,7 @@ def test_strided_input_and_empty(gpu_required):
 
 
 @pytest.mark.parametrize("env", [{"ORBFE_BLUR_PLANES": "1"}, {"ORBFE_FAST_NO_TMA": "1"}, {"ORBFE_BLUR_PLANES": "1", "ORBFE_FAST_NO_TMA": "1"}] +
-                         [{"ORBFE_FAST_ARC": str(a), "ORBFE_FAST_CTAS": "4"} for a in (-1, 0, 4, 8, 12, 16)] + [{"ORBFE_FAST_ARC": "12", "ORBFE_FAST_CTAS": "3"}, {"ORBFE_FAST_ARC": "16", "ORBFE_FAST_CTAS": "4"}])
+                         [{"ORBFE_FAST_ARC": str(a), "ORBFE_FAST_CTAS": "4"} for a in (-1, 0, 4, 8, 12, 16)] + [{"ORBFE_FAST_ARC": "12", "ORBFE_FAST_CTAS": "3"}, {"ORBFE_FAST_ARC": "16", "ORBFE_FAST_CTAS": "4"}, {"ORBFE_PDL": "0"}])
 def test_alternate_kernel_paths(gpu_required, env, monkeypatch):
     """The variants behind environment switches (whole-level blur7 + describe instead of the fused descriptor kernel;
     plain staged FAST tiles instead of the TMA pipeline; every compiled form of the FAST arc network, integer-ALU-only
