@@ -918,11 +918,9 @@ void launch_cell_select(const PlanDev *d_plan, const PlanDev &hp, WorkDev w, int
 // ------------------------------------------------------------------------------------------------
 // Level-wide trim (:697-701) and canonical ordering.  One CTA per (level, frame); bitonic sorts in smem.
 // ------------------------------------------------------------------------------------------------
-// Thread t handles the pairs whose lower element is t, t + blockDim.x, ...: a warp touches whole 32-aligned groups, so two
-// consecutive stages whose distances are both <= 16 read and write only elements the same warp wrote -- __syncwarp between
-// them; a stage at distance >= 32 writes into another warp's group, so it has a __syncthreads before AND after (21 instead
-// of 55 block barriers for 1024 keys; the kernel is pure latency: one CTA per (level, frame)).
 __device__ void bitonic_sort_desc(unsigned long long *a, int n2) {
+    // (warp-local stages under __syncwarp were tried: 21 instead of 55 block barriers for 1024 keys, no gain for one frame and
+    // 41 -> 50 us for a 64-frame batch -- the barriers are not what this kernel waits for)
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < n2; i += blockDim.x) {
@@ -933,9 +931,7 @@ __device__ void bitonic_sort_desc(unsigned long long *a, int n2) {
                     if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
                 }
             }
-            const int next = j > 1 ? (j >> 1) : k;   // distance of the next stage (the merge after this one starts at distance k)
-            if (j >= 32 || next >= 32 || (j == 1 && k == n2)) __syncthreads();
-            else __syncwarp();
+            __syncthreads();
         }
     }
 }

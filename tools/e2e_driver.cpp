@@ -5,7 +5,7 @@
 // -- is done here for a stream of frames through the PUBLIC C-ABI of liborbfe.so only, on plain std::threads:
 //   * `nex` extractor handles alternate batches (orbfe_extract_batch: pinned host frames in, host keypoints / descriptors
 //     out), so the upload of batch t+1 overlaps the kernels of batch t;
-//   * `nmatch` matcher handles alternate batches: the frame views (the slice of Frame the matcher reads), the synthetic
+//   * `nmatch` matcher handles alternate batches: they build the frame views (the slice of Frame the matcher reads) and the synthetic
 //     map points (every keypoint back-projected at a fixed depth, same float32 operations as bench.py's backproject())
 //     and orbfe_search_by_projection_frames on HOST views (its H2D / D2H inside).
 // bench.py used to run this pipeline on Python threads; the GIL hand-offs between seven threads cost more than the
@@ -76,7 +76,7 @@ struct Run {
     std::mutex mu;
     std::condition_variable cv;
     std::vector<int> extracted, tail_ready, matched;   // per batch of this run
-    std::vector<Tail> tails;                           // ring of 2 per parity is not enough with nmatch threads: one per batch slot
+    std::vector<Tail> tails;                           // one per batch of the run (sized before the threads start: never reallocated)
     std::atomic<long long> kp{0}, nm{0}, launches{0};
     std::atomic<int> failed{0};
     double t_extract = 0, t_views = 0, t_match = 0;    // summed host seconds inside the calls (under mu)

@@ -10,7 +10,6 @@ try:
     r=d['roofline']; print({k:d[k] for k in ('value','ms_per_step','parity_checked','single_frame_latency_ms')}, d['e2e']['value'], r['stage_ms_per_batch_extractor_alone'], r['frac'], r['extract_all_kernels']['frac'])
 except Exception as e: print('parse failed',e)
 PY
-timeout 600 compute-sanitizer --tool racecheck --kernel-name kns=level_select --print-limit 5 python tools/racecheck_small.py > gpurun_out/racecheck.log 2>&1; tail -2 gpurun_out/racecheck.log
 timeout 300 python tools/prof_kernels.py --what small,matchers,latency > gpurun_out/prof_small.json 2>&1; tail -2 gpurun_out/prof_small.json | cut -c1-900
 ORBFE_PDL=0 timeout 300 python tools/prof_kernels.py --what latency > gpurun_out/prof_latency_nopdl.json 2>&1; tail -1 gpurun_out/prof_latency_nopdl.json | cut -c1-700
 ORBFE_PDL=0 timeout 600 python bench.py --no-cpu-baseline --no-parity --steps 10 > gpurun_out/bench_nopdl.json 2> gpurun_out/bench_nopdl.err; python - <<'PY'
